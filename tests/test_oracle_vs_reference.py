@@ -1,0 +1,95 @@
+"""Pins oracle/shannon_oracle.py to the REAL reference (loaded from /root/reference through
+oracle/ref_loader.py).  Runs only where the reference tree exists (the build container);
+on the GPU box the committed fixtures in tests/golden/ carry the same pin."""
+import os
+
+import pytest
+
+import helpers
+from oracle import ref_loader, shannon_oracle
+
+pytestmark = pytest.mark.skipif(not ref_loader.available(),
+                                reason="reference tree not present (GPU box)")
+
+SAMPLES = os.path.join(ref_loader.REFERENCE_DIR, "Samples")
+
+
+def both(case, **kw):
+    ref_ec = ref_loader.load("extension_correction")
+    ref_kfc = ref_loader.load("kmers_for_component")
+    a = helpers.run_frontend(ref_ec.extension_correction, ref_kfc.kmers_for_component,
+                             case, "ref", **kw)
+    b = helpers.run_frontend(shannon_oracle.extension_correction,
+                             shannon_oracle.kmers_for_component, case, "ora", **kw)
+    helpers.assert_same_run(a, b, "oracle vs reference")
+    return a, b
+
+
+def test_sample_se(workdir):
+    seqs = helpers.read_fasta_seqs(os.path.join(SAMPLES, "SE_read.fasta"))
+    both(helpers.make_case(workdir, 24, seqs))
+
+
+def test_sample_pe_subset(workdir):
+    s1 = helpers.read_fasta_seqs(os.path.join(SAMPLES, "PE_read_1.fasta"))[:600]
+    s2 = helpers.read_fasta_seqs(os.path.join(SAMPLES, "PE_read_2.fasta"))[:600]
+    both(helpers.make_case(workdir, 24, s1, s2))
+
+
+@pytest.mark.parametrize("seed,ntx,npairs,psize", [(1, 12, 1500, 500), (2, 30, 3000, 2),
+                                                   (3, 40, 6000, 1)])
+def test_synthetic_pe(workdir, seed, ntx, npairs, psize):
+    s1, s2 = helpers.synthetic_seqs(ntx, npairs, seed)
+    case = helpers.make_case(workdir, 24, s1, s2)
+    a, _ = both(case, partition_size=psize)
+    if psize < 10:
+        assert any(f.startswith("component1") for f in os.listdir(a[0])), \
+            "case was meant to exercise the gpmetis branch"
+
+
+def test_synthetic_se_inmem_and_small_k(workdir):
+    s1, _ = helpers.synthetic_seqs(10, 1500, 7)
+    both(helpers.make_case(workdir, 16, s1), inMem=True, partition_size=2, min_length=50)
+
+
+def test_double_stranded_load_flag(workdir):
+    s1, s2 = helpers.synthetic_seqs(8, 800, 11)
+    case = helpers.make_case(workdir, 24, s1, s2, double_stranded=False)
+    both(case, double_stranded_load=True, ec_inMem=False)
+
+
+def _repeat_rich_reads(seed, n_reads, read_len, genome_len, n_genomes):
+    """Low-entropy genomes with copied segments: forces weight ties, repeated r-mers/C-mers,
+    self-overlapping contigs -- the tie-break paths of duplicate_check and the DFS."""
+    import random
+    rnd = random.Random(seed)
+    genomes = []
+    for _ in range(n_genomes):
+        g = [rnd.choice("ACGT") for _ in range(genome_len)]
+        for _ in range(3):                       # copy a segment somewhere else
+            a = rnd.randrange(0, genome_len - 40)
+            b = rnd.randrange(0, genome_len - 40)
+            g[b:b + 30] = g[a:a + 30]
+        genomes.append("".join(g))
+    # isoform-like variants: splice out a middle piece
+    for g in list(genomes):
+        a = rnd.randrange(20, len(g) // 2)
+        genomes.append(g[:a] + g[a + 25:])
+    reads = []
+    for _ in range(n_reads):
+        g = rnd.choice(genomes)
+        s = rnd.randrange(0, len(g) - read_len + 1)
+        r = list(g[s:s + read_len])
+        if rnd.random() < 0.3:
+            r[rnd.randrange(read_len)] = rnd.choice("ACGT")
+        reads.append("".join(r))
+    return reads
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_repeat_rich_small_k(workdir, seed):
+    reads = _repeat_rich_reads(seed, 400, 40, 160, 4)
+    K = [8, 10, 12, 15][seed % 4]
+    case = helpers.make_case(workdir, K, reads)
+    both(case, min_weight=2, min_length=20 + seed, partition_size=1 + seed % 3,
+         inMem=bool(seed & 1))
