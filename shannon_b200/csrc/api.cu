@@ -1,0 +1,467 @@
+// extern "C" entry points of libshannon_b200.so (see include/shannon_b200.h).
+#include "common.cuh"
+#include "selfjoin.cuh"
+
+// implemented in the other translation units
+void shn_table_dump_impl(shn_ctx* c, uint64_t* h_keys, uint32_t* h_weights, uint32_t* h_idx);
+void shn_parse_kmer_file_impl(const char* path, uint64_t** keys_out, uint32_t** counts_out,
+                              uint64_t* n_out, int* k1_out);
+void shn_load_fasta_impl(const char* path, int64_t n_fixed, char** bases_out, uint64_t** offs_out,
+                         uint64_t* n_out);
+void shn_write_fasta_subset_impl(const char* path, int append, const char* bases,
+                                 const uint64_t* offsets, const uint32_t* read_idx, uint64_t m,
+                                 uint64_t first_index, const char* suffix);
+void shn_write_k1mer_windows_impl(const char* path, const char* bases, const uint64_t* offsets,
+                                  const uint32_t* contig_ids, uint64_t m, int k1,
+                                  const uint32_t* weights, const uint64_t* win_off);
+void shn_l3_run_impl(shn_ctx* c, uint32_t min_weight, uint32_t min_length);
+void shn_l3_get_sizes_impl(shn_ctx* c, shn_l3_sizes* out);
+void shn_l3_get_walks_impl(shn_ctx* c, uint64_t* seed_keys, uint32_t* n_left, uint32_t* n_right,
+                           uint64_t* tot_wt, uint8_t* flags);
+void shn_l3_get_contigs_impl(shn_ctx* c, char* bases, uint64_t* offsets);
+void shn_l3_get_allowed_impl(shn_ctx* c, uint64_t* keys, uint32_t* weights);
+void shn_l3_get_edges_impl(shn_ctx* c, uint32_t* a, uint32_t* b, uint32_t* weight, uint32_t* fp);
+void shn_l3_get_labels_impl(shn_ctx* c, uint32_t* label);
+void shn_l4_map_add_contigs_impl(shn_ctx* c, const char* bases, const uint64_t* offsets,
+                                 const uint32_t* comp_of_contig, uint64_t n_contigs, int k1,
+                                 int reset, uint64_t expected_total, int on_device);
+void shn_l4_map_set_weights_impl(shn_ctx* c, const uint64_t* keys, const uint32_t* weights,
+                                 uint64_t n, int on_device);
+void shn_l4_map_window_weights_impl(shn_ctx* c, const char* bases, const uint64_t* offsets,
+                                    uint64_t n_contigs, int k1, uint32_t* h_weights);
+void shn_l4_load_reads_impl(shn_ctx* c, int mate, const char* bases, const uint64_t* offsets,
+                            uint64_t n, int on_device);
+void shn_l4_assign_impl(shn_ctx* c, int paired, int k1, uint64_t* n_assign, uint64_t* n_lookups,
+                        uint64_t* n_valid);
+void shn_l4_get_assignments_impl(shn_ctx* c, uint32_t n_comps, uint64_t* h_offs, uint32_t* h_idx);
+void shn_synth_pairs_impl(shn_ctx* c, const uint8_t* tx, const uint64_t* tx_offs, const uint64_t* thr,
+                          uint64_t n_tx, uint64_t n_pairs, uint64_t first_pair, uint64_t seed,
+                          int read_len, int frag_len, uint32_t err_thr, char* m1, char* m2);
+void shn_revcomp_reads_impl(shn_ctx* c, const char* in, char* out, uint64_t n_reads, int read_len);
+void shn_count_k1mers_impl(shn_ctx* c, const char* const* arrays, const uint64_t* n_reads,
+                           int n_arrays, int read_len, int k1, uint64_t expected_distinct,
+                           uint64_t** keys_dev, uint32_t** counts_dev, uint64_t* n_distinct);
+void shn_count_free(shn_ctx* c);
+void shn_pack_kmers_impl(shn_ctx* c, const char* d_ascii, uint64_t n, int k1, uint64_t* d_keys);
+
+static thread_local std::string g_last_error;
+
+[[noreturn]] void shn_throw(const char* file, int line, const std::string& msg) {
+  const char* base = strrchr(file, '/');
+  throw ShnError(std::string(base ? base + 1 : file) + ":" + std::to_string(line) + ": " + msg);
+}
+
+#define SHN_API_BEGIN try {
+#define SHN_API_END(ctx)                                   \
+  return 0;                                                \
+  }                                                        \
+  catch (const std::exception& e) {                        \
+    g_last_error = e.what();                               \
+    if (ctx) (ctx)->last_error = e.what();                 \
+    return 1;                                              \
+  }                                                        \
+  catch (...) {                                            \
+    g_last_error = "unknown error";                        \
+    if (ctx) (ctx)->last_error = g_last_error;             \
+    return 1;                                              \
+  }
+
+static void bind(shn_ctx* c) {
+  SHN_CHECK(c != nullptr, "null context");
+  CUDA_CHECK(cudaSetDevice(c->device));
+}
+
+extern "C" {
+
+const char* shn_version(void) { return "shannon_b200 0.1 (sm_100a)"; }
+
+const char* shn_last_error(shn_ctx* ctx) {
+  if (ctx) return ctx->last_error.c_str();
+  return g_last_error.c_str();
+}
+
+int shn_create(int device, shn_ctx** out) {
+  shn_ctx* c = nullptr;
+  SHN_API_BEGIN
+  SHN_CHECK(out != nullptr, "null out pointer");
+  *out = nullptr;
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev == 0)
+    SHN_FAIL(std::string("no CUDA device available (") + cudaGetErrorString(e) +
+             "); shannon_b200 has no CPU fallback");
+  SHN_CHECK(device >= 0 && device < n_dev, "device index out of range");
+  CUDA_CHECK(cudaSetDevice(device));
+  c = new shn_ctx();
+  c->device = device;
+  cudaDeviceProp prop;
+  CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+  c->sm_count = prop.multiProcessorCount;
+  CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CUDA_CHECK(cudaEventCreate(&c->t0));
+  CUDA_CHECK(cudaEventCreate(&c->t1));
+  CUDA_CHECK(cudaEventCreate(&c->p0));
+  CUDA_CHECK(cudaEventCreate(&c->p1));
+  *out = c;
+  SHN_API_END(c)
+}
+
+void shn_destroy(shn_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  shn_l3_free(c);
+  shn_l4_free(c);
+  shn_count_free(c);
+  c->table.release();
+  c->cub_tmp.release();
+  c->flush_buf.release();
+  c->counters.release();
+  cudaEventDestroy(c->t0);
+  cudaEventDestroy(c->t1);
+  cudaEventDestroy(c->p0);
+  cudaEventDestroy(c->p1);
+  cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int shn_device_info(shn_ctx* c, int* sm_count, uint64_t* free_bytes, uint64_t* total_bytes) {
+  SHN_API_BEGIN
+  bind(c);
+  size_t f = 0, t = 0;
+  CUDA_CHECK(cudaMemGetInfo(&f, &t));
+  if (sm_count) *sm_count = c->sm_count;
+  if (free_bytes) *free_bytes = f;
+  if (total_bytes) *total_bytes = t;
+  SHN_API_END(c)
+}
+
+int shn_dev_alloc(shn_ctx* c, uint64_t bytes, void** dptr) {
+  SHN_API_BEGIN
+  bind(c);
+  *dptr = nullptr;
+  if (bytes) {
+    cudaError_t e = cudaMalloc(dptr, bytes);
+    if (e != cudaSuccess)
+      SHN_FAIL("cudaMalloc(" + std::to_string(bytes) + ") failed: " + cudaGetErrorString(e));
+  }
+  SHN_API_END(c)
+}
+int shn_dev_free(shn_ctx* c, void* dptr) {
+  SHN_API_BEGIN
+  bind(c);
+  if (dptr) CUDA_CHECK(cudaFree(dptr));
+  SHN_API_END(c)
+}
+int shn_host_alloc_pinned(shn_ctx* c, uint64_t bytes, void** hptr) {
+  SHN_API_BEGIN
+  bind(c);
+  *hptr = nullptr;
+  if (bytes) CUDA_CHECK(cudaMallocHost(hptr, bytes));
+  SHN_API_END(c)
+}
+int shn_host_free_pinned(shn_ctx* c, void* hptr) {
+  SHN_API_BEGIN
+  bind(c);
+  if (hptr) CUDA_CHECK(cudaFreeHost(hptr));
+  SHN_API_END(c)
+}
+int shn_memcpy_h2d(shn_ctx* c, void* dst, const void* src, uint64_t bytes) {
+  SHN_API_BEGIN
+  bind(c);
+  if (bytes) {
+    CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  }
+  SHN_API_END(c)
+}
+int shn_memcpy_d2h(shn_ctx* c, void* dst, const void* src, uint64_t bytes) {
+  SHN_API_BEGIN
+  bind(c);
+  if (bytes) {
+    CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  }
+  SHN_API_END(c)
+}
+int shn_sync(shn_ctx* c) {
+  SHN_API_BEGIN
+  bind(c);
+  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  SHN_API_END(c)
+}
+int shn_timer_start(shn_ctx* c) {
+  SHN_API_BEGIN
+  bind(c);
+  CUDA_CHECK(cudaEventRecord(c->t0, c->stream));
+  SHN_API_END(c)
+}
+int shn_timer_stop(shn_ctx* c, float* ms) {
+  SHN_API_BEGIN
+  bind(c);
+  CUDA_CHECK(cudaEventRecord(c->t1, c->stream));
+  CUDA_CHECK(cudaEventSynchronize(c->t1));
+  CUDA_CHECK(cudaEventElapsedTime(ms, c->t0, c->t1));
+  SHN_API_END(c)
+}
+int shn_prof_enable(shn_ctx* c, int enable) {
+  SHN_API_BEGIN
+  bind(c);
+  c->prof_on = enable != 0;
+  if (enable) c->prof.clear();
+  SHN_API_END(c)
+}
+int shn_prof_get(shn_ctx* c, const char* name, double* total_ms, uint64_t* launches) {
+  SHN_API_BEGIN
+  SHN_CHECK(c != nullptr, "null context");
+  auto it = c->prof.find(name);
+  *total_ms = it == c->prof.end() ? 0.0 : it->second.ms;
+  *launches = it == c->prof.end() ? 0 : it->second.launches;
+  SHN_API_END(c)
+}
+int shn_prof_dump(shn_ctx* c, char* buf, uint64_t buf_bytes) {
+  SHN_API_BEGIN
+  SHN_CHECK(c != nullptr && buf != nullptr && buf_bytes > 0, "bad arguments");
+  std::string s;
+  for (auto& kv : c->prof)
+    s += kv.first + "\t" + std::to_string(kv.second.ms) + "\t" + std::to_string(kv.second.launches) + "\n";
+  if (s.size() + 1 > buf_bytes) s.resize(buf_bytes - 1);
+  memcpy(buf, s.c_str(), s.size() + 1);
+  SHN_API_END(c)
+}
+uint64_t shn_launch_count(shn_ctx* c) { return c ? c->launches : 0; }
+
+int shn_flush_l2(shn_ctx* c) {
+  SHN_API_BEGIN
+  bind(c);
+  const uint64_t bytes = 256ull << 20;  // > 126 MB L2
+  c->flush_buf.reserve(bytes);
+  CUDA_CHECK(cudaMemsetAsync(c->flush_buf.p, 0x5A, bytes, c->stream));
+  SHN_API_END(c)
+}
+
+// ---- host IO -----------------------------------------------------------------------------------
+int shn_parse_kmer_file(shn_ctx* c, const char* path, uint64_t** keys, uint32_t** counts, uint64_t* n,
+                        int* k1) {
+  SHN_API_BEGIN
+  shn_parse_kmer_file_impl(path, keys, counts, n, k1);
+  SHN_API_END(c)
+}
+void shn_host_free(void* p) { free(p); }
+int shn_load_fasta(shn_ctx* c, const char* path, int64_t n_fixed, char** bases, uint64_t** offsets,
+                   uint64_t* n) {
+  SHN_API_BEGIN
+  shn_load_fasta_impl(path, n_fixed, bases, offsets, n);
+  SHN_API_END(c)
+}
+int shn_write_fasta_subset(shn_ctx* c, const char* path, int append, const char* bases,
+                           const uint64_t* offsets, const uint32_t* read_idx, uint64_t m,
+                           uint64_t first_index, const char* suffix) {
+  SHN_API_BEGIN
+  shn_write_fasta_subset_impl(path, append, bases, offsets, read_idx, m, first_index, suffix);
+  SHN_API_END(c)
+}
+int shn_write_k1mer_windows(shn_ctx* c, const char* path, const char* bases, const uint64_t* offsets,
+                            const uint32_t* contig_ids, uint64_t m, int k1, const uint32_t* weights,
+                            const uint64_t* win_off) {
+  SHN_API_BEGIN
+  shn_write_k1mer_windows_impl(path, bases, offsets, contig_ids, m, k1, weights, win_off);
+  SHN_API_END(c)
+}
+
+// ---- table -------------------------------------------------------------------------------------
+int shn_pack_kmers(shn_ctx* c, const char* ascii, uint64_t n, int k1, uint64_t* keys, int on_device) {
+  SHN_API_BEGIN
+  bind(c);
+  SHN_CHECK(k1 >= 1 && k1 <= 32, "k1 must be in 1..32");
+  if (n) {
+    DevBuf sa, sk;
+    const char* d_ascii = (const char*)InputView::get(c, ascii, n * (uint64_t)k1, on_device, sa);
+    uint64_t* d_keys = keys;
+    if (!on_device) {
+      sk.reserve(n * 8);
+      d_keys = sk.as<uint64_t>();
+    }
+    shn_pack_kmers_impl(c, d_ascii, n, k1, d_keys);
+    if (!on_device)
+      CUDA_CHECK(cudaMemcpyAsync(keys, d_keys, n * 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  }
+  SHN_API_END(c)
+}
+
+int shn_table_build(shn_ctx* c, const uint64_t* keys, const uint32_t* counts, uint64_t n, int k1,
+                    int double_stranded, int on_device) {
+  SHN_API_BEGIN
+  bind(c);
+  shn_l3_free(c);
+  DevBuf sk, sc;
+  const uint64_t* dk = (const uint64_t*)InputView::get(c, keys, n * 8, on_device, sk);
+  const uint32_t* dc = (const uint32_t*)InputView::get(c, counts, n * 4, on_device, sc);
+  shn_table_build_impl(c, dk, dc, n, k1, double_stranded);
+  SHN_API_END(c)
+}
+
+int shn_table_stats(shn_ctx* c, uint64_t* n_distinct, uint64_t* n_lowcomplexity, uint64_t* n_slots,
+                    int* k1) {
+  SHN_API_BEGIN
+  SHN_CHECK(c != nullptr, "null context");
+  if (n_distinct) *n_distinct = c->n_distinct;
+  if (n_lowcomplexity) *n_lowcomplexity = c->n_lowcomplexity;
+  if (n_slots) *n_slots = c->n_buckets * 2;
+  if (k1) *k1 = c->k1;
+  SHN_API_END(c)
+}
+
+int shn_table_lookup(shn_ctx* c, const uint64_t* keys, uint64_t n, uint32_t* weights, uint8_t* found,
+                     int on_device) {
+  SHN_API_BEGIN
+  bind(c);
+  if (n) {
+    DevBuf sk, sw, sf;
+    const uint64_t* dk = (const uint64_t*)InputView::get(c, keys, n * 8, on_device, sk);
+    uint32_t* dw = weights;
+    uint8_t* df = found;
+    if (!on_device) {
+      sw.reserve(n * 4);
+      sf.reserve(n);
+      dw = sw.as<uint32_t>();
+      df = sf.as<uint8_t>();
+    }
+    shn_table_lookup_impl(c, dk, n, dw, df);
+    if (!on_device) {
+      if (weights) CUDA_CHECK(cudaMemcpyAsync(weights, dw, n * 4, cudaMemcpyDeviceToHost, c->stream));
+      if (found) CUDA_CHECK(cudaMemcpyAsync(found, df, n, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  }
+  SHN_API_END(c)
+}
+
+int shn_table_dump(shn_ctx* c, uint64_t* keys, uint32_t* weights, uint32_t* first_idx) {
+  SHN_API_BEGIN
+  bind(c);
+  shn_table_dump_impl(c, keys, weights, first_idx);
+  SHN_API_END(c)
+}
+
+// ---- L3 ----------------------------------------------------------------------------------------
+int shn_l3_run(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
+  SHN_API_BEGIN
+  bind(c);
+  shn_l3_run_impl(c, min_weight, min_length);
+  SHN_API_END(c)
+}
+int shn_l3_get_sizes(shn_ctx* c, shn_l3_sizes* out) {
+  SHN_API_BEGIN
+  bind(c);
+  shn_l3_get_sizes_impl(c, out);
+  SHN_API_END(c)
+}
+int shn_l3_get_walks(shn_ctx* c, uint64_t* seed_keys, uint32_t* n_left, uint32_t* n_right,
+                     uint64_t* tot_wt, uint8_t* flags) {
+  SHN_API_BEGIN
+  bind(c);
+  shn_l3_get_walks_impl(c, seed_keys, n_left, n_right, tot_wt, flags);
+  SHN_API_END(c)
+}
+int shn_l3_get_contigs(shn_ctx* c, char* bases, uint64_t* offsets) {
+  SHN_API_BEGIN
+  bind(c);
+  shn_l3_get_contigs_impl(c, bases, offsets);
+  SHN_API_END(c)
+}
+int shn_l3_get_allowed(shn_ctx* c, uint64_t* keys, uint32_t* weights) {
+  SHN_API_BEGIN
+  bind(c);
+  shn_l3_get_allowed_impl(c, keys, weights);
+  SHN_API_END(c)
+}
+int shn_l3_get_edges(shn_ctx* c, uint32_t* a, uint32_t* b, uint32_t* weight, uint32_t* first_pos_in_b) {
+  SHN_API_BEGIN
+  bind(c);
+  shn_l3_get_edges_impl(c, a, b, weight, first_pos_in_b);
+  SHN_API_END(c)
+}
+int shn_l3_get_labels(shn_ctx* c, uint32_t* label) {
+  SHN_API_BEGIN
+  bind(c);
+  shn_l3_get_labels_impl(c, label);
+  SHN_API_END(c)
+}
+
+// ---- L4 ----------------------------------------------------------------------------------------
+int shn_l4_map_add_contigs(shn_ctx* c, const char* bases, const uint64_t* offsets,
+                           const uint32_t* comp_of_contig, uint64_t n_contigs, int k1, int reset,
+                           uint64_t expected_total_k1mers) {
+  SHN_API_BEGIN
+  bind(c);
+  shn_l4_map_add_contigs_impl(c, bases, offsets, comp_of_contig, n_contigs, k1, reset,
+                              expected_total_k1mers, 0);
+  SHN_API_END(c)
+}
+int shn_l4_map_set_weights(shn_ctx* c, const uint64_t* dict_keys, const uint32_t* dict_weights,
+                           uint64_t n) {
+  SHN_API_BEGIN
+  bind(c);
+  shn_l4_map_set_weights_impl(c, dict_keys, dict_weights, n, 0);
+  SHN_API_END(c)
+}
+int shn_l4_map_window_weights(shn_ctx* c, const char* bases, const uint64_t* offsets,
+                              uint64_t n_contigs, int k1, uint32_t* weights) {
+  SHN_API_BEGIN
+  bind(c);
+  shn_l4_map_window_weights_impl(c, bases, offsets, n_contigs, k1, weights);
+  SHN_API_END(c)
+}
+int shn_l4_load_reads(shn_ctx* c, int mate, const char* bases, const uint64_t* offsets,
+                      uint64_t n_reads, int on_device) {
+  SHN_API_BEGIN
+  bind(c);
+  shn_l4_load_reads_impl(c, mate, bases, offsets, n_reads, on_device);
+  SHN_API_END(c)
+}
+int shn_l4_assign(shn_ctx* c, int paired, int k1, uint64_t* n_assignments, uint64_t* n_lookups,
+                  uint64_t* n_valid_records) {
+  SHN_API_BEGIN
+  bind(c);
+  shn_l4_assign_impl(c, paired, k1, n_assignments, n_lookups, n_valid_records);
+  SHN_API_END(c)
+}
+int shn_l4_get_assignments(shn_ctx* c, uint32_t n_comps, uint64_t* comp_offsets, uint32_t* record_idx) {
+  SHN_API_BEGIN
+  bind(c);
+  shn_l4_get_assignments_impl(c, n_comps, comp_offsets, record_idx);
+  SHN_API_END(c)
+}
+
+// ---- inputs of the path --------------------------------------------------------------------------
+int shn_synth_pairs(shn_ctx* c, const uint8_t* tx_codes, const uint64_t* tx_offs,
+                    const uint64_t* thresholds, uint64_t n_tx, uint64_t n_pairs, uint64_t first_pair,
+                    uint64_t seed, int read_len, int frag_len, uint32_t err_threshold_24,
+                    char* mate1_dev, char* mate2_dev) {
+  SHN_API_BEGIN
+  bind(c);
+  shn_synth_pairs_impl(c, tx_codes, tx_offs, thresholds, n_tx, n_pairs, first_pair, seed, read_len,
+                       frag_len, err_threshold_24, mate1_dev, mate2_dev);
+  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  SHN_API_END(c)
+}
+int shn_revcomp_reads(shn_ctx* c, const char* in_dev, char* out_dev, uint64_t n_reads, int read_len) {
+  SHN_API_BEGIN
+  bind(c);
+  shn_revcomp_reads_impl(c, in_dev, out_dev, n_reads, read_len);
+  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  SHN_API_END(c)
+}
+int shn_count_k1mers(shn_ctx* c, const char* const* read_arrays_dev, const uint64_t* n_reads,
+                     int n_arrays, int read_len, int k1, uint64_t expected_distinct,
+                     uint64_t** keys_dev, uint32_t** counts_dev, uint64_t* n_distinct) {
+  SHN_API_BEGIN
+  bind(c);
+  shn_count_k1mers_impl(c, read_arrays_dev, n_reads, n_arrays, read_len, k1, expected_distinct,
+                        keys_dev, counts_dev, n_distinct);
+  SHN_API_END(c)
+}
+
+}  // extern "C"

@@ -1,0 +1,253 @@
+// Shared declarations for the shannon_b200 CUDA library (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/shannon_b200.h"
+
+// ---------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------
+struct ShnError : public std::runtime_error {
+  explicit ShnError(const std::string& m) : std::runtime_error(m) {}
+};
+
+[[noreturn]] void shn_throw(const char* file, int line, const std::string& msg);
+
+#define SHN_FAIL(msg) shn_throw(__FILE__, __LINE__, (msg))
+#define SHN_CHECK(cond, msg) \
+  do {                       \
+    if (!(cond)) SHN_FAIL(msg); \
+  } while (0)
+#define CUDA_CHECK(expr)                                                            \
+  do {                                                                              \
+    cudaError_t _e = (expr);                                                        \
+    if (_e != cudaSuccess)                                                          \
+      SHN_FAIL(std::string(#expr) + " -> " + cudaGetErrorName(_e) + ": " +          \
+               cudaGetErrorString(_e));                                             \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------
+// 2-bit k-mer arithmetic (host + device).  Code: A=0 G=1 C=2 T=3, complement = 3-code.
+// ---------------------------------------------------------------------------------------
+#define SHN_HD __host__ __device__ __forceinline__
+
+static const uint64_t SHN_EMPTY_KEY = 0xFFFFFFFFFFFFFFFFull;
+
+// ASCII -> code, 4 for anything that is not ACGT/acgt.
+SHN_HD uint32_t shn_code_of(uint32_t c) {
+  c &= 0xDFu;  // upper-case
+  // (c>>1)&3 : A->0 C->1 T->2 G->3 ; remap to A0 G1 C2 T3 with the constant 0b01'11'10'00
+  uint32_t x = (c >> 1) & 3u;
+  uint32_t code = (0x78u >> (2u * x)) & 3u;
+  bool ok = (c == 'A') | (c == 'C') | (c == 'G') | (c == 'T');
+  return ok ? code : 4u;
+}
+// strict variant used for reads: lower case is NOT a base (read.strip('ACTG'))
+SHN_HD uint32_t shn_code_of_strict(uint32_t c) {
+  uint32_t x = (c >> 1) & 3u;
+  uint32_t code = (0x78u >> (2u * x)) & 3u;
+  bool ok = (c == 'A') | (c == 'C') | (c == 'G') | (c == 'T');
+  return ok ? code : 4u;
+}
+SHN_HD char shn_base_of(uint32_t code) { return "AGCT"[code & 3u]; }
+
+SHN_HD uint64_t shn_kmer_mask(int k) { return k >= 32 ? ~0ull : ((1ull << (2 * k)) - 1ull); }
+
+// reverse complement of a k-base key
+SHN_HD uint64_t shn_revcomp(uint64_t x, int k) {
+  x = ~x;  // complement every pair (3 - code)
+  x = ((x >> 2) & 0x3333333333333333ull) | ((x & 0x3333333333333333ull) << 2);
+  x = ((x >> 4) & 0x0F0F0F0F0F0F0F0Full) | ((x & 0x0F0F0F0F0F0F0F0Full) << 4);
+  x = ((x >> 8) & 0x00FF00FF00FF00FFull) | ((x & 0x00FF00FF00FF00FFull) << 8);
+  x = ((x >> 16) & 0x0000FFFF0000FFFFull) | ((x & 0x0000FFFF0000FFFFull) << 16);
+  x = (x >> 32) | (x << 32);
+  return x >> (64 - 2 * k);
+}
+
+#if defined(__CUDA_ARCH__)
+#define SHN_POPC64(x) __popcll(x)
+#else
+#define SHN_POPC64(x) __builtin_popcountll(x)
+#endif
+
+// lowComplexity (extension_correction.py:142-149): max base count >= k-2
+SHN_HD bool shn_low_complexity(uint64_t x, int k) {
+  const uint64_t m = 0x5555555555555555ull & shn_kmer_mask(k);
+  uint64_t lo = x & m, hi = (x >> 1) & m;
+  int nT = SHN_POPC64(hi & lo);
+  int nC = SHN_POPC64(hi & ~lo);
+  int nG = SHN_POPC64(~hi & lo & m);
+  int nA = k - nT - nC - nG;
+  int mx = nA > nC ? nA : nC;
+  mx = mx > nG ? mx : nG;
+  mx = mx > nT ? mx : nT;
+  return mx >= k - 2;
+}
+
+// murmur3 fmix64
+SHN_HD uint64_t shn_mix64(uint64_t x) {
+  x ^= x >> 33;
+  x *= 0xFF51AFD7ED558CCDull;
+  x ^= x >> 33;
+  x *= 0xC4CEB9FE1A85EC53ull;
+  x ^= x >> 33;
+  return x;
+}
+
+// map A0 G1 C2 T3 pairs to A0 C1 G2 T3 pairs (swap the two bits of every pair): integer order of
+// the result is the ASCII order of the k-mer string.
+SHN_HD uint64_t shn_ascii_order_key(uint64_t x) {
+  return ((x & 0x5555555555555555ull) << 1) | ((x >> 1) & 0x5555555555555555ull);
+}
+
+// ---------------------------------------------------------------------------------------
+// K1-mer table: open addressing, 32-byte buckets of two 16-byte slots (one DRAM sector per
+// probe), linear probing over buckets.
+// ---------------------------------------------------------------------------------------
+struct __align__(16) ShnSlot {
+  uint64_t key;     // SHN_EMPTY_KEY when free
+  uint32_t weight;  // sum of counts; bit 31 = traversed (set by the walk kernels)
+  uint32_t idx;     // first-occurrence index in the input (dict insertion order)
+};
+static const uint32_t SHN_TRAVERSED = 0x80000000u;
+static const uint32_t SHN_WEIGHT_MASK = 0x7FFFFFFFu;
+static const uint32_t SHN_NONE32 = 0xFFFFFFFFu;
+
+struct ShnTableView {
+  ShnSlot* slots;      // 2 * n_buckets
+  uint64_t n_buckets;
+  __device__ __forceinline__ uint64_t bucket_of(uint64_t key) const {
+    return __umul64hi(shn_mix64(key), n_buckets);
+  }
+};
+
+// ---------------------------------------------------------------------------------------
+// device buffers and the context
+// ---------------------------------------------------------------------------------------
+struct DevBuf {
+  void* p = nullptr;
+  uint64_t bytes = 0;
+  DevBuf() {}
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+  // grow-only (re)allocation; contents are NOT preserved
+  void reserve(uint64_t nbytes) {
+    if (nbytes <= bytes) return;
+    release();
+    if (nbytes == 0) return;
+    cudaError_t e = cudaMalloc(&p, nbytes);
+    if (e != cudaSuccess) {
+      p = nullptr;
+      SHN_FAIL("cudaMalloc(" + std::to_string(nbytes) + " bytes) failed: " + cudaGetErrorString(e));
+    }
+    bytes = nbytes;
+  }
+  template <typename T>
+  T* as() const {
+    return reinterpret_cast<T*>(p);
+  }
+};
+
+struct ProfEntry {
+  double ms = 0;
+  uint64_t launches = 0;
+};
+
+struct L3State;
+struct L4State;
+
+struct shn_ctx {
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  std::string last_error;
+  cudaEvent_t t0 = nullptr, t1 = nullptr;
+  // profiling
+  bool prof_on = false;
+  cudaEvent_t p0 = nullptr, p1 = nullptr;
+  std::map<std::string, ProfEntry> prof;
+  uint64_t launches = 0;
+  // scratch
+  DevBuf cub_tmp;
+  DevBuf flush_buf;
+  DevBuf counters;  // small device array of uint64 counters
+  // K1-mer weight table
+  DevBuf table;
+  uint64_t n_buckets = 0;
+  int k1 = 0;
+  uint64_t n_distinct = 0, n_lowcomplexity = 0, n_items = 0;
+  L3State* l3 = nullptr;
+  L4State* l4 = nullptr;
+
+  ShnTableView view() const { return ShnTableView{table.as<ShnSlot>(), n_buckets}; }
+  void* tmp(uint64_t bytes) {
+    cub_tmp.reserve(bytes);
+    return cub_tmp.p;
+  }
+};
+
+// RAII profiling scope: brackets a launch group with events when profiling is enabled.
+struct ProfScope {
+  shn_ctx* c;
+  const char* name;
+  uint64_t n;
+  ProfScope(shn_ctx* ctx, const char* nm, uint64_t launches = 1) : c(ctx), name(nm), n(launches) {
+    c->launches += n;
+    if (c->prof_on) cudaEventRecord(c->p0, c->stream);
+  }
+  ~ProfScope() {
+    if (c->prof_on) {
+      cudaEventRecord(c->p1, c->stream);
+      cudaEventSynchronize(c->p1);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, c->p0, c->p1);
+      ProfEntry& e = c->prof[name];
+      e.ms += ms;
+      e.launches += n;
+    }
+  }
+};
+
+static inline unsigned shn_grid(uint64_t n, unsigned block) {
+  uint64_t g = (n + block - 1) / block;
+  if (g == 0) g = 1;
+  if (g > 0x7FFFFFFFull) SHN_FAIL("grid too large");
+  return (unsigned)g;
+}
+
+#define KERNEL_CHECK() CUDA_CHECK(cudaGetLastError())
+
+// copies with on_device switch ------------------------------------------------------------
+struct InputView {
+  // Makes `n_bytes` of caller data available on the device: either the pointer itself
+  // (on_device) or a staged copy in `stage`.
+  static const void* get(shn_ctx* c, const void* p, uint64_t n_bytes, int on_device, DevBuf& stage) {
+    if (on_device || n_bytes == 0) return p;
+    stage.reserve(n_bytes);
+    CUDA_CHECK(cudaMemcpyAsync(stage.p, p, n_bytes, cudaMemcpyHostToDevice, c->stream));
+    return stage.p;
+  }
+};
+
+// implemented in the individual translation units ------------------------------------------
+void shn_table_build_impl(shn_ctx* c, const uint64_t* d_keys, const uint32_t* d_counts, uint64_t n,
+                          int k1, int double_stranded);
+void shn_table_lookup_impl(shn_ctx* c, const uint64_t* d_keys, uint64_t n, uint32_t* d_weights,
+                           uint8_t* d_found);
+void shn_l3_free(shn_ctx* c);
+void shn_l4_free(shn_ctx* c);

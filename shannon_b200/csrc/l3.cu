@@ -1,0 +1,1192 @@
+// a3-a9: seeds, greedy walks, shape filter, duplicate filter, contig graph, components
+// (run_correction, extension_correction.py:334-450) on the K1-mer table of table.cu.
+//
+// Exactness argument (DESIGN.md "walks"): a walk only ever probes successors/predecessors of its
+// current K1-mer, so it stays inside one connected component of the K1-mer successor graph and
+// two walks in different components never read or write the same table slot.  The sequential
+// pop order of the reference therefore only matters *within* a component: we label components
+// with a lock-free union-find, give every component to one thread, and that thread replays its
+// component's seeds in global pop order (weight desc, later input line first).  The union of all
+// per-component replays is bit-identical to the reference's single sequential loop.
+#include <cub/cub.cuh>
+
+#include <cmath>
+
+#include "common.cuh"
+#include "selfjoin.cuh"
+#include "table_dev.cuh"
+
+struct L3State {
+  uint32_t min_weight = 0, min_length = 0;
+  shn_l3_sizes sz;
+  // per started walk, pop order
+  DevBuf w_seed_slot;   // uint32
+  DevBuf w_nl, w_nr;    // uint32
+  DevBuf w_totwt;       // uint64
+  DevBuf w_logstart;    // uint64
+  DevBuf walk_log;      // uint8 base codes, one per traversed K1-mer (seed entries unused)
+  std::vector<uint32_t> h_cand_walk;  // walk index of every candidate (passes length+hyperbola)
+  std::vector<uint8_t> h_cand_dup;    // duplicate_check() result per candidate
+  std::vector<uint8_t> h_cand_acc;    // accepted per candidate
+  // accepted contigs
+  DevBuf contig_codes;   // uint8 codes of all candidates, later compacted to accepted
+  DevBuf contig_offs;    // uint64 [n_contigs+1]
+  std::vector<uint64_t> h_contig_offs;
+  DevBuf allowed_keys, allowed_w;
+  PairTable edges;       // hi=b, lo=a, count=weight, min_i=first pos in b
+  DevBuf labels;         // uint32 [n_contigs+1]
+  L3State() { memset(&sz, 0, sizeof(sz)); }
+};
+
+namespace {
+
+constexpr int kBlock = 256;
+
+// ---- seeds ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock)
+    seed_count_kernel(const ShnSlot* __restrict__ slots, uint64_t n_slots, uint32_t min_weight,
+                      unsigned long long* counters) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  unsigned long long mine = 0;
+  for (; i < n_slots; i += stride) {
+    uint4 v = __ldg(reinterpret_cast<const uint4*>(slots) + i);
+    bool occ = !(v.x == 0xFFFFFFFFu && v.y == 0xFFFFFFFFu);
+    mine += (occ && v.z >= min_weight) ? 1 : 0;
+  }
+  typedef cub::BlockReduce<unsigned long long, kBlock> BR;
+  __shared__ typename BR::TempStorage tmp;
+  unsigned long long tot = BR(tmp).Sum(mine);
+  if (threadIdx.x == 0 && tot) atomicAdd(&counters[0], tot);
+}
+
+// (sort key, slot) for every K1-mer with weight >= min_weight; sort key ascending = pop order:
+// weight descending, then first-occurrence index descending (stable ascending sort + pop()).
+__global__ void __launch_bounds__(kBlock)
+    seed_emit_kernel(const ShnSlot* __restrict__ slots, uint64_t n_slots, uint32_t min_weight,
+                     uint64_t* __restrict__ skey, uint32_t* __restrict__ sslot,
+                     unsigned long long* cursor) {
+  __shared__ unsigned long long block_base;
+  __shared__ int warp_off[kBlock / 32];
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint4 v = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0, 0);
+  if (i < n_slots) v = __ldg(reinterpret_cast<const uint4*>(slots) + i);
+  bool occ = !(v.x == 0xFFFFFFFFu && v.y == 0xFFFFFFFFu);
+  bool is_seed = occ && v.z >= min_weight;
+  unsigned b = __ballot_sync(0xFFFFFFFFu, is_seed);
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) warp_off[warp] = __popc(b);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int tot = 0;
+    for (int w = 0; w < kBlock / 32; ++w) {
+      int cc = warp_off[w];
+      warp_off[w] = tot;
+      tot += cc;
+    }
+    block_base = tot ? atomicAdd(cursor, (unsigned long long)tot) : 0ull;
+  }
+  __syncthreads();
+  if (is_seed) {
+    uint64_t o = block_base + warp_off[warp] + __popc(b & ((1u << lane) - 1u));
+    skey[o] = ((uint64_t)(~v.z) << 32) | (uint64_t)(~v.w);
+    sslot[o] = (uint32_t)i;
+  }
+}
+
+// ---- raw components: lock-free union-find over table slots ---------------------------------
+__global__ void __launch_bounds__(kBlock) uf_init_kernel(uint32_t* parent, uint64_t n) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) parent[i] = (uint32_t)i;
+}
+
+__device__ __forceinline__ uint32_t uf_find(uint32_t* parent, uint32_t x) {
+  uint32_t p = __ldcg(&parent[x]);
+  while (p != x) {
+    uint32_t gp = __ldcg(&parent[p]);
+    if (gp != p) parent[x] = gp;  // path halving; x is not a root, so this never races a link
+    x = p;
+    p = gp;
+  }
+  return x;
+}
+
+// read-only variant (no path compression): safe while other threads overwrite parent[i] <- root
+__device__ __forceinline__ uint32_t uf_find_ro(const uint32_t* parent, uint32_t x) {
+  uint32_t p = __ldcg(&parent[x]);
+  while (p != x) {
+    x = p;
+    p = __ldcg(&parent[x]);
+  }
+  return x;
+}
+
+__device__ __forceinline__ void uf_union(uint32_t* parent, uint32_t a, uint32_t b) {
+  for (;;) {
+    a = uf_find(parent, a);
+    b = uf_find(parent, b);
+    if (a == b) return;
+    if (a < b) {
+      uint32_t t = a;
+      a = b;
+      b = t;
+    }
+    // link the larger root under the smaller one: the final root is the minimum slot index
+    if (atomicCAS(&parent[a], a, b) == a) return;
+  }
+}
+
+__global__ void __launch_bounds__(kBlock)
+    uf_edges_kernel(ShnTableView t, uint32_t* parent, uint64_t n_slots, int k1) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_slots) return;
+  uint64_t key = t.slots[i].key;
+  if (key == SHN_EMPTY_KEY) return;
+  const uint64_t mask = shn_kmer_mask(k1);
+  uint64_t pre = (key << 2) & mask;
+#pragma unroll
+  for (uint64_t b = 0; b < 4; ++b) {
+    uint32_t w;
+    uint64_t s = table_find(t, pre | b, &w);
+    if (s != ~0ull && s != i) uf_union(parent, (uint32_t)i, (uint32_t)s);
+  }
+}
+
+// parent[i] <- root for occupied slots; roots get flag 1
+__global__ void __launch_bounds__(kBlock)
+    uf_flatten_kernel(const ShnSlot* __restrict__ slots, uint32_t* parent, uint64_t n_slots,
+                      uint32_t* __restrict__ is_root) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_slots) return;
+  bool occ = slots[i].key != SHN_EMPTY_KEY;
+  uint32_t root = (uint32_t)i;
+  if (occ) root = uf_find_ro(parent, (uint32_t)i);
+  is_root[i] = (occ && root == (uint32_t)i) ? 1u : 0u;
+  if (occ && root != (uint32_t)i) parent[i] = root;
+}
+
+// comp id of every occupied slot + node count per component
+__global__ void __launch_bounds__(kBlock)
+    comp_count_kernel(const ShnSlot* __restrict__ slots, const uint32_t* __restrict__ parent,
+                      const uint32_t* __restrict__ root_id, uint64_t n_slots,
+                      uint32_t* __restrict__ comp_nodes) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_slots) return;
+  if (slots[i].key == SHN_EMPTY_KEY) return;
+  atomicAdd(&comp_nodes[root_id[parent[i]]], 1u);  // parent[i] is the root after flatten
+}
+
+__global__ void __launch_bounds__(kBlock)
+    seed_comp_kernel(const uint32_t* __restrict__ seed_slot, const uint32_t* __restrict__ parent,
+                     const uint32_t* __restrict__ root_id, uint64_t n_seeds,
+                     uint32_t* __restrict__ seed_comp, uint32_t* __restrict__ rank,
+                     uint32_t* __restrict__ comp_seeds) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_seeds) return;
+  uint32_t cid = root_id[parent[seed_slot[i]]];
+  seed_comp[i] = cid;
+  rank[i] = (uint32_t)i;
+  atomicAdd(&comp_seeds[cid], 1u);
+}
+
+__global__ void __launch_bounds__(kBlock)
+    comp_work_kernel(const uint32_t* __restrict__ comp_nodes, const uint32_t* __restrict__ comp_seeds,
+                     uint32_t n_comps, uint32_t* __restrict__ work, uint32_t* __restrict__ ids,
+                     unsigned long long* counters) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool active = false;
+  if (i < n_comps) {
+    active = comp_seeds[i] > 0;
+    work[i] = active ? comp_nodes[i] : 0u;
+    ids[i] = i;
+  }
+  int tot = __syncthreads_count(active);
+  if (threadIdx.x == 0 && tot) atomicAdd(&counters[0], (unsigned long long)tot);
+}
+
+__global__ void __launch_bounds__(kBlock)
+    gather_walks_kernel(const uint32_t* __restrict__ sel, uint64_t n_walks,
+                        const uint32_t* __restrict__ seed_slot, const uint32_t* __restrict__ nl_r,
+                        const uint32_t* __restrict__ nr_r, const uint64_t* __restrict__ tot_r,
+                        const uint64_t* __restrict__ ls_r, int k1, uint32_t min_length,
+                        uint32_t* __restrict__ w_slot, uint32_t* __restrict__ w_nl,
+                        uint32_t* __restrict__ w_nr, uint64_t* __restrict__ w_tot,
+                        uint64_t* __restrict__ w_ls, uint8_t* __restrict__ is_long) {
+  uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= n_walks) return;
+  uint32_t r = sel[w];
+  uint32_t nl = nl_r[r], nr = nr_r[r];
+  w_slot[w] = seed_slot[r];
+  w_nl[w] = nl;
+  w_nr[w] = nr;
+  w_tot[w] = tot_r[r];
+  w_ls[w] = ls_r[r];
+  is_long[w] = ((uint64_t)nl + nr + (uint64_t)k1 >= (uint64_t)min_length) ? 1 : 0;  // len(contig)
+}
+
+__global__ void __launch_bounds__(kBlock)
+    gather_long_kernel(const uint32_t* __restrict__ idx, uint64_t n, const uint32_t* __restrict__ w_nl,
+                       const uint32_t* __restrict__ w_nr, const uint64_t* __restrict__ w_tot,
+                       uint32_t* __restrict__ nl, uint32_t* __restrict__ nr, uint64_t* __restrict__ tot) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t w = idx[i];
+  nl[i] = w_nl[w];
+  nr[i] = w_nr[w];
+  tot[i] = w_tot[w];
+}
+
+// ---- greedy walks: one thread per component, one walk step per loop iteration --------------
+struct WalkArgs {
+  ShnTableView t;
+  int k1;
+  uint32_t n_comps;
+  const uint32_t* comp_order;   // components sorted by seed count (descending)
+  const uint64_t* seed_off;     // [n_comps+1] into ranks_by_comp
+  const uint32_t* ranks_by_comp;  // seed ranks grouped by component, ascending inside a group
+  const uint32_t* seed_slot;    // by rank
+  const uint64_t* log_off;      // [n_comps+1] into walk_log
+  uint8_t* walk_log;
+  // per seed rank outputs
+  uint8_t* started;
+  uint32_t* nl;
+  uint32_t* nr;
+  uint64_t* totwt;
+  uint64_t* logstart;
+  unsigned long long* counters;  // [0]=traversed [1]=max steps of a thread [2]=log overflow
+};
+
+__global__ void __launch_bounds__(128) walk_kernel(WalkArgs a) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= a.n_comps) return;
+  const uint32_t comp = a.comp_order[t];
+  uint64_t sp = a.seed_off[comp];
+  const uint64_t se = a.seed_off[comp + 1];
+  uint64_t lp = a.log_off[comp];
+  const uint64_t le = a.log_off[comp + 1];
+  const uint64_t mask = shn_kmer_mask(a.k1);
+  const int top = 2 * (a.k1 - 1);
+  ShnSlot* slots = a.t.slots;
+
+  int phase = 0;  // 0 = fetch next seed, 1 = extend right, 2 = extend left
+  uint32_t rank = 0, nl = 0, nr = 0;
+  uint64_t seed_key = 0, cur = 0, tot = 0, my_log = 0;
+  unsigned long long steps = 0, traversed = 0;
+  bool overflow = false;
+
+  for (;;) {
+    if (phase == 0) {
+      if (sp == se) break;
+      rank = a.ranks_by_comp[sp++];
+      uint32_t slot = a.seed_slot[rank];
+      uint4 v = __ldcg(reinterpret_cast<const uint4*>(slots) + slot);
+      if (v.z & SHN_TRAVERSED) continue;                       // extension_correction.py:346
+      slots[slot].weight = v.z | SHN_TRAVERSED;                // :347
+      seed_key = ((uint64_t)v.y << 32) | v.x;
+      cur = seed_key;
+      tot = v.z & SHN_WEIGHT_MASK;
+      nl = nr = 0;
+      my_log = lp;
+      if (lp < le) a.walk_log[lp] = 0xFF;  // the seed's own log entry (unused)
+      else overflow = true;
+      ++lp;
+      ++traversed;
+      phase = 1;
+      continue;
+    }
+    ++steps;
+    // the four candidates in the reference's tie order A,G,C,T = codes 0..3 (:10,229)
+    uint64_t cand[4];
+    uint64_t bkt[4];
+    uint4 s0[4], s1[4];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      cand[b] = phase == 1 ? (((cur << 2) & mask) | (uint64_t)b) : ((cur >> 2) | ((uint64_t)b << top));
+      bkt[b] = a.t.bucket_of(cand[b]);
+    }
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {  // 8 independent 16-byte loads in flight
+      s0[b] = __ldcg(reinterpret_cast<const uint4*>(slots + 2 * bkt[b]));
+      s1[b] = __ldcg(reinterpret_cast<const uint4*>(slots + 2 * bkt[b] + 1));
+    }
+    int best = -1;
+    uint32_t best_w = 0;
+    uint64_t best_slot = 0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      uint64_t k0 = ((uint64_t)s0[b].y << 32) | s0[b].x, k1v = ((uint64_t)s1[b].y << 32) | s1[b].x;
+      uint64_t slot = ~0ull;
+      uint32_t wraw = 0;
+      if (k0 == cand[b]) {
+        slot = 2 * bkt[b];
+        wraw = s0[b].z;
+      } else if (k1v == cand[b]) {
+        slot = 2 * bkt[b] + 1;
+        wraw = s1[b].z;
+      } else if (k0 != SHN_EMPTY_KEY && k1v != SHN_EMPTY_KEY) {
+        // full bucket without a match: continue the linear probe (rare at load <= 0.5)
+        ShnTableView tv = a.t;
+        uint64_t bb = bkt[b] + 1 == tv.n_buckets ? 0 : bkt[b] + 1;
+        for (;;) {
+          const uint4 x0 = __ldcg(reinterpret_cast<const uint4*>(slots + 2 * bb));
+          const uint4 x1 = __ldcg(reinterpret_cast<const uint4*>(slots + 2 * bb + 1));
+          uint64_t y0 = ((uint64_t)x0.y << 32) | x0.x, y1 = ((uint64_t)x1.y << 32) | x1.x;
+          if (y0 == cand[b]) {
+            slot = 2 * bb;
+            wraw = x0.z;
+            break;
+          }
+          if (y1 == cand[b]) {
+            slot = 2 * bb + 1;
+            wraw = x1.z;
+            break;
+          }
+          if (y0 == SHN_EMPTY_KEY || y1 == SHN_EMPTY_KEY) break;
+          bb = bb + 1 == tv.n_buckets ? 0 : bb + 1;
+        }
+      }
+      if (slot != ~0ull && !(wraw & SHN_TRAVERSED)) {
+        uint32_t w = wraw & SHN_WEIGHT_MASK;
+        if (best < 0 || w > best_w) {  // strict '>' keeps the first of equals (argmax, :159-166)
+          best = b;
+          best_w = w;
+          best_slot = slot;
+        }
+      }
+    }
+    if (best < 0) {
+      if (phase == 1) {  // right extension exhausted: extend left from the seed (:349-350)
+        phase = 2;
+        cur = seed_key;
+      } else {
+        a.started[rank] = 1;
+        a.nl[rank] = nl;
+        a.nr[rank] = nr;
+        a.totwt[rank] = tot;
+        a.logstart[rank] = my_log;
+        phase = 0;
+      }
+      continue;
+    }
+    slots[best_slot].weight = best_w | SHN_TRAVERSED;  // traversed.add(last), :235
+    if (lp < le) a.walk_log[lp] = (uint8_t)best;
+    else overflow = true;
+    ++lp;
+    ++traversed;
+    tot += best_w;
+    if (phase == 1) ++nr; else ++nl;
+    cur = cand[best];
+  }
+  atomicAdd(&a.counters[0], traversed);
+  atomicMax(&a.counters[1], steps);
+  if (overflow) atomicAdd(&a.counters[2], 1ull);
+}
+
+// ---- contig assembly from the walk log -----------------------------------------------------
+// one thread per output base of the candidate contigs
+__global__ void __launch_bounds__(kBlock)
+    assemble_kernel(const ShnSlot* __restrict__ slots, const uint8_t* __restrict__ walk_log,
+                    const uint32_t* __restrict__ cand_walk, const uint64_t* __restrict__ cand_off,
+                    uint64_t n_cand, uint64_t total, const uint32_t* __restrict__ w_seed_slot,
+                    const uint32_t* __restrict__ w_nl, const uint32_t* __restrict__ w_nr,
+                    const uint64_t* __restrict__ w_logstart, int k1, uint8_t* __restrict__ out) {
+  uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= total) return;
+  uint64_t lo = 0, hi = n_cand;
+  while (hi - lo > 1) {
+    uint64_t mid = (lo + hi) >> 1;
+    if (__ldg(&cand_off[mid]) <= g)
+      lo = mid;
+    else
+      hi = mid;
+  }
+  uint32_t w = cand_walk[lo];
+  uint64_t q = g - cand_off[lo];
+  uint32_t nl = w_nl[w], nr = w_nr[w];
+  uint64_t ls = w_logstart[w];
+  uint8_t code;
+  if (q < nl) {
+    code = walk_log[ls + 1 + nr + (nl - 1 - q)];            // reversed(left_extension)
+  } else if (q < (uint64_t)nl + k1) {
+    uint64_t key = slots[w_seed_slot[w]].key;                 // start_kmer
+    code = (uint8_t)((key >> (2 * (k1 - 1 - (int)(q - nl)))) & 3u);
+  } else {
+    code = walk_log[ls + 1 + (q - nl - k1)];                  // right_extension
+  }
+  out[g] = code;
+}
+
+// (key, owner, pos) entries of all length-L windows of the given contigs (2-bit codes)
+__global__ void __launch_bounds__(kBlock)
+    window_entries_kernel(const uint8_t* __restrict__ codes, const uint64_t* __restrict__ offs,
+                          const uint64_t* __restrict__ ent_off, uint64_t n_contigs, uint64_t total,
+                          int L, uint32_t owner_base, uint64_t* __restrict__ keys,
+                          uint32_t* __restrict__ owner, uint32_t* __restrict__ pos) {
+  uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= total) return;
+  uint64_t lo = 0, hi = n_contigs;
+  while (hi - lo > 1) {
+    uint64_t mid = (lo + hi) >> 1;
+    if (__ldg(&offs[mid]) <= g)
+      lo = mid;
+    else
+      hi = mid;
+  }
+  uint64_t start = offs[lo], end = offs[lo + 1];
+  if (g + L > end) return;
+  uint64_t x = 0;
+  for (int j = 0; j < L; ++j) x = (x << 2) | (uint64_t)(codes[g + j] & 3u);
+  uint64_t o = ent_off[lo] + (g - start);
+  keys[o] = x;
+  owner[o] = owner_base + (uint32_t)lo;
+  pos[o] = (uint32_t)(g - start);
+}
+
+__global__ void __launch_bounds__(kBlock)
+    window_counts_kernel(const uint64_t* __restrict__ offs, uint64_t n, int L, uint64_t* __restrict__ cnt) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > n) return;
+  if (i == n) {
+    cnt[i] = 0;
+    return;
+  }
+  uint64_t len = offs[i + 1] - offs[i];
+  cnt[i] = len >= (uint64_t)L ? len - L + 1 : 0;
+}
+
+// ---- duplicate filter: frontier rounds over the pair table ---------------------------------
+// status: 0 = unresolved, 1 = accepted, 2 = rejected.  Candidate j resolves once every partner
+// d < j that shares an r-mer with it is resolved; the lowest unresolved candidate always is.
+__global__ void __launch_bounds__(kBlock)
+    dup_round_kernel(const uint64_t* __restrict__ seg_off, const uint32_t* __restrict__ lo,
+                     const uint32_t* __restrict__ count, const uint32_t* __restrict__ max_i,
+                     const uint32_t* __restrict__ covered, const uint64_t* __restrict__ cand_off,
+                     uint64_t n_cand, const uint8_t* __restrict__ status_in,
+                     uint8_t* __restrict__ status_out, uint8_t* __restrict__ dup_flag,
+                     unsigned long long* counters) {
+  uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_cand) return;
+  uint8_t st = status_in[j];
+  if (st != 0) {
+    status_out[j] = st;
+    return;
+  }
+  bool ready = true;
+  // best = accepted partner with max (count, last hit position, id)  -- duplicate_check's
+  // `>=` running maximum, extension_correction.py:251-259 (closed form in SURVEY 8a a6)
+  uint32_t b_cnt = 0, b_last = 0, b_cov = 0;
+  bool have = false;
+  for (uint64_t p = seg_off[j]; p < seg_off[j + 1]; ++p) {
+    uint8_t sd = status_in[lo[p]];
+    if (sd == 0) {
+      ready = false;
+      break;
+    }
+    if (sd != 1) continue;
+    uint32_t cnt = count[p], last = max_i[p];
+    // partners are sorted by id ascending, so '>=' on (count,last) lets the larger id win ties
+    if (!have || cnt > b_cnt || (cnt == b_cnt && last >= b_last)) {
+      have = true;
+      b_cnt = cnt;
+      b_last = last;
+      b_cov = covered[p];
+    }
+  }
+  if (!ready) {
+    status_out[j] = 0;
+    atomicAdd(&counters[0], 1ull);
+    return;
+  }
+  uint64_t len = cand_off[j + 1] - cand_off[j];
+  bool dup = have && (2ull * b_cov > len);  // sum(a) > 0.5*len, :267
+  dup_flag[j] = dup ? 1 : 0;
+  status_out[j] = dup ? 2 : 1;
+}
+
+__global__ void __launch_bounds__(kBlock)
+    seg_offsets_kernel(const uint32_t* __restrict__ hi, uint64_t n_pairs, uint64_t n_owner,
+                       uint64_t* __restrict__ seg_off) {
+  // seg_off[j] = first pair index with hi >= j, for j in 0..n_owner
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > n_pairs) return;
+  uint64_t prev = i == 0 ? 0 : (uint64_t)hi[i - 1] + 1;
+  uint64_t cur = i == n_pairs ? n_owner + 1 : (uint64_t)hi[i] + 1;
+  if (cur > n_owner + 1) cur = n_owner + 1;
+  for (uint64_t c = prev; c < cur; ++c) seg_off[c] = i;
+}
+
+// ---- compaction of accepted candidates -----------------------------------------------------
+__global__ void __launch_bounds__(kBlock)
+    copy_contigs_kernel(const uint8_t* __restrict__ src, const uint64_t* __restrict__ src_off,
+                        const uint32_t* __restrict__ acc_cand, const uint64_t* __restrict__ dst_off,
+                        uint64_t n_acc, uint64_t total, uint8_t* __restrict__ dst) {
+  uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= total) return;
+  uint64_t lo = 0, hi = n_acc;
+  while (hi - lo > 1) {
+    uint64_t mid = (lo + hi) >> 1;
+    if (__ldg(&dst_off[mid]) <= g)
+      lo = mid;
+    else
+      hi = mid;
+  }
+  dst[g] = src[src_off[acc_cand[lo]] + (g - dst_off[lo])];
+}
+
+__global__ void __launch_bounds__(kBlock)
+    allowed_weights_kernel(ShnTableView t, const uint64_t* __restrict__ keys, uint64_t n,
+                           uint32_t* __restrict__ w_out, unsigned long long* counters) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t w = 0;
+  uint64_t s = table_find(t, keys[i], &w);
+  if (s == ~0ull) atomicAdd(&counters[0], 1ull);
+  w_out[i] = w & SHN_WEIGHT_MASK;
+}
+
+// ---- contig components: min-label propagation over the (small) edge list --------------------
+__global__ void __launch_bounds__(kBlock) label_init_kernel(uint32_t* label, uint64_t n) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) label[i] = (uint32_t)i;
+}
+
+__global__ void __launch_bounds__(kBlock)
+    label_hook_kernel(const uint32_t* __restrict__ a, const uint32_t* __restrict__ b, uint64_t n_edges,
+                      uint32_t* label, unsigned long long* changed) {
+  uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_edges) return;
+  uint32_t la = label[a[e]], lb = label[b[e]];
+  if (la == lb) return;
+  uint32_t lo = la < lb ? la : lb, hi = la < lb ? lb : la;
+  atomicAdd(changed, 1ull);
+  // hook the larger label's representative under the smaller label
+  atomicMin(&label[hi], lo);
+  atomicMin(&label[a[e]], lo);
+  atomicMin(&label[b[e]], lo);
+}
+
+__global__ void __launch_bounds__(kBlock)
+    label_jump_kernel(uint32_t* label, uint64_t n, unsigned long long* changed) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t l = label[i];
+  uint32_t ll = label[l];
+  if (ll < l) {
+    label[i] = ll;
+    atomicAdd(changed, 1ull);
+  }
+}
+
+template <typename T>
+void d2h(shn_ctx* c, std::vector<T>& dst, const void* src, uint64_t n) {
+  dst.resize(n);
+  if (n) CUDA_CHECK(cudaMemcpyAsync(dst.data(), src, n * sizeof(T), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+}
+
+template <typename T>
+void h2d(shn_ctx* c, DevBuf& dst, const std::vector<T>& src) {
+  dst.reserve(std::max<uint64_t>(src.size(), 1) * sizeof(T));
+  if (!src.empty())
+    CUDA_CHECK(cudaMemcpyAsync(dst.p, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice,
+                               c->stream));
+  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+}
+
+unsigned long long* zero_counters(shn_ctx* c) {
+  c->counters.reserve(64 * sizeof(unsigned long long));
+  unsigned long long* ctr = c->counters.as<unsigned long long>();
+  CUDA_CHECK(cudaMemsetAsync(ctr, 0, 8 * sizeof(unsigned long long), c->stream));
+  return ctr;
+}
+
+void read_counters(shn_ctx* c, unsigned long long* h, int n) {
+  CUDA_CHECK(cudaMemcpyAsync(h, c->counters.p, n * sizeof(unsigned long long),
+                             cudaMemcpyDeviceToHost, c->stream));
+  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+}
+
+template <typename InT, typename OutT>
+void exclusive_sum(shn_ctx* c, const InT* in, OutT* out, uint64_t n) {
+  size_t tb = 0;
+  CUDA_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, tb, in, out, (int64_t)n, c->stream));
+  CUDA_CHECK(cub::DeviceScan::ExclusiveSum(c->tmp(tb), tb, in, out, (int64_t)n, c->stream));
+}
+
+struct CastU64 {
+  __device__ __forceinline__ uint64_t operator()(uint32_t x) const { return (uint64_t)x; }
+};
+void exclusive_sum_u32(shn_ctx* c, const uint32_t* in, uint64_t* out, uint64_t n) {
+  cub::TransformInputIterator<uint64_t, CastU64, const uint32_t*> it(in, CastU64());
+  size_t tb = 0;
+  CUDA_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, tb, it, out, (int64_t)n, c->stream));
+  CUDA_CHECK(cub::DeviceScan::ExclusiveSum(c->tmp(tb), tb, it, out, (int64_t)n, c->stream));
+}
+
+// The length and hyperbola terms of extension_correction.py:353,361, evaluated on the host with
+// the same double expression order and the same libm pow() CPython's math.pow calls.
+bool passes_shape(uint64_t length, uint64_t tot_wt, uint64_t tot_kmer, uint32_t min_weight,
+                  uint32_t min_length) {
+  volatile double avg_wt = (double)tot_wt / (double)(tot_kmer > 1 ? tot_kmer : 1);
+  volatile double lhs = (double)length * pow(avg_wt, 1 / 4.0);
+  volatile double rhs = (double)(2ull * min_length) * pow((double)min_weight, 1 / 4.0);
+  return length >= min_length && lhs >= rhs;
+}
+
+}  // namespace
+
+void shn_l3_free(shn_ctx* c) {
+  delete c->l3;
+  c->l3 = nullptr;
+}
+
+void shn_l3_run_impl(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
+  SHN_CHECK(c->n_buckets > 0, "no K1-mer table built (call shn_table_build first)");
+  shn_l3_free(c);
+  L3State* s = c->l3 = new L3State();
+  s->min_weight = min_weight;
+  s->min_length = min_length;
+  const int k1 = c->k1;
+  const uint64_t n_slots = c->n_buckets * 2;
+  SHN_CHECK(n_slots < 0xFFFFFFFFull, "table too large for 32-bit slot indices");
+  ShnTableView tv = c->view();
+  cudaStream_t st = c->stream;
+  unsigned long long h[8];
+  const unsigned stream_grid =
+      (unsigned)std::min<uint64_t>((n_slots + kBlock - 1) / kBlock, (uint64_t)c->sm_count * 32);
+
+  // ---- a3: seeds in pop order -------------------------------------------------------------
+  unsigned long long* ctr = zero_counters(c);
+  {
+    ProfScope ps(c, "seed_count");
+    seed_count_kernel<<<stream_grid, kBlock, 0, st>>>(tv.slots, n_slots, min_weight, ctr);
+    KERNEL_CHECK();
+  }
+  read_counters(c, h, 1);
+  const uint64_t n_seeds = h[0];
+  s->sz.n_seeds = n_seeds;
+  DevBuf seed_slot;  // by rank
+  seed_slot.reserve(std::max<uint64_t>(n_seeds, 1) * 4);
+  if (n_seeds) {
+    DevBuf skey, sslot, skey2;
+    skey.reserve(n_seeds * 8);
+    skey2.reserve(n_seeds * 8);
+    sslot.reserve(n_seeds * 4);
+    ctr = zero_counters(c);
+    {
+      ProfScope ps(c, "seed_emit");
+      seed_emit_kernel<<<shn_grid(n_slots, kBlock), kBlock, 0, st>>>(
+          tv.slots, n_slots, min_weight, skey.as<uint64_t>(), sslot.as<uint32_t>(), ctr);
+      KERNEL_CHECK();
+    }
+    ProfScope ps(c, "seed_sort");
+    size_t tb = 0;
+    CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, tb, skey.as<uint64_t>(), skey2.as<uint64_t>(),
+                                               sslot.as<uint32_t>(), seed_slot.as<uint32_t>(),
+                                               (int64_t)n_seeds, 0, 64, st));
+    CUDA_CHECK(cub::DeviceRadixSort::SortPairs(c->tmp(tb), tb, skey.as<uint64_t>(),
+                                               skey2.as<uint64_t>(), sslot.as<uint32_t>(),
+                                               seed_slot.as<uint32_t>(), (int64_t)n_seeds, 0, 64, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+  }
+
+  // ---- raw components of the successor graph ------------------------------------------------
+  DevBuf parent, root_flag, root_id;
+  parent.reserve(n_slots * 4);
+  root_flag.reserve((n_slots + 1) * 4);
+  root_id.reserve((n_slots + 1) * 4);
+  {
+    ProfScope ps(c, "uf_init");
+    uf_init_kernel<<<stream_grid, kBlock, 0, st>>>(parent.as<uint32_t>(), n_slots);
+    KERNEL_CHECK();
+  }
+  {
+    ProfScope ps(c, "uf_edges");
+    uf_edges_kernel<<<shn_grid(n_slots, kBlock), kBlock, 0, st>>>(tv, parent.as<uint32_t>(), n_slots, k1);
+    KERNEL_CHECK();
+  }
+  {
+    ProfScope ps(c, "uf_flatten");
+    CUDA_CHECK(cudaMemsetAsync(root_flag.as<uint32_t>() + n_slots, 0, 4, st));
+    uf_flatten_kernel<<<shn_grid(n_slots, kBlock), kBlock, 0, st>>>(tv.slots, parent.as<uint32_t>(),
+                                                                   n_slots, root_flag.as<uint32_t>());
+    KERNEL_CHECK();
+  }
+  uint32_t n_comps = 0;
+  {
+    ProfScope ps(c, "comp_ids");
+    exclusive_sum(c, root_flag.as<uint32_t>(), root_id.as<uint32_t>(), n_slots + 1);
+    CUDA_CHECK(cudaMemcpyAsync(&n_comps, root_id.as<uint32_t>() + n_slots, 4, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+  }
+  root_flag.release();
+  s->sz.n_raw_comps = n_comps;
+
+  DevBuf comp_nodes, comp_seeds, log_off, seed_off;
+  comp_nodes.reserve(((uint64_t)n_comps + 1) * 4);
+  comp_seeds.reserve(((uint64_t)n_comps + 1) * 4);
+  log_off.reserve(((uint64_t)n_comps + 1) * 8);
+  seed_off.reserve(((uint64_t)n_comps + 1) * 8);
+  CUDA_CHECK(cudaMemsetAsync(comp_nodes.p, 0, ((uint64_t)n_comps + 1) * 4, st));
+  CUDA_CHECK(cudaMemsetAsync(comp_seeds.p, 0, ((uint64_t)n_comps + 1) * 4, st));
+  {
+    ProfScope ps(c, "comp_count");
+    comp_count_kernel<<<shn_grid(n_slots, kBlock), kBlock, 0, st>>>(
+        tv.slots, parent.as<uint32_t>(), root_id.as<uint32_t>(), n_slots, comp_nodes.as<uint32_t>());
+    KERNEL_CHECK();
+  }
+  DevBuf seed_comp, rank_in, seed_comp_s, ranks_by_comp;
+  seed_comp.reserve(std::max<uint64_t>(n_seeds, 1) * 4);
+  rank_in.reserve(std::max<uint64_t>(n_seeds, 1) * 4);
+  seed_comp_s.reserve(std::max<uint64_t>(n_seeds, 1) * 4);
+  ranks_by_comp.reserve(std::max<uint64_t>(n_seeds, 1) * 4);
+  if (n_seeds) {
+    ProfScope ps(c, "seed_group", 3);
+    seed_comp_kernel<<<shn_grid(n_seeds, kBlock), kBlock, 0, st>>>(
+        seed_slot.as<uint32_t>(), parent.as<uint32_t>(), root_id.as<uint32_t>(), n_seeds,
+        seed_comp.as<uint32_t>(), rank_in.as<uint32_t>(), comp_seeds.as<uint32_t>());
+    KERNEL_CHECK();
+    int bits = 1;
+    while (bits < 32 && (n_comps >> bits)) ++bits;
+    size_t tb = 0;  // stable: ranks stay ascending inside a component
+    CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, tb, seed_comp.as<uint32_t>(),
+                                               seed_comp_s.as<uint32_t>(), rank_in.as<uint32_t>(),
+                                               ranks_by_comp.as<uint32_t>(), (int64_t)n_seeds, 0, bits, st));
+    CUDA_CHECK(cub::DeviceRadixSort::SortPairs(c->tmp(tb), tb, seed_comp.as<uint32_t>(),
+                                               seed_comp_s.as<uint32_t>(), rank_in.as<uint32_t>(),
+                                               ranks_by_comp.as<uint32_t>(), (int64_t)n_seeds, 0, bits, st));
+  }
+  parent.release();
+  root_id.release();
+  exclusive_sum_u32(c, comp_nodes.as<uint32_t>(), log_off.as<uint64_t>(), (uint64_t)n_comps + 1);
+  exclusive_sum_u32(c, comp_seeds.as<uint32_t>(), seed_off.as<uint64_t>(), (uint64_t)n_comps + 1);
+  // components that own at least one seed, in descending node count: similar-sized components
+  // share a warp and the big ones start first
+  DevBuf comp_order;
+  comp_order.reserve(std::max<uint32_t>(n_comps, 1) * 4);
+  uint32_t n_active = 0;
+  if (n_comps) {
+    DevBuf ids, work, work_s;
+    ids.reserve((uint64_t)n_comps * 4);
+    work.reserve((uint64_t)n_comps * 4);
+    work_s.reserve((uint64_t)n_comps * 4);
+    ctr = zero_counters(c);
+    ProfScope ps(c, "comp_order", 2);
+    comp_work_kernel<<<shn_grid(n_comps, kBlock), kBlock, 0, st>>>(
+        comp_nodes.as<uint32_t>(), comp_seeds.as<uint32_t>(), n_comps, work.as<uint32_t>(),
+        ids.as<uint32_t>(), ctr);
+    KERNEL_CHECK();
+    size_t tb = 0;
+    CUDA_CHECK(cub::DeviceRadixSort::SortPairsDescending(
+        nullptr, tb, work.as<uint32_t>(), work_s.as<uint32_t>(), ids.as<uint32_t>(),
+        comp_order.as<uint32_t>(), (int64_t)n_comps, 0, 32, st));
+    CUDA_CHECK(cub::DeviceRadixSort::SortPairsDescending(
+        c->tmp(tb), tb, work.as<uint32_t>(), work_s.as<uint32_t>(), ids.as<uint32_t>(),
+        comp_order.as<uint32_t>(), (int64_t)n_comps, 0, 32, st));
+    read_counters(c, h, 1);
+    n_active = (uint32_t)h[0];
+  }
+
+  // ---- a4: greedy walks -----------------------------------------------------------------------
+  const uint64_t n_nodes = c->n_distinct;
+  s->walk_log.reserve(std::max<uint64_t>(n_nodes, 1));
+  DevBuf started, nl_r, nr_r, tot_r, ls_r;
+  started.reserve(std::max<uint64_t>(n_seeds, 1));
+  nl_r.reserve(std::max<uint64_t>(n_seeds, 1) * 4);
+  nr_r.reserve(std::max<uint64_t>(n_seeds, 1) * 4);
+  tot_r.reserve(std::max<uint64_t>(n_seeds, 1) * 8);
+  ls_r.reserve(std::max<uint64_t>(n_seeds, 1) * 8);
+  CUDA_CHECK(cudaMemsetAsync(started.p, 0, std::max<uint64_t>(n_seeds, 1), st));
+  ctr = zero_counters(c);
+  if (n_active) {
+    WalkArgs a;
+    a.t = tv;
+    a.k1 = k1;
+    a.n_comps = n_active;
+    a.comp_order = comp_order.as<uint32_t>();
+    a.seed_off = seed_off.as<uint64_t>();
+    a.ranks_by_comp = ranks_by_comp.as<uint32_t>();
+    a.seed_slot = seed_slot.as<uint32_t>();
+    a.log_off = log_off.as<uint64_t>();
+    a.walk_log = s->walk_log.as<uint8_t>();
+    a.started = started.as<uint8_t>();
+    a.nl = nl_r.as<uint32_t>();
+    a.nr = nr_r.as<uint32_t>();
+    a.totwt = tot_r.as<uint64_t>();
+    a.logstart = ls_r.as<uint64_t>();
+    a.counters = ctr;
+    ProfScope ps(c, "walk");
+    walk_kernel<<<shn_grid(n_active, 128), 128, 0, st>>>(a);
+    KERNEL_CHECK();
+  }
+  read_counters(c, h, 3);
+  SHN_CHECK(h[2] == 0, "internal error: walk log overflow (component node count mismatch)");
+  s->sz.n_traversed = h[0];
+  s->sz.walk_rounds = h[1];
+
+  // started walks in pop order (device compaction), then the walks long enough to matter
+  uint64_t n_walks = 0, n_long = 0;
+  std::vector<uint32_t> h_long_idx, h_long_nl, h_long_nr;
+  std::vector<uint64_t> h_long_tot;
+  if (n_seeds) {
+    DevBuf sel, nsel;
+    sel.reserve(n_seeds * 4);
+    nsel.reserve(8);
+    ProfScope ps(c, "walk_compact", 6);
+    cub::CountingInputIterator<uint32_t> it(0);
+    size_t tb = 0;
+    CUDA_CHECK(cub::DeviceSelect::Flagged(nullptr, tb, it, started.as<uint8_t>(), sel.as<uint32_t>(),
+                                          nsel.as<uint64_t>(), (int64_t)n_seeds, st));
+    CUDA_CHECK(cub::DeviceSelect::Flagged(c->tmp(tb), tb, it, started.as<uint8_t>(), sel.as<uint32_t>(),
+                                          nsel.as<uint64_t>(), (int64_t)n_seeds, st));
+    CUDA_CHECK(cudaMemcpyAsync(&n_walks, nsel.p, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    const uint64_t nw1 = std::max<uint64_t>(n_walks, 1);
+    s->w_seed_slot.reserve(nw1 * 4);
+    s->w_nl.reserve(nw1 * 4);
+    s->w_nr.reserve(nw1 * 4);
+    s->w_totwt.reserve(nw1 * 8);
+    s->w_logstart.reserve(nw1 * 8);
+    if (n_walks) {
+      DevBuf is_long, long_idx, l_nl, l_nr, l_tot;
+      is_long.reserve(n_walks);
+      long_idx.reserve(n_walks * 4);
+      gather_walks_kernel<<<shn_grid(n_walks, kBlock), kBlock, 0, st>>>(
+          sel.as<uint32_t>(), n_walks, seed_slot.as<uint32_t>(), nl_r.as<uint32_t>(),
+          nr_r.as<uint32_t>(), tot_r.as<uint64_t>(), ls_r.as<uint64_t>(), k1, min_length,
+          s->w_seed_slot.as<uint32_t>(), s->w_nl.as<uint32_t>(), s->w_nr.as<uint32_t>(),
+          s->w_totwt.as<uint64_t>(), s->w_logstart.as<uint64_t>(), is_long.as<uint8_t>());
+      KERNEL_CHECK();
+      tb = 0;
+      CUDA_CHECK(cub::DeviceSelect::Flagged(nullptr, tb, it, is_long.as<uint8_t>(), long_idx.as<uint32_t>(),
+                                            nsel.as<uint64_t>(), (int64_t)n_walks, st));
+      CUDA_CHECK(cub::DeviceSelect::Flagged(c->tmp(tb), tb, it, is_long.as<uint8_t>(),
+                                            long_idx.as<uint32_t>(), nsel.as<uint64_t>(),
+                                            (int64_t)n_walks, st));
+      CUDA_CHECK(cudaMemcpyAsync(&n_long, nsel.p, 8, cudaMemcpyDeviceToHost, st));
+      CUDA_CHECK(cudaStreamSynchronize(st));
+      if (n_long) {
+        l_nl.reserve(n_long * 4);
+        l_nr.reserve(n_long * 4);
+        l_tot.reserve(n_long * 8);
+        gather_long_kernel<<<shn_grid(n_long, kBlock), kBlock, 0, st>>>(
+            long_idx.as<uint32_t>(), n_long, s->w_nl.as<uint32_t>(), s->w_nr.as<uint32_t>(),
+            s->w_totwt.as<uint64_t>(), l_nl.as<uint32_t>(), l_nr.as<uint32_t>(), l_tot.as<uint64_t>());
+        KERNEL_CHECK();
+        d2h(c, h_long_idx, long_idx.p, n_long);
+        d2h(c, h_long_nl, l_nl.p, n_long);
+        d2h(c, h_long_nr, l_nr.p, n_long);
+        d2h(c, h_long_tot, l_tot.p, n_long);
+      }
+    }
+  }
+  s->sz.n_walks = n_walks;
+
+  // ---- a5: length + hyperbola filter (host doubles, same expression as the reference) -------
+  std::vector<uint32_t>& cand_walk = s->h_cand_walk;
+  cand_walk.clear();
+  std::vector<uint64_t> cand_off(1, 0);
+  for (uint64_t i = 0; i < n_long; ++i) {
+    uint64_t tot_kmer = (uint64_t)h_long_nl[i] + h_long_nr[i] + 1;
+    uint64_t len = tot_kmer + k1 - 1;
+    if (passes_shape(len, h_long_tot[i], tot_kmer, min_weight, min_length)) {
+      cand_walk.push_back(h_long_idx[i]);
+      cand_off.push_back(cand_off.back() + len);
+    }
+  }
+  const uint64_t n_cand = cand_walk.size();
+  const uint64_t cand_bases = cand_off.back();
+  s->sz.n_candidates = n_cand;
+
+  DevBuf d_cand_walk, d_cand_off, cand_codes;
+  h2d(c, d_cand_walk, cand_walk);
+  h2d(c, d_cand_off, cand_off);
+  cand_codes.reserve(std::max<uint64_t>(cand_bases, 1));
+  if (cand_bases) {
+    ProfScope ps(c, "assemble");
+    assemble_kernel<<<shn_grid(cand_bases, kBlock), kBlock, 0, st>>>(
+        tv.slots, s->walk_log.as<uint8_t>(), d_cand_walk.as<uint32_t>(), d_cand_off.as<uint64_t>(),
+        n_cand, cand_bases, s->w_seed_slot.as<uint32_t>(), s->w_nl.as<uint32_t>(),
+        s->w_nr.as<uint32_t>(), s->w_logstart.as<uint64_t>(), k1, cand_codes.as<uint8_t>());
+    KERNEL_CHECK();
+  }
+
+  // ---- a6: duplicate filter ------------------------------------------------------------------
+  std::vector<uint8_t> h_status(n_cand, 1);
+  std::vector<uint8_t> h_dup(n_cand, 0);
+  const int R = 15;  // extension_correction.py:357
+  if (n_cand) {
+    DevBuf ent_cnt, ent_off;
+    ent_cnt.reserve((n_cand + 1) * 8);
+    ent_off.reserve((n_cand + 1) * 8);
+    window_counts_kernel<<<shn_grid(n_cand + 1, kBlock), kBlock, 0, st>>>(d_cand_off.as<uint64_t>(),
+                                                                          n_cand, R, ent_cnt.as<uint64_t>());
+    KERNEL_CHECK();
+    exclusive_sum(c, ent_cnt.as<uint64_t>(), ent_off.as<uint64_t>(), n_cand + 1);
+    uint64_t n_ent = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&n_ent, ent_off.as<uint64_t>() + n_cand, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    PairTable pt;
+    if (n_ent) {
+      DevBuf keys, owner, pos;
+      keys.reserve(n_ent * 8);
+      owner.reserve(n_ent * 4);
+      pos.reserve(n_ent * 4);
+      {
+        ProfScope ps(c, "rmer_entries");
+        window_entries_kernel<<<shn_grid(cand_bases, kBlock), kBlock, 0, st>>>(
+            cand_codes.as<uint8_t>(), d_cand_off.as<uint64_t>(), ent_off.as<uint64_t>(), n_cand,
+            cand_bases, R, 0u, keys.as<uint64_t>(), owner.as<uint32_t>(), pos.as<uint32_t>());
+        KERNEL_CHECK();
+      }
+      ProfScope ps(c, "rmer_join", 12);
+      shn_self_join(c, keys.as<uint64_t>(), owner.as<uint32_t>(), pos.as<uint32_t>(), n_ent, 2 * R, R, &pt);
+    }
+    if (pt.n) {
+      DevBuf seg_off, st_a, st_b, dupf;
+      seg_off.reserve((n_cand + 2) * 8);
+      st_a.reserve(n_cand);
+      st_b.reserve(n_cand);
+      dupf.reserve(n_cand);
+      CUDA_CHECK(cudaMemsetAsync(st_a.p, 0, n_cand, st));
+      CUDA_CHECK(cudaMemsetAsync(dupf.p, 0, n_cand, st));
+      seg_offsets_kernel<<<shn_grid(pt.n + 1, kBlock), kBlock, 0, st>>>(pt.hi.as<uint32_t>(), pt.n,
+                                                                        n_cand, seg_off.as<uint64_t>());
+      KERNEL_CHECK();
+      uint64_t rounds = 0;
+      for (;;) {
+        ctr = zero_counters(c);
+        {
+          ProfScope ps(c, "dup_round");
+          dup_round_kernel<<<shn_grid(n_cand, kBlock), kBlock, 0, st>>>(
+              seg_off.as<uint64_t>(), pt.lo.as<uint32_t>(), pt.count.as<uint32_t>(),
+              pt.max_i.as<uint32_t>(), pt.covered.as<uint32_t>(), d_cand_off.as<uint64_t>(), n_cand,
+              st_a.as<uint8_t>(), st_b.as<uint8_t>(), dupf.as<uint8_t>(), ctr);
+          KERNEL_CHECK();
+        }
+        ++rounds;
+        read_counters(c, h, 1);
+        std::swap(st_a.p, st_b.p);
+        std::swap(st_a.bytes, st_b.bytes);
+        if (h[0] == 0) break;
+        SHN_CHECK(rounds <= n_cand + 1, "internal error: duplicate filter does not converge");
+      }
+      s->sz.dup_rounds = rounds;
+      d2h(c, h_status, st_a.p, n_cand);
+      d2h(c, h_dup, dupf.p, n_cand);
+    }
+  }
+  // accepted contigs, acceptance order = pop order
+  std::vector<uint32_t> acc_cand;
+  std::vector<uint64_t> acc_off(1, 0);
+  s->h_cand_dup = h_dup;
+  s->h_cand_acc.assign(n_cand, 0);
+  for (uint64_t j = 0; j < n_cand; ++j) {
+    if (h_status[j] == 1) {
+      s->h_cand_acc[j] = 1;
+      acc_cand.push_back((uint32_t)j);
+      acc_off.push_back(acc_off.back() + (cand_off[j + 1] - cand_off[j]));
+    }
+  }
+  const uint64_t n_contigs = acc_cand.size();
+  const uint64_t contig_bases = acc_off.back();
+  s->sz.n_contigs = n_contigs;
+  s->sz.contig_bases = contig_bases;
+  s->h_contig_offs = acc_off;
+  h2d(c, s->contig_offs, acc_off);
+  s->contig_codes.reserve(std::max<uint64_t>(contig_bases, 1));
+  if (contig_bases) {
+    DevBuf d_acc;
+    h2d(c, d_acc, acc_cand);
+    ProfScope ps(c, "copy_contigs");
+    copy_contigs_kernel<<<shn_grid(contig_bases, kBlock), kBlock, 0, st>>>(
+        cand_codes.as<uint8_t>(), d_cand_off.as<uint64_t>(), d_acc.as<uint32_t>(),
+        s->contig_offs.as<uint64_t>(), n_contigs, contig_bases, s->contig_codes.as<uint8_t>());
+    KERNEL_CHECK();
+    CUDA_CHECK(cudaStreamSynchronize(st));
+  }
+  cand_codes.release();
+
+  // ---- a7: allowed K1-mers with weights, in contig order ------------------------------------
+  uint64_t n_allowed = 0;
+  if (n_contigs) {
+    DevBuf cnt, off, owner, pos;
+    cnt.reserve((n_contigs + 1) * 8);
+    off.reserve((n_contigs + 1) * 8);
+    window_counts_kernel<<<shn_grid(n_contigs + 1, kBlock), kBlock, 0, st>>>(
+        s->contig_offs.as<uint64_t>(), n_contigs, k1, cnt.as<uint64_t>());
+    KERNEL_CHECK();
+    exclusive_sum(c, cnt.as<uint64_t>(), off.as<uint64_t>(), n_contigs + 1);
+    CUDA_CHECK(cudaMemcpyAsync(&n_allowed, off.as<uint64_t>() + n_contigs, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    s->allowed_keys.reserve(std::max<uint64_t>(n_allowed, 1) * 8);
+    s->allowed_w.reserve(std::max<uint64_t>(n_allowed, 1) * 4);
+    if (n_allowed) {
+      owner.reserve(n_allowed * 4);
+      pos.reserve(n_allowed * 4);
+      ctr = zero_counters(c);
+      ProfScope ps(c, "allowed", 2);
+      window_entries_kernel<<<shn_grid(contig_bases, kBlock), kBlock, 0, st>>>(
+          s->contig_codes.as<uint8_t>(), s->contig_offs.as<uint64_t>(), off.as<uint64_t>(), n_contigs,
+          contig_bases, k1, 1u, s->allowed_keys.as<uint64_t>(), owner.as<uint32_t>(), pos.as<uint32_t>());
+      KERNEL_CHECK();
+      allowed_weights_kernel<<<shn_grid(n_allowed, kBlock), kBlock, 0, st>>>(
+          tv, s->allowed_keys.as<uint64_t>(), n_allowed, s->allowed_w.as<uint32_t>(), ctr);
+      KERNEL_CHECK();
+      read_counters(c, h, 1);
+      SHN_CHECK(h[0] == 0, "internal error: a contig K1-mer is missing from the table");
+    }
+  }
+  s->sz.n_allowed = n_allowed;
+
+  // ---- a8: contig C-mer graph (C = K1-1) --------------------------------------------------------
+  const int C = k1 - 1;
+  s->labels.reserve((n_contigs + 1) * 4);
+  label_init_kernel<<<shn_grid(n_contigs + 1, kBlock), kBlock, 0, st>>>(s->labels.as<uint32_t>(),
+                                                                        n_contigs + 1);
+  KERNEL_CHECK();
+  if (n_contigs && C >= 1) {
+    DevBuf cnt, off;
+    cnt.reserve((n_contigs + 1) * 8);
+    off.reserve((n_contigs + 1) * 8);
+    window_counts_kernel<<<shn_grid(n_contigs + 1, kBlock), kBlock, 0, st>>>(
+        s->contig_offs.as<uint64_t>(), n_contigs, C, cnt.as<uint64_t>());
+    KERNEL_CHECK();
+    exclusive_sum(c, cnt.as<uint64_t>(), off.as<uint64_t>(), n_contigs + 1);
+    uint64_t n_ent = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&n_ent, off.as<uint64_t>() + n_contigs, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    if (n_ent) {
+      DevBuf keys, owner, pos;
+      keys.reserve(n_ent * 8);
+      owner.reserve(n_ent * 4);
+      pos.reserve(n_ent * 4);
+      {
+        ProfScope ps(c, "cmer_entries");
+        window_entries_kernel<<<shn_grid(contig_bases, kBlock), kBlock, 0, st>>>(
+            s->contig_codes.as<uint8_t>(), s->contig_offs.as<uint64_t>(), off.as<uint64_t>(), n_contigs,
+            contig_bases, C, 1u, keys.as<uint64_t>(), owner.as<uint32_t>(), pos.as<uint32_t>());
+        KERNEL_CHECK();
+      }
+      ProfScope ps(c, "cmer_join", 12);
+      shn_self_join(c, keys.as<uint64_t>(), owner.as<uint32_t>(), pos.as<uint32_t>(), n_ent, 2 * C, 1,
+                    &s->edges);
+    }
+  }
+  s->sz.n_edges = s->edges.n;
+
+  // ---- a9: components of the contig graph (label = minimum contig index) ----------------------
+  if (s->edges.n) {
+    ProfScope ps(c, "contig_components", 2);
+    for (int it = 0;; ++it) {
+      ctr = zero_counters(c);
+      label_hook_kernel<<<shn_grid(s->edges.n, kBlock), kBlock, 0, st>>>(
+          s->edges.lo.as<uint32_t>(), s->edges.hi.as<uint32_t>(), s->edges.n, s->labels.as<uint32_t>(), ctr);
+      KERNEL_CHECK();
+      label_jump_kernel<<<shn_grid(n_contigs + 1, kBlock), kBlock, 0, st>>>(s->labels.as<uint32_t>(),
+                                                                            n_contigs + 1, ctr);
+      KERNEL_CHECK();
+      read_counters(c, h, 1);
+      if (h[0] == 0) break;
+      SHN_CHECK(it < 100000, "internal error: label propagation does not converge");
+    }
+  }
+  CUDA_CHECK(cudaStreamSynchronize(st));
+}
+
+// ---- getters -----------------------------------------------------------------------------------
+namespace {
+L3State* need_l3(shn_ctx* c) {
+  SHN_CHECK(c->l3 != nullptr, "shn_l3_run has not been called on this context");
+  return c->l3;
+}
+
+__global__ void __launch_bounds__(kBlock)
+    seed_keys_kernel(const ShnSlot* __restrict__ slots, const uint32_t* __restrict__ w_slot, uint64_t n,
+                     uint64_t* __restrict__ keys) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) keys[i] = slots[w_slot[i]].key;
+}
+
+__global__ void __launch_bounds__(kBlock)
+    codes_to_ascii_kernel(const uint8_t* __restrict__ codes, uint64_t n, char* __restrict__ out) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = shn_base_of(codes[i]);
+}
+}  // namespace
+
+void shn_l3_get_sizes_impl(shn_ctx* c, shn_l3_sizes* out) { *out = need_l3(c)->sz; }
+
+void shn_l3_get_walks_impl(shn_ctx* c, uint64_t* seed_keys, uint32_t* n_left, uint32_t* n_right,
+                           uint64_t* tot_wt, uint8_t* flags) {
+  L3State* s = need_l3(c);
+  uint64_t n = s->sz.n_walks;
+  if (n == 0) return;
+  cudaStream_t st = c->stream;
+  if (seed_keys) {
+    DevBuf keys;
+    keys.reserve(n * 8);
+    seed_keys_kernel<<<shn_grid(n, kBlock), kBlock, 0, st>>>(c->view().slots, s->w_seed_slot.as<uint32_t>(),
+                                                            n, keys.as<uint64_t>());
+    KERNEL_CHECK();
+    CUDA_CHECK(cudaMemcpyAsync(seed_keys, keys.p, n * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+  }
+  if (n_left) CUDA_CHECK(cudaMemcpyAsync(n_left, s->w_nl.p, n * 4, cudaMemcpyDeviceToHost, st));
+  if (n_right) CUDA_CHECK(cudaMemcpyAsync(n_right, s->w_nr.p, n * 4, cudaMemcpyDeviceToHost, st));
+  if (tot_wt) CUDA_CHECK(cudaMemcpyAsync(tot_wt, s->w_totwt.p, n * 8, cudaMemcpyDeviceToHost, st));
+  CUDA_CHECK(cudaStreamSynchronize(st));
+  if (flags) {
+    memset(flags, 0, n);
+    for (size_t j = 0; j < s->h_cand_walk.size(); ++j) {
+      uint8_t f = 1;
+      if (s->h_cand_dup[j]) f |= 2;
+      if (s->h_cand_acc[j]) f |= 4;
+      flags[s->h_cand_walk[j]] = f;
+    }
+  }
+}
+
+void shn_l3_get_contigs_impl(shn_ctx* c, char* bases, uint64_t* offsets) {
+  L3State* s = need_l3(c);
+  uint64_t nb = s->sz.contig_bases;
+  memcpy(offsets, s->h_contig_offs.data(), s->h_contig_offs.size() * 8);
+  if (nb == 0) return;
+  DevBuf ascii;
+  ascii.reserve(nb);
+  codes_to_ascii_kernel<<<shn_grid(nb, kBlock), kBlock, 0, c->stream>>>(s->contig_codes.as<uint8_t>(), nb,
+                                                                       ascii.as<char>());
+  KERNEL_CHECK();
+  CUDA_CHECK(cudaMemcpyAsync(bases, ascii.p, nb, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+}
+
+void shn_l3_get_allowed_impl(shn_ctx* c, uint64_t* keys, uint32_t* weights) {
+  L3State* s = need_l3(c);
+  uint64_t n = s->sz.n_allowed;
+  if (n == 0) return;
+  if (keys) CUDA_CHECK(cudaMemcpyAsync(keys, s->allowed_keys.p, n * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (weights)
+    CUDA_CHECK(cudaMemcpyAsync(weights, s->allowed_w.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+}
+
+void shn_l3_get_edges_impl(shn_ctx* c, uint32_t* a, uint32_t* b, uint32_t* weight, uint32_t* fp) {
+  L3State* s = need_l3(c);
+  uint64_t n = s->edges.n;
+  if (n == 0) return;
+  cudaStream_t st = c->stream;
+  if (a) CUDA_CHECK(cudaMemcpyAsync(a, s->edges.lo.p, n * 4, cudaMemcpyDeviceToHost, st));
+  if (b) CUDA_CHECK(cudaMemcpyAsync(b, s->edges.hi.p, n * 4, cudaMemcpyDeviceToHost, st));
+  if (weight) CUDA_CHECK(cudaMemcpyAsync(weight, s->edges.count.p, n * 4, cudaMemcpyDeviceToHost, st));
+  if (fp) CUDA_CHECK(cudaMemcpyAsync(fp, s->edges.min_i.p, n * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_CHECK(cudaStreamSynchronize(st));
+}
+
+void shn_l3_get_labels_impl(shn_ctx* c, uint32_t* label) {
+  L3State* s = need_l3(c);
+  CUDA_CHECK(cudaMemcpyAsync(label, s->labels.p, (s->sz.n_contigs + 1) * 4, cudaMemcpyDeviceToHost,
+                             c->stream));
+  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+}

@@ -1,0 +1,638 @@
+// a10-a12: K1-mer -> component map and read partition (kmers_for_component.py:186-205,239-305,
+// 322-423,452-477).
+//
+// Component map: open-addressing table, 32-byte buckets of two 16-byte slots
+// {key u64, comp0 u32, comp1 u32}; a K1-mer belongs to at most two components (its 'c' partition
+// and the 'r2_c' twin of the repartition pass).  Weights for the per-component k1mer files live
+// in a side array indexed by slot and are touched only by shn_l4_map_window_weights.
+//
+// Reads: 2-bit packed, MSB-first 32 bases per uint64 word, ceil(len/32) words per read.
+// Assignment: 8 lanes per record (4 samples x 2 mates for 100 bp, K=24); each lane extracts one
+// sampled K1-mer, probes one 32-byte sector; the union over the record is formed with shuffles.
+//
+// Algorithmic bytes per record: 32 B packed words + 8 B (offset,len) per read,
+// 32 B per probe, 8 B per assignment written.
+#include <cub/cub.cuh>
+
+#include "common.cuh"
+
+struct __align__(16) CompSlot {
+  uint64_t key;
+  uint32_t comp0, comp1;
+};
+
+struct PackedReads {
+  DevBuf words;   // uint64
+  DevBuf woff;    // uint64 [n+1] word offsets
+  DevBuf len;     // uint32 [n]   length, bit 31 = contains a non-ACGT character
+  uint64_t n = 0;
+  uint64_t n_words = 0;
+};
+
+struct L4State {
+  DevBuf map;       // CompSlot[2*n_buckets]
+  DevBuf map_w;     // uint32 weight per slot
+  uint64_t n_buckets = 0;
+  int k1 = 0;
+  uint64_t n_keys = 0;
+  PackedReads reads[2];
+  DevBuf assign;    // uint64 entries (comp << 32 | record), sorted + unique after shn_l4_assign
+  uint64_t n_assign = 0;
+  DevBuf stage_a, stage_b, stage_c;
+};
+
+namespace {
+
+constexpr int kBlock = 256;
+constexpr uint32_t kLenBad = 0x80000000u;
+
+struct CompMapView {
+  CompSlot* slots;
+  uint64_t n_buckets;
+  __device__ __forceinline__ uint64_t bucket_of(uint64_t key) const {
+    return __umul64hi(shn_mix64(key), n_buckets);
+  }
+};
+
+__global__ void __launch_bounds__(kBlock) map_clear_kernel(CompSlot* slots, uint32_t* w, uint64_t n) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  uint4 v = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+  for (; i < n; i += stride) {
+    reinterpret_cast<uint4*>(slots)[i] = v;
+    w[i] = 0;
+  }
+}
+
+// index of the contig that contains concatenated-base position g: last c with offs[c] <= g
+__device__ __forceinline__ uint64_t find_segment(const uint64_t* __restrict__ offs, uint64_t n,
+                                                 uint64_t g) {
+  uint64_t lo = 0, hi = n;  // invariant offs[lo] <= g < offs[hi]
+  while (hi - lo > 1) {
+    uint64_t mid = (lo + hi) >> 1;
+    if (__ldg(&offs[mid]) <= g)
+      lo = mid;
+    else
+      hi = mid;
+  }
+  return lo;
+}
+
+// packs bases[p .. p+k) ; returns false if a non-ACGT character is met
+__device__ __forceinline__ bool pack_window(const char* __restrict__ bases, uint64_t p, int k,
+                                            uint64_t* out) {
+  uint64_t x = 0;
+  bool ok = true;
+  for (int j = 0; j < k; ++j) {
+    uint32_t code = shn_code_of_strict((uint8_t)__ldg(&bases[p + j]));
+    ok &= code < 4;
+    x = (x << 2) | (code & 3u);
+  }
+  *out = x;
+  return ok;
+}
+
+__device__ __forceinline__ uint64_t map_find(const CompMapView& m, uint64_t key) {
+  uint64_t b = m.bucket_of(key);
+  for (;;) {
+    const CompSlot* s = m.slots + 2 * b;
+    const uint4 s0 = __ldg(reinterpret_cast<const uint4*>(&s[0]));
+    const uint4 s1 = __ldg(reinterpret_cast<const uint4*>(&s[1]));
+    uint64_t k0 = ((uint64_t)s0.y << 32) | s0.x, k1 = ((uint64_t)s1.y << 32) | s1.x;
+    if (k0 == key) return 2 * b;
+    if (k1 == key) return 2 * b + 1;
+    if (k0 == SHN_EMPTY_KEY || k1 == SHN_EMPTY_KEY) return ~0ull;
+    b = (b + 1 == m.n_buckets) ? 0 : b + 1;
+  }
+}
+
+// counters: [0]=new keys [1]=non-ACGT windows [2]=more than two components for a K1-mer
+__global__ void __launch_bounds__(kBlock)
+    map_add_kernel(CompMapView m, const char* __restrict__ bases, const uint64_t* __restrict__ offs,
+                   const uint32_t* __restrict__ comp_of, uint64_t n_contigs, uint64_t total_bases,
+                   int k1, unsigned long long* counters) {
+  uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int n_new = 0, n_bad = 0, n_over = 0;
+  if (g < total_bases) {
+    uint64_t c = find_segment(offs, n_contigs, g);
+    uint64_t end = __ldg(&offs[c + 1]);
+    if (g + k1 <= end) {
+      uint64_t key;
+      if (!pack_window(bases, g, k1, &key)) {
+        n_bad = 1;
+      } else {
+        uint32_t comp = __ldg(&comp_of[c]);
+        uint64_t b = m.bucket_of(key);
+        CompSlot* slot = nullptr;
+        while (!slot) {
+          CompSlot* s = m.slots + 2 * b;
+          const ulonglong2 s0 = __ldcg(reinterpret_cast<const ulonglong2*>(&s[0]));
+          const ulonglong2 s1 = __ldcg(reinterpret_cast<const ulonglong2*>(&s[1]));
+          uint64_t k[2] = {s0.x, s1.x};
+#pragma unroll
+          for (int j = 0; j < 2 && !slot; ++j) {
+            if (k[j] == key) {
+              slot = &s[j];
+            } else if (k[j] == SHN_EMPTY_KEY) {
+              unsigned long long old =
+                  atomicCAS(reinterpret_cast<unsigned long long*>(&s[j].key),
+                            (unsigned long long)SHN_EMPTY_KEY, (unsigned long long)key);
+              if (old == SHN_EMPTY_KEY) {
+                n_new = 1;
+                slot = &s[j];
+              } else if (old == key) {
+                slot = &s[j];
+              }
+            }
+          }
+          b = (b + 1 == m.n_buckets) ? 0 : b + 1;
+        }
+        uint32_t old = atomicCAS(&slot->comp0, SHN_NONE32, comp);
+        if (old != SHN_NONE32 && old != comp) {
+          old = atomicCAS(&slot->comp1, SHN_NONE32, comp);
+          if (old != SHN_NONE32 && old != comp) n_over = 1;
+        }
+      }
+    }
+  }
+  int t_new = __syncthreads_count(n_new), t_bad = __syncthreads_count(n_bad),
+      t_over = __syncthreads_count(n_over);
+  if (threadIdx.x == 0) {
+    if (t_new) atomicAdd(&counters[0], (unsigned long long)t_new);
+    if (t_bad) atomicAdd(&counters[1], (unsigned long long)t_bad);
+    if (t_over) atomicAdd(&counters[2], (unsigned long long)t_over);
+  }
+}
+
+__global__ void __launch_bounds__(kBlock)
+    map_set_weights_kernel(CompMapView m, uint32_t* __restrict__ map_w,
+                           const uint64_t* __restrict__ keys, const uint32_t* __restrict__ weights,
+                           uint64_t n) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint64_t slot = map_find(m, keys[i]);
+  if (slot != ~0ull) map_w[slot] = weights[i];
+}
+
+__global__ void __launch_bounds__(kBlock)
+    window_count_kernel(const uint64_t* __restrict__ offs, uint64_t n_contigs, int k1,
+                        uint64_t* __restrict__ nwin) {
+  uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_contigs) return;
+  uint64_t len = offs[c + 1] - offs[c];
+  nwin[c] = len >= (uint64_t)k1 ? len - k1 + 1 : 0;
+}
+
+__global__ void __launch_bounds__(kBlock)
+    map_window_weights_kernel(CompMapView m, const uint32_t* __restrict__ map_w,
+                              const char* __restrict__ bases, const uint64_t* __restrict__ offs,
+                              const uint64_t* __restrict__ win_off, uint64_t n_contigs,
+                              uint64_t total_bases, int k1, uint32_t* __restrict__ out) {
+  uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= total_bases) return;
+  uint64_t c = find_segment(offs, n_contigs, g);
+  uint64_t start = __ldg(&offs[c]), end = __ldg(&offs[c + 1]);
+  if (g + k1 > end) return;
+  uint64_t key;
+  uint32_t w = 0;
+  if (pack_window(bases, g, k1, &key)) {
+    uint64_t slot = map_find(m, key);
+    if (slot != ~0ull) w = map_w[slot];
+  }
+  out[win_off[c] + (g - start)] = w;
+}
+
+// ---- read packing -------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock)
+    read_words_kernel(const uint64_t* __restrict__ offs, uint64_t n, uint64_t* __restrict__ nwords) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint64_t len = offs[i + 1] - offs[i];
+  nwords[i] = (len + 31) >> 5;
+}
+
+// 8 lanes per read, one 32-base word per lane and iteration
+__global__ void __launch_bounds__(kBlock)
+    pack_reads_kernel(const char* __restrict__ bases, const uint64_t* __restrict__ offs,
+                      const uint64_t* __restrict__ woff, uint64_t n, uint64_t* __restrict__ words,
+                      uint32_t* __restrict__ len_out) {
+  uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t i = t >> 3;
+  int lane8 = (int)(t & 7);
+  bool active = i < n;
+  uint64_t start = 0, len = 0, wbase = 0;
+  if (active) {
+    start = __ldg(&offs[i]);
+    len = __ldg(&offs[i + 1]) - start;
+    wbase = __ldg(&woff[i]);
+  }
+  uint64_t nw = (len + 31) >> 5;
+  bool bad = false;
+  for (uint64_t w = lane8; w < nw; w += 8) {
+    uint64_t x = 0;
+    uint64_t p = start + 32 * w;
+    int cnt = (int)min((uint64_t)32, len - 32 * w);
+    for (int j = 0; j < cnt; ++j) {
+      uint32_t code = shn_code_of_strict((uint8_t)__ldg(&bases[p + j]));
+      bad |= code >= 4;
+      x = (x << 2) | (code & 3u);
+    }
+    x <<= 2 * (32 - cnt);  // left-align a partial last word
+    words[wbase + w] = x;
+  }
+  // OR the bad flags of the 8 lanes of this read
+  unsigned b = __ballot_sync(0xFFFFFFFFu, bad);
+  unsigned grp = (b >> ((threadIdx.x & 31) & ~7)) & 0xFFu;
+  if (active && lane8 == 0) {
+    len_out[i] = (uint32_t)len | (grp ? kLenBad : 0u);
+  }
+}
+
+struct ReadsView {
+  const uint64_t* words;
+  const uint64_t* woff;
+  const uint32_t* len;
+};
+
+__device__ __forceinline__ uint64_t extract_kmer(const uint64_t* __restrict__ words, uint64_t wbase,
+                                                 uint32_t st, int k1) {
+  uint64_t wi = wbase + (st >> 5);
+  int sh = (int)(st & 31);
+  uint64_t x = __ldg(&words[wi]) << (2 * sh);
+  if (sh + k1 > 32) x |= __ldg(&words[wi + 1]) >> (64 - 2 * sh);
+  return x >> (64 - 2 * k1);
+}
+
+// number of sampled K1-mers of a read of length len (get_rmers, kmers_for_component.py:186-192)
+__device__ __forceinline__ uint32_t n_samples(uint32_t len, uint32_t k1) {
+  if (len < k1) return 0;  // one too-short key that can never be in the map
+  return (len - k1 + k1 - 1) / k1 + 1;
+}
+
+// counters: [0]=entries appended [1]=lookups [2]=valid records [3]=overflow
+__global__ void __launch_bounds__(kBlock)
+    assign_kernel(CompMapView m, ReadsView r0, ReadsView r1, int paired, uint64_t n_records, int k1,
+                  uint64_t* __restrict__ out, uint64_t out_cap, unsigned long long* counters) {
+  uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t rec = t >> 3;
+  int lane8 = (int)(t & 7);
+  int lane = threadIdx.x & 31;
+  int grp_base = lane & ~7;
+  bool active = rec < n_records;
+  uint32_t len0 = 0, len1 = 0;
+  uint64_t wb0 = 0, wb1 = 0;
+  bool valid = false;
+  if (active) {
+    len0 = __ldg(&r0.len[rec]);
+    wb0 = __ldg(&r0.woff[rec]);
+    if (paired) {
+      len1 = __ldg(&r1.len[rec]);
+      wb1 = __ldg(&r1.woff[rec]);
+    }
+    valid = !((len0 | len1) & kLenBad);
+  }
+  uint32_t ns0 = valid ? n_samples(len0, k1) : 0;
+  uint32_t ns1 = (valid && paired) ? n_samples(len1, k1) : 0;
+  uint32_t ns = ns0 + ns1;
+  // all 32 lanes iterate the same number of rounds so that the shuffles stay converged
+  uint32_t max_ns = ns;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) max_ns = max(max_ns, __shfl_xor_sync(0xFFFFFFFFu, max_ns, o));
+  unsigned long long my_lookups = 0;
+  for (uint32_t base_s = 0; base_s < max_ns; base_s += 8) {
+    uint32_t s = base_s + lane8;
+    uint32_t v0 = SHN_NONE32, v1 = SHN_NONE32;
+    if (s < ns) {
+      bool second = s >= ns0;
+      uint32_t si = second ? s - ns0 : s;
+      uint32_t len = second ? len1 : len0;
+      uint32_t nsm = second ? ns1 : ns0;
+      // offsets 0, k1, 2*k1, ... and the last window (read[-k1:])
+      uint32_t st = (si + 1 == nsm) ? len - k1 : si * k1;
+      uint64_t key = extract_kmer(second ? r1.words : r0.words, second ? wb1 : wb0, st, k1);
+      uint64_t slot = map_find(m, key);
+      my_lookups++;
+      if (slot != ~0ull) {
+        const uint4 sv = __ldg(reinterpret_cast<const uint4*>(&m.slots[slot]));
+        v0 = sv.z;
+        v1 = sv.w;
+      }
+    }
+    // dedup inside the 8-lane group: keep the first occurrence of every component id
+    if (v1 == v0) v1 = SHN_NONE32;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      uint32_t o0 = __shfl_sync(0xFFFFFFFFu, v0, grp_base + j);
+      uint32_t o1 = __shfl_sync(0xFFFFFFFFu, v1, grp_base + j);
+      if (j < lane8) {
+        if (v0 == o0 || v0 == o1) v0 = SHN_NONE32;
+        if (v1 == o0 || v1 == o1) v1 = SHN_NONE32;
+      }
+    }
+    // warp-aggregated append
+    unsigned b0 = __ballot_sync(0xFFFFFFFFu, v0 != SHN_NONE32);
+    unsigned b1 = __ballot_sync(0xFFFFFFFFu, v1 != SHN_NONE32);
+    int total = __popc(b0) + __popc(b1);
+    if (total) {
+      unsigned long long base = 0;
+      if (lane == 0) base = atomicAdd(&counters[0], (unsigned long long)total);
+      base = __shfl_sync(0xFFFFFFFFu, base, 0);
+      unsigned lower = (1u << lane) - 1u;
+      uint64_t p0 = base + __popc(b0 & lower);
+      uint64_t p1 = base + __popc(b0) + __popc(b1 & lower);
+      if (base + total <= out_cap) {
+        if (v0 != SHN_NONE32) out[p0] = ((uint64_t)v0 << 32) | rec;
+        if (v1 != SHN_NONE32) out[p1] = ((uint64_t)v1 << 32) | rec;
+      } else if (lane == 0) {
+        atomicAdd(&counters[3], 1ull);
+      }
+    }
+  }
+  // per-block totals
+  __shared__ unsigned long long sh_lookups;
+  if (threadIdx.x == 0) sh_lookups = 0;
+  __syncthreads();
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) my_lookups += __shfl_xor_sync(0xFFFFFFFFu, my_lookups, o);
+  if (lane == 0 && my_lookups) atomicAdd(&sh_lookups, my_lookups);
+  int nvalid = __syncthreads_count(valid && lane8 == 0);
+  if (threadIdx.x == 0) {
+    if (sh_lookups) atomicAdd(&counters[1], sh_lookups);
+    if (nvalid) atomicAdd(&counters[2], (unsigned long long)nvalid);
+  }
+}
+
+__global__ void __launch_bounds__(kBlock)
+    comp_offsets_kernel(const uint64_t* __restrict__ entries, uint64_t n, uint32_t n_comps,
+                        uint64_t* __restrict__ offs) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > n) return;
+  // offs[c] = first entry index with comp >= c
+  uint32_t prev = i == 0 ? 0u : (uint32_t)(entries[i - 1] >> 32) + 1u;
+  uint32_t cur = i == n ? n_comps + 1u : (uint32_t)(entries[i] >> 32) + 1u;
+  if (cur > n_comps + 1u) cur = n_comps + 1u;
+  for (uint32_t c = prev; c < cur; ++c) offs[c] = i;
+}
+
+__global__ void __launch_bounds__(kBlock)
+    entries_low32_kernel(const uint64_t* __restrict__ entries, uint64_t n, uint32_t* __restrict__ out) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (uint32_t)entries[i];
+}
+
+L4State* l4_of(shn_ctx* c) {
+  if (!c->l4) c->l4 = new L4State();
+  return c->l4;
+}
+
+CompMapView map_view(L4State* s) { return CompMapView{s->map.as<CompSlot>(), s->n_buckets}; }
+
+unsigned long long* zero_counters(shn_ctx* c) {
+  c->counters.reserve(64 * sizeof(unsigned long long));
+  unsigned long long* ctr = c->counters.as<unsigned long long>();
+  CUDA_CHECK(cudaMemsetAsync(ctr, 0, 8 * sizeof(unsigned long long), c->stream));
+  return ctr;
+}
+
+void read_counters(shn_ctx* c, unsigned long long* h, int n) {
+  CUDA_CHECK(cudaMemcpyAsync(h, c->counters.p, n * sizeof(unsigned long long),
+                             cudaMemcpyDeviceToHost, c->stream));
+  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+}
+
+}  // namespace
+
+void shn_l4_free(shn_ctx* c) {
+  delete c->l4;
+  c->l4 = nullptr;
+}
+
+void shn_l4_map_add_contigs_impl(shn_ctx* c, const char* bases, const uint64_t* offsets,
+                                 const uint32_t* comp_of_contig, uint64_t n_contigs, int k1,
+                                 int reset, uint64_t expected_total, int on_device) {
+  SHN_CHECK(k1 >= 1 && k1 <= 32, "k1 must be in 1..32");
+  L4State* s = l4_of(c);
+  if (reset) {
+    uint64_t nb = expected_total < 1024 ? 1024 : expected_total;
+    s->map.reserve(nb * 2 * sizeof(CompSlot));
+    s->map_w.reserve(nb * 2 * sizeof(uint32_t));
+    s->n_buckets = nb;
+    s->k1 = k1;
+    s->n_keys = 0;
+    ProfScope ps(c, "l4_map_clear");
+    unsigned grid =
+        (unsigned)std::min<uint64_t>((nb * 2 + kBlock - 1) / kBlock, (uint64_t)c->sm_count * 32);
+    map_clear_kernel<<<grid, kBlock, 0, c->stream>>>(s->map.as<CompSlot>(), s->map_w.as<uint32_t>(),
+                                                     nb * 2);
+    KERNEL_CHECK();
+  }
+  SHN_CHECK(s->n_buckets > 0, "component map not initialised (call with reset != 0 first)");
+  SHN_CHECK(k1 == s->k1, "k1 differs from the component map's");
+  if (n_contigs == 0) return;
+  uint64_t total = 0;
+  const uint64_t* d_offs;
+  if (on_device) {
+    d_offs = offsets;
+    CUDA_CHECK(cudaMemcpyAsync(&total, offsets + n_contigs, 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  } else {
+    total = offsets[n_contigs];
+    d_offs = (const uint64_t*)InputView::get(c, offsets, (n_contigs + 1) * 8, 0, s->stage_b);
+  }
+  const char* d_bases = (const char*)InputView::get(c, bases, total, on_device, s->stage_a);
+  const uint32_t* d_comp =
+      (const uint32_t*)InputView::get(c, comp_of_contig, n_contigs * 4, on_device, s->stage_c);
+  SHN_CHECK(s->n_keys + total <= s->n_buckets * 2,
+            "component map too small: expected_total_k1mers was underestimated");
+  unsigned long long* ctr = zero_counters(c);
+  if (total) {
+    ProfScope ps(c, "l4_map_add");
+    map_add_kernel<<<shn_grid(total, kBlock), kBlock, 0, c->stream>>>(
+        map_view(s), d_bases, d_offs, d_comp, n_contigs, total, k1, ctr);
+    KERNEL_CHECK();
+  }
+  unsigned long long h[3];
+  read_counters(c, h, 3);
+  SHN_CHECK(h[1] == 0, "contig contains a character outside ACGT");
+  SHN_CHECK(h[2] == 0, "a K1-mer belongs to more than two components (unsupported)");
+  s->n_keys += h[0];
+}
+
+void shn_l4_map_set_weights_impl(shn_ctx* c, const uint64_t* keys, const uint32_t* weights,
+                                 uint64_t n, int on_device) {
+  L4State* s = l4_of(c);
+  SHN_CHECK(s->n_buckets > 0, "component map not initialised");
+  if (n == 0) return;
+  const uint64_t* d_keys = (const uint64_t*)InputView::get(c, keys, n * 8, on_device, s->stage_a);
+  const uint32_t* d_w = (const uint32_t*)InputView::get(c, weights, n * 4, on_device, s->stage_b);
+  ProfScope ps(c, "l4_map_set_weights");
+  map_set_weights_kernel<<<shn_grid(n, kBlock), kBlock, 0, c->stream>>>(
+      map_view(s), s->map_w.as<uint32_t>(), d_keys, d_w, n);
+  KERNEL_CHECK();
+  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+}
+
+void shn_l4_map_window_weights_impl(shn_ctx* c, const char* bases, const uint64_t* offsets,
+                                    uint64_t n_contigs, int k1, uint32_t* h_weights) {
+  L4State* s = l4_of(c);
+  SHN_CHECK(s->n_buckets > 0, "component map not initialised");
+  if (n_contigs == 0) return;
+  uint64_t total = offsets[n_contigs];
+  const uint64_t* d_offs = (const uint64_t*)InputView::get(c, offsets, (n_contigs + 1) * 8, 0, s->stage_b);
+  const char* d_bases = (const char*)InputView::get(c, bases, total, 0, s->stage_a);
+  DevBuf nwin, winoff, out;
+  nwin.reserve((n_contigs + 1) * 8);
+  winoff.reserve((n_contigs + 1) * 8);
+  CUDA_CHECK(cudaMemsetAsync(nwin.p, 0, (n_contigs + 1) * 8, c->stream));
+  window_count_kernel<<<shn_grid(n_contigs, kBlock), kBlock, 0, c->stream>>>(d_offs, n_contigs, k1,
+                                                                             nwin.as<uint64_t>());
+  KERNEL_CHECK();
+  size_t tb = 0;
+  CUDA_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, tb, nwin.as<uint64_t>(), winoff.as<uint64_t>(),
+                                           (int)(n_contigs + 1), c->stream));
+  CUDA_CHECK(cub::DeviceScan::ExclusiveSum(c->tmp(tb), tb, nwin.as<uint64_t>(), winoff.as<uint64_t>(),
+                                           (int)(n_contigs + 1), c->stream));
+  uint64_t total_win = 0;
+  CUDA_CHECK(cudaMemcpyAsync(&total_win, winoff.as<uint64_t>() + n_contigs, 8, cudaMemcpyDeviceToHost,
+                             c->stream));
+  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  if (total_win == 0) return;
+  out.reserve(total_win * 4);
+  {
+    ProfScope ps(c, "l4_window_weights");
+    map_window_weights_kernel<<<shn_grid(total, kBlock), kBlock, 0, c->stream>>>(
+        map_view(s), s->map_w.as<uint32_t>(), d_bases, d_offs, winoff.as<uint64_t>(), n_contigs, total,
+        k1, out.as<uint32_t>());
+    KERNEL_CHECK();
+  }
+  CUDA_CHECK(cudaMemcpyAsync(h_weights, out.p, total_win * 4, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+}
+
+void shn_l4_load_reads_impl(shn_ctx* c, int mate, const char* bases, const uint64_t* offsets,
+                            uint64_t n, int on_device) {
+  SHN_CHECK(mate == 0 || mate == 1, "mate must be 0 or 1");
+  L4State* s = l4_of(c);
+  PackedReads& pr = s->reads[mate];
+  pr.n = n;
+  pr.n_words = 0;
+  if (n == 0) return;
+  SHN_CHECK(n < 0xFFFFFFFFull, "at most 2^32-1 read records per call");
+  uint64_t total = 0;
+  const uint64_t* d_offs;
+  if (on_device) {
+    d_offs = offsets;
+    CUDA_CHECK(cudaMemcpyAsync(&total, offsets + n, 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  } else {
+    total = offsets[n];
+    d_offs = (const uint64_t*)InputView::get(c, offsets, (n + 1) * 8, 0, s->stage_b);
+  }
+  const char* d_bases = (const char*)InputView::get(c, bases, total, on_device, s->stage_a);
+  DevBuf nwords;
+  nwords.reserve((n + 1) * 8);
+  pr.woff.reserve((n + 1) * 8);
+  pr.len.reserve(n * 4);
+  CUDA_CHECK(cudaMemsetAsync(nwords.p, 0, (n + 1) * 8, c->stream));
+  {
+    ProfScope ps(c, "read_word_offsets", 2);
+    read_words_kernel<<<shn_grid(n, kBlock), kBlock, 0, c->stream>>>(d_offs, n, nwords.as<uint64_t>());
+    KERNEL_CHECK();
+    size_t tb = 0;
+    CUDA_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, tb, nwords.as<uint64_t>(), pr.woff.as<uint64_t>(),
+                                             (int64_t)(n + 1), c->stream));
+    CUDA_CHECK(cub::DeviceScan::ExclusiveSum(c->tmp(tb), tb, nwords.as<uint64_t>(),
+                                             pr.woff.as<uint64_t>(), (int64_t)(n + 1), c->stream));
+  }
+  CUDA_CHECK(cudaMemcpyAsync(&pr.n_words, pr.woff.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost,
+                             c->stream));
+  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  pr.words.reserve((pr.n_words + 1) * 8);  // +1: extract_kmer may touch one word past a read
+  CUDA_CHECK(cudaMemsetAsync(pr.words.as<uint64_t>() + pr.n_words, 0, 8, c->stream));
+  {
+    ProfScope ps(c, "pack_reads");
+    pack_reads_kernel<<<shn_grid(n * 8, kBlock), kBlock, 0, c->stream>>>(
+        d_bases, d_offs, pr.woff.as<uint64_t>(), n, pr.words.as<uint64_t>(), pr.len.as<uint32_t>());
+    KERNEL_CHECK();
+  }
+  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+}
+
+void shn_l4_assign_impl(shn_ctx* c, int paired, int k1, uint64_t* n_assign, uint64_t* n_lookups,
+                        uint64_t* n_valid) {
+  L4State* s = l4_of(c);
+  SHN_CHECK(s->n_buckets > 0, "component map not initialised");
+  SHN_CHECK(k1 == s->k1, "k1 differs from the component map's");
+  uint64_t n = s->reads[0].n;
+  if (paired) SHN_CHECK(s->reads[1].n == n, "mate files hold different numbers of records");
+  s->n_assign = 0;
+  *n_assign = *n_lookups = *n_valid = 0;
+  if (n == 0) return;
+  ReadsView r0{s->reads[0].words.as<uint64_t>(), s->reads[0].woff.as<uint64_t>(),
+               s->reads[0].len.as<uint32_t>()};
+  ReadsView r1 = r0;
+  if (paired)
+    r1 = ReadsView{s->reads[1].words.as<uint64_t>(), s->reads[1].woff.as<uint64_t>(),
+                   s->reads[1].len.as<uint32_t>()};
+  uint64_t cap = std::max<uint64_t>(2 * n, 1024);
+  unsigned long long h[4];
+  for (int attempt = 0;; ++attempt) {
+    s->assign.reserve(cap * 8);
+    unsigned long long* ctr = zero_counters(c);
+    {
+      ProfScope ps(c, "l4_assign");
+      assign_kernel<<<shn_grid(n * 8, kBlock), kBlock, 0, c->stream>>>(
+          map_view(s), r0, r1, paired, n, k1, s->assign.as<uint64_t>(), cap, ctr);
+      KERNEL_CHECK();
+    }
+    read_counters(c, h, 4);
+    if (h[3] == 0) break;
+    SHN_CHECK(attempt < 2, "assignment buffer overflow after resize");
+    cap = h[0] + 1024;  // exact size known now
+  }
+  uint64_t m = h[0];
+  *n_lookups = h[1];
+  *n_valid = h[2];
+  if (m > 0) {
+    // sort by (component, record) and drop duplicates (records longer than 8 samples)
+    DevBuf sorted, nuniq;
+    sorted.reserve(m * 8);
+    nuniq.reserve(8);
+    ProfScope ps(c, "l4_sort_unique", 3);
+    size_t tb = 0;
+    CUDA_CHECK(cub::DeviceRadixSort::SortKeys(nullptr, tb, s->assign.as<uint64_t>(),
+                                              sorted.as<uint64_t>(), (int64_t)m, 0, 64, c->stream));
+    CUDA_CHECK(cub::DeviceRadixSort::SortKeys(c->tmp(tb), tb, s->assign.as<uint64_t>(),
+                                              sorted.as<uint64_t>(), (int64_t)m, 0, 64, c->stream));
+    tb = 0;
+    CUDA_CHECK(cub::DeviceSelect::Unique(nullptr, tb, sorted.as<uint64_t>(), s->assign.as<uint64_t>(),
+                                         nuniq.as<uint64_t>(), (int64_t)m, c->stream));
+    CUDA_CHECK(cub::DeviceSelect::Unique(c->tmp(tb), tb, sorted.as<uint64_t>(),
+                                         s->assign.as<uint64_t>(), nuniq.as<uint64_t>(), (int64_t)m,
+                                         c->stream));
+    CUDA_CHECK(cudaMemcpyAsync(&m, nuniq.p, 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  }
+  s->n_assign = m;
+  *n_assign = m;
+}
+
+void shn_l4_get_assignments_impl(shn_ctx* c, uint32_t n_comps, uint64_t* h_offs, uint32_t* h_idx) {
+  L4State* s = l4_of(c);
+  uint64_t m = s->n_assign;
+  DevBuf offs, idx;
+  offs.reserve((uint64_t)(n_comps + 2) * 8);
+  idx.reserve((m + 1) * 4);
+  comp_offsets_kernel<<<shn_grid(m + 1, kBlock), kBlock, 0, c->stream>>>(s->assign.as<uint64_t>(), m,
+                                                                         n_comps, offs.as<uint64_t>());
+  KERNEL_CHECK();
+  if (m) {
+    entries_low32_kernel<<<shn_grid(m, kBlock), kBlock, 0, c->stream>>>(s->assign.as<uint64_t>(), m,
+                                                                        idx.as<uint32_t>());
+    KERNEL_CHECK();
+    CUDA_CHECK(cudaMemcpyAsync(h_idx, idx.p, m * 4, cudaMemcpyDeviceToHost, c->stream));
+  }
+  CUDA_CHECK(cudaMemcpyAsync(h_offs, offs.p, (uint64_t)(n_comps + 1) * 8, cudaMemcpyDeviceToHost,
+                             c->stream));
+  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+}

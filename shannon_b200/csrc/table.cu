@@ -1,0 +1,267 @@
+// a1/a2: K1-mer -> weight table (load_kmers + lowComplexity, extension_correction.py:202-221,
+// 142-149) as an open-addressing hash table in HBM.
+//
+// Layout: 32-byte buckets of two 16-byte slots {key u64, weight u32, first_idx u32}; a probe
+// touches exactly one 32-byte DRAM sector.  Bucket = mulhi(mix64(key), n_buckets), linear
+// probing over buckets.  Load factor <= 0.5 (slots), so ~1.1 sectors per probe on average.
+//
+// Algorithmic bytes: insert = 8 B key + 4 B count streamed + one sector
+// read-modify-write (64 B) = 76 B per input line; lookup = 8 B + 32 B + 5 B out = 45 B.
+#include <cub/cub.cuh>
+
+#include "common.cuh"
+#include "table_dev.cuh"
+
+namespace {
+
+constexpr int kBlock = 256;
+
+__global__ void __launch_bounds__(kBlock) table_clear_kernel(ShnSlot* slots, uint64_t n_slots) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  // one 16-byte store per slot, fully coalesced
+  uint4 v;
+  v.x = 0xFFFFFFFFu;
+  v.y = 0xFFFFFFFFu;  // key = EMPTY
+  v.z = 0u;           // weight
+  v.w = 0xFFFFFFFFu;  // first_idx = +inf for atomicMin
+  for (; i < n_slots; i += stride) reinterpret_cast<uint4*>(slots)[i] = v;
+}
+
+// counters: [0]=new keys [1]=low-complexity lines [3]=bad key / index overflow
+__global__ void __launch_bounds__(kBlock)
+    table_insert_kernel(ShnTableView t, const uint64_t* __restrict__ keys,
+                        const uint32_t* __restrict__ counts, uint64_t n, int k1, int ds,
+                        unsigned long long* counters) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int n_new = 0, n_low = 0, n_bad = 0;
+  if (i < n) {
+    uint64_t key = keys[i];
+    uint32_t w = counts[i];
+    uint64_t base_idx = ds ? 2 * i : i;
+    if ((key & ~shn_kmer_mask(k1)) || base_idx + 1 >= 0x7FFFFFFFull || w > SHN_WEIGHT_MASK) {
+      n_bad = 1;
+    } else if (shn_low_complexity(key, k1)) {  // rc(kmer) is low-complexity iff kmer is
+      n_low = 1;
+    } else {
+      const int reps = ds ? 2 : 1;
+      for (int r = 0; r < reps; ++r) {
+        uint64_t kk = r == 0 ? key : shn_revcomp(key, k1);
+        uint64_t slot = table_upsert_slot(t, kk, &n_new);
+        if (slot == ~0ull) {
+          n_bad = 1;
+          break;
+        }
+        atomicAdd(&t.slots[slot].weight, w);  // RED: result unused (overflow is checked later)
+        atomicMin(&t.slots[slot].idx, (uint32_t)(base_idx + r));
+      }
+    }
+  }
+  // one atomic per block and counter instead of one per thread
+  int tot_new = __syncthreads_count(n_new & 1) + 2 * __syncthreads_count(n_new >> 1);
+  int tot_low = __syncthreads_count(n_low);
+  int tot_bad = __syncthreads_count(n_bad);
+  if (threadIdx.x == 0) {
+    if (tot_new) atomicAdd(&counters[0], (unsigned long long)tot_new);
+    if (tot_low) atomicAdd(&counters[1], (unsigned long long)tot_low);
+    if (tot_bad) atomicAdd(&counters[3], (unsigned long long)tot_bad);
+  }
+}
+
+// weights with bit 31 set mean a count sum overflowed the 31-bit weight field
+__global__ void __launch_bounds__(kBlock)
+    table_check_kernel(const ShnSlot* __restrict__ slots, uint64_t n_slots,
+                       unsigned long long* counters) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  int bad = 0;
+  for (; i < n_slots; i += stride) {
+    uint4 v = __ldg(reinterpret_cast<const uint4*>(slots) + i);
+    bad |= (v.z & SHN_TRAVERSED) ? 1 : 0;
+  }
+  int tot = __syncthreads_count(bad);
+  if (threadIdx.x == 0 && tot) atomicAdd(&counters[2], (unsigned long long)tot);
+}
+
+__global__ void __launch_bounds__(kBlock)
+    table_lookup_kernel(ShnTableView t, const uint64_t* __restrict__ keys, uint64_t n,
+                        uint32_t* __restrict__ weights, uint8_t* __restrict__ found) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint64_t key = keys[i];
+  uint64_t b = t.bucket_of(key);
+  uint32_t w = 0;
+  uint8_t f = 0;
+  for (;;) {
+    const ShnSlot* s = t.slots + 2 * b;
+    const uint4 s0 = __ldg(reinterpret_cast<const uint4*>(&s[0]));
+    const uint4 s1 = __ldg(reinterpret_cast<const uint4*>(&s[1]));
+    uint64_t k0 = ((uint64_t)s0.y << 32) | s0.x, k1_ = ((uint64_t)s1.y << 32) | s1.x;
+    if (k0 == key) {
+      w = s0.z & SHN_WEIGHT_MASK;
+      f = 1;
+      break;
+    }
+    if (k1_ == key) {
+      w = s1.z & SHN_WEIGHT_MASK;
+      f = 1;
+      break;
+    }
+    if (k0 == SHN_EMPTY_KEY || k1_ == SHN_EMPTY_KEY) break;
+    b = (b + 1 == t.n_buckets) ? 0 : b + 1;
+  }
+  if (weights) weights[i] = w;
+  if (found) found[i] = f;
+}
+
+struct OccupiedSlot {
+  const ShnSlot* slots;
+  __device__ bool operator()(uint64_t i) const { return slots[i].key != SHN_EMPTY_KEY; }
+};
+
+__global__ void __launch_bounds__(kBlock)
+    table_dump_gather_kernel(const ShnSlot* __restrict__ slots, const uint64_t* __restrict__ sel,
+                             uint64_t n, uint64_t* keys, uint32_t* weights, uint32_t* idx) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  ShnSlot s = slots[sel[i]];
+  keys[i] = s.key;
+  weights[i] = s.weight & SHN_WEIGHT_MASK;
+  idx[i] = s.idx;
+}
+
+__global__ void __launch_bounds__(kBlock)
+    pack_kmers_kernel(const char* __restrict__ ascii, uint64_t n, int k1, uint64_t* __restrict__ keys,
+                      unsigned long long* counters) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int bad = 0;
+  if (i < n) {
+    const char* p = ascii + i * (uint64_t)k1;
+    uint64_t x = 0;
+    for (int j = 0; j < k1; ++j) {
+      uint32_t code = shn_code_of((uint8_t)__ldg(&p[j]));  // kmer.upper(), :214
+      bad |= code > 3;
+      x = (x << 2) | (code & 3u);
+    }
+    keys[i] = x;
+  }
+  int tot = __syncthreads_count(bad);
+  if (threadIdx.x == 0 && tot) atomicAdd(&counters[0], (unsigned long long)tot);
+}
+
+}  // namespace
+
+void shn_pack_kmers_impl(shn_ctx* c, const char* d_ascii, uint64_t n, int k1, uint64_t* d_keys) {
+  c->counters.reserve(64 * sizeof(unsigned long long));
+  unsigned long long* ctr = c->counters.as<unsigned long long>();
+  CUDA_CHECK(cudaMemsetAsync(ctr, 0, 8, c->stream));
+  {
+    ProfScope ps(c, "pack_kmers");
+    pack_kmers_kernel<<<shn_grid(n, kBlock), kBlock, 0, c->stream>>>(d_ascii, n, k1, d_keys, ctr);
+    KERNEL_CHECK();
+  }
+  unsigned long long h = 0;
+  CUDA_CHECK(cudaMemcpyAsync(&h, ctr, 8, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  SHN_CHECK(h == 0, "k-mer contains a character outside ACGT");
+}
+
+void shn_table_build_impl(shn_ctx* c, const uint64_t* d_keys, const uint32_t* d_counts, uint64_t n,
+                          int k1, int double_stranded) {
+  SHN_CHECK(k1 >= 1 && k1 <= 32, "k1 must be in 1..32 (K <= 31); wider keys are not built yet");
+  uint64_t items = n * (double_stranded ? 2 : 1);
+  SHN_CHECK(items < 0x7FFFFFFFull, "more than 2^31-1 input K1-mers per table");
+  // slots >= 2 * items  (load factor <= 0.5)  => buckets >= items
+  uint64_t n_buckets = items < 1024 ? 1024 : items;
+  c->table.reserve(n_buckets * 2 * sizeof(ShnSlot));
+  c->n_buckets = n_buckets;
+  c->k1 = k1;
+  c->n_items = items;
+  c->counters.reserve(64 * sizeof(unsigned long long));
+  unsigned long long* ctr = c->counters.as<unsigned long long>();
+  CUDA_CHECK(cudaMemsetAsync(ctr, 0, 8 * sizeof(unsigned long long), c->stream));
+  {
+    ProfScope ps(c, "table_clear");
+    unsigned grid = (unsigned)std::min<uint64_t>((n_buckets * 2 + kBlock - 1) / kBlock,
+                                                 (uint64_t)c->sm_count * 32);
+    table_clear_kernel<<<grid, kBlock, 0, c->stream>>>(c->table.as<ShnSlot>(), n_buckets * 2);
+    KERNEL_CHECK();
+  }
+  if (n > 0) {
+    ProfScope ps(c, "table_insert");
+    table_insert_kernel<<<shn_grid(n, kBlock), kBlock, 0, c->stream>>>(c->view(), d_keys, d_counts,
+                                                                       n, k1, double_stranded, ctr);
+    KERNEL_CHECK();
+  }
+  {
+    ProfScope ps(c, "table_check");
+    unsigned grid = (unsigned)std::min<uint64_t>((n_buckets * 2 + kBlock - 1) / kBlock,
+                                                 (uint64_t)c->sm_count * 32);
+    table_check_kernel<<<grid, kBlock, 0, c->stream>>>(c->table.as<ShnSlot>(), n_buckets * 2, ctr);
+    KERNEL_CHECK();
+  }
+  unsigned long long h[4];
+  CUDA_CHECK(cudaMemcpyAsync(h, ctr, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  SHN_CHECK(h[3] == 0, "table build: key wider than 2*k1 bits, count >= 2^31 or input index overflow");
+  SHN_CHECK(h[2] == 0, "table build: a K1-mer weight exceeds 2^31-1");
+  c->n_distinct = h[0];
+  c->n_lowcomplexity = h[1];
+}
+
+void shn_table_lookup_impl(shn_ctx* c, const uint64_t* d_keys, uint64_t n, uint32_t* d_weights,
+                           uint8_t* d_found) {
+  SHN_CHECK(c->n_buckets > 0, "no table built");
+  if (n == 0) return;
+  ProfScope ps(c, "table_lookup");
+  table_lookup_kernel<<<shn_grid(n, kBlock), kBlock, 0, c->stream>>>(c->view(), d_keys, n, d_weights,
+                                                                     d_found);
+  KERNEL_CHECK();
+}
+
+// dump sorted by first-occurrence index --------------------------------------------------
+void shn_table_dump_impl(shn_ctx* c, uint64_t* h_keys, uint32_t* h_weights, uint32_t* h_idx) {
+  SHN_CHECK(c->n_buckets > 0, "no table built");
+  uint64_t n_slots = c->n_buckets * 2, n = c->n_distinct;
+  if (n == 0) return;
+  DevBuf sel, nsel, keys, w, idx, keys2, w2, idx2;
+  sel.reserve(n * 8);
+  nsel.reserve(8);
+  keys.reserve(n * 8);
+  w.reserve(n * 4);
+  idx.reserve(n * 4);
+  keys2.reserve(n * 8);
+  w2.reserve(n * 4);
+  idx2.reserve(n * 4);
+  cub::CountingInputIterator<uint64_t> it(0);
+  OccupiedSlot pred{c->table.as<ShnSlot>()};
+  size_t tb = 0;
+  SHN_CHECK(n_slots < 0x7FFFFFFFull, "table dump limited to < 2^31 slots");
+  CUDA_CHECK(cub::DeviceSelect::If(nullptr, tb, it, sel.as<uint64_t>(), nsel.as<uint64_t>(),
+                                   (int)n_slots, pred, c->stream));
+  CUDA_CHECK(cub::DeviceSelect::If(c->tmp(tb), tb, it, sel.as<uint64_t>(), nsel.as<uint64_t>(),
+                                   (int)n_slots, pred, c->stream));
+  table_dump_gather_kernel<<<shn_grid(n, kBlock), kBlock, 0, c->stream>>>(
+      c->table.as<ShnSlot>(), sel.as<uint64_t>(), n, keys.as<uint64_t>(), w.as<uint32_t>(),
+      idx.as<uint32_t>());
+  KERNEL_CHECK();
+  // sort by idx: two passes (keys, then weights) sharing the same sort key
+  tb = 0;
+  CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, tb, idx.as<uint32_t>(), idx2.as<uint32_t>(),
+                                             keys.as<uint64_t>(), keys2.as<uint64_t>(), (int)n, 0, 32,
+                                             c->stream));
+  CUDA_CHECK(cub::DeviceRadixSort::SortPairs(c->tmp(tb), tb, idx.as<uint32_t>(), idx2.as<uint32_t>(),
+                                             keys.as<uint64_t>(), keys2.as<uint64_t>(), (int)n, 0, 32,
+                                             c->stream));
+  tb = 0;
+  CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, tb, idx.as<uint32_t>(), idx2.as<uint32_t>(),
+                                             w.as<uint32_t>(), w2.as<uint32_t>(), (int)n, 0, 32,
+                                             c->stream));
+  CUDA_CHECK(cub::DeviceRadixSort::SortPairs(c->tmp(tb), tb, idx.as<uint32_t>(), idx2.as<uint32_t>(),
+                                             w.as<uint32_t>(), w2.as<uint32_t>(), (int)n, 0, 32,
+                                             c->stream));
+  CUDA_CHECK(cudaMemcpyAsync(h_keys, keys2.p, n * 8, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_CHECK(cudaMemcpyAsync(h_weights, w2.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_CHECK(cudaMemcpyAsync(h_idx, idx2.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+}

@@ -1,0 +1,243 @@
+"""Drop-in replacement of the reference's ``extension_correction.py`` (same entry point, argv
+contract, return value and output files; extension_correction.py:528-549, 309-524) running on
+the B200 through libshannon_b200.so.  Host code here only parses arguments, orders contig-level
+results (the DFS of :417-434 over the GPU-built contig graph) and writes the text files.
+"""
+import os
+import sys
+import time
+from collections.abc import Mapping
+
+import numpy as np
+
+from . import _lib
+
+_CODE_TO_ASCII = np.frombuffer(b"AGCT", dtype=np.uint8)
+_default_ctx = None
+
+
+def get_context(device=None):
+    """Process-wide default GPU context (device from SHANNON_B200_DEVICE / LOCAL_RANK / 0)."""
+    global _default_ctx
+    if _default_ctx is None:
+        if device is None:
+            device = int(os.environ.get("SHANNON_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+        _default_ctx = _lib.Context(device)
+    return _default_ctx
+
+
+def decode_kmers(keys, k1):
+    """uint64 packed keys -> (n, k1) uint8 ASCII matrix."""
+    keys = np.asarray(keys, dtype=np.uint64)
+    shifts = (2 * (k1 - 1 - np.arange(k1))).astype(np.uint64)
+    codes = ((keys[:, None] >> shifts[None, :]) & np.uint64(3)).astype(np.uint8)
+    return _CODE_TO_ASCII[codes]
+
+
+def encode_kmer(s):
+    x = 0
+    for ch in s:
+        x = (x << 2) | "AGCT".index(ch)
+    return x
+
+
+class AllowedKmerDict(Mapping):
+    """``allowed_kmer_dict`` (extension_correction.py:404-408) backed by the packed arrays the
+    GPU produced.  Behaves like the reference's ``dict[str, int]`` (iteration in contig order,
+    ``get``, ``clear``) and lets ``kmers_for_component`` pick up the arrays without a detour
+    through millions of Python strings."""
+
+    def __init__(self, keys, weights, k1):
+        self.keys_packed = np.asarray(keys, dtype=np.uint64)
+        self.weights = np.asarray(weights, dtype=np.uint32)
+        self.k1 = k1
+        self._index = None
+
+    def _idx(self):
+        if self._index is None:
+            self._index = dict(zip(self.keys_packed.tolist(), self.weights.tolist()))
+        return self._index
+
+    def __len__(self):
+        return len(self.keys_packed)
+
+    def __iter__(self):
+        if len(self.keys_packed) == 0:
+            return iter(())
+        mat = decode_kmers(self.keys_packed, self.k1)
+        return iter(mat.tobytes().decode()[i:i + self.k1]
+                    for i in range(0, mat.size, self.k1))
+
+    def __getitem__(self, kmer):
+        if not isinstance(kmer, str) or len(kmer) != self.k1 or kmer.strip("ACGT"):
+            raise KeyError(kmer)
+        return self._idx()[encode_kmer(kmer)]
+
+    def clear(self):  # shannon.py:469
+        self.keys_packed = np.empty(0, dtype=np.uint64)
+        self.weights = np.empty(0, dtype=np.uint32)
+        self._index = None
+
+
+def contig_adjacency(n_contigs, a, b, w, fp):
+    """contig_connections (extension_correction.py:372-389) in the reference's dict insertion
+    order, from the GPU's distinct edge list (a < b, multiplicity w, fp = first C-mer position in
+    b shared with a): node x first gets its earlier neighbours ordered by (fp, id) -- they are
+    connected while x itself is being indexed -- then later contigs in ascending id."""
+    adj = [[] for _ in range(n_contigs + 1)]
+    if len(a):
+        a = a.astype(np.int64)
+        b = b.astype(np.int64)
+        lower = np.lexsort((a, fp.astype(np.int64), b))      # by b, then fp, then a
+        for e in lower.tolist():
+            adj[b[e]].append((int(a[e]), int(w[e])))
+        higher = np.lexsort((b, a))                          # by a, then b
+        for e in higher.tolist():
+            adj[a[e]].append((int(b[e]), int(w[e])))
+    return adj
+
+
+def dfs_components(n_contigs, adj):
+    """extension_correction.py:417-434: iterative DFS in ascending contig index; member order is
+    the pop order.  Returns {root: [members]} in insertion order."""
+    comp_of = [0] * (n_contigs + 1)
+    seen = [False] * (n_contigs + 1)
+    component2contig = {}
+    for root in range(1, n_contigs + 1):
+        if comp_of[root]:
+            continue
+        members = component2contig[root] = []
+        stack = [root]
+        seen[root] = True
+        while stack:
+            cur = stack.pop()
+            comp_of[cur] = root
+            members.append(cur)
+            for nb, _ in adj[cur]:
+                if not seen[nb]:
+                    stack.append(nb)
+                    seen[nb] = True
+    return component2contig, comp_of
+
+
+def run_correction(infile, outfile, min_weight, min_length, double_stranded,
+                   comp_directory_name, comp_size_threshold, polyA_del=True, inMem=False,
+                   nJobs=1, reads_files=(), ctx=None):
+    """extension_correction.py:309-524.  Returns (allowed_kmer_dict, reads)."""
+    if not polyA_del:
+        raise NotImplementedError("polyA_del=False is never used by the reference driver")
+    ctx = ctx or get_context()
+    print('nJobs:' + str(nJobs))
+    print('reads_files:' + ' '.join(reads_files))
+    f_log = open(comp_directory_name + "/before_sp_log.txt", 'w')
+    print("{:s}: Starting Kmer error correction..".format(time.asctime()))
+    f_log.write("{:s}: Starting..".format(time.asctime()) + "\n")
+
+    keys, counts, k1 = ctx.parse_kmer_file(infile)
+    ctx.table_build(keys, counts, k1, double_stranded)
+    stats = ctx.table_stats()
+    if stats["n_distinct"] == 0:
+        raise StopIteration("no K1-mers loaded")  # the reference fails on next(iter(kmers)) here
+    del keys, counts
+    print("{:s}: {:d} K-mers loaded.".format(time.asctime(), stats["n_distinct"]))
+    f_log.write("{:s}: {:d} K-mers loaded.".format(time.asctime(), stats["n_distinct"]) + "\n")
+    f_log.write("{:s}: Reads loading in background process.".format(time.asctime()) + "\n")
+
+    sizes = ctx.l3_run(min_weight, min_length)
+    n_contigs = sizes["n_contigs"]
+    bases, offs = ctx.l3_contigs()
+    text = bases.tobytes().decode()
+    o = offs.tolist()
+    contigs = [None] + [text[o[i]:o[i + 1]] for i in range(n_contigs)]
+    with open(outfile + '_contig', 'w') as f1:
+        f1.write("".join(c + "\n" for c in contigs[1:]))
+
+    a_keys, a_w = ctx.l3_allowed()
+    allowed_kmer_dict = AllowedKmerDict(a_keys, a_w, k1)
+    n_allowed = len(allowed_kmer_dict)
+    print("{:s}: {:d} K-mers remaining after error correction.".format(time.asctime(), n_allowed))
+    f_log.write("{:s}: {:d} K-mers remaining after error correction.".format(
+        time.asctime(), n_allowed) + " \n")
+    with open(outfile, 'w') as f:
+        if not inMem and n_allowed:
+            mat = decode_kmers(a_keys, k1)
+            lines = np.empty((n_allowed, k1 + 1), dtype=np.uint8)
+            lines[:, :k1] = mat
+            lines[:, k1] = ord("\t")
+            txt = lines.tobytes().decode()
+            f.write("".join(txt[i:i + k1 + 1] + str(w) + "\n"
+                            for i, w in zip(range(0, len(txt), k1 + 1), a_w.tolist())))
+    f_log.write("{:s}: {:d} K-mers written to file.".format(time.asctime(), n_allowed) + " \n")
+
+    f_log.write(str(time.asctime()) + ": " + "Before dfs " + "\n")
+    ea, eb, ew, efp = ctx.l3_edges()
+    adj = contig_adjacency(n_contigs, ea, eb, ew, efp)
+    component2contig, comp_of = dfs_components(n_contigs, adj)
+    labels = ctx.l3_labels()
+    if n_contigs and not np.array_equal(labels[1:], np.asarray(comp_of[1:], dtype=np.uint32)):
+        raise _lib.ShnError("internal error: GPU component labels disagree with the DFS partition")
+    f_log.write(str(time.asctime()) + ": " + "After dfs " + "\n")
+    n_edges = dict((c, 0) for c in component2contig)
+    for x in ea.tolist():
+        n_edges[comp_of[x]] += 1
+    f_log.write(str(time.asctime()) + ": " + "After Edges Loaded " + "\n")
+
+    d = comp_directory_name
+    new_comp_num = 1
+    remaining_file_curr_size = 0
+    remaining_file_num = 1
+    single_contig_index = 0
+    single_contigs = open(d + "/reconstructed_single_contigs.fasta", 'w')
+    non_comp_contigs = open(d + "/remaining_contigs" + str(remaining_file_num) + ".txt", 'w')
+    for component, members in component2contig.items():
+        if len(members) == 1:
+            single_contigs.write('>Single_' + str(single_contig_index) + '\n' + contigs[members[0]] + '\n')
+            single_contig_index += 1
+            continue
+        if len(members) > comp_size_threshold:
+            code = dict((c, i + 1) for i, c in enumerate(members))
+            with open(d + "/component" + str(new_comp_num) + ".txt", 'w') as f:
+                f.write(str(len(members)) + "\t" + str(n_edges[component]) + "\t" + "001" + "\n")
+                for c in members:
+                    f.write("".join(str(code[nb]) + "\t" + str(wt) + "\t" for nb, wt in adj[c]) + "\n")
+            with open(d + "/component" + str(new_comp_num) + "contigs" + ".txt", 'w') as f:
+                f.write("".join(contigs[c] + "\n" for c in members))
+            new_comp_num += 1
+        else:
+            non_comp_contigs.write("".join(contigs[c] + "\n" for c in members))
+            remaining_file_curr_size += len(members)
+            if remaining_file_curr_size > comp_size_threshold:
+                remaining_file_num += 1
+                non_comp_contigs.close()
+                non_comp_contigs = open(d + "/remaining_contigs" + str(remaining_file_num) + ".txt", 'w')
+                remaining_file_curr_size = 0
+    single_contigs.close()
+    non_comp_contigs.close()
+    f_log.write(str(time.asctime()) + ": " + "Metis Input File Created " + "\n")
+    f_log.write("{:s}: Read-loader in background process joinig back.".format(time.asctime()) + "\n")
+    reads = []
+    f_log.write("{:s}: {:d} Reads loaded in background process.".format(time.asctime(), len(reads)) + "\n")
+    f_log.close()
+    return allowed_kmer_dict, reads
+
+
+def extension_correction(arguments, inMem=False):
+    """Same argv contract as extension_correction.py:528-549:
+    [-d] infile outfile min_weight min_length comp_dir comp_size_threshold [nJobs [reads1 [reads2]]]"""
+    double_stranded = '-d' in arguments
+    arguments = [a for a in arguments if len(a) > 0 and a[0] != '-']
+    infile, outfile = arguments[:2]
+    min_weight, min_length = int(arguments[2]), int(arguments[3])
+    comp_directory_name, comp_size_threshold = arguments[4], int(arguments[5])
+    nJobs = int(arguments[6]) if len(arguments) > 6 else 1
+    reads_files = list(arguments[7:9]) if len(arguments) > 7 else []
+    return run_correction(infile, outfile, min_weight, min_length, double_stranded,
+                          comp_directory_name, comp_size_threshold, True, inMem, nJobs, reads_files)
+
+
+if __name__ == '__main__':
+    if len(sys.argv) == 1:
+        argv = ['kmers.dict', 'allowed_kmers.dict', '1', '1', '-d']
+    else:
+        argv = sys.argv[1:]
+    extension_correction(argv)
