@@ -138,7 +138,7 @@ int shn_l3_get_contigs(shn_ctx* ctx, char* bases, uint64_t* offsets);
 int shn_l3_get_allowed(shn_ctx* ctx, uint64_t* keys, uint32_t* weights);
 /* contig_connections (:372-389) as distinct undirected edges a<b (1-based contig indices) with
  * multiplicity weight and, for the insertion order of b's neighbour dict, the first C-mer
- * position in b shared with a.  Sorted by (a,b). */
+ * position in b shared with a.  Sorted by (b,a). */
 int shn_l3_get_edges(shn_ctx* ctx, uint32_t* a, uint32_t* b, uint32_t* weight,
                      uint32_t* first_pos_in_b);
 /* component label per contig (index 0 unused) = minimum contig index of its component
