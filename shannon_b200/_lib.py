@@ -181,6 +181,9 @@ class Context(HostIO):
 
     def close(self):
         if getattr(self, "h", None):
+            for hp in getattr(self, "_pinned", []):
+                self.lib.shn_host_free_pinned(self.h, vp(hp))
+            self._pinned = []
             self.lib.shn_destroy(self.h)
             self.h = None
 
@@ -213,6 +216,21 @@ class Context(HostIO):
         if arr.nbytes:
             self.h2d(d, arr)
         return d
+
+    def pinned_empty(self, n, dtype):
+        """numpy array over page-locked host memory (falls back to pageable memory)."""
+        dtype = np.dtype(dtype)
+        nbytes = max(int(n) * dtype.itemsize, 1)
+        p = vp()
+        try:
+            self.call("shn_host_alloc_pinned", C.c_uint64(nbytes), C.byref(p))
+        except ShnError:
+            return np.empty(int(n), dtype=dtype)
+        buf = (C.c_uint8 * nbytes).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=dtype, count=int(n))
+        self._pinned = getattr(self, "_pinned", [])
+        self._pinned.append(p.value)
+        return arr
 
     def sync(self):
         self.call("shn_sync")
@@ -348,6 +366,9 @@ class Context(HostIO):
                   C.c_uint64(len(comp)), int(k1), int(bool(reset)), C.c_uint64(int(expected_total)))
 
     def l4_map_set_weights(self, keys, weights):
+        if keys is None:   # use the allowed set of this context's last l3_run, on the device
+            self.call("shn_l4_map_set_weights", None, None, C.c_uint64(0))
+            return
         keys = np.ascontiguousarray(keys, dtype=np.uint64)
         weights = np.ascontiguousarray(weights, dtype=np.uint32)
         self.call("shn_l4_map_set_weights", ptr(keys), ptr(weights), C.c_uint64(len(keys)))

@@ -22,6 +22,7 @@ void shn_l3_get_contigs_impl(shn_ctx* c, char* bases, uint64_t* offsets);
 void shn_l3_get_allowed_impl(shn_ctx* c, uint64_t* keys, uint32_t* weights);
 void shn_l3_get_edges_impl(shn_ctx* c, uint32_t* a, uint32_t* b, uint32_t* weight, uint32_t* fp);
 void shn_l3_get_labels_impl(shn_ctx* c, uint32_t* label);
+void shn_l3_allowed_dev(shn_ctx* c, const uint64_t** keys, const uint32_t** weights, uint64_t* n);
 void shn_l4_map_add_contigs_impl(shn_ctx* c, const char* bases, const uint64_t* offsets,
                                  const uint32_t* comp_of_contig, uint64_t n_contigs, int k1,
                                  int reset, uint64_t expected_total, int on_device);
@@ -45,6 +46,7 @@ void shn_count_free(shn_ctx* c);
 void shn_pack_kmers_impl(shn_ctx* c, const char* d_ascii, uint64_t n, int k1, uint64_t* d_keys);
 
 static thread_local std::string g_last_error;
+thread_local DevPool* g_shn_pool = nullptr;
 
 [[noreturn]] void shn_throw(const char* file, int line, const std::string& msg) {
   const char* base = strrchr(file, '/');
@@ -69,6 +71,7 @@ static thread_local std::string g_last_error;
 static void bind(shn_ctx* c) {
   SHN_CHECK(c != nullptr, "null context");
   CUDA_CHECK(cudaSetDevice(c->device));
+  g_shn_pool = &c->pool;
 }
 
 extern "C" {
@@ -109,6 +112,7 @@ int shn_create(int device, shn_ctx** out) {
 void shn_destroy(shn_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
+  g_shn_pool = &c->pool;
   cudaStreamSynchronize(c->stream);
   shn_l3_free(c);
   shn_l4_free(c);
@@ -117,11 +121,16 @@ void shn_destroy(shn_ctx* c) {
   c->cub_tmp.release();
   c->flush_buf.release();
   c->counters.release();
+  c->prof_resolve();
+  for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
   cudaEventDestroy(c->t0);
   cudaEventDestroy(c->t1);
   cudaEventDestroy(c->p0);
   cudaEventDestroy(c->p1);
+  cudaStreamSynchronize(c->stream);
+  c->pool.trim();
   cudaStreamDestroy(c->stream);
+  g_shn_pool = nullptr;
   delete c;
 }
 
@@ -207,6 +216,7 @@ int shn_timer_stop(shn_ctx* c, float* ms) {
 int shn_prof_enable(shn_ctx* c, int enable) {
   SHN_API_BEGIN
   bind(c);
+  c->prof_resolve();
   c->prof_on = enable != 0;
   if (enable) c->prof.clear();
   SHN_API_END(c)
@@ -214,6 +224,7 @@ int shn_prof_enable(shn_ctx* c, int enable) {
 int shn_prof_get(shn_ctx* c, const char* name, double* total_ms, uint64_t* launches) {
   SHN_API_BEGIN
   SHN_CHECK(c != nullptr, "null context");
+  c->prof_resolve();
   auto it = c->prof.find(name);
   *total_ms = it == c->prof.end() ? 0.0 : it->second.ms;
   *launches = it == c->prof.end() ? 0 : it->second.launches;
@@ -222,6 +233,7 @@ int shn_prof_get(shn_ctx* c, const char* name, double* total_ms, uint64_t* launc
 int shn_prof_dump(shn_ctx* c, char* buf, uint64_t buf_bytes) {
   SHN_API_BEGIN
   SHN_CHECK(c != nullptr && buf != nullptr && buf_bytes > 0, "bad arguments");
+  c->prof_resolve();
   std::string s;
   for (auto& kv : c->prof)
     s += kv.first + "\t" + std::to_string(kv.second.ms) + "\t" + std::to_string(kv.second.launches) + "\n";
@@ -308,7 +320,7 @@ int shn_table_stats(shn_ctx* c, uint64_t* n_distinct, uint64_t* n_lowcomplexity,
   SHN_CHECK(c != nullptr, "null context");
   if (n_distinct) *n_distinct = c->n_distinct;
   if (n_lowcomplexity) *n_lowcomplexity = c->n_lowcomplexity;
-  if (n_slots) *n_slots = c->n_buckets * 2;
+  if (n_slots) *n_slots = c->n_buckets * SHN_BSLOTS;
   if (k1) *k1 = c->k1;
   SHN_API_END(c)
 }
@@ -404,7 +416,15 @@ int shn_l4_map_set_weights(shn_ctx* c, const uint64_t* dict_keys, const uint32_t
                            uint64_t n) {
   SHN_API_BEGIN
   bind(c);
-  shn_l4_map_set_weights_impl(c, dict_keys, dict_weights, n, 0);
+  if (dict_keys == nullptr) {  // k1mer_dictionary = the allowed set this ctx's shn_l3_run produced
+    const uint64_t* dk;
+    const uint32_t* dw;
+    uint64_t dn;
+    shn_l3_allowed_dev(c, &dk, &dw, &dn);
+    shn_l4_map_set_weights_impl(c, dk, dw, dn, 1);
+  } else {
+    shn_l4_map_set_weights_impl(c, dict_keys, dict_weights, n, 0);
+  }
   SHN_API_END(c)
 }
 int shn_l4_map_window_weights(shn_ctx* c, const char* bases, const uint64_t* offsets,

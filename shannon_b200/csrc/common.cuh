@@ -110,20 +110,23 @@ SHN_HD uint64_t shn_ascii_order_key(uint64_t x) {
 }
 
 // ---------------------------------------------------------------------------------------
-// K1-mer table: open addressing, 32-byte buckets of two 16-byte slots (one DRAM sector per
-// probe), linear probing over buckets.
+// K1-mer table: open addressing, 64-byte buckets of four 16-byte slots (one DRAM burst per probe),
+// linear probing over buckets; see table_dev.cuh.
 // ---------------------------------------------------------------------------------------
 struct __align__(16) ShnSlot {
   uint64_t key;     // SHN_EMPTY_KEY when free
-  uint32_t weight;  // sum of counts; bit 31 = traversed (set by the walk kernels)
+  uint32_t weight;  // sum of counts (30 bits); bit 31 = traversed (walk kernels); bit 30 of the
+                    // bucket's slot 0 = an insert walked past this full bucket
   uint32_t idx;     // first-occurrence index in the input (dict insertion order)
 };
 static const uint32_t SHN_TRAVERSED = 0x80000000u;
-static const uint32_t SHN_WEIGHT_MASK = 0x7FFFFFFFu;
+static const uint32_t SHN_OVERFLOW = 0x40000000u;
+static const uint32_t SHN_WEIGHT_MASK = 0x3FFFFFFFu;
+#define SHN_BSLOTS 4
 static const uint32_t SHN_NONE32 = 0xFFFFFFFFu;
 
 struct ShnTableView {
-  ShnSlot* slots;      // 2 * n_buckets
+  ShnSlot* slots;      // SHN_BSLOTS * n_buckets
   uint64_t n_buckets;
   __device__ __forceinline__ uint64_t bucket_of(uint64_t key) const {
     return __umul64hi(shn_mix64(key), n_buckets);
@@ -133,27 +136,103 @@ struct ShnTableView {
 // ---------------------------------------------------------------------------------------
 // device buffers and the context
 // ---------------------------------------------------------------------------------------
+// Caching device allocator, one per context.  Every kernel of a context runs on that context's
+// single stream, so a block handed back by one buffer can be reused by the next allocation without
+// synchronisation (stream order protects it).  Blocks are never returned to the driver between
+// steps: after the first pass of a workload every allocation is a free-list hit (cudaMalloc /
+// cudaFree of multi-GB blocks cost tens to hundreds of ms and serialise the device).
+struct DevPool {
+  std::multimap<uint64_t, void*> free_blocks;   // size -> block
+  std::map<void*, uint64_t> live;                // block -> size
+  uint64_t cached_bytes = 0, live_bytes = 0;
+  static uint64_t round_up(uint64_t n) {
+    const uint64_t g = n >= (64ull << 20) ? (2ull << 20) : 512ull;
+    return (n + g - 1) / g * g;
+  }
+  void* alloc(uint64_t nbytes) {
+    const uint64_t want = round_up(nbytes);
+    auto it = free_blocks.lower_bound(want);
+    if (it != free_blocks.end() && it->first <= want + want / 4 + (1ull << 20)) {
+      void* p = it->second;
+      uint64_t sz = it->first;
+      free_blocks.erase(it);
+      cached_bytes -= sz;
+      live[p] = sz;
+      live_bytes += sz;
+      return p;
+    }
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      trim();  // give cached blocks back to the driver and retry once
+      e = cudaMalloc(&p, want);
+    }
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      SHN_FAIL("device allocation of " + std::to_string(want) + " bytes failed: " +
+               cudaGetErrorString(e));
+    }
+    live[p] = want;
+    live_bytes += want;
+    return p;
+  }
+  void release(void* p) {
+    auto it = live.find(p);
+    if (it == live.end()) {
+      cudaFree(p);
+      return;
+    }
+    free_blocks.emplace(it->second, p);
+    cached_bytes += it->second;
+    live_bytes -= it->second;
+    live.erase(it);
+  }
+  void trim() {
+    cudaDeviceSynchronize();
+    for (auto& kv : free_blocks) cudaFree(kv.second);
+    free_blocks.clear();
+    cached_bytes = 0;
+  }
+};
+
+extern thread_local DevPool* g_shn_pool;  // set by bind() in api.cu
+
 struct DevBuf {
   void* p = nullptr;
   uint64_t bytes = 0;
+  DevPool* pool = nullptr;
   DevBuf() {}
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
   ~DevBuf() { release(); }
   void release() {
-    if (p) cudaFree(p);
+    if (p) {
+      if (pool)
+        pool->release(p);
+      else
+        cudaFree(p);
+    }
     p = nullptr;
     bytes = 0;
+    pool = nullptr;
   }
   // grow-only (re)allocation; contents are NOT preserved
   void reserve(uint64_t nbytes) {
     if (nbytes <= bytes) return;
     release();
     if (nbytes == 0) return;
-    cudaError_t e = cudaMalloc(&p, nbytes);
-    if (e != cudaSuccess) {
-      p = nullptr;
-      SHN_FAIL("cudaMalloc(" + std::to_string(nbytes) + " bytes) failed: " + cudaGetErrorString(e));
+    pool = g_shn_pool;
+    if (pool) {
+      p = pool->alloc(nbytes);
+    } else {
+      cudaError_t e = cudaMalloc(&p, nbytes);
+      if (e != cudaSuccess) {
+        p = nullptr;
+        cudaGetLastError();
+        SHN_FAIL("device allocation of " + std::to_string(nbytes) + " bytes failed: " +
+                 cudaGetErrorString(e));
+      }
     }
     bytes = nbytes;
   }
@@ -166,6 +245,11 @@ struct DevBuf {
 struct ProfEntry {
   double ms = 0;
   uint64_t launches = 0;
+};
+struct ProfPending {  // an event pair recorded on the stream, resolved lazily (no sync per kernel)
+  cudaEvent_t e0, e1;
+  std::string name;
+  uint64_t launches;
 };
 
 struct L3State;
@@ -181,7 +265,35 @@ struct shn_ctx {
   bool prof_on = false;
   cudaEvent_t p0 = nullptr, p1 = nullptr;
   std::map<std::string, ProfEntry> prof;
+  std::vector<ProfPending> prof_pending;
+  std::vector<cudaEvent_t> prof_pool;
   uint64_t launches = 0;
+  cudaEvent_t prof_event() {
+    if (!prof_pool.empty()) {
+      cudaEvent_t e = prof_pool.back();
+      prof_pool.pop_back();
+      return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+  }
+  // fold all finished event pairs into `prof` (synchronises the stream)
+  void prof_resolve() {
+    if (prof_pending.empty()) return;
+    cudaStreamSynchronize(stream);
+    for (auto& p : prof_pending) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, p.e0, p.e1);
+      ProfEntry& e = prof[p.name];
+      e.ms += ms;
+      e.launches += p.launches;
+      prof_pool.push_back(p.e0);
+      prof_pool.push_back(p.e1);
+    }
+    prof_pending.clear();
+  }
+  DevPool pool;
   // scratch
   DevBuf cub_tmp;
   DevBuf flush_buf;
@@ -201,24 +313,25 @@ struct shn_ctx {
   }
 };
 
-// RAII profiling scope: brackets a launch group with events when profiling is enabled.
+// RAII profiling scope: brackets a launch group with a pair of CUDA events on the ctx stream
+// when profiling is enabled.  Nothing synchronises here; times are read in prof_resolve().
 struct ProfScope {
   shn_ctx* c;
   const char* name;
   uint64_t n;
+  cudaEvent_t e0 = nullptr;
   ProfScope(shn_ctx* ctx, const char* nm, uint64_t launches = 1) : c(ctx), name(nm), n(launches) {
     c->launches += n;
-    if (c->prof_on) cudaEventRecord(c->p0, c->stream);
+    if (c->prof_on) {
+      e0 = c->prof_event();
+      cudaEventRecord(e0, c->stream);
+    }
   }
   ~ProfScope() {
-    if (c->prof_on) {
-      cudaEventRecord(c->p1, c->stream);
-      cudaEventSynchronize(c->p1);
-      float ms = 0;
-      cudaEventElapsedTime(&ms, c->p0, c->p1);
-      ProfEntry& e = c->prof[name];
-      e.ms += ms;
-      e.launches += n;
+    if (e0) {
+      cudaEvent_t e1 = c->prof_event();
+      cudaEventRecord(e1, c->stream);
+      c->prof_pending.push_back(ProfPending{e0, e1, name, n});
     }
   }
 };

@@ -5,7 +5,7 @@
 // current K1-mer, so it stays inside one connected component of the K1-mer successor graph and
 // two walks in different components never read or write the same table slot.  The sequential
 // pop order of the reference therefore only matters *within* a component: we label components
-// with a lock-free union-find, give every component to one thread, and that thread replays its
+// with a lock-free union-find, give every component to one warp, and that warp replays its
 // component's seeds in global pop order (weight desc, later input line first).  The union of all
 // per-component replays is bit-identical to the reference's single sequential loop.
 #include <cub/cub.cuh>
@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(kBlock)
   for (; i < n_slots; i += stride) {
     uint4 v = __ldg(reinterpret_cast<const uint4*>(slots) + i);
     bool occ = !(v.x == 0xFFFFFFFFu && v.y == 0xFFFFFFFFu);
-    mine += (occ && v.z >= min_weight) ? 1 : 0;
+    mine += (occ && (v.z & SHN_WEIGHT_MASK) >= min_weight) ? 1 : 0;
   }
   typedef cub::BlockReduce<unsigned long long, kBlock> BR;
   __shared__ typename BR::TempStorage tmp;
@@ -72,7 +72,8 @@ __global__ void __launch_bounds__(kBlock)
   uint4 v = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0, 0);
   if (i < n_slots) v = __ldg(reinterpret_cast<const uint4*>(slots) + i);
   bool occ = !(v.x == 0xFFFFFFFFu && v.y == 0xFFFFFFFFu);
-  bool is_seed = occ && v.z >= min_weight;
+  const uint32_t wt = v.z & SHN_WEIGHT_MASK;
+  bool is_seed = occ && wt >= min_weight;
   unsigned b = __ballot_sync(0xFFFFFFFFu, is_seed);
   int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (lane == 0) warp_off[warp] = __popc(b);
@@ -89,7 +90,7 @@ __global__ void __launch_bounds__(kBlock)
   __syncthreads();
   if (is_seed) {
     uint64_t o = block_base + warp_off[warp] + __popc(b & ((1u << lane) - 1u));
-    skey[o] = ((uint64_t)(~v.z) << 32) | (uint64_t)(~v.w);
+    skey[o] = ((uint64_t)(~wt) << 32) | (uint64_t)(~v.w);
     sslot[o] = (uint32_t)i;
   }
 }
@@ -191,6 +192,21 @@ __global__ void __launch_bounds__(kBlock)
 }
 
 __global__ void __launch_bounds__(kBlock)
+    gather_u32_kernel(const uint32_t* __restrict__ src, const uint32_t* __restrict__ idx, uint64_t n,
+                      uint32_t* __restrict__ dst) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[idx[i]];
+}
+
+// dst[i] = table[src[idx[i]]]
+__global__ void __launch_bounds__(kBlock)
+    gather2_u32_kernel(const uint32_t* __restrict__ table, const uint32_t* __restrict__ src,
+                       const uint32_t* __restrict__ idx, uint64_t n, uint32_t* __restrict__ dst) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = table[src[idx[i]]];
+}
+
+__global__ void __launch_bounds__(kBlock)
     comp_work_kernel(const uint32_t* __restrict__ comp_nodes, const uint32_t* __restrict__ comp_seeds,
                      uint32_t n_comps, uint32_t* __restrict__ work, uint32_t* __restrict__ ids,
                      unsigned long long* counters) {
@@ -237,14 +253,71 @@ __global__ void __launch_bounds__(kBlock)
   tot[i] = w_tot[w];
 }
 
-// ---- greedy walks: one thread per component, one walk step per loop iteration --------------
+// ---- component-local copy of the table for the walks ------------------------------------------
+// The walks of one component only ever touch that component's K1-mers.  In the global table those
+// are scattered over the whole multi-GB allocation (every probe = TLB miss + DRAM round trip); here
+// they are re-hashed into one contiguous region per component (load 0.5), so the component that
+// ends up on the critical path works out of a few tens of MB that stay resident in the 126 MB L2.
+__global__ void __launch_bounds__(kBlock)
+    region_size_kernel(const uint32_t* __restrict__ comp_nodes, const uint32_t* __restrict__ comp_seeds,
+                       uint32_t n_comps, uint64_t* __restrict__ nb) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > n_comps) return;
+  // only components that own a seed are ever walked
+  nb[i] = (i < n_comps && comp_seeds[i] > 0) ? ((uint64_t)comp_nodes[i] + 1) / 2 + 1 : 0;
+}
+
+__global__ void __launch_bounds__(kBlock)
+    local_clear_kernel(ShnSlot* slots, uint64_t n_slots) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  uint4 v = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u);
+  for (; i < n_slots; i += stride) reinterpret_cast<uint4*>(slots)[i] = v;
+}
+
+__global__ void __launch_bounds__(kBlock)
+    repack_kernel(const ShnSlot* __restrict__ slots, uint64_t n_slots,
+                  const uint32_t* __restrict__ parent, const uint32_t* __restrict__ root_id,
+                  const uint64_t* __restrict__ region_off, ShnSlot* local,
+                  uint32_t* __restrict__ local_of, unsigned long long* counters) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int bad = 0;
+  if (i < n_slots) {
+    uint4 v = __ldg(reinterpret_cast<const uint4*>(slots) + i);
+    uint64_t key = ((uint64_t)v.y << 32) | v.x;
+    uint32_t loc = SHN_NONE32;
+    if (key != SHN_EMPTY_KEY) {
+      uint32_t cid = root_id[parent[i]];
+      uint64_t b0 = region_off[cid], nb = region_off[cid + 1] - b0;
+      if (nb) {
+        ShnTableView t{local + SHN_BSLOTS * b0, nb};
+        int is_new = 0;
+        uint64_t s = table_upsert_slot(t, key, &is_new);
+        if (s == ~0ull || !is_new) {
+          bad = 1;
+        } else {
+          // weight without flags; an overflow flag set meanwhile on this slot must survive
+          atomicAdd(&t.slots[s].weight, v.z & SHN_WEIGHT_MASK);
+          loc = (uint32_t)(SHN_BSLOTS * b0 + s);
+        }
+      }
+    }
+    local_of[i] = loc;
+  }
+  int tot = __syncthreads_count(bad);
+  if (threadIdx.x == 0 && tot) atomicAdd(&counters[0], (unsigned long long)tot);
+}
+
+// ---- greedy walks -----------------------------------------------------------------------
 struct WalkArgs {
-  ShnTableView t;
+  ShnSlot* local;               // component-local table (all regions)
+  const uint64_t* region_off;   // [n_comps+1] first bucket of every component's region
   int k1;
   uint32_t n_comps;
   const uint32_t* comp_order;   // components sorted by seed count (descending)
   const uint64_t* seed_off;     // [n_comps+1] into ranks_by_comp
   const uint32_t* ranks_by_comp;  // seed ranks grouped by component, ascending inside a group
+  const uint32_t* slots_by_comp;  // table slot of the same seeds
   const uint32_t* seed_slot;    // by rank
   const uint64_t* log_off;      // [n_comps+1] into walk_log
   uint8_t* walk_log;
@@ -257,130 +330,190 @@ struct WalkArgs {
   unsigned long long* counters;  // [0]=traversed [1]=max steps of a thread [2]=log overflow
 };
 
-__global__ void __launch_bounds__(128) walk_kernel(WalkArgs a) {
-  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= a.n_comps) return;
-  const uint32_t comp = a.comp_order[t];
-  uint64_t sp = a.seed_off[comp];
-  const uint64_t se = a.seed_off[comp + 1];
+// One WARP per component.  Seeds are scanned 32 at a time (one coalesced load of the slot
+// indices, one gather of the traversed flags, a ballot).  A walk advances TWO K1-mers per memory
+// round trip: lanes 0..3 probe the four successors (predecessors) c_b of the current node and, in
+// the same round, lanes 4..19 probe the sixteen second-level nodes succ(c_b, b'); after the
+// first arg-max picks c_w the second step is decided from lanes 4+4w..7+4w, whose traversed
+// flags are still exact except for c_w itself (marked after the fetch; compared by key).  The
+// arg-max keeps the reference's tie order A,G,C,T.  The kernel is bound by the dependent-probe
+// latency of the longest component, not by issue slots or bandwidth.
+constexpr int kWalkBlock = 128;
+
+__global__ void __launch_bounds__(kWalkBlock, 4) walk_kernel(WalkArgs a) {
+  const unsigned FULL = 0xFFFFFFFFu;
+  const int lane = threadIdx.x & 31;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (warp >= a.n_comps) return;  // whole warps only
+  const uint32_t comp = a.comp_order[warp];
+  const uint64_t s_begin = a.seed_off[comp], s_end = a.seed_off[comp + 1];
   uint64_t lp = a.log_off[comp];
   const uint64_t le = a.log_off[comp + 1];
   const uint64_t mask = shn_kmer_mask(a.k1);
   const int top = 2 * (a.k1 - 1);
-  ShnSlot* slots = a.t.slots;
-
-  int phase = 0;  // 0 = fetch next seed, 1 = extend right, 2 = extend left
-  uint32_t rank = 0, nl = 0, nr = 0;
-  uint64_t seed_key = 0, cur = 0, tot = 0, my_log = 0;
-  unsigned long long steps = 0, traversed = 0;
+  ShnSlot* slots = a.local;     // slot indices of this kernel are indices into the local table
+  const uint64_t r0 = a.region_off[comp];
+  const ShnTableView tv{a.local + SHN_BSLOTS * r0, a.region_off[comp + 1] - r0};
+  const uint64_t slot_base = SHN_BSLOTS * r0;
+  unsigned long long rounds = 0, traversed = 0;
   bool overflow = false;
+  // role of this lane inside a round: level 1 (lanes 0..3), level 2 (lanes 4..19), idle
+  const int lvl = lane < 4 ? 1 : (lane < 20 ? 2 : 0);
+  const uint64_t b1 = lvl == 1 ? lane : ((lane - 4) >> 2);  // first appended base
+  const uint64_t b2 = (lane - 4) & 3;                       // second appended base (level 2)
 
-  for (;;) {
-    if (phase == 0) {
-      if (sp == se) break;
-      rank = a.ranks_by_comp[sp++];
-      uint32_t slot = a.seed_slot[rank];
-      uint4 v = __ldcg(reinterpret_cast<const uint4*>(slots) + slot);
-      if (v.z & SHN_TRAVERSED) continue;                       // extension_correction.py:346
-      slots[slot].weight = v.z | SHN_TRAVERSED;                // :347
-      seed_key = ((uint64_t)v.y << 32) | v.x;
-      cur = seed_key;
-      tot = v.z & SHN_WEIGHT_MASK;
-      nl = nr = 0;
-      my_log = lp;
-      if (lp < le) a.walk_log[lp] = 0xFF;  // the seed's own log entry (unused)
-      else overflow = true;
+  for (uint64_t base = s_begin; base < s_end; base += 32) {
+    // ---- scan 32 seeds of this component (pop order) -------------------------------------
+    const uint64_t si = base + lane;
+    const bool have = si < s_end;
+    uint32_t my_rank = 0, my_slot = 0, my_w = SHN_TRAVERSED;
+    if (have) {
+      my_rank = a.ranks_by_comp[si];
+      my_slot = a.slots_by_comp[si];
+      my_w = __ldcg(&slots[my_slot].weight);
+    }
+    unsigned pending = __ballot_sync(FULL, have && !(my_w & SHN_TRAVERSED));
+    while (pending) {
+      const int j = __ffs(pending) - 1;
+      pending &= pending - 1;
+      const uint32_t slot = __shfl_sync(FULL, my_slot, j);
+      const uint32_t rank = __shfl_sync(FULL, my_rank, j);
+      // fresh look: an earlier walk of this batch may have traversed it meanwhile (:346)
+      const uint4 v = __ldcg(reinterpret_cast<const uint4*>(slots) + slot);
+      if (v.z & SHN_TRAVERSED) continue;  // warp-uniform
+      const uint64_t seed_key = ((uint64_t)v.y << 32) | v.x;
+      if (lane == 0) {
+        slots[slot].weight = v.z | SHN_TRAVERSED;  // traversed.add(start_kmer), :347
+        if (lp < le) a.walk_log[lp] = 0xFF;         // the seed's own (unused) log entry
+      }
+      overflow |= lp >= le;
+      const uint64_t my_log = lp;
       ++lp;
       ++traversed;
-      phase = 1;
-      continue;
-    }
-    ++steps;
-    // the four candidates in the reference's tie order A,G,C,T = codes 0..3 (:10,229)
-    uint64_t cand[4];
-    uint64_t bkt[4];
-    uint4 s0[4], s1[4];
-#pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      cand[b] = phase == 1 ? (((cur << 2) & mask) | (uint64_t)b) : ((cur >> 2) | ((uint64_t)b << top));
-      bkt[b] = a.t.bucket_of(cand[b]);
-    }
-#pragma unroll
-    for (int b = 0; b < 4; ++b) {  // 8 independent 16-byte loads in flight
-      s0[b] = __ldcg(reinterpret_cast<const uint4*>(slots + 2 * bkt[b]));
-      s1[b] = __ldcg(reinterpret_cast<const uint4*>(slots + 2 * bkt[b] + 1));
-    }
-    int best = -1;
-    uint32_t best_w = 0;
-    uint64_t best_slot = 0;
-#pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      uint64_t k0 = ((uint64_t)s0[b].y << 32) | s0[b].x, k1v = ((uint64_t)s1[b].y << 32) | s1[b].x;
-      uint64_t slot = ~0ull;
-      uint32_t wraw = 0;
-      if (k0 == cand[b]) {
-        slot = 2 * bkt[b];
-        wraw = s0[b].z;
-      } else if (k1v == cand[b]) {
-        slot = 2 * bkt[b] + 1;
-        wraw = s1[b].z;
-      } else if (k0 != SHN_EMPTY_KEY && k1v != SHN_EMPTY_KEY) {
-        // full bucket without a match: continue the linear probe (rare at load <= 0.5)
-        ShnTableView tv = a.t;
-        uint64_t bb = bkt[b] + 1 == tv.n_buckets ? 0 : bkt[b] + 1;
+      uint64_t tot = v.z & SHN_WEIGHT_MASK;
+      uint32_t n_dir[2] = {0, 0};
+      __syncwarp();
+#pragma unroll 1
+      for (int dir = 0; dir < 2; ++dir) {  // right extension first, then left (:349-350)
+        uint64_t cur = seed_key;
         for (;;) {
-          const uint4 x0 = __ldcg(reinterpret_cast<const uint4*>(slots + 2 * bb));
-          const uint4 x1 = __ldcg(reinterpret_cast<const uint4*>(slots + 2 * bb + 1));
-          uint64_t y0 = ((uint64_t)x0.y << 32) | x0.x, y1 = ((uint64_t)x1.y << 32) | x1.x;
-          if (y0 == cand[b]) {
-            slot = 2 * bb;
-            wraw = x0.z;
-            break;
+          ++rounds;
+          // candidate keys in the reference's tie order A,G,C,T = codes 0..3 (:10,229)
+          uint64_t cand = 0, cslot = ~0ull;
+          uint32_t wraw = 0;
+          int state = 0;       // 1 found, 0 absent, -1 undecided after the two prefetched buckets
+          uint64_t nextb = 0;  // where an undecided lane would continue
+          if (lvl) {
+            if (dir == 0) {
+              cand = ((cur << 2) & mask) | b1;
+              if (lvl == 2) cand = ((cand << 2) & mask) | b2;
+            } else {
+              cand = (cur >> 2) | (b1 << top);
+              if (lvl == 2) cand = (cand >> 2) | (b2 << top);
+            }
+            // home bucket and its successor in the same memory round
+            uint64_t hb = tv.bucket_of(cand);
+            uint64_t hb1 = (hb + 1 == tv.n_buckets) ? 0 : hb + 1;
+            ShnBucket bk0, bk1;
+            table_load_bucket(tv, hb, &bk0);
+            table_load_bucket(tv, hb1, &bk1);
+            int jj = 0;
+            state = table_match_bucket(bk0, cand, &jj, &wraw);
+            if (state == 1) {
+              cslot = slot_base + SHN_BSLOTS * hb + jj;
+            } else if (state < 0) {
+              state = table_match_bucket(bk1, cand, &jj, &wraw);
+              if (state == 1) cslot = slot_base + SHN_BSLOTS * hb1 + jj;
+              nextb = (hb1 + 1 == tv.n_buckets) ? 0 : hb1 + 1;
+            }
           }
-          if (y1 == cand[b]) {
-            slot = 2 * bb + 1;
-            wraw = x1.z;
-            break;
+          // only the lanes a decision actually depends on pay for longer probe sequences
+          if (lvl == 1 && state < 0) {
+            ShnTableView t2 = tv;
+            for (;;) {
+              ShnBucket bk;
+              table_load_bucket(t2, nextb, &bk);
+              int jj = 0;
+              state = table_match_bucket(bk, cand, &jj, &wraw);
+              if (state == 1) cslot = slot_base + SHN_BSLOTS * nextb + jj;
+              if (state >= 0) break;
+              nextb = (nextb + 1 == t2.n_buckets) ? 0 : nextb + 1;
+            }
           }
-          if (y0 == SHN_EMPTY_KEY || y1 == SHN_EMPTY_KEY) break;
-          bb = bb + 1 == tv.n_buckets ? 0 : bb + 1;
+          bool ok = cslot != ~0ull && !(wraw & SHN_TRAVERSED);
+          // ---- first step: arg-max weight over lanes 0..3, first of equals wins (:159-166) ---
+          unsigned long long score =
+              ok ? ((((unsigned long long)(wraw & SHN_WEIGHT_MASK) + 1ull) << 2) | (unsigned)(3 - (lane & 3)))
+                 : 0ull;
+          unsigned long long m = __shfl_xor_sync(FULL, score, 1);
+          m = m > score ? m : score;
+          unsigned long long o = __shfl_xor_sync(FULL, m, 2);
+          m = o > m ? o : m;  // max of my aligned group of four lanes
+          const unsigned long long s1 = __shfl_sync(FULL, m, 0);
+          if (s1 == 0) break;  // warp-uniform: no extension
+          const int w1 = 3 - (int)(s1 & 3ull);
+          const uint32_t bw1 = (uint32_t)((s1 >> 2) - 1ull);
+          const uint64_t c1 = __shfl_sync(FULL, cand, w1);
+          if (lane == w1) slots[cslot].weight = wraw | SHN_TRAVERSED;  // traversed.add(last), :235
+          if (lane == 0 && lp < le) a.walk_log[lp] = (uint8_t)w1;
+          overflow |= lp >= le;
+          ++lp;
+          ++traversed;
+          tot += bw1;
+          ++n_dir[dir];
+          // ---- second step from the prefetched level: group 4+4*w1; c1 is traversed by now ---
+          const int g2 = 4 + 4 * w1;
+          if (lane >= g2 && lane < g2 + 4 && state < 0) {
+            for (;;) {
+              ShnBucket bk;
+              table_load_bucket(tv, nextb, &bk);
+              int jj = 0;
+              state = table_match_bucket(bk, cand, &jj, &wraw);
+              if (state == 1) cslot = slot_base + SHN_BSLOTS * nextb + jj;
+              if (state >= 0) break;
+              nextb = (nextb + 1 == tv.n_buckets) ? 0 : nextb + 1;
+            }
+            ok = cslot != ~0ull && !(wraw & SHN_TRAVERSED);
+          }
+          ok = ok && cand != c1;
+          score = ok ? ((((unsigned long long)(wraw & SHN_WEIGHT_MASK) + 1ull) << 2) | (unsigned)(3 - (lane & 3)))
+                     : 0ull;
+          m = __shfl_xor_sync(FULL, score, 1);
+          m = m > score ? m : score;
+          o = __shfl_xor_sync(FULL, m, 2);
+          m = o > m ? o : m;
+          const unsigned long long s2 = __shfl_sync(FULL, m, g2);
+          if (s2 == 0) {
+            __syncwarp();
+            break;  // warp-uniform: the walk ends at c1 in this direction
+          }
+          const int w2 = 3 - (int)(s2 & 3ull);
+          const uint32_t bw2 = (uint32_t)((s2 >> 2) - 1ull);
+          cur = __shfl_sync(FULL, cand, g2 + w2);
+          if (lane == g2 + w2) slots[cslot].weight = wraw | SHN_TRAVERSED;
+          if (lane == 0 && lp < le) a.walk_log[lp] = (uint8_t)w2;
+          overflow |= lp >= le;
+          ++lp;
+          ++traversed;
+          tot += bw2;
+          ++n_dir[dir];
+          __syncwarp();  // orders the flag stores before the next round of probes
         }
       }
-      if (slot != ~0ull && !(wraw & SHN_TRAVERSED)) {
-        uint32_t w = wraw & SHN_WEIGHT_MASK;
-        if (best < 0 || w > best_w) {  // strict '>' keeps the first of equals (argmax, :159-166)
-          best = b;
-          best_w = w;
-          best_slot = slot;
-        }
-      }
-    }
-    if (best < 0) {
-      if (phase == 1) {  // right extension exhausted: extend left from the seed (:349-350)
-        phase = 2;
-        cur = seed_key;
-      } else {
+      if (lane == 0) {
         a.started[rank] = 1;
-        a.nl[rank] = nl;
-        a.nr[rank] = nr;
+        a.nr[rank] = n_dir[0];
+        a.nl[rank] = n_dir[1];
         a.totwt[rank] = tot;
         a.logstart[rank] = my_log;
-        phase = 0;
       }
-      continue;
     }
-    slots[best_slot].weight = best_w | SHN_TRAVERSED;  // traversed.add(last), :235
-    if (lp < le) a.walk_log[lp] = (uint8_t)best;
-    else overflow = true;
-    ++lp;
-    ++traversed;
-    tot += best_w;
-    if (phase == 1) ++nr; else ++nl;
-    cur = cand[best];
   }
-  atomicAdd(&a.counters[0], traversed);
-  atomicMax(&a.counters[1], steps);
-  if (overflow) atomicAdd(&a.counters[2], 1ull);
+  if (lane == 0) {
+    atomicAdd(&a.counters[0], traversed);
+    atomicMax(&a.counters[1], rounds);
+    if (overflow) atomicAdd(&a.counters[2], 1ull);
+  }
 }
 
 // ---- contig assembly from the walk log -----------------------------------------------------
@@ -472,26 +605,40 @@ __global__ void __launch_bounds__(kBlock)
     status_out[j] = st;
     return;
   }
-  bool ready = true;
   // best = accepted partner with max (count, last hit position, id)  -- duplicate_check's
-  // `>=` running maximum, extension_correction.py:251-259 (closed form in SURVEY 8a a6)
+  // `>=` running maximum, extension_correction.py:251-259 (closed form in SURVEY 8a a6).
+  // Partners are sorted by id ascending, so '>=' on (count,last) lets the larger id win ties.
+  // An unresolved partner only matters if it could still become that maximum.
   uint32_t b_cnt = 0, b_last = 0, b_cov = 0;
-  bool have = false;
+  uint32_t u_cnt = 0, u_last = 0;
+  bool have = false, have_u = false, u_after_best = false;
   for (uint64_t p = seg_off[j]; p < seg_off[j + 1]; ++p) {
     uint8_t sd = status_in[lo[p]];
-    if (sd == 0) {
-      ready = false;
-      break;
-    }
-    if (sd != 1) continue;
+    if (sd == 2) continue;
     uint32_t cnt = count[p], last = max_i[p];
-    // partners are sorted by id ascending, so '>=' on (count,last) lets the larger id win ties
-    if (!have || cnt > b_cnt || (cnt == b_cnt && last >= b_last)) {
-      have = true;
-      b_cnt = cnt;
-      b_last = last;
-      b_cov = covered[p];
+    if (sd == 1) {
+      if (!have || cnt > b_cnt || (cnt == b_cnt && last >= b_last)) {
+        have = true;
+        b_cnt = cnt;
+        b_last = last;
+        b_cov = covered[p];
+        u_after_best = false;
+      }
+    } else {  // unresolved: remember the strongest one, and whether it comes after `best`
+      if (!have_u || cnt > u_cnt || (cnt == u_cnt && last >= u_last)) {
+        have_u = true;
+        u_cnt = cnt;
+        u_last = last;
+      }
+      if (have && cnt == b_cnt && last == b_last) u_after_best = true;  // larger id, equal key
     }
+  }
+  bool ready = !have_u;
+  if (have_u && have) {
+    // the strongest unresolved partner loses against `best` even if it gets accepted
+    bool u_wins = u_cnt > b_cnt || (u_cnt == b_cnt && u_last > b_last) ||
+                  (u_cnt == b_cnt && u_last == b_last && u_after_best);
+    ready = !u_wins;
   }
   if (!ready) {
     status_out[j] = 0;
@@ -648,7 +795,7 @@ void shn_l3_run_impl(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
   s->min_weight = min_weight;
   s->min_length = min_length;
   const int k1 = c->k1;
-  const uint64_t n_slots = c->n_buckets * 2;
+  const uint64_t n_slots = c->n_buckets * SHN_BSLOTS;
   SHN_CHECK(n_slots < 0xFFFFFFFFull, "table too large for 32-bit slot indices");
   ShnTableView tv = c->view();
   cudaStream_t st = c->stream;
@@ -757,6 +904,39 @@ void shn_l3_run_impl(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
                                                seed_comp_s.as<uint32_t>(), rank_in.as<uint32_t>(),
                                                ranks_by_comp.as<uint32_t>(), (int64_t)n_seeds, 0, bits, st));
   }
+  // component-local copy of the table (regions of the components that own seeds)
+  DevBuf region_nb, region_off, local, local_of, slots_by_comp;
+  region_nb.reserve(((uint64_t)n_comps + 1) * 8);
+  region_off.reserve(((uint64_t)n_comps + 1) * 8);
+  slots_by_comp.reserve(std::max<uint64_t>(n_seeds, 1) * 4);
+  uint64_t local_buckets = 0;
+  if (n_seeds) {
+    ProfScope ps(c, "repack", 5);
+    region_size_kernel<<<shn_grid((uint64_t)n_comps + 1, kBlock), kBlock, 0, st>>>(
+        comp_nodes.as<uint32_t>(), comp_seeds.as<uint32_t>(), n_comps, region_nb.as<uint64_t>());
+    KERNEL_CHECK();
+    exclusive_sum(c, region_nb.as<uint64_t>(), region_off.as<uint64_t>(), (uint64_t)n_comps + 1);
+    CUDA_CHECK(cudaMemcpyAsync(&local_buckets, region_off.as<uint64_t>() + n_comps, 8,
+                               cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    SHN_CHECK(local_buckets * SHN_BSLOTS < 0xFFFFFFFFull, "component-local table too large");
+    local.reserve(std::max<uint64_t>(local_buckets, 1) * SHN_BSLOTS * sizeof(ShnSlot));
+    local_of.reserve(n_slots * 4);
+    local_clear_kernel<<<stream_grid, kBlock, 0, st>>>(local.as<ShnSlot>(), local_buckets * SHN_BSLOTS);
+    KERNEL_CHECK();
+    ctr = zero_counters(c);
+    repack_kernel<<<shn_grid(n_slots, kBlock), kBlock, 0, st>>>(
+        tv.slots, n_slots, parent.as<uint32_t>(), root_id.as<uint32_t>(), region_off.as<uint64_t>(),
+        local.as<ShnSlot>(), local_of.as<uint32_t>(), ctr);
+    KERNEL_CHECK();
+    gather2_u32_kernel<<<shn_grid(n_seeds, kBlock), kBlock, 0, st>>>(
+        local_of.as<uint32_t>(), seed_slot.as<uint32_t>(), ranks_by_comp.as<uint32_t>(), n_seeds,
+        slots_by_comp.as<uint32_t>());
+    KERNEL_CHECK();
+    read_counters(c, h, 1);
+    SHN_CHECK(h[0] == 0, "internal error: component-local table repack failed");
+    local_of.release();
+  }
   parent.release();
   root_id.release();
   exclusive_sum_u32(c, comp_nodes.as<uint32_t>(), log_off.as<uint64_t>(), (uint64_t)n_comps + 1);
@@ -801,12 +981,14 @@ void shn_l3_run_impl(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
   ctr = zero_counters(c);
   if (n_active) {
     WalkArgs a;
-    a.t = tv;
+    a.local = local.as<ShnSlot>();
+    a.region_off = region_off.as<uint64_t>();
     a.k1 = k1;
     a.n_comps = n_active;
     a.comp_order = comp_order.as<uint32_t>();
     a.seed_off = seed_off.as<uint64_t>();
     a.ranks_by_comp = ranks_by_comp.as<uint32_t>();
+    a.slots_by_comp = slots_by_comp.as<uint32_t>();
     a.seed_slot = seed_slot.as<uint32_t>();
     a.log_off = log_off.as<uint64_t>();
     a.walk_log = s->walk_log.as<uint8_t>();
@@ -817,7 +999,7 @@ void shn_l3_run_impl(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
     a.logstart = ls_r.as<uint64_t>();
     a.counters = ctr;
     ProfScope ps(c, "walk");
-    walk_kernel<<<shn_grid(n_active, 128), 128, 0, st>>>(a);
+    walk_kernel<<<shn_grid((uint64_t)n_active * 32, kWalkBlock), kWalkBlock, 0, st>>>(a);
     KERNEL_CHECK();
   }
   read_counters(c, h, 3);
@@ -940,8 +1122,8 @@ void shn_l3_run_impl(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
             cand_bases, R, 0u, keys.as<uint64_t>(), owner.as<uint32_t>(), pos.as<uint32_t>());
         KERNEL_CHECK();
       }
-      ProfScope ps(c, "rmer_join", 12);
-      shn_self_join(c, keys.as<uint64_t>(), owner.as<uint32_t>(), pos.as<uint32_t>(), n_ent, 2 * R, R, &pt);
+      shn_self_join(c, keys.as<uint64_t>(), owner.as<uint32_t>(), pos.as<uint32_t>(), n_ent, 2 * R, R, &pt,
+                    "rmer");
     }
     if (pt.n) {
       DevBuf seg_off, st_a, st_b, dupf;
@@ -1069,9 +1251,8 @@ void shn_l3_run_impl(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
             contig_bases, C, 1u, keys.as<uint64_t>(), owner.as<uint32_t>(), pos.as<uint32_t>());
         KERNEL_CHECK();
       }
-      ProfScope ps(c, "cmer_join", 12);
       shn_self_join(c, keys.as<uint64_t>(), owner.as<uint32_t>(), pos.as<uint32_t>(), n_ent, 2 * C, 1,
-                    &s->edges);
+                    &s->edges, "cmer");
     }
   }
   s->sz.n_edges = s->edges.n;
@@ -1117,6 +1298,14 @@ __global__ void __launch_bounds__(kBlock)
 }  // namespace
 
 void shn_l3_get_sizes_impl(shn_ctx* c, shn_l3_sizes* out) { *out = need_l3(c)->sz; }
+
+// device-resident allowed set (keys, weights) for the L4 map when caller and callee share the ctx
+void shn_l3_allowed_dev(shn_ctx* c, const uint64_t** keys, const uint32_t** weights, uint64_t* n) {
+  L3State* s = need_l3(c);
+  *keys = s->allowed_keys.as<uint64_t>();
+  *weights = s->allowed_w.as<uint32_t>();
+  *n = s->sz.n_allowed;
+}
 
 void shn_l3_get_walks_impl(shn_ctx* c, uint64_t* seed_keys, uint32_t* n_left, uint32_t* n_right,
                            uint64_t* tot_wt, uint8_t* flags) {

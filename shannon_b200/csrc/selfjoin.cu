@@ -1,6 +1,8 @@
 // See selfjoin.cuh.  Sort-based, race-free, deterministic.
 #include <cub/cub.cuh>
 
+#include <memory>
+
 #include "selfjoin.cuh"
 
 namespace {
@@ -132,7 +134,11 @@ int bits_for(uint64_t max_value) {
 }  // namespace
 
 void shn_self_join(shn_ctx* c, const uint64_t* d_keys, const uint32_t* d_owner,
-                   const uint32_t* d_pos, uint64_t n, int key_bits, uint32_t r, PairTable* out) {
+                   const uint32_t* d_pos, uint64_t n, int key_bits, uint32_t r, PairTable* out,
+                   const char* tag) {
+  const std::string T(tag);
+  const std::string n_sort = T + "_sort_keys", n_heads = T + "_runs", n_emit = T + "_emit_events",
+                    n_sort2 = T + "_sort_events", n_reduce = T + "_reduce_pairs";
   out->n = 0;
   if (n == 0) return;
   SHN_CHECK(n < 0xFFFFFFFFull, "self-join: more than 2^32-1 entries");
@@ -141,6 +147,7 @@ void shn_self_join(shn_ctx* c, const uint64_t* d_keys, const uint32_t* d_owner,
   keys_s.reserve(n * 8);
   idx.reserve(n * 4);
   idx_s.reserve(n * 4);
+  std::unique_ptr<ProfScope> ps(new ProfScope(c, n_sort.c_str(), 2));
   iota_kernel<<<shn_grid(n, kBlock), kBlock, 0, st>>>(idx.as<uint32_t>(), n);
   KERNEL_CHECK();
   size_t tb = 0;
@@ -150,6 +157,8 @@ void shn_self_join(shn_ctx* c, const uint64_t* d_keys, const uint32_t* d_owner,
   CUDA_CHECK(cub::DeviceRadixSort::SortPairs(c->tmp(tb), tb, d_keys, keys_s.as<uint64_t>(),
                                              idx.as<uint32_t>(), idx_s.as<uint32_t>(), (int64_t)n, 0,
                                              key_bits, st));
+  ps.reset();
+  ps.reset(new ProfScope(c, n_heads.c_str(), 7));
   owner_s.reserve(n * 4);
   pos_s.reserve(n * 4);
   run_head.reserve(n * 4);
@@ -194,6 +203,7 @@ void shn_self_join(shn_ctx* c, const uint64_t* d_keys, const uint32_t* d_owner,
     max_owner = h[0];
     max_pos = h[1];
   }
+  ps.reset();
   if (n_events == 0) return;
   int bo = bits_for(max_owner), bp = bits_for(max_pos);
   SHN_CHECK(2 * bo + bp <= 64, "self-join: contig count / length exceed the 64-bit event key budget");
@@ -201,16 +211,21 @@ void shn_self_join(shn_ctx* c, const uint64_t* d_keys, const uint32_t* d_owner,
   DevBuf ev, ev_s;
   ev.reserve(n_events * 8);
   ev_s.reserve(n_events * 8);
+  ps.reset(new ProfScope(c, n_emit.c_str(), 1));
   emit_events_kernel<<<shn_grid(n_events, kBlock), kBlock, 0, st>>>(
       ev_off.as<uint64_t>(), run_start.as<uint32_t>(), owner_s.as<uint32_t>(), pos_s.as<uint32_t>(), n,
       n_events, bo, bp, ev.as<uint64_t>());
   KERNEL_CHECK();
+  ps.reset();
+  ps.reset(new ProfScope(c, n_sort2.c_str(), 1));
   tb = 0;
   CUDA_CHECK(cub::DeviceRadixSort::SortKeys(nullptr, tb, ev.as<uint64_t>(), ev_s.as<uint64_t>(),
                                             (int64_t)n_events, 0, 2 * bo + bp, st));
   CUDA_CHECK(cub::DeviceRadixSort::SortKeys(c->tmp(tb), tb, ev.as<uint64_t>(), ev_s.as<uint64_t>(),
                                             (int64_t)n_events, 0, 2 * bo + bp, st));
   ev.release();
+  ps.reset();
+  ps.reset(new ProfScope(c, n_reduce.c_str(), 2));
   // segmented reduction per (j, d)
   DevBuf ukeys, agg, nruns;
   ukeys.reserve(n_events * 8);
@@ -243,6 +258,7 @@ void shn_self_join(shn_ctx* c, const uint64_t* d_keys, const uint32_t* d_owner,
       out->lo.as<uint32_t>(), out->count.as<uint32_t>(), out->min_i.as<uint32_t>(),
       out->max_i.as<uint32_t>(), out->covered.as<uint32_t>());
   KERNEL_CHECK();
+  ps.reset();
   CUDA_CHECK(cudaStreamSynchronize(st));
   out->n = n_pairs;
 }

@@ -22,4 +22,5 @@ struct PairTable {
 // keys: n entries generated in (owner ascending, pos ascending) order; key_bits: significant bits.
 // r: interval length for `covered`.
 void shn_self_join(shn_ctx* c, const uint64_t* d_keys, const uint32_t* d_owner,
-                   const uint32_t* d_pos, uint64_t n, int key_bits, uint32_t r, PairTable* out);
+                   const uint32_t* d_pos, uint64_t n, int key_bits, uint32_t r, PairTable* out,
+                   const char* tag);

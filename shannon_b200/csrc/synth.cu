@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(kBlock)
   if (occ) {
     uint64_t o = block_base + warp_off[warp] + __popc(b & ((1u << lane) - 1u));
     skeys[o] = shn_ascii_order_key(key);
-    counts[o] = v.z;
+    counts[o] = v.z & SHN_WEIGHT_MASK;
   }
 }
 
@@ -192,9 +192,9 @@ void shn_count_k1mers_impl(shn_ctx* c, const char* const* arrays, const uint64_t
   SHN_CHECK(k1 >= 1 && k1 <= 32 && read_len >= k1, "bad k1 / read length");
   uint64_t total_windows = 0;
   for (int a = 0; a < n_arrays; ++a) total_windows += n_reads[a] * (uint64_t)(read_len - k1 + 1);
-  uint64_t nb = std::max<uint64_t>(1024, std::min(expected_distinct, total_windows));
+  uint64_t nb = std::max<uint64_t>(256, (std::min(expected_distinct, total_windows) + 1) / 2);
   DevBuf table;
-  table.reserve(nb * 2 * sizeof(ShnSlot));
+  table.reserve(nb * SHN_BSLOTS * sizeof(ShnSlot));
   ShnTableView view{table.as<ShnSlot>(), nb};
   c->counters.reserve(64 * sizeof(unsigned long long));
   unsigned long long* ctr = c->counters.as<unsigned long long>();
@@ -202,8 +202,8 @@ void shn_count_k1mers_impl(shn_ctx* c, const char* const* arrays, const uint64_t
   {
     ProfScope ps(c, "count_clear");
     unsigned grid =
-        (unsigned)std::min<uint64_t>((nb * 2 + kBlock - 1) / kBlock, (uint64_t)c->sm_count * 32);
-    count_clear_kernel<<<grid, kBlock, 0, c->stream>>>(view.slots, nb * 2);
+        (unsigned)std::min<uint64_t>((nb * SHN_BSLOTS + kBlock - 1) / kBlock, (uint64_t)c->sm_count * 32);
+    count_clear_kernel<<<grid, kBlock, 0, c->stream>>>(view.slots, nb * SHN_BSLOTS);
     KERNEL_CHECK();
   }
   for (int a = 0; a < n_arrays; ++a) {
@@ -230,8 +230,8 @@ void shn_count_k1mers_impl(shn_ctx* c, const char* const* arrays, const uint64_t
     CUDA_CHECK(cudaMemsetAsync(ctr, 0, 8, c->stream));
     {
       ProfScope ps(c, "count_compact");
-      count_compact_kernel<<<shn_grid(nb * 2, kBlock), kBlock, 0, c->stream>>>(
-          view.slots, nb * 2, skeys.as<uint64_t>(), cnt.as<uint32_t>(), ctr);
+      count_compact_kernel<<<shn_grid(nb * SHN_BSLOTS, kBlock), kBlock, 0, c->stream>>>(
+          view.slots, nb * SHN_BSLOTS, skeys.as<uint64_t>(), cnt.as<uint32_t>(), ctr);
       KERNEL_CHECK();
     }
     ProfScope ps(c, "count_sort", 2);

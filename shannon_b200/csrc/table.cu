@@ -1,12 +1,12 @@
 // a1/a2: K1-mer -> weight table (load_kmers + lowComplexity, extension_correction.py:202-221,
 // 142-149) as an open-addressing hash table in HBM.
 //
-// Layout: 32-byte buckets of two 16-byte slots {key u64, weight u32, first_idx u32}; a probe
-// touches exactly one 32-byte DRAM sector.  Bucket = mulhi(mix64(key), n_buckets), linear
-// probing over buckets.  Load factor <= 0.5 (slots), so ~1.1 sectors per probe on average.
+// Layout: 64-byte buckets of four 16-byte slots {key u64, weight u32, first_idx u32}; a probe
+// moves one 64-byte DRAM burst.  Bucket = mulhi(mix64(key), n_buckets), linear probing over
+// buckets with an overflow flag per bucket (table_dev.cuh).  Load factor <= 0.5.
 //
-// Algorithmic bytes: insert = 8 B key + 4 B count streamed + one sector
-// read-modify-write (64 B) = 76 B per input line; lookup = 8 B + 32 B + 5 B out = 45 B.
+// Algorithmic bytes: insert = 8 B key + 4 B count streamed + one bucket
+// read-modify-write (2 x 64 B) = 140 B per input line; lookup = 8 B + 64 B + 5 B out = 77 B.
 #include <cub/cub.cuh>
 
 #include "common.cuh"
@@ -52,7 +52,8 @@ __global__ void __launch_bounds__(kBlock)
           n_bad = 1;
           break;
         }
-        atomicAdd(&t.slots[slot].weight, w);  // RED: result unused (overflow is checked later)
+        uint32_t old = atomicAdd(&t.slots[slot].weight, w);
+        if ((uint64_t)(old & SHN_WEIGHT_MASK) + w > (uint64_t)SHN_WEIGHT_MASK) n_bad = 1;
         atomicMin(&t.slots[slot].idx, (uint32_t)(base_idx + r));
       }
     }
@@ -68,48 +69,15 @@ __global__ void __launch_bounds__(kBlock)
   }
 }
 
-// weights with bit 31 set mean a count sum overflowed the 31-bit weight field
-__global__ void __launch_bounds__(kBlock)
-    table_check_kernel(const ShnSlot* __restrict__ slots, uint64_t n_slots,
-                       unsigned long long* counters) {
-  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  int bad = 0;
-  for (; i < n_slots; i += stride) {
-    uint4 v = __ldg(reinterpret_cast<const uint4*>(slots) + i);
-    bad |= (v.z & SHN_TRAVERSED) ? 1 : 0;
-  }
-  int tot = __syncthreads_count(bad);
-  if (threadIdx.x == 0 && tot) atomicAdd(&counters[2], (unsigned long long)tot);
-}
-
 __global__ void __launch_bounds__(kBlock)
     table_lookup_kernel(ShnTableView t, const uint64_t* __restrict__ keys, uint64_t n,
                         uint32_t* __restrict__ weights, uint8_t* __restrict__ found) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  uint64_t key = keys[i];
-  uint64_t b = t.bucket_of(key);
-  uint32_t w = 0;
-  uint8_t f = 0;
-  for (;;) {
-    const ShnSlot* s = t.slots + 2 * b;
-    const uint4 s0 = __ldg(reinterpret_cast<const uint4*>(&s[0]));
-    const uint4 s1 = __ldg(reinterpret_cast<const uint4*>(&s[1]));
-    uint64_t k0 = ((uint64_t)s0.y << 32) | s0.x, k1_ = ((uint64_t)s1.y << 32) | s1.x;
-    if (k0 == key) {
-      w = s0.z & SHN_WEIGHT_MASK;
-      f = 1;
-      break;
-    }
-    if (k1_ == key) {
-      w = s1.z & SHN_WEIGHT_MASK;
-      f = 1;
-      break;
-    }
-    if (k0 == SHN_EMPTY_KEY || k1_ == SHN_EMPTY_KEY) break;
-    b = (b + 1 == t.n_buckets) ? 0 : b + 1;
-  }
+  uint32_t wraw = 0;
+  uint64_t slot = table_find(t, keys[i], &wraw);
+  uint32_t w = slot == ~0ull ? 0u : (wraw & SHN_WEIGHT_MASK);
+  uint8_t f = slot == ~0ull ? 0 : 1;
   if (weights) weights[i] = w;
   if (found) found[i] = f;
 }
@@ -171,9 +139,9 @@ void shn_table_build_impl(shn_ctx* c, const uint64_t* d_keys, const uint32_t* d_
   SHN_CHECK(k1 >= 1 && k1 <= 32, "k1 must be in 1..32 (K <= 31); wider keys are not built yet");
   uint64_t items = n * (double_stranded ? 2 : 1);
   SHN_CHECK(items < 0x7FFFFFFFull, "more than 2^31-1 input K1-mers per table");
-  // slots >= 2 * items  (load factor <= 0.5)  => buckets >= items
-  uint64_t n_buckets = items < 1024 ? 1024 : items;
-  c->table.reserve(n_buckets * 2 * sizeof(ShnSlot));
+  // slots >= 2 * items  (load factor <= 0.5)  => buckets >= items / 2 (4 slots each)
+  uint64_t n_buckets = items < 1024 ? 256 : (items + 1) / 2;
+  c->table.reserve(n_buckets * SHN_BSLOTS * sizeof(ShnSlot));
   c->n_buckets = n_buckets;
   c->k1 = k1;
   c->n_items = items;
@@ -182,9 +150,9 @@ void shn_table_build_impl(shn_ctx* c, const uint64_t* d_keys, const uint32_t* d_
   CUDA_CHECK(cudaMemsetAsync(ctr, 0, 8 * sizeof(unsigned long long), c->stream));
   {
     ProfScope ps(c, "table_clear");
-    unsigned grid = (unsigned)std::min<uint64_t>((n_buckets * 2 + kBlock - 1) / kBlock,
+    unsigned grid = (unsigned)std::min<uint64_t>((n_buckets * SHN_BSLOTS + kBlock - 1) / kBlock,
                                                  (uint64_t)c->sm_count * 32);
-    table_clear_kernel<<<grid, kBlock, 0, c->stream>>>(c->table.as<ShnSlot>(), n_buckets * 2);
+    table_clear_kernel<<<grid, kBlock, 0, c->stream>>>(c->table.as<ShnSlot>(), n_buckets * SHN_BSLOTS);
     KERNEL_CHECK();
   }
   if (n > 0) {
@@ -193,18 +161,10 @@ void shn_table_build_impl(shn_ctx* c, const uint64_t* d_keys, const uint32_t* d_
                                                                        n, k1, double_stranded, ctr);
     KERNEL_CHECK();
   }
-  {
-    ProfScope ps(c, "table_check");
-    unsigned grid = (unsigned)std::min<uint64_t>((n_buckets * 2 + kBlock - 1) / kBlock,
-                                                 (uint64_t)c->sm_count * 32);
-    table_check_kernel<<<grid, kBlock, 0, c->stream>>>(c->table.as<ShnSlot>(), n_buckets * 2, ctr);
-    KERNEL_CHECK();
-  }
   unsigned long long h[4];
   CUDA_CHECK(cudaMemcpyAsync(h, ctr, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
   CUDA_CHECK(cudaStreamSynchronize(c->stream));
-  SHN_CHECK(h[3] == 0, "table build: key wider than 2*k1 bits, count >= 2^31 or input index overflow");
-  SHN_CHECK(h[2] == 0, "table build: a K1-mer weight exceeds 2^31-1");
+  SHN_CHECK(h[3] == 0, "table build: key wider than 2*k1 bits, a K1-mer weight above 2^30-1, or input index overflow");
   c->n_distinct = h[0];
   c->n_lowcomplexity = h[1];
 }
@@ -222,7 +182,7 @@ void shn_table_lookup_impl(shn_ctx* c, const uint64_t* d_keys, uint64_t n, uint3
 // dump sorted by first-occurrence index --------------------------------------------------
 void shn_table_dump_impl(shn_ctx* c, uint64_t* h_keys, uint32_t* h_weights, uint32_t* h_idx) {
   SHN_CHECK(c->n_buckets > 0, "no table built");
-  uint64_t n_slots = c->n_buckets * 2, n = c->n_distinct;
+  uint64_t n_slots = c->n_buckets * SHN_BSLOTS, n = c->n_distinct;
   if (n == 0) return;
   DevBuf sel, nsel, keys, w, idx, keys2, w2, idx2;
   sel.reserve(n * 8);

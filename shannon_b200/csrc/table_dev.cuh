@@ -1,6 +1,89 @@
 // Device-side primitives of the K1-mer table (shared by table.cu, l3.cu, synth.cu).
+//
+// Bucket = SHN_BSLOTS (4) slots of 16 bytes = 64 bytes, 64-byte aligned: one DRAM burst / two L2
+// sectors per probe.  A key lives in the first bucket of its probe sequence (linear over buckets)
+// that had a free slot when it was inserted.  An insert that walks past a full bucket sets that
+// bucket's OVERFLOW flag (bit 30 of slot 0's weight word); a lookup stops at the first bucket that
+// holds the key, has a free slot, or has no overflow flag -- so ~95 % of the probes for ABSENT keys
+// (three of the four successor probes of every walk step) finish after one bucket at load 0.5.
 #pragma once
 #include "common.cuh"
+
+struct ShnBucket {
+  uint4 s[SHN_BSLOTS];
+  __device__ __forceinline__ uint64_t key(int j) const { return ((uint64_t)s[j].y << 32) | s[j].x; }
+};
+
+__device__ __forceinline__ void table_load_bucket(const ShnTableView& t, uint64_t b, ShnBucket* out) {
+  const uint4* p = reinterpret_cast<const uint4*>(t.slots + SHN_BSLOTS * b);
+#pragma unroll
+  for (int j = 0; j < SHN_BSLOTS; ++j) out->s[j] = __ldcg(p + j);  // .cg: data changes under atomics
+}
+
+// Looks `key` up in an already loaded bucket.  Returns 1 = found (slot index in *j_out, raw weight
+// word in *w_out), 0 = definitely absent, -1 = undecided: continue with the next bucket.
+__device__ __forceinline__ int table_match_bucket(const ShnBucket& bk, uint64_t key, int* j_out,
+                                                  uint32_t* w_out) {
+  bool has_empty = false;
+  int found = -1;
+  uint32_t w = 0;
+#pragma unroll
+  for (int j = 0; j < SHN_BSLOTS; ++j) {  // fully unrolled: no dynamic register indexing
+    uint64_t k = bk.key(j);
+    if (k == key) {
+      found = j;
+      w = bk.s[j].z;
+    }
+    has_empty |= k == SHN_EMPTY_KEY;
+  }
+  if (found >= 0) {
+    *j_out = found;
+    *w_out = w;
+    return 1;
+  }
+  if (has_empty || !(bk.s[0].z & SHN_OVERFLOW)) return 0;
+  return -1;
+}
+
+// Read-only probe: slot index of `key` or ~0; *w_out = raw weight word (flag bits included).
+__device__ __forceinline__ uint64_t table_find(const ShnTableView& t, uint64_t key, uint32_t* w_out) {
+  uint64_t b = t.bucket_of(key);
+  for (;;) {
+    ShnBucket bk;
+    table_load_bucket(t, b, &bk);
+    int j = 0;
+    int r = table_match_bucket(bk, key, &j, w_out);
+    if (r == 1) return SHN_BSLOTS * b + j;
+    if (r == 0) return ~0ull;
+    b = (b + 1 == t.n_buckets) ? 0 : b + 1;
+  }
+}
+
+// Latency-critical variant for dependent probe chains (walks): loads the home bucket AND its
+// successor in the same memory round, so the ~5 % of probes that have to continue past an
+// overflowed bucket do not pay a second DRAM round trip.
+__device__ __forceinline__ uint64_t table_find2(const ShnTableView& t, uint64_t key, uint32_t* w_out) {
+  uint64_t b = t.bucket_of(key);
+  uint64_t b_next = (b + 1 == t.n_buckets) ? 0 : b + 1;
+  ShnBucket bk0, bk1;
+  table_load_bucket(t, b, &bk0);
+  table_load_bucket(t, b_next, &bk1);
+  int j = 0;
+  int r = table_match_bucket(bk0, key, &j, w_out);
+  if (r == 1) return SHN_BSLOTS * b + j;
+  if (r == 0) return ~0ull;
+  r = table_match_bucket(bk1, key, &j, w_out);
+  if (r == 1) return SHN_BSLOTS * b_next + j;
+  if (r == 0) return ~0ull;
+  b = (b_next + 1 == t.n_buckets) ? 0 : b_next + 1;
+  for (;;) {  // third bucket and beyond: ~0.3 % of probes
+    table_load_bucket(t, b, &bk0);
+    r = table_match_bucket(bk0, key, &j, w_out);
+    if (r == 1) return SHN_BSLOTS * b + j;
+    if (r == 0) return ~0ull;
+    b = (b + 1 == t.n_buckets) ? 0 : b + 1;
+  }
+}
 
 // Finds or claims the slot of `key`; returns its global slot index (~0 if the table is full);
 // *is_new += 1 if this call claimed a free slot.
@@ -8,50 +91,28 @@ __device__ __forceinline__ uint64_t table_upsert_slot(const ShnTableView& t, uin
                                                       int* is_new) {
   uint64_t b = t.bucket_of(key);
   for (uint64_t probes = 0; probes < t.n_buckets; ++probes) {
-    ShnSlot* s = t.slots + 2 * b;
-    // both slots of the bucket in one 32-byte sector; .cg: concurrent CAS traffic lives in L2
-    const ulonglong2 s0 = __ldcg(reinterpret_cast<const ulonglong2*>(&s[0]));
-    const ulonglong2 s1 = __ldcg(reinterpret_cast<const ulonglong2*>(&s[1]));
-    uint64_t k[2] = {s0.x, s1.x};
+    ShnSlot* s = t.slots + SHN_BSLOTS * b;
+    ShnBucket bk;
+    table_load_bucket(t, b, &bk);
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      uint64_t cur = k[j];
-      if (cur == key) return 2 * b + j;
+    for (int j = 0; j < SHN_BSLOTS; ++j) {
+      uint64_t cur = bk.key(j);
+      if (cur == key) return SHN_BSLOTS * b + j;
       if (cur == SHN_EMPTY_KEY) {
         unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(&s[j].key),
                                            (unsigned long long)SHN_EMPTY_KEY,
                                            (unsigned long long)key);
         if (old == SHN_EMPTY_KEY) {
           *is_new += 1;
-          return 2 * b + j;
+          return SHN_BSLOTS * b + j;
         }
-        if (old == key) return 2 * b + j;
-        // somebody else took this slot for a different key: keep probing
+        if (old == key) return SHN_BSLOTS * b + j;
+        // somebody else took this slot for a different key: keep scanning
       }
     }
+    // every slot holds another key: leave the trail marker for lookups, then move on
+    if (!(bk.s[0].z & SHN_OVERFLOW)) atomicOr(&s[0].weight, SHN_OVERFLOW);
     b = (b + 1 == t.n_buckets) ? 0 : b + 1;
   }
   return ~0ull;
-}
-
-// Read-only probe: slot index of `key` or ~0; *w_out = raw weight word (bit 31 = traversed).
-__device__ __forceinline__ uint64_t table_find(const ShnTableView& t, uint64_t key,
-                                               uint32_t* w_out) {
-  uint64_t b = t.bucket_of(key);
-  for (;;) {
-    const ShnSlot* s = t.slots + 2 * b;
-    const uint4 s0 = __ldcg(reinterpret_cast<const uint4*>(&s[0]));
-    const uint4 s1 = __ldcg(reinterpret_cast<const uint4*>(&s[1]));
-    uint64_t k0 = ((uint64_t)s0.y << 32) | s0.x, k1 = ((uint64_t)s1.y << 32) | s1.x;
-    if (k0 == key) {
-      *w_out = s0.z;
-      return 2 * b;
-    }
-    if (k1 == key) {
-      *w_out = s1.z;
-      return 2 * b + 1;
-    }
-    if (k0 == SHN_EMPTY_KEY || k1 == SHN_EMPTY_KEY) return ~0ull;
-    b = (b + 1 == t.n_buckets) ? 0 : b + 1;
-  }
 }

@@ -11,8 +11,9 @@ from collections.abc import Mapping
 import numpy as np
 
 from . import _lib
+from .pipeline import (contig_adjacency, correct, decode_kmers, dfs_components,  # noqa: F401
+                       pack_components)
 
-_CODE_TO_ASCII = np.frombuffer(b"AGCT", dtype=np.uint8)
 _default_ctx = None
 
 
@@ -24,14 +25,6 @@ def get_context(device=None):
             device = int(os.environ.get("SHANNON_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
         _default_ctx = _lib.Context(device)
     return _default_ctx
-
-
-def decode_kmers(keys, k1):
-    """uint64 packed keys -> (n, k1) uint8 ASCII matrix."""
-    keys = np.asarray(keys, dtype=np.uint64)
-    shifts = (2 * (k1 - 1 - np.arange(k1))).astype(np.uint64)
-    codes = ((keys[:, None] >> shifts[None, :]) & np.uint64(3)).astype(np.uint8)
-    return _CODE_TO_ASCII[codes]
 
 
 def encode_kmer(s):
@@ -79,47 +72,6 @@ class AllowedKmerDict(Mapping):
         self._index = None
 
 
-def contig_adjacency(n_contigs, a, b, w, fp):
-    """contig_connections (extension_correction.py:372-389) in the reference's dict insertion
-    order, from the GPU's distinct edge list (a < b, multiplicity w, fp = first C-mer position in
-    b shared with a): node x first gets its earlier neighbours ordered by (fp, id) -- they are
-    connected while x itself is being indexed -- then later contigs in ascending id."""
-    adj = [[] for _ in range(n_contigs + 1)]
-    if len(a):
-        a = a.astype(np.int64)
-        b = b.astype(np.int64)
-        lower = np.lexsort((a, fp.astype(np.int64), b))      # by b, then fp, then a
-        for e in lower.tolist():
-            adj[b[e]].append((int(a[e]), int(w[e])))
-        higher = np.lexsort((b, a))                          # by a, then b
-        for e in higher.tolist():
-            adj[a[e]].append((int(b[e]), int(w[e])))
-    return adj
-
-
-def dfs_components(n_contigs, adj):
-    """extension_correction.py:417-434: iterative DFS in ascending contig index; member order is
-    the pop order.  Returns {root: [members]} in insertion order."""
-    comp_of = [0] * (n_contigs + 1)
-    seen = [False] * (n_contigs + 1)
-    component2contig = {}
-    for root in range(1, n_contigs + 1):
-        if comp_of[root]:
-            continue
-        members = component2contig[root] = []
-        stack = [root]
-        seen[root] = True
-        while stack:
-            cur = stack.pop()
-            comp_of[cur] = root
-            members.append(cur)
-            for nb, _ in adj[cur]:
-                if not seen[nb]:
-                    stack.append(nb)
-                    seen[nb] = True
-    return component2contig, comp_of
-
-
 def run_correction(infile, outfile, min_weight, min_length, double_stranded,
                    comp_directory_name, comp_size_threshold, polyA_del=True, inMem=False,
                    nJobs=1, reads_files=(), ctx=None):
@@ -134,25 +86,17 @@ def run_correction(infile, outfile, min_weight, min_length, double_stranded,
     f_log.write("{:s}: Starting..".format(time.asctime()) + "\n")
 
     keys, counts, k1 = ctx.parse_kmer_file(infile)
-    ctx.table_build(keys, counts, k1, double_stranded)
-    stats = ctx.table_stats()
-    if stats["n_distinct"] == 0:
-        raise StopIteration("no K1-mers loaded")  # the reference fails on next(iter(kmers)) here
+    cor = correct(ctx, keys, counts, k1, double_stranded, min_weight, min_length)
     del keys, counts
-    print("{:s}: {:d} K-mers loaded.".format(time.asctime(), stats["n_distinct"]))
-    f_log.write("{:s}: {:d} K-mers loaded.".format(time.asctime(), stats["n_distinct"]) + "\n")
+    print("{:s}: {:d} K-mers loaded.".format(time.asctime(), cor.n_loaded))
+    f_log.write("{:s}: {:d} K-mers loaded.".format(time.asctime(), cor.n_loaded) + "\n")
     f_log.write("{:s}: Reads loading in background process.".format(time.asctime()) + "\n")
 
-    sizes = ctx.l3_run(min_weight, min_length)
-    n_contigs = sizes["n_contigs"]
-    bases, offs = ctx.l3_contigs()
-    text = bases.tobytes().decode()
-    o = offs.tolist()
-    contigs = [None] + [text[o[i]:o[i + 1]] for i in range(n_contigs)]
+    contigs = cor.contigs
     with open(outfile + '_contig', 'w') as f1:
         f1.write("".join(c + "\n" for c in contigs[1:]))
 
-    a_keys, a_w = ctx.l3_allowed()
+    a_keys, a_w = cor.allowed_keys, cor.allowed_weights
     allowed_kmer_dict = AllowedKmerDict(a_keys, a_w, k1)
     n_allowed = len(allowed_kmer_dict)
     print("{:s}: {:d} K-mers remaining after error correction.".format(time.asctime(), n_allowed))
@@ -168,18 +112,9 @@ def run_correction(infile, outfile, min_weight, min_length, double_stranded,
             f.write("".join(txt[i:i + k1 + 1] + str(w) + "\n"
                             for i, w in zip(range(0, len(txt), k1 + 1), a_w.tolist())))
     f_log.write("{:s}: {:d} K-mers written to file.".format(time.asctime(), n_allowed) + " \n")
-
     f_log.write(str(time.asctime()) + ": " + "Before dfs " + "\n")
-    ea, eb, ew, efp = ctx.l3_edges()
-    adj = contig_adjacency(n_contigs, ea, eb, ew, efp)
-    component2contig, comp_of = dfs_components(n_contigs, adj)
-    labels = ctx.l3_labels()
-    if n_contigs and not np.array_equal(labels[1:], np.asarray(comp_of[1:], dtype=np.uint32)):
-        raise _lib.ShnError("internal error: GPU component labels disagree with the DFS partition")
+    adj, component2contig, n_edges = cor.adj, cor.component2contig, cor.n_edges
     f_log.write(str(time.asctime()) + ": " + "After dfs " + "\n")
-    n_edges = dict((c, 0) for c in component2contig)
-    for x in ea.tolist():
-        n_edges[comp_of[x]] += 1
     f_log.write(str(time.asctime()) + ": " + "After Edges Loaded " + "\n")
 
     d = comp_directory_name

@@ -10,6 +10,7 @@ import numpy as np
 
 from . import _lib
 from .extension_correction import AllowedKmerDict, get_context
+from .pipeline import build_component_map, contig_arrays, partition_reads
 from .weight_updated_graph import weight_updated_graph
 
 
@@ -126,17 +127,10 @@ def kmers_for_component(k1mer_dictionary, kmer_directory, reads, reads_files, di
                 add("cremaining" + str(i + 1), line.split()[0])
 
     # ---- k1mers2component on the device (a10) -------------------------------------------------
-    ctg_text = "".join(c for c, _ in entries)
-    ctg_bases = np.frombuffer(ctg_text.encode(), dtype=np.uint8)
-    ctg_offs = np.zeros(len(entries) + 1, dtype=np.uint64)
-    if entries:
-        ctg_offs[1:] = np.cumsum([len(c) for c, _ in entries])
+    ctg_bases, ctg_offs = contig_arrays([c for c, _ in entries])
     ctg_comp = np.asarray([cid for _, cid in entries], dtype=np.uint32)
-    lens = np.diff(ctg_offs.astype(np.int64))
-    total_windows = int(np.maximum(lens - k1 + 1, 0).sum())
-    ctx.l4_map_add_contigs(ctg_bases, ctg_offs, ctg_comp, k1, True, total_windows)
     d_keys, d_w = _dict_arrays(ctx, k1mer_dictionary, k1)
-    ctx.l4_map_set_weights(d_keys, d_w)
+    build_component_map(ctx, ctg_bases, ctg_offs, ctg_comp, k1, d_keys, d_w)
     write_log(str(time.asctime()) + ": " + "k1mers2component dictionary created ")
 
     # ---- read partition (a11) ---------------------------------------------------------------
@@ -145,16 +139,13 @@ def kmers_for_component(k1mer_dictionary, kmer_directory, reads, reads_files, di
     rb0, ro0 = ctx.load_fasta(reads_files[0])
     n_records = len(ro0) - 1
     read_bases, read_offs = [rb0], [ro0]
-    ctx.l4_load_reads(0, rb0, ro0)
     if paired_end:
         rb1, ro1 = ctx.load_fasta(reads_files[1], n_records)
         read_bases.append(rb1)
         read_offs.append(ro1)
-        ctx.l4_load_reads(1, rb1, ro1)
-    n_assign, _, _ = ctx.l4_assign(paired_end, k1)
     n_comps = len(new_components)
-    comp_offs, rec_idx = ctx.l4_assignments(n_comps, n_assign)
-    comp_offs = comp_offs.astype(np.int64)
+    comp_offs, rec_idx, _ = partition_reads(
+        ctx, [(b, o, None, False) for b, o in zip(read_bases, read_offs)], paired_end, k1, n_comps)
 
     part = [dict() for _ in range(n_files)]
     read_text = [b.tobytes().decode() for b in read_bases] if inMem else None
