@@ -99,6 +99,20 @@ int shn_pack_kmers(shn_ctx* ctx, const char* ascii, uint64_t n, int k1, uint64_t
  * index 2i / 2i+1).  Replaces any previous table of this ctx. */
 int shn_table_build(shn_ctx* ctx, const uint64_t* keys, const uint32_t* counts, uint64_t n,
                     int k1, int double_stranded, int on_device);
+/* Sharded build: like shn_table_build on device pointers, but entry i carries its own
+ * global input-line index (the seed tie-break must see the order of the un-sharded input). */
+int shn_table_build_indexed(shn_ctx* ctx, const uint64_t* keys_dev, const uint32_t* counts_dev,
+                            const uint32_t* line_idx_dev, uint64_t n, int k1);
+/* Owner rank of every key (low 32 bits of fmix64(key), independent of the bucket hash) and the
+ * stable partition of the batch by owner: perm_dev[j] = source index of the j-th routed element,
+ * counts_host[r] = elements owned by rank r.  Feeds an all-to-all whose send buffer must be
+ * contiguous per destination. */
+int shn_route_plan(shn_ctx* ctx, const uint64_t* keys_dev, uint64_t n, uint32_t nranks,
+                   uint32_t* perm_dev, uint64_t* counts_host);
+/* dst[i] = src[perm[i]] (scatter == 0) or dst[perm[i]] = src[i] (scatter != 0); elem_bytes in
+ * {1,4,8}; all device pointers. */
+int shn_permute(shn_ctx* ctx, const void* src_dev, const uint32_t* perm_dev, uint64_t n,
+                int elem_bytes, int scatter, void* dst_dev);
 int shn_table_stats(shn_ctx* ctx, uint64_t* n_distinct, uint64_t* n_lowcomplexity,
                     uint64_t* n_slots, int* k1);
 /* `kmer in kmers` / `kmers[kmer]`: weight (0 if absent) and found flag (0/1) per query. */

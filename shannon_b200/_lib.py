@@ -57,6 +57,9 @@ SIGNATURES = {
     "shn_write_k1mer_windows": (C.c_int, [vp, C.c_char_p, vp, vp, vp, C.c_uint64, C.c_int, vp, vp]),
     "shn_pack_kmers": (C.c_int, [vp, vp, C.c_uint64, C.c_int, vp, C.c_int]),
     "shn_table_build": (C.c_int, [vp, vp, vp, C.c_uint64, C.c_int, C.c_int, C.c_int]),
+    "shn_table_build_indexed": (C.c_int, [vp, vp, vp, vp, C.c_uint64, C.c_int]),
+    "shn_route_plan": (C.c_int, [vp, vp, C.c_uint64, C.c_uint32, vp, u64p]),
+    "shn_permute": (C.c_int, [vp, vp, vp, C.c_uint64, C.c_int, C.c_int, vp]),
     "shn_table_stats": (C.c_int, [vp, u64p, u64p, u64p, C.POINTER(C.c_int)]),
     "shn_table_lookup": (C.c_int, [vp, vp, C.c_uint64, vp, vp, C.c_int]),
     "shn_table_dump": (C.c_int, [vp, vp, vp, vp]),
@@ -282,6 +285,19 @@ class Context(HostIO):
             n = len(keys)
         self.call("shn_table_build", ptr(keys), ptr(counts), C.c_uint64(n), int(k1),
                   int(bool(double_stranded)), int(bool(on_device)))
+
+    def table_build_indexed(self, d_keys, d_counts, d_line_idx, n, k1):
+        self.call("shn_table_build_indexed", vp(d_keys), vp(d_counts), vp(d_line_idx), C.c_uint64(n),
+                  int(k1))
+
+    def route_plan(self, d_keys, n, nranks, d_perm):
+        counts = (C.c_uint64 * nranks)()
+        self.call("shn_route_plan", vp(d_keys), C.c_uint64(n), C.c_uint32(nranks), vp(d_perm), counts)
+        return [int(x) for x in counts]
+
+    def permute(self, d_src, d_perm, n, elem_bytes, d_dst, scatter=False):
+        self.call("shn_permute", vp(d_src), vp(d_perm), C.c_uint64(n), int(elem_bytes),
+                  int(bool(scatter)), vp(d_dst))
 
     def table_stats(self):
         nd, nl, ns = C.c_uint64(), C.c_uint64(), C.c_uint64()

@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "libshannon_b200.so")
-SOURCES = ["api.cu", "table.cu", "l3.cu", "l4.cu", "selfjoin.cu", "synth.cu", "hostio.cpp"]
+SOURCES = ["api.cu", "table.cu", "l3.cu", "l4.cu", "selfjoin.cu", "synth.cu", "route.cu", "hostio.cpp"]
 HEADERS = ["common.cuh", "table_dev.cuh", "selfjoin.cuh", os.path.join("..", "..", "include", "shannon_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

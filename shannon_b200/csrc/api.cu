@@ -44,6 +44,10 @@ void shn_count_k1mers_impl(shn_ctx* c, const char* const* arrays, const uint64_t
                            uint64_t** keys_dev, uint32_t** counts_dev, uint64_t* n_distinct);
 void shn_count_free(shn_ctx* c);
 void shn_pack_kmers_impl(shn_ctx* c, const char* d_ascii, uint64_t n, int k1, uint64_t* d_keys);
+void shn_route_plan_impl(shn_ctx* c, const uint64_t* d_keys, uint64_t n, uint32_t nranks,
+                         uint32_t* d_perm, uint64_t* h_counts);
+void shn_permute_impl(shn_ctx* c, const void* src, const uint32_t* d_perm, uint64_t n, int elem_bytes,
+                      int scatter, void* dst);
 
 static thread_local std::string g_last_error;
 thread_local DevPool* g_shn_pool = nullptr;
@@ -311,6 +315,31 @@ int shn_table_build(shn_ctx* c, const uint64_t* keys, const uint32_t* counts, ui
   const uint64_t* dk = (const uint64_t*)InputView::get(c, keys, n * 8, on_device, sk);
   const uint32_t* dc = (const uint32_t*)InputView::get(c, counts, n * 4, on_device, sc);
   shn_table_build_impl(c, dk, dc, n, k1, double_stranded);
+  SHN_API_END(c)
+}
+
+int shn_table_build_indexed(shn_ctx* c, const uint64_t* keys_dev, const uint32_t* counts_dev,
+                            const uint32_t* line_idx_dev, uint64_t n, int k1) {
+  SHN_API_BEGIN
+  bind(c);
+  shn_l3_free(c);
+  shn_table_build_impl(c, keys_dev, counts_dev, n, k1, 0, line_idx_dev);
+  SHN_API_END(c)
+}
+
+int shn_route_plan(shn_ctx* c, const uint64_t* keys_dev, uint64_t n, uint32_t nranks, uint32_t* perm_dev,
+                   uint64_t* counts_host) {
+  SHN_API_BEGIN
+  bind(c);
+  shn_route_plan_impl(c, keys_dev, n, nranks, perm_dev, counts_host);
+  SHN_API_END(c)
+}
+
+int shn_permute(shn_ctx* c, const void* src_dev, const uint32_t* perm_dev, uint64_t n, int elem_bytes,
+                int scatter, void* dst_dev) {
+  SHN_API_BEGIN
+  bind(c);
+  shn_permute_impl(c, src_dev, perm_dev, n, elem_bytes, scatter, dst_dev);
   SHN_API_END(c)
 }
 

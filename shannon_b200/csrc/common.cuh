@@ -359,7 +359,7 @@ struct InputView {
 
 // implemented in the individual translation units ------------------------------------------
 void shn_table_build_impl(shn_ctx* c, const uint64_t* d_keys, const uint32_t* d_counts, uint64_t n,
-                          int k1, int double_stranded);
+                          int k1, int double_stranded, const uint32_t* d_line_idx = nullptr);
 void shn_table_lookup_impl(shn_ctx* c, const uint64_t* d_keys, uint64_t n, uint32_t* d_weights,
                            uint8_t* d_found);
 void shn_l3_free(shn_ctx* c);

@@ -31,15 +31,16 @@ __global__ void __launch_bounds__(kBlock) table_clear_kernel(ShnSlot* slots, uin
 // counters: [0]=new keys [1]=low-complexity lines [3]=bad key / index overflow
 __global__ void __launch_bounds__(kBlock)
     table_insert_kernel(ShnTableView t, const uint64_t* __restrict__ keys,
-                        const uint32_t* __restrict__ counts, uint64_t n, int k1, int ds,
-                        unsigned long long* counters) {
+                        const uint32_t* __restrict__ counts, const uint32_t* __restrict__ line_idx,
+                        uint64_t n, int k1, int ds, unsigned long long* counters) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int n_new = 0, n_low = 0, n_bad = 0;
   if (i < n) {
     uint64_t key = keys[i];
     uint32_t w = counts[i];
-    uint64_t base_idx = ds ? 2 * i : i;
-    if ((key & ~shn_kmer_mask(k1)) || base_idx + 1 >= 0x7FFFFFFFull || w > SHN_WEIGHT_MASK) {
+    // explicit line indices (sharded build: the global input line of every routed key)
+    uint64_t base_idx = line_idx ? (uint64_t)line_idx[i] : (ds ? 2 * i : i);
+    if ((key & ~shn_kmer_mask(k1)) || base_idx + 1 >= 0xFFFFFFFFull || w > SHN_WEIGHT_MASK) {
       n_bad = 1;
     } else if (shn_low_complexity(key, k1)) {  // rc(kmer) is low-complexity iff kmer is
       n_low = 1;
@@ -135,10 +136,11 @@ void shn_pack_kmers_impl(shn_ctx* c, const char* d_ascii, uint64_t n, int k1, ui
 }
 
 void shn_table_build_impl(shn_ctx* c, const uint64_t* d_keys, const uint32_t* d_counts, uint64_t n,
-                          int k1, int double_stranded) {
+                          int k1, int double_stranded, const uint32_t* d_line_idx) {
+  SHN_CHECK(!(double_stranded && d_line_idx), "explicit line indices exclude double_stranded");
   SHN_CHECK(k1 >= 1 && k1 <= 32, "k1 must be in 1..32 (K <= 31); wider keys are not built yet");
   uint64_t items = n * (double_stranded ? 2 : 1);
-  SHN_CHECK(items < 0x7FFFFFFFull, "more than 2^31-1 input K1-mers per table");
+  SHN_CHECK(items < 0xFFFFFFFEull, "more than 2^32-2 input K1-mers per table");
   // slots >= 2 * items  (load factor <= 0.5)  => buckets >= items / 2 (4 slots each)
   uint64_t n_buckets = items < 1024 ? 256 : (items + 1) / 2;
   c->table.reserve(n_buckets * SHN_BSLOTS * sizeof(ShnSlot));
@@ -158,7 +160,8 @@ void shn_table_build_impl(shn_ctx* c, const uint64_t* d_keys, const uint32_t* d_
   if (n > 0) {
     ProfScope ps(c, "table_insert");
     table_insert_kernel<<<shn_grid(n, kBlock), kBlock, 0, c->stream>>>(c->view(), d_keys, d_counts,
-                                                                       n, k1, double_stranded, ctr);
+                                                                       d_line_idx, n, k1,
+                                                                       double_stranded, ctr);
     KERNEL_CHECK();
   }
   unsigned long long h[4];

@@ -1,0 +1,79 @@
+"""2-GPU test (NCCL) of the hash-sharded K1-mer table: device routing kernels + all-to-all +
+indexed build + distributed lookups, checked against the numpy twin.  Skipped with < 2 GPUs."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import helpers  # noqa: F401
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out_dir):
+    import dist_testlib
+    from shannon_b200 import _lib
+    from shannon_b200 import dist as sdist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        rng = np.random.default_rng(9)
+        n, k1 = 300000, 25
+        keys = rng.integers(0, 1 << (2 * k1), size=n, dtype=np.uint64)
+        keys[::11] = keys[5]
+        # keep only keys that survive the low-complexity filter trivially (random 25-mers do)
+        counts = rng.integers(1, 90, size=n).astype(np.int32)
+        lo, hi = sdist.shard_range(n, rank, world)
+        ctx = _lib.Context(rank)
+        ops = sdist.GpuOps(ctx, rank)
+        tab = sdist.ShardedKmerTable(ops)
+        dk = torch.from_numpy(keys[lo:hi].view(np.int64).copy()).cuda()
+        dc = torch.from_numpy(counts[lo:hi].copy()).cuda()
+        # device routing plan == numpy twin
+        perm, cnts = ops.plan(dk, world)
+        own = dist_testlib.owner_of(keys[lo:hi], world)
+        assert cnts == np.bincount(own, minlength=world).tolist()
+        assert perm.cpu().numpy().tolist() == np.argsort(own, kind="stable").tolist()
+        tab.build(dk, dc, lo, k1)
+        exp = {}
+        for i, (k, c) in enumerate(zip(keys.tolist(), counts.tolist())):
+            e = exp.setdefault(k, [0, i])
+            e[0] += c
+        mine = dict((k, v) for k, v in exp.items()
+                    if dist_testlib.owner_of(np.array([k], dtype=np.uint64), world)[0] == rank)
+        gk, gw, gi = ctx.table_dump()
+        assert dict(zip(gk.tolist(), zip(gw.tolist(), gi.tolist()))) == \
+            dict((k, (v[0], v[1])) for k, v in mine.items())
+        q = np.concatenate([keys[rng.integers(0, n, size=200000)],
+                            rng.integers(0, 1 << 50, size=100000, dtype=np.uint64)])
+        np.random.default_rng(rank).shuffle(q)
+        w, f = tab.lookup(torch.from_numpy(q.view(np.int64).copy()).cuda())
+        ops.sync()
+        assert w.cpu().tolist() == [exp.get(k, [0])[0] for k in q.tolist()]
+        assert f.cpu().tolist() == [int(k in exp) for k in q.tolist()]
+        ctx.close()
+        open(os.path.join(out_dir, "ok%d" % rank), "w").close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_table_two_gpus(tmp_path):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert sorted(os.listdir(tmp_path)) == ["ok0", "ok1"]

@@ -1,0 +1,100 @@
+"""world_size-2 gloo tests (CPU) of the N>1 host logic: routing plan, variable all-to-all,
+sharded build / lookup protocol of shannon_b200.dist, and the range sharding bench.py uses."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import helpers  # noqa: F401  (sys.path)
+from shannon_b200 import dist as sdist
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _make_input(seed=5, n=4000, k1=25):
+    rng = np.random.default_rng(seed)
+    keys = rng.integers(0, 1 << (2 * k1), size=n, dtype=np.uint64)
+    keys[::7] = keys[3]                 # repeated lines accumulate; first line index is the minimum
+    counts = rng.integers(1, 50, size=n).astype(np.int32)
+    return keys, counts
+
+
+def _worker(rank, world, port, out_dir):
+    import dist_testlib
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        keys, counts = _make_input()
+        lo, hi = sdist.shard_range(len(keys), rank, world)
+        ops = dist_testlib.NumpyOps()
+        tab = sdist.ShardedKmerTable(ops)
+        n_local = tab.build(torch.from_numpy(keys[lo:hi].view(np.int64).copy()),
+                            torch.from_numpy(counts[lo:hi].copy()), lo, 25)
+        # every key landed on its owner, with summed counts and the global first line
+        own = dist_testlib.owner_of(np.array(list(ops.table), dtype=np.uint64), world) \
+            if ops.table else np.zeros(0)
+        assert (own == rank).all()
+        exp = {}
+        for i, (k, c) in enumerate(zip(keys.tolist(), counts.tolist())):
+            e = exp.setdefault(k, [0, i])
+            e[0] += c
+        mine = dict((k, v) for k, v in exp.items()
+                    if dist_testlib.owner_of(np.array([k], dtype=np.uint64), world)[0] == rank)
+        assert ops.table == mine
+        tot = torch.tensor([n_local])
+        dist.all_reduce(tot)
+        assert int(tot) == len(keys)
+        # lookups from this rank: present keys (owned by anyone), absent keys, ragged batch size
+        rng = np.random.default_rng(100 + rank)
+        q = np.concatenate([keys[rng.integers(0, len(keys), size=500 + 37 * rank)],
+                            rng.integers(0, 1 << 50, size=300, dtype=np.uint64)])
+        rng.shuffle(q)
+        w, f = tab.lookup(torch.from_numpy(q.view(np.int64).copy()))
+        assert w.tolist() == [exp.get(k, [0])[0] for k in q.tolist()]
+        assert f.tolist() == [int(k in exp) for k in q.tolist()]
+        # an empty query batch on one rank must not dead-lock the collective
+        qe = q[:0] if rank == 0 else q[:5]
+        w, f = tab.lookup(torch.from_numpy(qe.view(np.int64).copy()))
+        assert len(w) == len(qe)
+        open(os.path.join(out_dir, "ok%d" % rank), "w").close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_table_protocol_world2(tmp_path):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert sorted(os.listdir(tmp_path)) == ["ok0", "ok1"]
+
+
+def test_shard_range_partitions_exactly():
+    for n in (0, 1, 7, 8, 1001):
+        for world in (1, 2, 3, 8):
+            r = [sdist.shard_range(n, k, world) for k in range(world)]
+            assert r[0][0] == 0 and r[-1][1] == n
+            assert all(r[i][1] == r[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in r]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_owner_hash_is_independent_of_bucket_hash():
+    """keys of one shard must still spread over all buckets of that shard's table (the table uses
+    the high bits of fmix64, the owner the low 32 bits)."""
+    import dist_testlib
+    from shannon_b200 import synth
+    keys = np.random.default_rng(1).integers(0, 1 << 50, size=200000, dtype=np.uint64)
+    own = dist_testlib.owner_of(keys, 8)
+    assert np.bincount(own, minlength=8).min() > 200000 / 8 * 0.9
+    hi = (synth.mix64(keys[own == 3]) >> np.uint64(54)).astype(np.int64)      # top 10 bits
+    assert np.bincount(hi, minlength=1024).min() > 0
