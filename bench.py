@@ -376,6 +376,44 @@ def main():
                "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
                "stage_wall_ms": stats_e.get("host_timings_ms")}
 
+    # ---- N > 1: the hash-sharded K1-mer table (all-to-all over NVLink) as a lookup service ------
+    dist_table = None
+    if world > 1:
+        from shannon_b200 import dist as sdist
+        ops = sdist.GpuOps(ctx, local_rank)
+        tab = sdist.ShardedKmerTable(ops)
+        n_k = wl.n_kmers
+        tk = torch.empty(n_k, dtype=torch.int64, device="cuda")
+        tc = torch.empty(n_k, dtype=torch.int32, device="cuda")
+        ctx.sync()
+        tk.copy_(torch.frombuffer(ctx.d2h(np.empty(n_k, np.uint64), wl.d_keys), dtype=torch.int64))
+        tc.copy_(torch.frombuffer(ctx.d2h(np.empty(n_k, np.uint32), wl.d_counts), dtype=torch.int32))
+        counts_all = [None] * world
+        dist.all_gather_object(counts_all, n_k)
+        first_line = sum(counts_all[:rank])
+        barrier()
+        t0 = time.perf_counter()
+        tab.build(tk, tc, first_line, K1)
+        barrier()
+        t_build = time.perf_counter() - t0
+        nq = min(n_k, 50_000_000)
+        q = tk[torch.randperm(n_k, device="cuda")[:nq]].contiguous()
+        tab.lookup(q[:1000])
+        barrier()
+        t0 = time.perf_counter()
+        w, f = tab.lookup(q)
+        barrier()
+        t_look = time.perf_counter() - t0
+        ok = bool(f.all().item())
+        tot_k = torch.tensor([float(n_k), float(nq)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tot_k)
+        dist_table = {"build_keys_per_s": float(tot_k[0]) / t_build,
+                      "lookups_per_s": float(tot_k[1]) / t_look, "all_found": ok,
+                      "alltoall_bytes_per_lookup": 8 + 4 + 1,
+                      "note": "keys of every rank's shard routed to hash owners with NCCL "
+                              "all_to_all_single; lookups = route, probe on the owner, route back"}
+        del tk, tc, q, w, f
+
     # ---- CPU baseline on a bounded sample (rank 0, N=1 only) + parity of the GPU path on it ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -408,7 +446,7 @@ def main():
             "assign_kernel_lookups_per_sec": (stats["lookups"] / (prof["l4_assign"][0] / args.steps / 1e3)
                                               if "l4_assign" in prof else None),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roofline, "cpu_baseline": cpu,
+            "roofline": roofline, "cpu_baseline": cpu, "dist_table": dist_table,
             "kernels": kern[:14],
             "kernel_ms_per_step": step_kernel_ms,
             "host_ms_per_step": ms_per_step - step_kernel_ms,

@@ -10,6 +10,7 @@
 // per-component replays is bit-identical to the reference's single sequential loop.
 #include <cub/cub.cuh>
 
+#include <algorithm>
 #include <cmath>
 
 #include "common.cuh"
@@ -138,8 +139,10 @@ __device__ __forceinline__ void uf_union(uint32_t* parent, uint32_t a, uint32_t 
   }
 }
 
-// One thread per K1-mer: the four successor probes are issued together (16 independent 16-byte
-// loads in flight), then the few successors that exist (1.2 on average) are linked.
+// One thread per K1-mer: probe the four successors, link the ones that exist (1.2 on average).
+// Measured: bound by the random 4-byte accesses of the union-find (two finds + CAS per link), not
+// by the table probes -- issuing the four bucket loads together (more registers, half the
+// occupancy) was 11 % slower.
 __global__ void __launch_bounds__(kBlock)
     uf_edges_kernel(ShnTableView t, uint32_t* parent, uint64_t n_slots, int k1) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -147,38 +150,13 @@ __global__ void __launch_bounds__(kBlock)
   uint64_t key = __ldg(&t.slots[i].key);
   if (key == SHN_EMPTY_KEY) return;
   const uint64_t mask = shn_kmer_mask(k1);
-  const uint64_t pre = (key << 2) & mask;
-  uint64_t hb[4];
-  ShnBucket bk[4];
+  uint64_t pre = (key << 2) & mask;
 #pragma unroll
-  for (int b = 0; b < 4; ++b) {
-    hb[b] = t.bucket_of(pre | (uint64_t)b);
-    table_load_bucket(t, hb[b], &bk[b]);
-  }
-  uint64_t succ[4];
-#pragma unroll
-  for (int b = 0; b < 4; ++b) {
-    int j = 0;
+  for (uint64_t b = 0; b < 4; ++b) {
     uint32_t w;
-    int r = table_match_bucket(bk[b], pre | (uint64_t)b, &j, &w);
-    succ[b] = ~0ull;
-    if (r == 1) {
-      succ[b] = SHN_BSLOTS * hb[b] + j;
-    } else if (r < 0) {  // rare: continue past an overflowed bucket
-      uint64_t nb = (hb[b] + 1 == t.n_buckets) ? 0 : hb[b] + 1;
-      for (;;) {
-        ShnBucket x;
-        table_load_bucket(t, nb, &x);
-        r = table_match_bucket(x, pre | (uint64_t)b, &j, &w);
-        if (r == 1) succ[b] = SHN_BSLOTS * nb + j;
-        if (r >= 0) break;
-        nb = (nb + 1 == t.n_buckets) ? 0 : nb + 1;
-      }
-    }
+    uint64_t s = table_find(t, pre | b, &w);
+    if (s != ~0ull && s != i) uf_union(parent, (uint32_t)i, (uint32_t)s);
   }
-#pragma unroll
-  for (int b = 0; b < 4; ++b)
-    if (succ[b] != ~0ull && succ[b] != i) uf_union(parent, (uint32_t)i, (uint32_t)succ[b]);
 }
 
 // parent[i] <- root for occupied slots; roots get flag 1
@@ -354,7 +332,8 @@ struct WalkArgs {
   uint32_t* nr;
   uint64_t* totwt;
   uint64_t* logstart;
-  unsigned long long* counters;  // [0]=traversed [1]=max steps of a thread [2]=log overflow
+  unsigned long long* counters;  // [0]=traversed [1]=max rounds of a warp [2]=log overflow
+  unsigned long long* trace;     // optional: per warp {end time ns, rounds, seeds} (SHN_WALK_TRACE)
 };
 
 // One WARP per component.  Seeds are scanned 32 at a time (one coalesced load of the slot
@@ -540,6 +519,13 @@ __global__ void __launch_bounds__(kWalkBlock, 4) walk_kernel(WalkArgs a) {
     atomicAdd(&a.counters[0], traversed);
     atomicMax(&a.counters[1], rounds);
     if (overflow) atomicAdd(&a.counters[2], 1ull);
+    if (a.trace) {
+      unsigned long long tns;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tns));
+      a.trace[3 * (uint64_t)warp] = tns;
+      a.trace[3 * (uint64_t)warp + 1] = rounds;
+      a.trace[3 * (uint64_t)warp + 2] = s_end - s_begin;
+    }
   }
 }
 
@@ -1025,9 +1011,39 @@ void shn_l3_run_impl(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
     a.totwt = tot_r.as<uint64_t>();
     a.logstart = ls_r.as<uint64_t>();
     a.counters = ctr;
-    ProfScope ps(c, "walk");
-    walk_kernel<<<shn_grid((uint64_t)n_active * 32, kWalkBlock), kWalkBlock, 0, st>>>(a);
-    KERNEL_CHECK();
+    a.trace = nullptr;
+    DevBuf trace;
+    const bool want_trace = getenv("SHN_WALK_TRACE") != nullptr;
+    if (want_trace) {
+      trace.reserve((uint64_t)n_active * 24);
+      a.trace = trace.as<unsigned long long>();
+    }
+    {
+      ProfScope ps(c, "walk");
+      walk_kernel<<<shn_grid((uint64_t)n_active * 32, kWalkBlock), kWalkBlock, 0, st>>>(a);
+      KERNEL_CHECK();
+    }
+    if (want_trace) {  // when does each component's warp finish? (tail = critical path)
+      std::vector<unsigned long long> tr;
+      d2h(c, tr, trace.p, (uint64_t)n_active * 3);
+      unsigned long long t_min = ~0ull, t_max = 0, r_sum = 0;
+      for (uint32_t w = 0; w < n_active; ++w) {
+        t_min = std::min(t_min, tr[3 * w]);
+        t_max = std::max(t_max, tr[3 * w]);
+        r_sum += tr[3 * w + 1];
+      }
+      std::vector<unsigned long long> ends;
+      for (uint32_t w = 0; w < n_active; ++w) ends.push_back(tr[3 * w] - t_min);
+      std::sort(ends.begin(), ends.end());
+      auto pct = [&](double p) { return ends[(size_t)(p * (ends.size() - 1))] / 1e6; };
+      fprintf(stderr,
+              "[walk trace] warps=%u total_rounds=%llu  finish-time spread (ms after the first warp "
+              "finished): p50=%.1f p90=%.1f p99=%.1f max=%.1f\n",
+              n_active, r_sum, pct(0.5), pct(0.9), pct(0.99), pct(1.0));
+      for (uint32_t w = 0; w < std::min<uint32_t>(n_active, 6); ++w)
+        fprintf(stderr, "[walk trace] largest component #%u: rounds=%llu seeds=%llu end=+%.1f ms\n", w,
+                tr[3 * w + 1], tr[3 * w + 2], (tr[3 * w] - t_min) / 1e6);
+    }
   }
   read_counters(c, h, 3);
   SHN_CHECK(h[2] == 0, "internal error: walk log overflow (component node count mismatch)");

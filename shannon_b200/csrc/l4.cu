@@ -15,6 +15,7 @@
 #include <cub/cub.cuh>
 
 #include "common.cuh"
+#include "table_dev.cuh"
 
 struct __align__(16) CompSlot {
   uint64_t key;
@@ -92,16 +93,21 @@ __device__ __forceinline__ bool pack_window(const char* __restrict__ bases, uint
   return ok;
 }
 
-__device__ __forceinline__ uint64_t map_find(const CompMapView& m, uint64_t key) {
+// 32-byte bucket = one 256-bit load; *comps = comp0 | comp1 << 32 of the matching slot
+__device__ __forceinline__ uint64_t map_find(const CompMapView& m, uint64_t key, uint64_t* comps) {
   uint64_t b = m.bucket_of(key);
   for (;;) {
-    const CompSlot* s = m.slots + 2 * b;
-    const uint4 s0 = __ldg(reinterpret_cast<const uint4*>(&s[0]));
-    const uint4 s1 = __ldg(reinterpret_cast<const uint4*>(&s[1]));
-    uint64_t k0 = ((uint64_t)s0.y << 32) | s0.x, k1 = ((uint64_t)s1.y << 32) | s1.x;
-    if (k0 == key) return 2 * b;
-    if (k1 == key) return 2 * b + 1;
-    if (k0 == SHN_EMPTY_KEY || k1 == SHN_EMPTY_KEY) return ~0ull;
+    uint64_t w[4];
+    shn_ld256_nc(m.slots + 2 * b, w);
+    if (w[0] == key) {
+      *comps = w[1];
+      return 2 * b;
+    }
+    if (w[2] == key) {
+      *comps = w[3];
+      return 2 * b + 1;
+    }
+    if (w[0] == SHN_EMPTY_KEY || w[2] == SHN_EMPTY_KEY) return ~0ull;
     b = (b + 1 == m.n_buckets) ? 0 : b + 1;
   }
 }
@@ -170,7 +176,8 @@ __global__ void __launch_bounds__(kBlock)
                            uint64_t n) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  uint64_t slot = map_find(m, keys[i]);
+  uint64_t comps;
+  uint64_t slot = map_find(m, keys[i], &comps);
   if (slot != ~0ull) map_w[slot] = weights[i];
 }
 
@@ -196,7 +203,8 @@ __global__ void __launch_bounds__(kBlock)
   uint64_t key;
   uint32_t w = 0;
   if (pack_window(bases, g, k1, &key)) {
-    uint64_t slot = map_find(m, key);
+    uint64_t comps;
+    uint64_t slot = map_find(m, key, &comps);
     if (slot != ~0ull) w = map_w[slot];
   }
   out[win_off[c] + (g - start)] = w;
@@ -310,12 +318,12 @@ __global__ void __launch_bounds__(kBlock)
       // offsets 0, k1, 2*k1, ... and the last window (read[-k1:])
       uint32_t st = (si + 1 == nsm) ? len - k1 : si * k1;
       uint64_t key = extract_kmer(second ? r1.words : r0.words, second ? wb1 : wb0, st, k1);
-      uint64_t slot = map_find(m, key);
+      uint64_t comps;
+      uint64_t slot = map_find(m, key, &comps);
       my_lookups++;
       if (slot != ~0ull) {
-        const uint4 sv = __ldg(reinterpret_cast<const uint4*>(&m.slots[slot]));
-        v0 = sv.z;
-        v1 = sv.w;
+        v0 = (uint32_t)comps;
+        v1 = (uint32_t)(comps >> 32);
       }
     }
     // dedup inside the 8-lane group: keep the first occurrence of every component id

@@ -9,15 +9,29 @@
 #pragma once
 #include "common.cuh"
 
+// 32-byte (two-slot) global load: one L2 sector per request instead of two 16-byte requests that
+// hit the same sector twice.  sm_100 has 256-bit LDG (SASS: LDG.E.ENL2.256).
+__device__ __forceinline__ void shn_ld256_cg(const void* p, uint64_t* w) {
+  asm volatile("ld.global.cg.v4.u64 {%0,%1,%2,%3}, [%4];"
+               : "=l"(w[0]), "=l"(w[1]), "=l"(w[2]), "=l"(w[3])
+               : "l"(p));
+}
+__device__ __forceinline__ void shn_ld256_nc(const void* p, uint64_t* w) {
+  asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];"
+               : "=l"(w[0]), "=l"(w[1]), "=l"(w[2]), "=l"(w[3])
+               : "l"(p));
+}
+
 struct ShnBucket {
-  uint4 s[SHN_BSLOTS];
-  __device__ __forceinline__ uint64_t key(int j) const { return ((uint64_t)s[j].y << 32) | s[j].x; }
+  uint64_t w[2 * SHN_BSLOTS];  // slot j = {w[2j] = key, w[2j+1] = weight | idx << 32}
+  __device__ __forceinline__ uint64_t key(int j) const { return w[2 * j]; }
+  __device__ __forceinline__ uint32_t weight(int j) const { return (uint32_t)w[2 * j + 1]; }
 };
 
 __device__ __forceinline__ void table_load_bucket(const ShnTableView& t, uint64_t b, ShnBucket* out) {
-  const uint4* p = reinterpret_cast<const uint4*>(t.slots + SHN_BSLOTS * b);
-#pragma unroll
-  for (int j = 0; j < SHN_BSLOTS; ++j) out->s[j] = __ldcg(p + j);  // .cg: data changes under atomics
+  const ShnSlot* p = t.slots + SHN_BSLOTS * b;  // 64-byte aligned
+  shn_ld256_cg(p, out->w);                      // .cg: data changes under atomics
+  shn_ld256_cg(p + 2, out->w + 4);
 }
 
 // Looks `key` up in an already loaded bucket.  Returns 1 = found (slot index in *j_out, raw weight
@@ -32,7 +46,7 @@ __device__ __forceinline__ int table_match_bucket(const ShnBucket& bk, uint64_t 
     uint64_t k = bk.key(j);
     if (k == key) {
       found = j;
-      w = bk.s[j].z;
+      w = bk.weight(j);
     }
     has_empty |= k == SHN_EMPTY_KEY;
   }
@@ -41,7 +55,7 @@ __device__ __forceinline__ int table_match_bucket(const ShnBucket& bk, uint64_t 
     *w_out = w;
     return 1;
   }
-  if (has_empty || !(bk.s[0].z & SHN_OVERFLOW)) return 0;
+  if (has_empty || !(bk.weight(0) & SHN_OVERFLOW)) return 0;
   return -1;
 }
 
@@ -111,7 +125,7 @@ __device__ __forceinline__ uint64_t table_upsert_slot(const ShnTableView& t, uin
       }
     }
     // every slot holds another key: leave the trail marker for lookups, then move on
-    if (!(bk.s[0].z & SHN_OVERFLOW)) atomicOr(&s[0].weight, SHN_OVERFLOW);
+    if (!(bk.weight(0) & SHN_OVERFLOW)) atomicOr(&s[0].weight, SHN_OVERFLOW);
     b = (b + 1 == t.n_buckets) ? 0 : b + 1;
   }
   return ~0ull;
