@@ -362,6 +362,8 @@ __global__ void __launch_bounds__(kWalkBlock, 4) walk_kernel(WalkArgs a) {
   const ShnTableView tv{a.local + SHN_BSLOTS * r0, a.region_off[comp + 1] - r0};
   const uint64_t slot_base = SHN_BSLOTS * r0;
   unsigned long long rounds = 0, traversed = 0;
+  long long mem_cycles = 0, t_begin = clock64();
+  const bool tracing = a.trace != nullptr;
   bool overflow = false;
   // role of this lane inside a round: level 1 (lanes 0..3), level 2 (lanes 4..19), idle
   const int lvl = lane < 4 ? 1 : (lane < 20 ? 2 : 0);
@@ -409,6 +411,7 @@ __global__ void __launch_bounds__(kWalkBlock, 4) walk_kernel(WalkArgs a) {
           uint32_t wraw = 0;
           int state = 0;       // 1 found, 0 absent, -1 undecided after the two prefetched buckets
           uint64_t nextb = 0;  // where an undecided lane would continue
+          long long tm0 = 0;
           if (lvl) {
             if (dir == 0) {
               cand = ((cur << 2) & mask) | b1;
@@ -421,13 +424,22 @@ __global__ void __launch_bounds__(kWalkBlock, 4) walk_kernel(WalkArgs a) {
             uint64_t hb = tv.bucket_of(cand);
             uint64_t hb1 = (hb + 1 == tv.n_buckets) ? 0 : hb + 1;
             ShnBucket bk0, bk1;
+            if (tracing) tm0 = clock64();
             table_load_bucket(tv, hb, &bk0);
-            table_load_bucket(tv, hb1, &bk1);
+            // the first decision must not wait for a second round trip: its four lanes also
+            // prefetch the next bucket of the probe sequence (6.5 % of probes continue)
+            if (lvl == 1) table_load_bucket(tv, hb1, &bk1);
+            if (tracing) {  // wait for the data here so the cycles are attributed to memory
+              volatile uint64_t sink = bk0.w[0] ^ bk0.w[4] ^ (lvl == 1 ? bk1.w[0] ^ bk1.w[4] : 0ull);
+              (void)sink;
+              mem_cycles += clock64() - tm0;
+            }
             int jj = 0;
             state = table_match_bucket(bk0, cand, &jj, &wraw);
+            nextb = hb1;
             if (state == 1) {
               cslot = slot_base + SHN_BSLOTS * hb + jj;
-            } else if (state < 0) {
+            } else if (state < 0 && lvl == 1) {
               state = table_match_bucket(bk1, cand, &jj, &wraw);
               if (state == 1) cslot = slot_base + SHN_BSLOTS * hb1 + jj;
               nextb = (hb1 + 1 == tv.n_buckets) ? 0 : hb1 + 1;
@@ -448,17 +460,14 @@ __global__ void __launch_bounds__(kWalkBlock, 4) walk_kernel(WalkArgs a) {
           }
           bool ok = cslot != ~0ull && !(wraw & SHN_TRAVERSED);
           // ---- first step: arg-max weight over lanes 0..3, first of equals wins (:159-166) ---
-          unsigned long long score =
-              ok ? ((((unsigned long long)(wraw & SHN_WEIGHT_MASK) + 1ull) << 2) | (unsigned)(3 - (lane & 3)))
-                 : 0ull;
-          unsigned long long m = __shfl_xor_sync(FULL, score, 1);
-          m = m > score ? m : score;
-          unsigned long long o = __shfl_xor_sync(FULL, m, 2);
-          m = o > m ? o : m;  // max of my aligned group of four lanes
-          const unsigned long long s1 = __shfl_sync(FULL, m, 0);
+          // score = (weight, 3 - code) + 1 in 32 bits (weights are < 2^30 - 1), 0 = no candidate
+          uint32_t score = ok ? ((((wraw & SHN_WEIGHT_MASK) << 2) | (uint32_t)(3 - (lane & 3))) + 1u) : 0u;
+          uint32_t m = max(score, __shfl_xor_sync(FULL, score, 1));
+          m = max(m, __shfl_xor_sync(FULL, m, 2));  // max of my aligned group of four lanes
+          const uint32_t s1 = __shfl_sync(FULL, m, 0);
           if (s1 == 0) break;  // warp-uniform: no extension
-          const int w1 = 3 - (int)(s1 & 3ull);
-          const uint32_t bw1 = (uint32_t)((s1 >> 2) - 1ull);
+          const int w1 = 3 - (int)((s1 - 1u) & 3u);
+          const uint32_t bw1 = (s1 - 1u) >> 2;
           const uint64_t c1 = __shfl_sync(FULL, cand, w1);
           if (lane == w1) slots[cslot].weight = wraw | SHN_TRAVERSED;  // traversed.add(last), :235
           if (lane == 0 && lp < le) a.walk_log[lp] = (uint8_t)w1;
@@ -482,19 +491,16 @@ __global__ void __launch_bounds__(kWalkBlock, 4) walk_kernel(WalkArgs a) {
             ok = cslot != ~0ull && !(wraw & SHN_TRAVERSED);
           }
           ok = ok && cand != c1;
-          score = ok ? ((((unsigned long long)(wraw & SHN_WEIGHT_MASK) + 1ull) << 2) | (unsigned)(3 - (lane & 3)))
-                     : 0ull;
-          m = __shfl_xor_sync(FULL, score, 1);
-          m = m > score ? m : score;
-          o = __shfl_xor_sync(FULL, m, 2);
-          m = o > m ? o : m;
-          const unsigned long long s2 = __shfl_sync(FULL, m, g2);
+          score = ok ? ((((wraw & SHN_WEIGHT_MASK) << 2) | (uint32_t)(3 - (lane & 3))) + 1u) : 0u;
+          m = max(score, __shfl_xor_sync(FULL, score, 1));
+          m = max(m, __shfl_xor_sync(FULL, m, 2));
+          const uint32_t s2 = __shfl_sync(FULL, m, g2);
           if (s2 == 0) {
             __syncwarp();
             break;  // warp-uniform: the walk ends at c1 in this direction
           }
-          const int w2 = 3 - (int)(s2 & 3ull);
-          const uint32_t bw2 = (uint32_t)((s2 >> 2) - 1ull);
+          const int w2 = 3 - (int)((s2 - 1u) & 3u);
+          const uint32_t bw2 = (s2 - 1u) >> 2;
           cur = __shfl_sync(FULL, cand, g2 + w2);
           if (lane == g2 + w2) slots[cslot].weight = wraw | SHN_TRAVERSED;
           if (lane == 0 && lp < le) a.walk_log[lp] = (uint8_t)w2;
@@ -524,7 +530,8 @@ __global__ void __launch_bounds__(kWalkBlock, 4) walk_kernel(WalkArgs a) {
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tns));
       a.trace[3 * (uint64_t)warp] = tns;
       a.trace[3 * (uint64_t)warp + 1] = rounds;
-      a.trace[3 * (uint64_t)warp + 2] = s_end - s_begin;
+      a.trace[3 * (uint64_t)warp + 2] = ((unsigned long long)(clock64() - t_begin) << 32) |
+                                        (unsigned long long)(mem_cycles >> 8);
     }
   }
 }

@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(kBlock)
     uint32_t w = counts[i];
     // explicit line indices (sharded build: the global input line of every routed key)
     uint64_t base_idx = line_idx ? (uint64_t)line_idx[i] : (ds ? 2 * i : i);
-    if ((key & ~shn_kmer_mask(k1)) || base_idx + 1 >= 0xFFFFFFFFull || w > SHN_WEIGHT_MASK) {
+    if ((key & ~shn_kmer_mask(k1)) || base_idx + 1 >= 0xFFFFFFFFull || w >= SHN_WEIGHT_MASK) {
       n_bad = 1;
     } else if (shn_low_complexity(key, k1)) {  // rc(kmer) is low-complexity iff kmer is
       n_low = 1;
@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(kBlock)
           break;
         }
         uint32_t old = atomicAdd(&t.slots[slot].weight, w);
-        if ((uint64_t)(old & SHN_WEIGHT_MASK) + w > (uint64_t)SHN_WEIGHT_MASK) n_bad = 1;
+        if ((uint64_t)(old & SHN_WEIGHT_MASK) + w >= (uint64_t)SHN_WEIGHT_MASK) n_bad = 1;
         atomicMin(&t.slots[slot].idx, (uint32_t)(base_idx + r));
       }
     }
@@ -167,7 +167,7 @@ void shn_table_build_impl(shn_ctx* c, const uint64_t* d_keys, const uint32_t* d_
   unsigned long long h[4];
   CUDA_CHECK(cudaMemcpyAsync(h, ctr, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
   CUDA_CHECK(cudaStreamSynchronize(c->stream));
-  SHN_CHECK(h[3] == 0, "table build: key wider than 2*k1 bits, a K1-mer weight above 2^30-1, or input index overflow");
+  SHN_CHECK(h[3] == 0, "table build: key wider than 2*k1 bits, a K1-mer weight above 2^30-2, or input index overflow");
   c->n_distinct = h[0];
   c->n_lowcomplexity = h[1];
 }
