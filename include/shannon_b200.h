@@ -137,7 +137,9 @@ typedef struct shn_l3_sizes {
   uint64_t n_allowed;      /* K1-mers of accepted contigs */
   uint64_t n_edges;        /* distinct undirected contig-contig edges */
   uint64_t dup_rounds;     /* frontier rounds the duplicate filter needed */
-  uint64_t walk_rounds;    /* longest per-component serial chain (steps) */
+  uint64_t walk_rounds;    /* longest per-component serial chain (2-step probe rounds) */
+  uint64_t n_spec_comps;   /* components walked with speculative windows */
+  uint64_t spec_windows;   /* windows those components needed */
 } shn_l3_sizes;
 int shn_l3_get_sizes(shn_ctx* ctx, shn_l3_sizes* out);
 /* Per started walk, in pop order: seed key, steps to the left/right, sum of weights, and flags

@@ -24,7 +24,8 @@ class ShnError(RuntimeError):
 class L3Sizes(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "n_seeds", "n_raw_comps", "n_walks", "n_traversed", "n_candidates", "n_contigs",
-        "contig_bases", "n_allowed", "n_edges", "dup_rounds", "walk_rounds")]
+        "contig_bases", "n_allowed", "n_edges", "dup_rounds", "walk_rounds", "n_spec_comps",
+        "spec_windows")]
 
 
 # name -> (restype, argtypes); must list every symbol declared in include/shannon_b200.h

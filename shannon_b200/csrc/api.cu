@@ -133,6 +133,7 @@ void shn_destroy(shn_ctx* c) {
   cudaEventDestroy(c->p1);
   cudaStreamSynchronize(c->stream);
   c->pool.trim();
+  if (c->stream2) cudaStreamDestroy(c->stream2);
   cudaStreamDestroy(c->stream);
   g_shn_pool = nullptr;
   delete c;

@@ -259,6 +259,7 @@ struct shn_ctx {
   int device = 0;
   int sm_count = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;  // second stream of the walk stage (created on demand)
   std::string last_error;
   cudaEvent_t t0 = nullptr, t1 = nullptr;
   // profiling

@@ -536,6 +536,307 @@ __global__ void __launch_bounds__(kWalkBlock, 4) walk_kernel(WalkArgs a) {
   }
 }
 
+// ---- speculative windowed walks for the large components ------------------------------------
+// The serial replay of one component is the critical path of the whole stage (latency of ~10^5
+// dependent probe rounds).  Large components are therefore given a CTA of kSpecWarps warps that
+// run the next kSpecWarps untraversed seeds of the pop order CONCURRENTLY and commit them IN ORDER
+// ("deterministic reservations"):
+//   * every walk of a window carries a stamp = 0xFFFFFFFF - seed position (earlier seed = larger
+//     stamp) and claims a K1-mer with atomicMax on the slot's (otherwise unused) idx word;
+//   * a candidate is blocked for a walk iff it is committed-traversed or stamped by an EARLIER
+//     seed (or by the walk itself); stamps of later seeds are ignored and overwritten (stolen);
+//   * after the window every walk re-reads its path: it is intact iff every slot still carries its
+//     stamp.  The longest prefix of intact walks is exactly what the sequential loop would have
+//     produced (an intact walk only ever yielded to walks before it, all of which are intact and
+//     final; nothing it examined-and-rejected can matter): those are
+//     committed (traversed bits, log, metas); the others clear their stamps and are retried in
+//     the next window, which starts at the first uncommitted seed.  The first walk of a window is
+//     always intact, so every window makes progress.
+constexpr int kSpecWarps = 16;
+
+struct SpecArgs {
+  WalkArgs w;
+  uint32_t* path_slot;  // [n_spec * kSpecWarps * path_cap]
+  uint8_t* path_base;
+  uint64_t path_cap;
+};
+
+__global__ void __launch_bounds__(kSpecWarps * 32, 1) walk_spec_kernel(SpecArgs sa) {
+  const WalkArgs& a = sa.w;
+  const unsigned FULL = 0xFFFFFFFFu;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const uint32_t comp = a.comp_order[blockIdx.x];
+  const uint64_t s_begin = a.seed_off[comp], s_end = a.seed_off[comp + 1];
+  const uint64_t le = a.log_off[comp + 1];
+  const uint64_t mask = shn_kmer_mask(a.k1);
+  const int top = 2 * (a.k1 - 1);
+  ShnSlot* slots = a.local;
+  const uint64_t r0 = a.region_off[comp];
+  const ShnTableView tv{a.local + SHN_BSLOTS * r0, a.region_off[comp + 1] - r0};
+  const uint64_t slot_base = SHN_BSLOTS * r0;
+  uint32_t* my_path_slot = sa.path_slot + ((uint64_t)blockIdx.x * kSpecWarps + warp) * sa.path_cap;
+  uint8_t* my_path_base = sa.path_base + ((uint64_t)blockIdx.x * kSpecWarps + warp) * sa.path_cap;
+  const int lvl = lane < 4 ? 1 : (lane < 20 ? 2 : 0);
+  const uint64_t b1 = lvl == 1 ? lane : ((lane - 4) >> 2);
+  const uint64_t b2 = (lane - 4) & 3;
+
+  __shared__ uint64_t sh_cursor, sh_cursor_after, sh_lp;
+  __shared__ uint32_t sh_win_pos[kSpecWarps], sh_win_slot[kSpecWarps], sh_len[kSpecWarps];
+  __shared__ uint32_t sh_intact[kSpecWarps];
+  __shared__ uint32_t sh_win_n;
+  if (threadIdx.x == 0) {
+    sh_cursor = s_begin;
+    sh_lp = a.log_off[comp];
+  }
+  unsigned long long rounds = 0, traversed = 0, windows = 0;
+  bool overflow = false;
+  __syncthreads();
+
+  for (;;) {
+    // ---- 1. warp 0 collects the next untraversed seeds in pop order ------------------------
+    if (warp == 0) {
+      uint32_t n = 0;
+      uint64_t pos = sh_cursor;
+      while (n < kSpecWarps && pos < s_end) {
+        const uint64_t si = pos + lane;
+        uint32_t slot = 0, wv = SHN_TRAVERSED;
+        if (si < s_end) {
+          slot = a.slots_by_comp[si];
+          wv = __ldcg(&slots[slot].weight);
+        }
+        unsigned fresh = __ballot_sync(FULL, si < s_end && !(wv & SHN_TRAVERSED));
+        uint64_t consumed = min((uint64_t)32, s_end - pos);
+        while (fresh && n < kSpecWarps) {
+          const int j = __ffs(fresh) - 1;
+          fresh &= fresh - 1;
+          const uint32_t sj = __shfl_sync(FULL, slot, j);
+          if (lane == 0) {
+            sh_win_pos[n] = (uint32_t)(pos + j - s_begin);
+            sh_win_slot[n] = sj;
+          }
+          ++n;
+          if (n == kSpecWarps) consumed = j + 1;
+        }
+        pos += consumed;
+      }
+      if (lane == 0) {
+        sh_win_n = n;
+        sh_cursor_after = pos;
+      }
+    }
+    __syncthreads();
+    const uint32_t win_n = sh_win_n;
+    if (win_n == 0) break;
+    ++windows;
+
+    // ---- 2. speculative walks -----------------------------------------------------------------
+    uint32_t len = 0, n_dir[2] = {0, 0};
+    uint64_t tot = 0;
+    uint32_t stamp = 0;
+    if (warp < (int)win_n) {
+      stamp = 0xFFFFFFFFu - sh_win_pos[warp];
+      const uint32_t seed_slot = sh_win_slot[warp];
+      // claim the seed; an earlier walk of this window may already hold it
+      uint32_t old = 0;
+      if (lane == 0) old = atomicMax(&slots[seed_slot].idx, stamp);
+      old = __shfl_sync(FULL, old, 0);
+      if (old < stamp) {
+        const uint4 v = __ldcg(reinterpret_cast<const uint4*>(slots) + seed_slot);
+        const uint64_t seed_key = ((uint64_t)v.y << 32) | v.x;
+        if (lane == 0) {
+          my_path_slot[0] = seed_slot;
+          my_path_base[0] = 0xFF;
+        }
+        len = 1;
+        tot = v.z & SHN_WEIGHT_MASK;
+#pragma unroll 1
+        for (int dir = 0; dir < 2; ++dir) {
+          uint64_t cur = seed_key;
+          bool go = true;
+          while (go) {
+            ++rounds;
+            uint64_t cand = 0, cslot = ~0ull;
+            uint32_t wraw = 0, cstamp = 0;
+            int state = 0;
+            uint64_t nextb = 0;
+            if (lvl) {
+              if (dir == 0) {
+                cand = ((cur << 2) & mask) | b1;
+                if (lvl == 2) cand = ((cand << 2) & mask) | b2;
+              } else {
+                cand = (cur >> 2) | (b1 << top);
+                if (lvl == 2) cand = (cand >> 2) | (b2 << top);
+              }
+              uint64_t hb = tv.bucket_of(cand);
+              uint64_t hb1 = (hb + 1 == tv.n_buckets) ? 0 : hb + 1;
+              ShnBucket bk0, bk1;
+              table_load_bucket(tv, hb, &bk0);
+              if (lvl == 1) table_load_bucket(tv, hb1, &bk1);
+              int jj = 0;
+              state = table_match_bucket2(bk0, cand, &jj, &wraw, &cstamp);
+              nextb = hb1;
+              if (state == 1) {
+                cslot = slot_base + SHN_BSLOTS * hb + jj;
+              } else if (state < 0 && lvl == 1) {
+                state = table_match_bucket2(bk1, cand, &jj, &wraw, &cstamp);
+                if (state == 1) cslot = slot_base + SHN_BSLOTS * hb1 + jj;
+                nextb = (hb1 + 1 == tv.n_buckets) ? 0 : hb1 + 1;
+              }
+            }
+            if (lvl == 1 && state < 0) {
+              for (;;) {
+                ShnBucket bk;
+                table_load_bucket(tv, nextb, &bk);
+                int jj = 0;
+                state = table_match_bucket2(bk, cand, &jj, &wraw, &cstamp);
+                if (state == 1) cslot = slot_base + SHN_BSLOTS * nextb + jj;
+                if (state >= 0) break;
+                nextb = (nextb + 1 == tv.n_buckets) ? 0 : nextb + 1;
+              }
+            }
+            // blocked: committed-traversed, or stamped by an earlier seed or by this walk
+            bool ok = cslot != ~0ull && !(wraw & SHN_TRAVERSED) && cstamp < stamp;
+            // ---- first step (re-decided if the claim loses a race against an earlier seed) -----
+            int w1 = -1;
+            uint32_t bw1 = 0;
+            for (;;) {
+              uint32_t score = ok ? ((((wraw & SHN_WEIGHT_MASK) << 2) | (uint32_t)(3 - (lane & 3))) + 1u) : 0u;
+              uint32_t m = max(score, __shfl_xor_sync(FULL, score, 1));
+              m = max(m, __shfl_xor_sync(FULL, m, 2));
+              const uint32_t s1 = __shfl_sync(FULL, m, 0);
+              if (s1 == 0) break;
+              const int wl = 3 - (int)((s1 - 1u) & 3u);
+              uint32_t o = 0;
+              if (lane == wl) o = atomicMax(&slots[cslot].idx, stamp);
+              o = __shfl_sync(FULL, o, wl);
+              if (o < stamp) {
+                w1 = wl;
+                bw1 = (s1 - 1u) >> 2;
+                break;
+              }
+              if (lane == wl) ok = false;  // an earlier seed got there first: blocked after all
+            }
+            if (w1 < 0) break;  // no extension in this direction
+            const uint64_t c1 = __shfl_sync(FULL, cand, w1);
+            const uint32_t c1slot = (uint32_t)__shfl_sync(FULL, (uint32_t)cslot, w1);
+            if (lane == 0) {
+              if (len < sa.path_cap) {
+                my_path_slot[len] = c1slot;
+                my_path_base[len] = (uint8_t)w1;
+              }
+            }
+            overflow |= len >= sa.path_cap;
+            ++len;
+            tot += bw1;
+            ++n_dir[dir];
+            // ---- second step from the prefetched level ---------------------------------------
+            const int g2 = 4 + 4 * w1;
+            if (lane >= g2 && lane < g2 + 4 && state < 0) {
+              for (;;) {
+                ShnBucket bk;
+                table_load_bucket(tv, nextb, &bk);
+                int jj = 0;
+                state = table_match_bucket2(bk, cand, &jj, &wraw, &cstamp);
+                if (state == 1) cslot = slot_base + SHN_BSLOTS * nextb + jj;
+                if (state >= 0) break;
+                nextb = (nextb + 1 == tv.n_buckets) ? 0 : nextb + 1;
+              }
+              ok = cslot != ~0ull && !(wraw & SHN_TRAVERSED) && cstamp < stamp;
+            }
+            ok = ok && cand != c1;
+            int w2 = -1;
+            uint32_t bw2 = 0;
+            for (;;) {
+              uint32_t score = ok ? ((((wraw & SHN_WEIGHT_MASK) << 2) | (uint32_t)(3 - (lane & 3))) + 1u) : 0u;
+              uint32_t m = max(score, __shfl_xor_sync(FULL, score, 1));
+              m = max(m, __shfl_xor_sync(FULL, m, 2));
+              const uint32_t s2 = __shfl_sync(FULL, m, g2);
+              if (s2 == 0) break;
+              const int wl = 3 - (int)((s2 - 1u) & 3u);
+              uint32_t o = 0;
+              if (lane == g2 + wl) o = atomicMax(&slots[cslot].idx, stamp);
+              o = __shfl_sync(FULL, o, g2 + wl);
+              if (o < stamp) {
+                w2 = wl;
+                bw2 = (s2 - 1u) >> 2;
+                break;
+              }
+              if (lane == g2 + wl) ok = false;
+            }
+            if (w2 < 0) {
+              go = false;  // the walk ends at c1 in this direction
+            } else {
+              cur = __shfl_sync(FULL, cand, g2 + w2);
+              const uint32_t c2slot = (uint32_t)__shfl_sync(FULL, (uint32_t)cslot, g2 + w2);
+              if (lane == 0 && len < sa.path_cap) {
+                my_path_slot[len] = c2slot;
+                my_path_base[len] = (uint8_t)w2;
+              }
+              overflow |= len >= sa.path_cap;
+              ++len;
+              tot += bw2;
+              ++n_dir[dir];
+            }
+            __syncwarp();
+          }
+        }
+      }
+      if (lane == 0) sh_len[warp] = len;
+    }
+    __syncthreads();  // all claims of the window are in L2
+
+    // ---- 3. is my path intact? ------------------------------------------------------------------
+    if (warp < (int)win_n) {
+      bool mine = true;
+      for (uint32_t e = lane; e < len; e += 32) mine &= __ldcg(&slots[my_path_slot[e]].idx) == stamp;
+      mine = __all_sync(FULL, mine);
+      if (lane == 0) sh_intact[warp] = mine ? 1u : 0u;
+    }
+    __syncthreads();
+    uint32_t P = 0;
+    while (P < win_n && sh_intact[P]) ++P;
+
+    // ---- 4. commit the intact prefix in order, roll the rest back ---------------------------
+    if (warp < (int)win_n) {
+      if ((uint32_t)warp < P) {
+        uint64_t off = sh_lp;
+        for (int q = 0; q < warp; ++q) off += sh_len[q];
+        for (uint32_t e = lane; e < len; e += 32) {
+          atomicOr(&slots[my_path_slot[e]].weight, SHN_TRAVERSED);
+          if (off + e < le) a.walk_log[off + e] = my_path_base[e];
+        }
+        overflow |= off + len > le;
+        if (lane == 0 && len) {
+          const uint32_t rank = a.ranks_by_comp[s_begin + sh_win_pos[warp]];
+          a.started[rank] = 1;
+          a.nr[rank] = n_dir[0];
+          a.nl[rank] = n_dir[1];
+          a.totwt[rank] = tot;
+          a.logstart[rank] = off;
+        }
+        traversed += len;
+      } else {
+        for (uint32_t e = lane; e < len; e += 32) atomicCAS(&slots[my_path_slot[e]].idx, stamp, 0u);
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint64_t add = 0;
+      for (uint32_t q = 0; q < P; ++q) add += sh_len[q];
+      sh_lp += add;
+      sh_cursor = P < win_n ? s_begin + sh_win_pos[P] : sh_cursor_after;
+    }
+    __syncthreads();
+  }
+  if (lane == 0) {
+    atomicAdd(&a.counters[0], traversed);
+    if (warp == 0) atomicMax(&a.counters[1], rounds);
+    if (overflow) atomicAdd(&a.counters[2], 1ull);
+    if (warp == 0) atomicAdd(&a.counters[3], windows);
+  }
+}
+
 // ---- contig assembly from the walk log -----------------------------------------------------
 // one thread per output base of the candidate contigs
 __global__ void __launch_bounds__(kBlock)
@@ -966,8 +1267,9 @@ void shn_l3_run_impl(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
   DevBuf comp_order;
   comp_order.reserve(std::max<uint32_t>(n_comps, 1) * 4);
   uint32_t n_active = 0;
+  DevBuf work_s;  // node counts of the active components, descending (same order as comp_order)
   if (n_comps) {
-    DevBuf ids, work, work_s;
+    DevBuf ids, work;
     ids.reserve((uint64_t)n_comps * 4);
     work.reserve((uint64_t)n_comps * 4);
     work_s.reserve((uint64_t)n_comps * 4);
@@ -1025,37 +1327,88 @@ void shn_l3_run_impl(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
       trace.reserve((uint64_t)n_active * 24);
       a.trace = trace.as<unsigned long long>();
     }
+    // large components: speculative windows (one CTA each); the rest: one warp each, on a second
+    // stream so that both kernels share the GPU
+    uint32_t n_spec = 0;
+    uint64_t path_cap = 0;
     {
-      ProfScope ps(c, "walk");
-      walk_kernel<<<shn_grid((uint64_t)n_active * 32, kWalkBlock), kWalkBlock, 0, st>>>(a);
-      KERNEL_CHECK();
+      const uint32_t peek = std::min<uint32_t>(n_active, 4096);
+      std::vector<uint32_t> top;
+      d2h(c, top, work_s.p, peek);
+      const char* env = getenv("SHN_SPEC_MIN_NODES");
+      const uint64_t min_nodes = env ? strtoull(env, nullptr, 10) : 60000ull;
+      const char* envb = getenv("SHN_SPEC_SCRATCH_GB");
+      const uint64_t budget = (envb ? strtoull(envb, nullptr, 10) : 16ull) << 30;  // scratch for the paths
+      path_cap = peek ? top[0] : 0;
+      // one speculative CTA per SM at most: beyond that the windows only burn probe bandwidth
+      while (n_spec < peek && n_spec < (uint32_t)c->sm_count && top[n_spec] >= min_nodes &&
+             (uint64_t)(n_spec + 1) * kSpecWarps * path_cap * 5 <= budget)
+        ++n_spec;
     }
+    DevBuf path_slot, path_base;
+    cudaEvent_t ev_fork = c->prof_event(), ev_join = c->prof_event();
+    {
+      ProfScope ps(c, "walk", 2);
+      if (n_spec < n_active) {
+        if (!c->stream2) CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+        CUDA_CHECK(cudaEventRecord(ev_fork, st));
+        CUDA_CHECK(cudaStreamWaitEvent(c->stream2, ev_fork, 0));
+      }
+      if (n_spec) {
+        SpecArgs sa;
+        sa.w = a;
+        sa.w.n_comps = n_spec;
+        sa.path_cap = path_cap;
+        path_slot.reserve((uint64_t)n_spec * kSpecWarps * path_cap * 4);
+        path_base.reserve((uint64_t)n_spec * kSpecWarps * path_cap);
+        sa.path_slot = path_slot.as<uint32_t>();
+        sa.path_base = path_base.as<uint8_t>();
+        walk_spec_kernel<<<n_spec, kSpecWarps * 32, 0, st>>>(sa);
+        KERNEL_CHECK();
+      }
+      if (n_spec < n_active) {
+        WalkArgs b = a;
+        b.comp_order = a.comp_order + n_spec;
+        b.n_comps = n_active - n_spec;
+        if (b.trace) b.trace += 3 * (uint64_t)n_spec;
+        walk_kernel<<<shn_grid((uint64_t)b.n_comps * 32, kWalkBlock), kWalkBlock, 0, c->stream2>>>(b);
+        KERNEL_CHECK();
+        CUDA_CHECK(cudaEventRecord(ev_join, c->stream2));
+        CUDA_CHECK(cudaStreamWaitEvent(st, ev_join, 0));
+      }
+    }
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    c->prof_pool.push_back(ev_fork);
+    c->prof_pool.push_back(ev_join);
+    s->sz.n_spec_comps = n_spec;
     if (want_trace) {  // when does each component's warp finish? (tail = critical path)
       std::vector<unsigned long long> tr;
       d2h(c, tr, trace.p, (uint64_t)n_active * 3);
       unsigned long long t_min = ~0ull, t_max = 0, r_sum = 0;
-      for (uint32_t w = 0; w < n_active; ++w) {
+      for (uint32_t w = n_spec; w < n_active; ++w) {
         t_min = std::min(t_min, tr[3 * w]);
         t_max = std::max(t_max, tr[3 * w]);
         r_sum += tr[3 * w + 1];
       }
       std::vector<unsigned long long> ends;
-      for (uint32_t w = 0; w < n_active; ++w) ends.push_back(tr[3 * w] - t_min);
+      for (uint32_t w = n_spec; w < n_active; ++w) ends.push_back(tr[3 * w] - t_min);
+      if (ends.empty()) ends.push_back(0);
       std::sort(ends.begin(), ends.end());
       auto pct = [&](double p) { return ends[(size_t)(p * (ends.size() - 1))] / 1e6; };
       fprintf(stderr,
               "[walk trace] warps=%u total_rounds=%llu  finish-time spread (ms after the first warp "
               "finished): p50=%.1f p90=%.1f p99=%.1f max=%.1f\n",
               n_active, r_sum, pct(0.5), pct(0.9), pct(0.99), pct(1.0));
-      for (uint32_t w = 0; w < std::min<uint32_t>(n_active, 6); ++w)
+      for (uint32_t w = n_spec; w < std::min<uint32_t>(n_active, n_spec + 6); ++w)
         fprintf(stderr, "[walk trace] largest component #%u: rounds=%llu seeds=%llu end=+%.1f ms\n", w,
                 tr[3 * w + 1], tr[3 * w + 2], (tr[3 * w] - t_min) / 1e6);
     }
   }
-  read_counters(c, h, 3);
+  read_counters(c, h, 4);
   SHN_CHECK(h[2] == 0, "internal error: walk log overflow (component node count mismatch)");
   s->sz.n_traversed = h[0];
   s->sz.walk_rounds = h[1];
+  s->sz.spec_windows = h[3];
 
   // started walks in pop order (device compaction), then the walks long enough to matter
   uint64_t n_walks = 0, n_long = 0;

@@ -59,6 +59,31 @@ __device__ __forceinline__ int table_match_bucket(const ShnBucket& bk, uint64_t 
   return -1;
 }
 
+// Same, also returning the slot's idx word (the claim stamp of the speculative walks).
+__device__ __forceinline__ int table_match_bucket2(const ShnBucket& bk, uint64_t key, int* j_out,
+                                                   uint32_t* w_out, uint32_t* idx_out) {
+  bool has_empty = false;
+  int found = -1;
+  uint64_t wi = 0;
+#pragma unroll
+  for (int j = 0; j < SHN_BSLOTS; ++j) {
+    uint64_t k = bk.key(j);
+    if (k == key) {
+      found = j;
+      wi = bk.w[2 * j + 1];
+    }
+    has_empty |= k == SHN_EMPTY_KEY;
+  }
+  if (found >= 0) {
+    *j_out = found;
+    *w_out = (uint32_t)wi;
+    *idx_out = (uint32_t)(wi >> 32);
+    return 1;
+  }
+  if (has_empty || !(bk.weight(0) & SHN_OVERFLOW)) return 0;
+  return -1;
+}
+
 // Read-only probe: slot index of `key` or ~0; *w_out = raw weight word (flag bits included).
 __device__ __forceinline__ uint64_t table_find(const ShnTableView& t, uint64_t key, uint32_t* w_out) {
   uint64_t b = t.bucket_of(key);

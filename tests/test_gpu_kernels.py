@@ -103,7 +103,11 @@ def test_pack_and_lowcomplexity_edge_cases(ctx):
 
 # ---- a3-a9 ---------------------------------------------------------------------------------
 @pytest.mark.parametrize("kind,seed", CASES)
-def test_l3_stages_equal_oracle(ctx, workdir, kind, seed):
+@pytest.mark.parametrize("spec", [False, True])
+def test_l3_stages_equal_oracle(ctx, workdir, kind, seed, spec, monkeypatch):
+    # spec=True forces the speculative windowed walk kernel (normally only used for components
+    # with >= 60 k K1-mers) onto every component
+    monkeypatch.setenv("SHN_SPEC_MIN_NODES", "1" if spec else "1000000000")
     case, min_weight, min_length = _case(workdir, kind, seed)
     out = case.outdir("o")
     res = so.run_correction(case.k1mer_org, out + "/k", min_weight, min_length, False, out, 2,
@@ -121,6 +125,7 @@ def test_l3_stages_equal_oracle(ctx, workdir, kind, seed):
     assert nr.tolist() == [w.n_right for w in exp]
     assert tot.tolist() == [w.tot_wt for w in exp]
     assert sz["n_traversed"] == len(res.traversed)
+    assert (sz["n_spec_comps"] > 0) == spec
     assert [bool(f & 1) for f in flags] == [w.passes_shape for w in exp]
     assert [bool(f & 2) for f in flags] == [w.passes_shape and w.duplicate for w in exp]
     assert [bool(f & 4) for f in flags] == [w.accepted for w in exp]

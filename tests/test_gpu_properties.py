@@ -114,3 +114,22 @@ def test_read_partition_properties(run):
         # but an assignment always implies a hit
         assert (not assigned[r]) or hit
     assert stats["lookups"] == 8 * stats["valid_records"] == 8 * reads[0].shape[0]
+
+
+def test_speculative_walks_equal_serial_walks_at_scale(run, monkeypatch):
+    """The speculative windowed kernel (racy by construction, exact by in-order commit) must
+    reproduce the one-warp-per-component replay bit for bit on every walk of the 1 M-pair input,
+    whichever components it is applied to."""
+    ctx, out, _, keys, counts = run
+    results = []
+    for min_nodes in ("1000000000", "1", "20000"):
+        monkeypatch.setenv("SHN_SPEC_MIN_NODES", min_nodes)
+        ctx.table_build(keys, counts, K1, False)
+        sz = ctx.l3_run(3, 75)
+        results.append((sz, ctx.l3_walks(), ctx.l3_contigs()))
+    assert results[0][0]["n_spec_comps"] == 0 and results[1][0]["n_spec_comps"] > 0
+    for sz, walks, (bases, offs) in results[1:]:
+        assert sz["n_traversed"] == results[0][0]["n_traversed"]
+        for x, y in zip(walks, results[0][1]):
+            assert np.array_equal(x, y)
+        assert np.array_equal(bases, results[0][2][0]) and np.array_equal(offs, results[0][2][1])
