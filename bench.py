@@ -141,7 +141,8 @@ class Workload(object):
             [self.d_r1, self.d_r2], [self.n_records, self.n_records], READ_LEN, K1,
             max(1 << 20, windows // 4))
         self.count_s = time.perf_counter() - t0
-        self.h_offs = (np.arange(self.n_records + 1, dtype=np.uint64) * np.uint64(READ_LEN))
+        self.h_offs = ctx.pinned_empty(self.n_records + 1, np.uint64)
+        self.h_offs[:] = np.arange(self.n_records + 1, dtype=np.uint64) * np.uint64(READ_LEN)
         self.d_offs = ctx.to_device(self.h_offs)
         self.host = None
 

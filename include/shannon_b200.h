@@ -181,6 +181,12 @@ int shn_l4_map_window_weights(shn_ctx* ctx, const char* bases, const uint64_t* o
  * :336,376).  mate = 0 or 1. */
 int shn_l4_load_reads(shn_ctx* ctx, int mate, const char* bases, const uint64_t* offsets,
                       uint64_t n_reads, int on_device);
+/* Same in two halves, so that the host->device copy overlaps earlier stages: _async starts the
+ * copy of the host buffers (pinned memory for real overlap; they must stay valid until _staged
+ * returns) on the context's copy stream and returns; _staged waits for it and packs. */
+int shn_l4_upload_reads_async(shn_ctx* ctx, int mate, const char* bases, const uint64_t* offsets,
+                              uint64_t n_reads);
+int shn_l4_load_reads_staged(shn_ctx* ctx, int mate);
 /* get_rmers/get_comps/get_comps_paired + the chunk loop (kmers_for_component.py:186-205,
  * 322-423): samples K1-mers at offsets 0,K1,2*K1,... (< len-K1) plus the last K1-mer of every
  * read (both mates when paired), takes the UNION of the component ids hit, and groups the

@@ -75,6 +75,8 @@ SIGNATURES = {
     "shn_l4_map_set_weights": (C.c_int, [vp, vp, vp, C.c_uint64]),
     "shn_l4_map_window_weights": (C.c_int, [vp, vp, vp, C.c_uint64, C.c_int, vp]),
     "shn_l4_load_reads": (C.c_int, [vp, C.c_int, vp, vp, C.c_uint64, C.c_int]),
+    "shn_l4_upload_reads_async": (C.c_int, [vp, C.c_int, vp, vp, C.c_uint64]),
+    "shn_l4_load_reads_staged": (C.c_int, [vp, C.c_int]),
     "shn_l4_assign": (C.c_int, [vp, C.c_int, C.c_int, u64p, u64p, u64p]),
     "shn_l4_get_assignments": (C.c_int, [vp, C.c_uint32, vp, vp]),
     "shn_synth_pairs": (C.c_int, [vp, vp, vp, vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64,
@@ -409,6 +411,15 @@ class Context(HostIO):
             n = len(offsets) - 1
         self.call("shn_l4_load_reads", int(mate), ptr(bases), ptr(offsets), C.c_uint64(n),
                   int(bool(on_device)))
+
+    def l4_upload_reads_async(self, mate, bases, offsets):
+        """bases/offsets: C-contiguous host arrays that stay alive until l4_load_reads_staged."""
+        assert bases.dtype == np.uint8 and offsets.dtype == np.uint64
+        self.call("shn_l4_upload_reads_async", int(mate), ptr(bases), ptr(offsets),
+                  C.c_uint64(len(offsets) - 1))
+
+    def l4_load_reads_staged(self, mate):
+        self.call("shn_l4_load_reads_staged", int(mate))
 
     def l4_assign(self, paired, k1):
         na, nl, nv = C.c_uint64(), C.c_uint64(), C.c_uint64()

@@ -14,6 +14,11 @@ void shn_write_fasta_subset_impl(const char* path, int append, const char* bases
 void shn_write_k1mer_windows_impl(const char* path, const char* bases, const uint64_t* offsets,
                                   const uint32_t* contig_ids, uint64_t m, int k1,
                                   const uint32_t* weights, const uint64_t* win_off);
+void shn_table_begin_impl(shn_ctx* c, uint64_t n, int k1, int double_stranded);
+void shn_table_insert_chunk_impl(shn_ctx* c, const uint64_t* d_keys, const uint32_t* d_counts,
+                                 const uint32_t* d_line_idx, uint64_t n, uint64_t first_line,
+                                 int double_stranded);
+void shn_table_finish_impl(shn_ctx* c);
 void shn_l3_run_impl(shn_ctx* c, uint32_t min_weight, uint32_t min_length);
 void shn_l3_get_sizes_impl(shn_ctx* c, shn_l3_sizes* out);
 void shn_l3_get_walks_impl(shn_ctx* c, uint64_t* seed_keys, uint32_t* n_left, uint32_t* n_right,
@@ -32,6 +37,9 @@ void shn_l4_map_window_weights_impl(shn_ctx* c, const char* bases, const uint64_
                                     uint64_t n_contigs, int k1, uint32_t* h_weights);
 void shn_l4_load_reads_impl(shn_ctx* c, int mate, const char* bases, const uint64_t* offsets,
                             uint64_t n, int on_device);
+void shn_l4_upload_reads_async_impl(shn_ctx* c, int mate, const char* bases, const uint64_t* offsets,
+                                    uint64_t n);
+void shn_l4_load_reads_staged_impl(shn_ctx* c, int mate);
 void shn_l4_assign_impl(shn_ctx* c, int paired, int k1, uint64_t* n_assign, uint64_t* n_lookups,
                         uint64_t* n_valid);
 void shn_l4_get_assignments_impl(shn_ctx* c, uint32_t n_comps, uint64_t* h_offs, uint32_t* h_idx);
@@ -312,10 +320,37 @@ int shn_table_build(shn_ctx* c, const uint64_t* keys, const uint32_t* counts, ui
   SHN_API_BEGIN
   bind(c);
   shn_l3_free(c);
-  DevBuf sk, sc;
-  const uint64_t* dk = (const uint64_t*)InputView::get(c, keys, n * 8, on_device, sk);
-  const uint32_t* dc = (const uint32_t*)InputView::get(c, counts, n * 4, on_device, sc);
-  shn_table_build_impl(c, dk, dc, n, k1, double_stranded);
+  if (on_device || n == 0) {
+    shn_table_build_impl(c, keys, counts, n, k1, double_stranded);
+  } else {
+    // host input: copy chunk i+1 on the copy stream while chunk i is being inserted
+    DevBuf sk, sc;
+    sk.reserve(n * 8);
+    sc.reserve(n * 4);
+    if (!c->stream2) CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+    shn_table_begin_impl(c, n, k1, double_stranded);
+    const uint64_t chunk = 32ull << 20;
+    std::vector<cudaEvent_t> evs;
+    {
+      cudaEvent_t ev = c->prof_event();  // the staging buffers may still be in use on the main stream
+      CUDA_CHECK(cudaEventRecord(ev, c->stream));
+      CUDA_CHECK(cudaStreamWaitEvent(c->stream2, ev, 0));
+      evs.push_back(ev);
+    }
+    for (uint64_t lo = 0; lo < n; lo += chunk) {
+      const uint64_t m = std::min(chunk, n - lo);
+      CUDA_CHECK(cudaMemcpyAsync(sk.as<uint64_t>() + lo, keys + lo, m * 8, cudaMemcpyHostToDevice, c->stream2));
+      CUDA_CHECK(cudaMemcpyAsync(sc.as<uint32_t>() + lo, counts + lo, m * 4, cudaMemcpyHostToDevice, c->stream2));
+      cudaEvent_t ev = c->prof_event();
+      CUDA_CHECK(cudaEventRecord(ev, c->stream2));
+      CUDA_CHECK(cudaStreamWaitEvent(c->stream, ev, 0));
+      evs.push_back(ev);
+      shn_table_insert_chunk_impl(c, sk.as<uint64_t>() + lo, sc.as<uint32_t>() + lo, nullptr, m, lo,
+                                  double_stranded);
+    }
+    shn_table_finish_impl(c);
+    for (cudaEvent_t ev : evs) c->prof_pool.push_back(ev);
+  }
   SHN_API_END(c)
 }
 
@@ -469,6 +504,19 @@ int shn_l4_load_reads(shn_ctx* c, int mate, const char* bases, const uint64_t* o
   SHN_API_BEGIN
   bind(c);
   shn_l4_load_reads_impl(c, mate, bases, offsets, n_reads, on_device);
+  SHN_API_END(c)
+}
+int shn_l4_upload_reads_async(shn_ctx* c, int mate, const char* bases, const uint64_t* offsets,
+                              uint64_t n_reads) {
+  SHN_API_BEGIN
+  bind(c);
+  shn_l4_upload_reads_async_impl(c, mate, bases, offsets, n_reads);
+  SHN_API_END(c)
+}
+int shn_l4_load_reads_staged(shn_ctx* c, int mate) {
+  SHN_API_BEGIN
+  bind(c);
+  shn_l4_load_reads_staged_impl(c, mate);
   SHN_API_END(c)
 }
 int shn_l4_assign(shn_ctx* c, int paired, int k1, uint64_t* n_assignments, uint64_t* n_lookups,

@@ -40,6 +40,10 @@ struct L4State {
   DevBuf assign;    // uint64 entries (comp << 32 | record), sorted + unique after shn_l4_assign
   uint64_t n_assign = 0;
   DevBuf stage_a, stage_b, stage_c;
+  // reads uploaded ahead of time on the copy stream (overlaps the H2D with the L3 stage)
+  DevBuf up_bases[2], up_offs[2];
+  uint64_t up_n[2] = {0, 0};
+  cudaEvent_t up_done[2] = {nullptr, nullptr};
 };
 
 namespace {
@@ -411,6 +415,9 @@ void read_counters(shn_ctx* c, unsigned long long* h, int n) {
 }  // namespace
 
 void shn_l4_free(shn_ctx* c) {
+  if (c->l4)
+    for (int m = 0; m < 2; ++m)
+      if (c->l4->up_done[m]) cudaEventDestroy(c->l4->up_done[m]);
   delete c->l4;
   c->l4 = nullptr;
 }
@@ -564,6 +571,42 @@ void shn_l4_load_reads_impl(shn_ctx* c, int mate, const char* bases, const uint6
     KERNEL_CHECK();
   }
   CUDA_CHECK(cudaStreamSynchronize(c->stream));
+}
+
+// Starts the host->device copy of one mate file on the context's second stream and returns
+// immediately; shn_l4_load_reads_staged() later waits for it and packs.  With pinned host memory
+// the copy overlaps whatever the main stream does meanwhile (the whole L3 stage in the pipeline).
+void shn_l4_upload_reads_async_impl(shn_ctx* c, int mate, const char* bases, const uint64_t* offsets,
+                                    uint64_t n) {
+  SHN_CHECK(mate == 0 || mate == 1, "mate must be 0 or 1");
+  L4State* s = l4_of(c);
+  if (!c->stream2) CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+  if (!s->up_done[mate]) CUDA_CHECK(cudaEventCreateWithFlags(&s->up_done[mate], cudaEventDisableTiming));
+  s->up_n[mate] = n;
+  const uint64_t total = n ? offsets[n] : 0;
+  s->up_bases[mate].reserve(std::max<uint64_t>(total, 1));
+  s->up_offs[mate].reserve((n + 1) * 8);
+  // the staging buffers may have been used by kernels still queued on the main stream
+  cudaEvent_t ev = c->prof_event();
+  CUDA_CHECK(cudaEventRecord(ev, c->stream));
+  CUDA_CHECK(cudaStreamWaitEvent(c->stream2, ev, 0));
+  c->prof_pool.push_back(ev);
+  if (total)
+    CUDA_CHECK(cudaMemcpyAsync(s->up_bases[mate].p, bases, total, cudaMemcpyHostToDevice, c->stream2));
+  CUDA_CHECK(cudaMemcpyAsync(s->up_offs[mate].p, offsets, (n + 1) * 8, cudaMemcpyHostToDevice, c->stream2));
+  CUDA_CHECK(cudaEventRecord(s->up_done[mate], c->stream2));
+}
+
+void shn_l4_load_reads_impl(shn_ctx* c, int mate, const char* bases, const uint64_t* offsets,
+                            uint64_t n, int on_device);
+
+void shn_l4_load_reads_staged_impl(shn_ctx* c, int mate) {
+  SHN_CHECK(mate == 0 || mate == 1, "mate must be 0 or 1");
+  L4State* s = l4_of(c);
+  SHN_CHECK(s->up_done[mate] != nullptr, "no upload in flight for this mate");
+  CUDA_CHECK(cudaStreamWaitEvent(c->stream, s->up_done[mate], 0));
+  shn_l4_load_reads_impl(c, mate, s->up_bases[mate].as<char>(), s->up_offs[mate].as<uint64_t>(),
+                         s->up_n[mate], 1);
 }
 
 void shn_l4_assign_impl(shn_ctx* c, int paired, int k1, uint64_t* n_assign, uint64_t* n_lookups,

@@ -32,14 +32,15 @@ __global__ void __launch_bounds__(kBlock) table_clear_kernel(ShnSlot* slots, uin
 __global__ void __launch_bounds__(kBlock)
     table_insert_kernel(ShnTableView t, const uint64_t* __restrict__ keys,
                         const uint32_t* __restrict__ counts, const uint32_t* __restrict__ line_idx,
-                        uint64_t n, int k1, int ds, unsigned long long* counters) {
+                        uint64_t n, uint64_t first_line, int k1, int ds,
+                        unsigned long long* counters) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int n_new = 0, n_low = 0, n_bad = 0;
   if (i < n) {
     uint64_t key = keys[i];
     uint32_t w = counts[i];
     // explicit line indices (sharded build: the global input line of every routed key)
-    uint64_t base_idx = line_idx ? (uint64_t)line_idx[i] : (ds ? 2 * i : i);
+    uint64_t base_idx = line_idx ? (uint64_t)line_idx[i] : (ds ? 2 * (first_line + i) : first_line + i);
     if ((key & ~shn_kmer_mask(k1)) || base_idx + 1 >= 0xFFFFFFFFull || w >= SHN_WEIGHT_MASK) {
       n_bad = 1;
     } else if (shn_low_complexity(key, k1)) {  // rc(kmer) is low-complexity iff kmer is
@@ -135,9 +136,9 @@ void shn_pack_kmers_impl(shn_ctx* c, const char* d_ascii, uint64_t n, int k1, ui
   SHN_CHECK(h == 0, "k-mer contains a character outside ACGT");
 }
 
-void shn_table_build_impl(shn_ctx* c, const uint64_t* d_keys, const uint32_t* d_counts, uint64_t n,
-                          int k1, int double_stranded, const uint32_t* d_line_idx) {
-  SHN_CHECK(!(double_stranded && d_line_idx), "explicit line indices exclude double_stranded");
+// The build in three parts so that a host-resident input can be copied in chunks on the copy
+// stream while earlier chunks are being inserted (shn_table_build, api.cu).
+void shn_table_begin_impl(shn_ctx* c, uint64_t n, int k1, int double_stranded) {
   SHN_CHECK(k1 >= 1 && k1 <= 32, "k1 must be in 1..32 (K <= 31); wider keys are not built yet");
   uint64_t items = n * (double_stranded ? 2 : 1);
   SHN_CHECK(items < 0xFFFFFFFEull, "more than 2^32-2 input K1-mers per table");
@@ -150,26 +151,40 @@ void shn_table_build_impl(shn_ctx* c, const uint64_t* d_keys, const uint32_t* d_
   c->counters.reserve(64 * sizeof(unsigned long long));
   unsigned long long* ctr = c->counters.as<unsigned long long>();
   CUDA_CHECK(cudaMemsetAsync(ctr, 0, 8 * sizeof(unsigned long long), c->stream));
-  {
-    ProfScope ps(c, "table_clear");
-    unsigned grid = (unsigned)std::min<uint64_t>((n_buckets * SHN_BSLOTS + kBlock - 1) / kBlock,
-                                                 (uint64_t)c->sm_count * 32);
-    table_clear_kernel<<<grid, kBlock, 0, c->stream>>>(c->table.as<ShnSlot>(), n_buckets * SHN_BSLOTS);
-    KERNEL_CHECK();
-  }
-  if (n > 0) {
-    ProfScope ps(c, "table_insert");
-    table_insert_kernel<<<shn_grid(n, kBlock), kBlock, 0, c->stream>>>(c->view(), d_keys, d_counts,
-                                                                       d_line_idx, n, k1,
-                                                                       double_stranded, ctr);
-    KERNEL_CHECK();
-  }
+  ProfScope ps(c, "table_clear");
+  unsigned grid = (unsigned)std::min<uint64_t>((n_buckets * SHN_BSLOTS + kBlock - 1) / kBlock,
+                                               (uint64_t)c->sm_count * 32);
+  table_clear_kernel<<<grid, kBlock, 0, c->stream>>>(c->table.as<ShnSlot>(), n_buckets * SHN_BSLOTS);
+  KERNEL_CHECK();
+}
+
+// lines [first_line, first_line + n) of the input; d_keys/d_counts point at this chunk
+void shn_table_insert_chunk_impl(shn_ctx* c, const uint64_t* d_keys, const uint32_t* d_counts,
+                                 const uint32_t* d_line_idx, uint64_t n, uint64_t first_line,
+                                 int double_stranded) {
+  if (n == 0) return;
+  ProfScope ps(c, "table_insert");
+  table_insert_kernel<<<shn_grid(n, kBlock), kBlock, 0, c->stream>>>(
+      c->view(), d_keys, d_counts, d_line_idx, n, first_line, c->k1, double_stranded,
+      c->counters.as<unsigned long long>());
+  KERNEL_CHECK();
+}
+
+void shn_table_finish_impl(shn_ctx* c) {
   unsigned long long h[4];
-  CUDA_CHECK(cudaMemcpyAsync(h, ctr, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_CHECK(cudaMemcpyAsync(h, c->counters.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
   CUDA_CHECK(cudaStreamSynchronize(c->stream));
   SHN_CHECK(h[3] == 0, "table build: key wider than 2*k1 bits, a K1-mer weight above 2^30-2, or input index overflow");
   c->n_distinct = h[0];
   c->n_lowcomplexity = h[1];
+}
+
+void shn_table_build_impl(shn_ctx* c, const uint64_t* d_keys, const uint32_t* d_counts, uint64_t n,
+                          int k1, int double_stranded, const uint32_t* d_line_idx) {
+  SHN_CHECK(!(double_stranded && d_line_idx), "explicit line indices exclude double_stranded");
+  shn_table_begin_impl(c, n, k1, double_stranded);
+  shn_table_insert_chunk_impl(c, d_keys, d_counts, d_line_idx, n, 0, double_stranded);
+  shn_table_finish_impl(c);
 }
 
 void shn_table_lookup_impl(shn_ctx* c, const uint64_t* d_keys, uint64_t n, uint32_t* d_weights,

@@ -151,11 +151,21 @@ def build_component_map(ctx, ctg_bases, ctg_offs, ctg_comp, k1, dict_keys, dict_
     return total_windows
 
 
-def partition_reads(ctx, mates, paired, k1, n_comps):
+def upload_reads_early(ctx, mates):
+    """Start the H2D copy of host-resident read files now (it overlaps the L3 stage)."""
+    for m, (bases, offs, n, on_dev) in enumerate(mates):
+        if not on_dev:
+            ctx.l4_upload_reads_async(m, bases, offs)
+
+
+def partition_reads(ctx, mates, paired, k1, n_comps, staged=False):
     """get_comps over all records (kmers_for_component.py:322-423).  mates: list of
     (bases, offsets, n, on_device).  Returns (comp_offsets, record_idx, stats)."""
     for m, (bases, offs, n, on_dev) in enumerate(mates):
-        ctx.l4_load_reads(m, bases, offs, n=n, on_device=on_dev)
+        if staged and not on_dev:
+            ctx.l4_load_reads_staged(m)
+        else:
+            ctx.l4_load_reads(m, bases, offs, n=n, on_device=on_dev)
     n_assign, n_lookups, n_valid = ctx.l4_assign(paired, k1)
     comp_offs, rec_idx = ctx.l4_assignments(n_comps, n_assign)
     return comp_offs.astype(np.int64), rec_idx, {"assignments": n_assign, "lookups": n_lookups,
@@ -169,6 +179,7 @@ def frontend_in_memory(ctx, keys, counts, k1, mates, paired, min_weight=3, min_l
     the gpmetis stand-in."""
     import time
     tm = {}
+    upload_reads_early(ctx, mates)
     cor = correct(ctx, keys, counts, k1, False, min_weight, min_length, on_device, n_kmers, tm,
                   fetch_allowed=False)
     t0 = time.perf_counter()
@@ -196,7 +207,7 @@ def frontend_in_memory(ctx, keys, counts, k1, mates, paired, min_weight=3, min_l
                         cor.allowed_keys, cor.allowed_weights)
     tm["map_build"] = time.perf_counter() - t0
     t0 = time.perf_counter()
-    comp_offs, rec_idx, stats = partition_reads(ctx, mates, paired, k1, n_comps)
+    comp_offs, rec_idx, stats = partition_reads(ctx, mates, paired, k1, n_comps, staged=True)
     tm["partition_reads"] = time.perf_counter() - t0
     stats["host_timings_ms"] = dict((k, 1000.0 * v) for k, v in tm.items())
     stats.update(cor.sizes)
