@@ -317,6 +317,7 @@ __global__ void __launch_bounds__(kBlock)
 struct WalkArgs {
   ShnSlot* local;               // component-local table (all regions)
   const uint64_t* region_off;   // [n_comps+1] first bucket of every component's region
+  uint64_t lookahead_min_buckets;  // walk_kernel: regions below this size walk without look-ahead
   int k1;
   uint32_t n_comps;
   const uint32_t* comp_order;   // components sorted by seed count (descending)
@@ -365,8 +366,12 @@ __global__ void __launch_bounds__(kWalkBlock, 4) walk_kernel(WalkArgs a) {
   long long mem_cycles = 0, t_begin = clock64();
   const bool tracing = a.trace != nullptr;
   bool overflow = false;
+  // Small components finish long before the large ones: they skip the second-level prefetch (one
+  // step per round, 4 instead of 20 probes) and leave the DRAM bandwidth to the components whose
+  // latency is the critical path.
+  const bool look = tv.n_buckets >= a.lookahead_min_buckets;
   // role of this lane inside a round: level 1 (lanes 0..3), level 2 (lanes 4..19), idle
-  const int lvl = lane < 4 ? 1 : (lane < 20 ? 2 : 0);
+  const int lvl = lane < 4 ? 1 : ((look && lane < 20) ? 2 : 0);
   const uint64_t b1 = lvl == 1 ? lane : ((lane - 4) >> 2);  // first appended base
   const uint64_t b2 = (lane - 4) & 3;                       // second appended base (level 2)
 
@@ -476,6 +481,11 @@ __global__ void __launch_bounds__(kWalkBlock, 4) walk_kernel(WalkArgs a) {
           ++traversed;
           tot += bw1;
           ++n_dir[dir];
+          if (!look) {  // warp-uniform: no prefetched level, continue from c1
+            cur = c1;
+            __syncwarp();
+            continue;
+          }
           // ---- second step from the prefetched level: group 4+4*w1; c1 is traversed by now ---
           const int g2 = 4 + 4 * w1;
           if (lane >= g2 && lane < g2 + 4 && state < 0) {
@@ -1305,6 +1315,10 @@ void shn_l3_run_impl(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
     WalkArgs a;
     a.local = local.as<ShnSlot>();
     a.region_off = region_off.as<uint64_t>();
+    {
+      const char* envl = getenv("SHN_LOOKAHEAD_MIN_NODES");
+      a.lookahead_min_buckets = (envl ? strtoull(envl, nullptr, 10) : 0ull) / 2;
+    }
     a.k1 = k1;
     a.n_comps = n_active;
     a.comp_order = comp_order.as<uint32_t>();

@@ -72,7 +72,7 @@ class Correction(object):
 
 
 def correct(ctx, keys, counts, k1, double_stranded, min_weight, min_length, on_device=False,
-            n=None, timings=None, fetch_allowed=True):
+            n=None, timings=None, fetch_allowed=True, after_table_build=None):
     """load_kmers .. DFS (extension_correction.py:317-450) on the GPU.  keys/counts: host numpy
     arrays, or device pointers with on_device=True and n given."""
     import time
@@ -80,6 +80,8 @@ def correct(ctx, keys, counts, k1, double_stranded, min_weight, min_length, on_d
     t0 = time.perf_counter()
     ctx.table_build(keys, counts, k1, double_stranded, on_device=on_device, n=n)
     tm["table_build"] = time.perf_counter() - t0
+    if after_table_build is not None:
+        after_table_build()      # e.g. start the read upload now that the copy engine is free
     cor = Correction()
     cor.k1 = k1
     cor.n_loaded = ctx.table_stats()["n_distinct"]
@@ -179,9 +181,8 @@ def frontend_in_memory(ctx, keys, counts, k1, mates, paired, min_weight=3, min_l
     the gpmetis stand-in."""
     import time
     tm = {}
-    upload_reads_early(ctx, mates)
     cor = correct(ctx, keys, counts, k1, False, min_weight, min_length, on_device, n_kmers, tm,
-                  fetch_allowed=False)
+                  fetch_allowed=False, after_table_build=lambda: upload_reads_early(ctx, mates))
     t0 = time.perf_counter()
     pk = pack_components(cor, partition_size)
     entries, comp_ids = [], []
