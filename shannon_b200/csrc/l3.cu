@@ -926,11 +926,11 @@ __global__ void __launch_bounds__(kBlock)
     dup_round_kernel(const uint64_t* __restrict__ seg_off, const uint32_t* __restrict__ lo,
                      const uint32_t* __restrict__ count, const uint32_t* __restrict__ max_i,
                      const uint32_t* __restrict__ covered, const uint64_t* __restrict__ cand_off,
-                     uint64_t n_cand, const uint8_t* __restrict__ status_in,
+                     uint64_t lo_cand, uint64_t hi_cand, const uint8_t* __restrict__ status_in,
                      uint8_t* __restrict__ status_out, uint8_t* __restrict__ dup_flag,
                      unsigned long long* counters) {
-  uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n_cand) return;
+  uint64_t j = lo_cand + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= hi_cand) return;
   uint8_t st = status_in[j];
   if (st != 0) {
     status_out[j] = st;
@@ -1526,7 +1526,7 @@ void shn_l3_run_impl(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
     uint64_t n_ent = 0;
     CUDA_CHECK(cudaMemcpyAsync(&n_ent, ent_off.as<uint64_t>() + n_cand, 8, cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaStreamSynchronize(st));
-    PairTable pt;
+    SelfJoin sj;
     if (n_ent) {
       DevBuf keys, owner, pos;
       keys.reserve(n_ent * 8);
@@ -1539,28 +1539,37 @@ void shn_l3_run_impl(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
             cand_bases, R, 0u, keys.as<uint64_t>(), owner.as<uint32_t>(), pos.as<uint32_t>());
         KERNEL_CHECK();
       }
-      shn_self_join(c, keys.as<uint64_t>(), owner.as<uint32_t>(), pos.as<uint32_t>(), n_ent, 2 * R, R, &pt,
-                    "rmer");
+      sj.prepare(c, "rmer", keys.as<uint64_t>(), owner.as<uint32_t>(), pos.as<uint32_t>(), n_ent, 2 * R, R);
     }
-    if (pt.n) {
-      DevBuf seg_off, st_a, st_b, dupf;
-      seg_off.reserve((n_cand + 2) * 8);
-      st_a.reserve(n_cand);
-      st_b.reserve(n_cand);
-      dupf.reserve(n_cand);
-      CUDA_CHECK(cudaMemsetAsync(st_a.p, 0, n_cand, st));
-      CUDA_CHECK(cudaMemsetAsync(dupf.p, 0, n_cand, st));
+    // Candidates are resolved in blocks of ascending rank: when a block is joined, every earlier
+    // candidate is already accepted or rejected, and rejected ones (the bulk: near-duplicates of a
+    // few accepted contigs) never produce match events again.
+    DevBuf seg_off, st_a, st_b, dupf;
+    seg_off.reserve((n_cand + 2) * 8);
+    st_a.reserve(n_cand);
+    st_b.reserve(n_cand);
+    dupf.reserve(n_cand);
+    CUDA_CHECK(cudaMemsetAsync(st_a.p, 0, n_cand, st));
+    CUDA_CHECK(cudaMemsetAsync(dupf.p, 0, n_cand, st));
+    const char* envb = getenv("SHN_DUP_BLOCKS");
+    const uint64_t n_blocks = std::max<uint64_t>(1, envb ? strtoull(envb, nullptr, 10) : 4);
+    const uint64_t block = std::max<uint64_t>(4096, (n_cand + n_blocks - 1) / n_blocks);
+    uint64_t rounds = 0;
+    PairTable pt;
+    for (uint64_t lo = 0; lo < n_cand; lo += block) {
+      const uint64_t hi = std::min(n_cand, lo + block);
+      sj.join((uint32_t)lo, (uint32_t)hi, st_a.as<uint8_t>(), &pt);
       seg_offsets_kernel<<<shn_grid(pt.n + 1, kBlock), kBlock, 0, st>>>(pt.hi.as<uint32_t>(), pt.n,
                                                                         n_cand, seg_off.as<uint64_t>());
       KERNEL_CHECK();
-      uint64_t rounds = 0;
-      for (;;) {
+      CUDA_CHECK(cudaMemcpyAsync(st_b.p, st_a.p, n_cand, cudaMemcpyDeviceToDevice, st));
+      for (uint64_t r_in_block = 0;; ++r_in_block) {
         ctr = zero_counters(c);
         {
           ProfScope ps(c, "dup_round");
-          dup_round_kernel<<<shn_grid(n_cand, kBlock), kBlock, 0, st>>>(
+          dup_round_kernel<<<shn_grid(hi - lo, kBlock), kBlock, 0, st>>>(
               seg_off.as<uint64_t>(), pt.lo.as<uint32_t>(), pt.count.as<uint32_t>(),
-              pt.max_i.as<uint32_t>(), pt.covered.as<uint32_t>(), d_cand_off.as<uint64_t>(), n_cand,
+              pt.max_i.as<uint32_t>(), pt.covered.as<uint32_t>(), d_cand_off.as<uint64_t>(), lo, hi,
               st_a.as<uint8_t>(), st_b.as<uint8_t>(), dupf.as<uint8_t>(), ctr);
           KERNEL_CHECK();
         }
@@ -1569,12 +1578,15 @@ void shn_l3_run_impl(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
         std::swap(st_a.p, st_b.p);
         std::swap(st_a.bytes, st_b.bytes);
         if (h[0] == 0) break;
-        SHN_CHECK(rounds <= n_cand + 1, "internal error: duplicate filter does not converge");
+        SHN_CHECK(r_in_block <= hi - lo + 1, "internal error: duplicate filter does not converge");
       }
-      s->sz.dup_rounds = rounds;
-      d2h(c, h_status, st_a.p, n_cand);
-      d2h(c, h_dup, dupf.p, n_cand);
+      // both buffers agree outside [lo, hi); make them agree inside as well
+      CUDA_CHECK(cudaMemcpyAsync(st_b.as<uint8_t>() + lo, st_a.as<uint8_t>() + lo, hi - lo,
+                                 cudaMemcpyDeviceToDevice, st));
     }
+    s->sz.dup_rounds = rounds;
+    d2h(c, h_status, st_a.p, n_cand);
+    d2h(c, h_dup, dupf.p, n_cand);
   }
   // accepted contigs, acceptance order = pop order
   std::vector<uint32_t> acc_cand;
@@ -1668,8 +1680,9 @@ void shn_l3_run_impl(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
             contig_bases, C, 1u, keys.as<uint64_t>(), owner.as<uint32_t>(), pos.as<uint32_t>());
         KERNEL_CHECK();
       }
-      shn_self_join(c, keys.as<uint64_t>(), owner.as<uint32_t>(), pos.as<uint32_t>(), n_ent, 2 * C, 1,
-                    &s->edges, "cmer");
+      SelfJoin cj;
+      cj.prepare(c, "cmer", keys.as<uint64_t>(), owner.as<uint32_t>(), pos.as<uint32_t>(), n_ent, 2 * C, 1);
+      cj.join(0u, 0xFFFFFFFFu, nullptr, &s->edges);
     }
   }
   s->sz.n_edges = s->edges.n;

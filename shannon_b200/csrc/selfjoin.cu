@@ -35,34 +35,48 @@ struct MaxOp {
   __device__ __forceinline__ uint32_t operator()(uint32_t a, uint32_t b) const { return a > b ? a : b; }
 };
 
+// number of qualifying partners of sorted entry p (0 for entries whose owner is outside [lo,hi))
 __global__ void __launch_bounds__(kBlock)
-    lowcount_kernel(const uint32_t* __restrict__ run_start, const uint32_t* __restrict__ grp_start,
-                    uint64_t n, uint64_t* __restrict__ lowcount) {
+    count_partners_kernel(const uint32_t* __restrict__ owner_s, const uint32_t* __restrict__ run_start,
+                          const uint32_t* __restrict__ grp_start, uint64_t n, uint32_t lo, uint32_t hi,
+                          const uint8_t* __restrict__ status, uint64_t* __restrict__ cnt) {
   uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p < n) lowcount[p] = (uint64_t)(grp_start[p] - run_start[p]);
-  if (p == n) lowcount[p] = 0;
+  if (p > n) return;
+  uint64_t c = 0;
+  if (p < n) {
+    uint32_t o = owner_s[p];
+    if (o >= lo && o < hi) {
+      uint32_t a = run_start[p], b = grp_start[p];
+      if (!status) {
+        c = b - a;
+      } else {
+        for (uint32_t q = a; q < b; ++q) {
+          uint32_t d = owner_s[q];
+          c += (d >= lo || status[d] == 1) ? 1 : 0;
+        }
+      }
+    }
+  }
+  cnt[p] = c;
 }
 
-// one thread per event e: p = last index with ev_off[p] <= e
+// one thread per sorted entry p: its events (j = owner(p), d = owner(q), i = pos(p))
 __global__ void __launch_bounds__(kBlock)
     emit_events_kernel(const uint64_t* __restrict__ ev_off, const uint32_t* __restrict__ run_start,
-                       const uint32_t* __restrict__ owner_s, const uint32_t* __restrict__ pos_s,
-                       uint64_t n, uint64_t n_events, int bits_owner, int bits_pos,
+                       const uint32_t* __restrict__ grp_start, const uint32_t* __restrict__ owner_s,
+                       const uint32_t* __restrict__ pos_s, uint64_t n, uint32_t lo, uint32_t hi,
+                       const uint8_t* __restrict__ status, int bits_owner, int bits_pos,
                        uint64_t* __restrict__ ev) {
-  uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= n_events) return;
-  uint64_t lo = 0, hi = n;  // ev_off[lo] <= e < ev_off[hi]  (ev_off[n] = n_events)
-  while (hi - lo > 1) {
-    uint64_t mid = (lo + hi) >> 1;
-    if (__ldg(&ev_off[mid]) <= e)
-      lo = mid;
-    else
-      hi = mid;
+  uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  uint64_t e = ev_off[p];
+  if (ev_off[p + 1] == e) return;
+  const uint64_t j = owner_s[p], i = pos_s[p];
+  const uint64_t head = (j << (bits_owner + bits_pos)) | i;
+  for (uint32_t q = run_start[p], b = grp_start[p]; q < b; ++q) {
+    uint32_t d = owner_s[q];
+    if (!status || d >= lo || status[d] == 1) ev[e++] = head | ((uint64_t)d << bits_pos);
   }
-  uint64_t p = lo;
-  uint64_t q = (uint64_t)run_start[p] + (e - ev_off[p]);
-  uint64_t j = owner_s[p], d = owner_s[q], i = pos_s[p];
-  ev[e] = (j << (bits_owner + bits_pos)) | (d << bits_pos) | i;
 }
 
 struct EvVal {
@@ -133,17 +147,17 @@ int bits_for(uint64_t max_value) {
 
 }  // namespace
 
-void shn_self_join(shn_ctx* c, const uint64_t* d_keys, const uint32_t* d_owner,
-                   const uint32_t* d_pos, uint64_t n, int key_bits, uint32_t r, PairTable* out,
-                   const char* tag) {
-  const std::string T(tag);
-  const std::string n_sort = T + "_sort_keys", n_heads = T + "_runs", n_emit = T + "_emit_events",
-                    n_sort2 = T + "_sort_events", n_reduce = T + "_reduce_pairs";
-  out->n = 0;
+void SelfJoin::prepare(shn_ctx* ctx, const char* tag_, const uint64_t* d_keys, const uint32_t* d_owner,
+                       const uint32_t* d_pos, uint64_t n_, int key_bits, uint32_t r_) {
+  c = ctx;
+  tag = tag_;
+  n = n_;
+  r = r_;
   if (n == 0) return;
   SHN_CHECK(n < 0xFFFFFFFFull, "self-join: more than 2^32-1 entries");
   cudaStream_t st = c->stream;
-  DevBuf keys_s, idx, idx_s, owner_s, pos_s, run_head, grp_head, run_start, grp_start, lowcount, ev_off;
+  const std::string n_sort = tag + "_sort_keys", n_heads = tag + "_runs";
+  DevBuf keys_s, idx, idx_s, run_head, grp_head;
   keys_s.reserve(n * 8);
   idx.reserve(n * 4);
   idx_s.reserve(n * 4);
@@ -158,7 +172,7 @@ void shn_self_join(shn_ctx* c, const uint64_t* d_keys, const uint32_t* d_owner,
                                              idx.as<uint32_t>(), idx_s.as<uint32_t>(), (int64_t)n, 0,
                                              key_bits, st));
   ps.reset();
-  ps.reset(new ProfScope(c, n_heads.c_str(), 7));
+  ps.reset(new ProfScope(c, n_heads.c_str(), 6));
   owner_s.reserve(n * 4);
   pos_s.reserve(n * 4);
   run_head.reserve(n * 4);
@@ -176,45 +190,53 @@ void shn_self_join(shn_ctx* c, const uint64_t* d_keys, const uint32_t* d_owner,
                                             run_start.as<uint32_t>(), MaxOp(), (int64_t)n, st));
   CUDA_CHECK(cub::DeviceScan::InclusiveScan(c->tmp(tb), tb, grp_head.as<uint32_t>(),
                                             grp_start.as<uint32_t>(), MaxOp(), (int64_t)n, st));
-  lowcount.reserve((n + 1) * 8);
-  ev_off.reserve((n + 1) * 8);
-  lowcount_kernel<<<shn_grid(n + 1, kBlock), kBlock, 0, st>>>(
-      run_start.as<uint32_t>(), grp_start.as<uint32_t>(), n, lowcount.as<uint64_t>());
-  KERNEL_CHECK();
+  // bit budget of the composite event key (j | d | i)
+  DevBuf mx;
+  mx.reserve(8);
   tb = 0;
-  CUDA_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, tb, lowcount.as<uint64_t>(), ev_off.as<uint64_t>(),
+  CUDA_CHECK(cub::DeviceReduce::Max(nullptr, tb, d_owner, mx.as<uint32_t>(), (int64_t)n, st));
+  CUDA_CHECK(cub::DeviceReduce::Max(c->tmp(tb), tb, d_owner, mx.as<uint32_t>(), (int64_t)n, st));
+  CUDA_CHECK(cub::DeviceReduce::Max(c->tmp(tb), tb, d_pos, mx.as<uint32_t>() + 1, (int64_t)n, st));
+  uint32_t h[2];
+  CUDA_CHECK(cudaMemcpyAsync(h, mx.p, 8, cudaMemcpyDeviceToHost, st));
+  CUDA_CHECK(cudaStreamSynchronize(st));
+  bits_owner = bits_for(h[0]);
+  bits_pos = bits_for(h[1]);
+  SHN_CHECK(2 * bits_owner + bits_pos <= 64,
+            "self-join: contig count / length exceed the 64-bit event key budget");
+}
+
+void SelfJoin::join(uint32_t lo, uint32_t hi, const uint8_t* d_status, PairTable* out) {
+  out->n = 0;
+  if (n == 0) return;
+  cudaStream_t st = c->stream;
+  const std::string n_emit = tag + "_emit_events", n_sort2 = tag + "_sort_events",
+                    n_reduce = tag + "_reduce_pairs";
+  const int bo = bits_owner, bp = bits_pos;
+  DevBuf cnt, ev_off;
+  cnt.reserve((n + 1) * 8);
+  ev_off.reserve((n + 1) * 8);
+  std::unique_ptr<ProfScope> ps(new ProfScope(c, n_emit.c_str(), 3));
+  count_partners_kernel<<<shn_grid(n + 1, kBlock), kBlock, 0, st>>>(
+      owner_s.as<uint32_t>(), run_start.as<uint32_t>(), grp_start.as<uint32_t>(), n, lo, hi, d_status,
+      cnt.as<uint64_t>());
+  KERNEL_CHECK();
+  size_t tb = 0;
+  CUDA_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, tb, cnt.as<uint64_t>(), ev_off.as<uint64_t>(),
                                            (int64_t)(n + 1), st));
-  CUDA_CHECK(cub::DeviceScan::ExclusiveSum(c->tmp(tb), tb, lowcount.as<uint64_t>(),
-                                           ev_off.as<uint64_t>(), (int64_t)(n + 1), st));
+  CUDA_CHECK(cub::DeviceScan::ExclusiveSum(c->tmp(tb), tb, cnt.as<uint64_t>(), ev_off.as<uint64_t>(),
+                                           (int64_t)(n + 1), st));
   uint64_t n_events = 0;
   CUDA_CHECK(cudaMemcpyAsync(&n_events, ev_off.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, st));
-  // bit budget of the composite event key (j | d | i)
-  uint32_t max_owner = 0, max_pos = 0;
-  {
-    DevBuf mx;
-    mx.reserve(8);
-    tb = 0;
-    CUDA_CHECK(cub::DeviceReduce::Max(nullptr, tb, d_owner, mx.as<uint32_t>(), (int64_t)n, st));
-    CUDA_CHECK(cub::DeviceReduce::Max(c->tmp(tb), tb, d_owner, mx.as<uint32_t>(), (int64_t)n, st));
-    CUDA_CHECK(cub::DeviceReduce::Max(c->tmp(tb), tb, d_pos, mx.as<uint32_t>() + 1, (int64_t)n, st));
-    uint32_t h[2];
-    CUDA_CHECK(cudaMemcpyAsync(h, mx.p, 8, cudaMemcpyDeviceToHost, st));
-    CUDA_CHECK(cudaStreamSynchronize(st));
-    max_owner = h[0];
-    max_pos = h[1];
-  }
-  ps.reset();
+  CUDA_CHECK(cudaStreamSynchronize(st));
   if (n_events == 0) return;
-  int bo = bits_for(max_owner), bp = bits_for(max_pos);
-  SHN_CHECK(2 * bo + bp <= 64, "self-join: contig count / length exceed the 64-bit event key budget");
-  SHN_CHECK(n_events < (1ull << 40), "self-join: more than 2^40 match events (repeat explosion)");
+  SHN_CHECK(n_events < 0x7FFFFFFFull, "self-join: more than 2^31-1 match events in one block");
   DevBuf ev, ev_s;
   ev.reserve(n_events * 8);
   ev_s.reserve(n_events * 8);
-  ps.reset(new ProfScope(c, n_emit.c_str(), 1));
-  emit_events_kernel<<<shn_grid(n_events, kBlock), kBlock, 0, st>>>(
-      ev_off.as<uint64_t>(), run_start.as<uint32_t>(), owner_s.as<uint32_t>(), pos_s.as<uint32_t>(), n,
-      n_events, bo, bp, ev.as<uint64_t>());
+  emit_events_kernel<<<shn_grid(n, kBlock), kBlock, 0, st>>>(
+      ev_off.as<uint64_t>(), run_start.as<uint32_t>(), grp_start.as<uint32_t>(), owner_s.as<uint32_t>(),
+      pos_s.as<uint32_t>(), n, lo, hi, d_status, bo, bp, ev.as<uint64_t>());
   KERNEL_CHECK();
   ps.reset();
   ps.reset(new ProfScope(c, n_sort2.c_str(), 1));
@@ -231,12 +253,11 @@ void shn_self_join(shn_ctx* c, const uint64_t* d_keys, const uint32_t* d_owner,
   ukeys.reserve(n_events * 8);
   agg.reserve(n_events * sizeof(EvVal));
   nruns.reserve(8);
-  cub::CountingInputIterator<uint64_t> cnt(0);
+  cub::CountingInputIterator<uint64_t> cit(0);
   cub::TransformInputIterator<uint64_t, EvKeyOf, cub::CountingInputIterator<uint64_t>> kin(
-      cnt, EvKeyOf{ev_s.as<uint64_t>(), bp});
+      cit, EvKeyOf{ev_s.as<uint64_t>(), bp});
   cub::TransformInputIterator<EvVal, EvValOf, cub::CountingInputIterator<uint64_t>> vin(
-      cnt, EvValOf{ev_s.as<uint64_t>(), n_events, bp, r});
-  SHN_CHECK(n_events < 0x7FFFFFFFull, "self-join: more than 2^31-1 match events");
+      cit, EvValOf{ev_s.as<uint64_t>(), n_events, bp, r});
   tb = 0;
   CUDA_CHECK(cub::DeviceReduce::ReduceByKey(nullptr, tb, kin, ukeys.as<uint64_t>(), vin,
                                             agg.as<EvVal>(), nruns.as<uint64_t>(), EvReduce(),
