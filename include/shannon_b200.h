@@ -171,6 +171,11 @@ int shn_l3_get_labels(shn_ctx* ctx, uint32_t* label);
 int shn_l4_map_add_contigs(shn_ctx* ctx, const char* bases, const uint64_t* offsets,
                            const uint32_t* comp_of_contig, uint64_t n_contigs, int k1, int reset,
                            uint64_t expected_total_k1mers);
+/* Same for the accepted contigs of this ctx's last shn_l3_run, which are still on the device:
+ * comp_of_contig[i] is the component of contig i+1 (acceptance order), 0xFFFFFFFF = the contig is
+ * not partitioned (single-contig components, extension_correction.py:467-473). */
+int shn_l4_map_add_l3_contigs(shn_ctx* ctx, const uint32_t* comp_of_contig, uint64_t n_contigs,
+                              int reset);
 int shn_l4_map_set_weights(shn_ctx* ctx, const uint64_t* dict_keys, const uint32_t* dict_weights,
                            uint64_t n);
 /* weight per K1-mer window of the given contigs, in order (component*k1mers_allowed.dict). */

@@ -72,6 +72,7 @@ SIGNATURES = {
     "shn_l3_get_edges": (C.c_int, [vp, vp, vp, vp, vp]),
     "shn_l3_get_labels": (C.c_int, [vp, vp]),
     "shn_l4_map_add_contigs": (C.c_int, [vp, vp, vp, vp, C.c_uint64, C.c_int, C.c_int, C.c_uint64]),
+    "shn_l4_map_add_l3_contigs": (C.c_int, [vp, vp, C.c_uint64, C.c_int]),
     "shn_l4_map_set_weights": (C.c_int, [vp, vp, vp, C.c_uint64]),
     "shn_l4_map_window_weights": (C.c_int, [vp, vp, vp, C.c_uint64, C.c_int, vp]),
     "shn_l4_load_reads": (C.c_int, [vp, C.c_int, vp, vp, C.c_uint64, C.c_int]),
@@ -383,6 +384,10 @@ class Context(HostIO):
         comp = np.ascontiguousarray(comp_of_contig, dtype=np.uint32)
         self.call("shn_l4_map_add_contigs", ptr(bases), ptr(offsets), ptr(comp),
                   C.c_uint64(len(comp)), int(k1), int(bool(reset)), C.c_uint64(int(expected_total)))
+
+    def l4_map_add_l3_contigs(self, comp_of_contig, reset=True):
+        comp = np.ascontiguousarray(comp_of_contig, dtype=np.uint32)
+        self.call("shn_l4_map_add_l3_contigs", ptr(comp), C.c_uint64(len(comp)), int(bool(reset)))
 
     def l4_map_set_weights(self, keys, weights):
         if keys is None:   # use the allowed set of this context's last l3_run, on the device

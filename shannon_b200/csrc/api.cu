@@ -30,7 +30,9 @@ void shn_l3_get_labels_impl(shn_ctx* c, uint32_t* label);
 void shn_l3_allowed_dev(shn_ctx* c, const uint64_t** keys, const uint32_t** weights, uint64_t* n);
 void shn_l4_map_add_contigs_impl(shn_ctx* c, const char* bases, const uint64_t* offsets,
                                  const uint32_t* comp_of_contig, uint64_t n_contigs, int k1,
-                                 int reset, uint64_t expected_total, int on_device);
+                                 int reset, uint64_t expected_total, int on_device, int is_codes);
+void shn_l3_contigs_dev(shn_ctx* c, const uint8_t** codes, const uint64_t** offs, uint64_t* n,
+                        uint64_t* n_allowed);
 void shn_l4_map_set_weights_impl(shn_ctx* c, const uint64_t* keys, const uint32_t* weights,
                                  uint64_t n, int on_device);
 void shn_l4_map_window_weights_impl(shn_ctx* c, const char* bases, const uint64_t* offsets,
@@ -474,7 +476,19 @@ int shn_l4_map_add_contigs(shn_ctx* c, const char* bases, const uint64_t* offset
   SHN_API_BEGIN
   bind(c);
   shn_l4_map_add_contigs_impl(c, bases, offsets, comp_of_contig, n_contigs, k1, reset,
-                              expected_total_k1mers, 0);
+                              expected_total_k1mers, 0, 0);
+  SHN_API_END(c)
+}
+int shn_l4_map_add_l3_contigs(shn_ctx* c, const uint32_t* comp_of_contig, uint64_t n_contigs, int reset) {
+  SHN_API_BEGIN
+  bind(c);
+  const uint8_t* codes;
+  const uint64_t* offs;
+  uint64_t n, n_allowed;
+  shn_l3_contigs_dev(c, &codes, &offs, &n, &n_allowed);
+  SHN_CHECK(n == n_contigs, "component id array does not match the number of accepted contigs");
+  shn_l4_map_add_contigs_impl(c, (const char*)codes, offs, comp_of_contig, n, c->k1, reset, n_allowed,
+                              1, 1);
   SHN_API_END(c)
 }
 int shn_l4_map_set_weights(shn_ctx* c, const uint64_t* dict_keys, const uint32_t* dict_weights,

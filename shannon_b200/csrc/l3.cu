@@ -1729,6 +1729,16 @@ __global__ void __launch_bounds__(kBlock)
 
 void shn_l3_get_sizes_impl(shn_ctx* c, shn_l3_sizes* out) { *out = need_l3(c)->sz; }
 
+// device-resident accepted contigs (2-bit codes, offsets) for the L4 map
+void shn_l3_contigs_dev(shn_ctx* c, const uint8_t** codes, const uint64_t** offs, uint64_t* n,
+                        uint64_t* n_allowed) {
+  L3State* s = need_l3(c);
+  *codes = s->contig_codes.as<uint8_t>();
+  *offs = s->contig_offs.as<uint64_t>();
+  *n = s->sz.n_contigs;
+  *n_allowed = s->sz.n_allowed;
+}
+
 // device-resident allowed set (keys, weights) for the L4 map when caller and callee share the ctx
 void shn_l3_allowed_dev(shn_ctx* c, const uint64_t** keys, const uint32_t** weights, uint64_t* n) {
   L3State* s = need_l3(c);

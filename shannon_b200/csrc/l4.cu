@@ -120,18 +120,24 @@ __device__ __forceinline__ uint64_t map_find(const CompMapView& m, uint64_t key,
 __global__ void __launch_bounds__(kBlock)
     map_add_kernel(CompMapView m, const char* __restrict__ bases, const uint64_t* __restrict__ offs,
                    const uint32_t* __restrict__ comp_of, uint64_t n_contigs, uint64_t total_bases,
-                   int k1, unsigned long long* counters) {
+                   int k1, int is_codes, unsigned long long* counters) {
   uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int n_new = 0, n_bad = 0, n_over = 0;
   if (g < total_bases) {
     uint64_t c = find_segment(offs, n_contigs, g);
     uint64_t end = __ldg(&offs[c + 1]);
-    if (g + k1 <= end) {
-      uint64_t key;
-      if (!pack_window(bases, g, k1, &key)) {
+    uint32_t comp = __ldg(&comp_of[c]);
+    if (g + k1 <= end && comp != SHN_NONE32) {  // comp == NONE: contig is not partitioned (single)
+      uint64_t key = 0;
+      bool okw = true;
+      if (is_codes) {
+        for (int j = 0; j < k1; ++j) key = (key << 2) | (uint64_t)((uint8_t)__ldg(&bases[g + j]) & 3u);
+      } else {
+        okw = pack_window(bases, g, k1, &key);
+      }
+      if (!okw) {
         n_bad = 1;
       } else {
-        uint32_t comp = __ldg(&comp_of[c]);
         uint64_t b = m.bucket_of(key);
         CompSlot* slot = nullptr;
         while (!slot) {
@@ -424,7 +430,7 @@ void shn_l4_free(shn_ctx* c) {
 
 void shn_l4_map_add_contigs_impl(shn_ctx* c, const char* bases, const uint64_t* offsets,
                                  const uint32_t* comp_of_contig, uint64_t n_contigs, int k1,
-                                 int reset, uint64_t expected_total, int on_device) {
+                                 int reset, uint64_t expected_total, int on_device, int is_codes) {
   SHN_CHECK(k1 >= 1 && k1 <= 32, "k1 must be in 1..32");
   L4State* s = l4_of(c);
   if (reset) {
@@ -455,15 +461,16 @@ void shn_l4_map_add_contigs_impl(shn_ctx* c, const char* bases, const uint64_t* 
     d_offs = (const uint64_t*)InputView::get(c, offsets, (n_contigs + 1) * 8, 0, s->stage_b);
   }
   const char* d_bases = (const char*)InputView::get(c, bases, total, on_device, s->stage_a);
+  // the component ids always come from the host (they are decided by the host-side packing)
   const uint32_t* d_comp =
-      (const uint32_t*)InputView::get(c, comp_of_contig, n_contigs * 4, on_device, s->stage_c);
+      (const uint32_t*)InputView::get(c, comp_of_contig, n_contigs * 4, 0, s->stage_c);
   SHN_CHECK(s->n_keys + total <= s->n_buckets * 2,
             "component map too small: expected_total_k1mers was underestimated");
   unsigned long long* ctr = zero_counters(c);
   if (total) {
     ProfScope ps(c, "l4_map_add");
     map_add_kernel<<<shn_grid(total, kBlock), kBlock, 0, c->stream>>>(
-        map_view(s), d_bases, d_offs, d_comp, n_contigs, total, k1, ctr);
+        map_view(s), d_bases, d_offs, d_comp, n_contigs, total, k1, is_codes, ctr);
     KERNEL_CHECK();
   }
   unsigned long long h[3];

@@ -94,7 +94,7 @@ def run_correction(infile, outfile, min_weight, min_length, double_stranded,
 
     contigs = cor.contigs
     with open(outfile + '_contig', 'w') as f1:
-        f1.write("".join(c + "\n" for c in contigs[1:]))
+        f1.write("".join(c + "\n" for c in contigs.strings()))
 
     a_keys, a_w = cor.allowed_keys, cor.allowed_weights
     allowed_kmer_dict = AllowedKmerDict(a_keys, a_w, k1)
@@ -113,7 +113,7 @@ def run_correction(infile, outfile, min_weight, min_length, double_stranded,
                             for i, w in zip(range(0, len(txt), k1 + 1), a_w.tolist())))
     f_log.write("{:s}: {:d} K-mers written to file.".format(time.asctime(), n_allowed) + " \n")
     f_log.write(str(time.asctime()) + ": " + "Before dfs " + "\n")
-    adj, component2contig, n_edges = cor.adj, cor.component2contig, cor.n_edges
+    component2contig, n_edges = cor.component2contig, cor.n_edges
     f_log.write(str(time.asctime()) + ": " + "After dfs " + "\n")
     f_log.write(str(time.asctime()) + ": " + "After Edges Loaded " + "\n")
 
@@ -134,7 +134,8 @@ def run_correction(infile, outfile, min_weight, min_length, double_stranded,
             with open(d + "/component" + str(new_comp_num) + ".txt", 'w') as f:
                 f.write(str(len(members)) + "\t" + str(n_edges[component]) + "\t" + "001" + "\n")
                 for c in members:
-                    f.write("".join(str(code[nb]) + "\t" + str(wt) + "\t" for nb, wt in adj[c]) + "\n")
+                    f.write("".join(str(code[nb]) + "\t" + str(wt) + "\t"
+                                    for nb, wt in cor.neighbours(c)) + "\n")
             with open(d + "/component" + str(new_comp_num) + "contigs" + ".txt", 'w') as f:
                 f.write("".join(contigs[c] + "\n" for c in members))
             new_comp_num += 1

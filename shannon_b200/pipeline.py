@@ -17,36 +17,49 @@ def decode_kmers(keys, k1):
     return _CODE_TO_ASCII[codes]
 
 
-def contig_adjacency(n_contigs, a, b, w, fp):
+def contig_adjacency_csr(n_contigs, a, b, w, fp):
     """contig_connections (extension_correction.py:372-389) in the reference's dict insertion
     order, from the GPU's distinct edge list (a < b, multiplicity w, fp = first C-mer position in
-    b shared with a): node x first gets its earlier neighbours ordered by (fp, id) -- they are
-    connected while x itself is being indexed -- then later contigs in ascending id."""
-    adj = [[] for _ in range(n_contigs + 1)]
-    if len(a):
-        a = a.astype(np.int64)
-        b = b.astype(np.int64)
-        wl = w.tolist()
-        al, bl = a.tolist(), b.tolist()
-        lower = np.lexsort((a, fp.astype(np.int64), b))      # by b, then fp, then a
-        for e in lower.tolist():
-            adj[bl[e]].append((al[e], wl[e]))
-        higher = np.lexsort((b, a))                          # by a, then b
-        for e in higher.tolist():
-            adj[al[e]].append((bl[e], wl[e]))
-    return adj
+    b shared with a), as CSR arrays (indptr, neighbour, weight) over contigs 0..n_contigs:
+    node x first gets its earlier neighbours ordered by (fp, id) -- they are connected while x
+    itself is being indexed -- then later contigs in ascending id."""
+    a = np.asarray(a, dtype=np.int64)
+    b = np.asarray(b, dtype=np.int64)
+    w = np.asarray(w, dtype=np.int64)
+    fp = np.asarray(fp, dtype=np.int64)
+    # one row per (node, neighbour): phase 0 = earlier neighbours keyed (fp, a), phase 1 = later (b, 0)
+    node = np.concatenate([b, a])
+    nbr = np.concatenate([a, b])
+    wt = np.concatenate([w, w])
+    phase = np.concatenate([np.zeros(len(a), np.int64), np.ones(len(a), np.int64)])
+    k1 = np.concatenate([fp, b])
+    k2 = np.concatenate([a, np.zeros(len(a), np.int64)])
+    order = np.lexsort((k2, k1, phase, node))
+    node, nbr, wt = node[order], nbr[order], wt[order]
+    indptr = np.zeros(n_contigs + 2, dtype=np.int64)
+    np.add.at(indptr, node + 1, 1)
+    indptr = np.cumsum(indptr)
+    return indptr, nbr, wt
 
 
-def dfs_components(n_contigs, adj):
+def contig_adjacency(n_contigs, a, b, w, fp):
+    """Same as lists of (neighbour, weight) per contig (index 0 unused)."""
+    indptr, nbr, wt = contig_adjacency_csr(n_contigs, a, b, w, fp)
+    ip, nl, wl = indptr.tolist(), nbr.tolist(), wt.tolist()
+    return [list(zip(nl[ip[x]:ip[x + 1]], wl[ip[x]:ip[x + 1]])) for x in range(n_contigs + 1)]
+
+
+def dfs_components_csr(n_contigs, indptr, nbr):
     """extension_correction.py:417-434: iterative DFS in ascending contig index; member order is
     the pop order.  Returns ({root: [members]} in insertion order, comp_of[contig])."""
+    ip, nl = indptr.tolist(), nbr.tolist()
     comp_of = [0] * (n_contigs + 1)
     seen = [False] * (n_contigs + 1)
     component2contig = {}
     for root in range(1, n_contigs + 1):
         if comp_of[root]:
             continue
-        if not adj[root]:                       # isolated contig: a singleton component
+        if ip[root] == ip[root + 1]:            # isolated contig: a singleton component
             comp_of[root] = root
             seen[root] = True
             component2contig[root] = [root]
@@ -58,17 +71,64 @@ def dfs_components(n_contigs, adj):
             cur = stack.pop()
             comp_of[cur] = root
             members.append(cur)
-            for nb, _ in adj[cur]:
+            for nb in nl[ip[cur]:ip[cur + 1]]:
                 if not seen[nb]:
                     stack.append(nb)
                     seen[nb] = True
     return component2contig, comp_of
 
 
+def dfs_components(n_contigs, adj):
+    """Same on adjacency lists (as returned by contig_adjacency)."""
+    indptr = np.zeros(n_contigs + 2, dtype=np.int64)
+    indptr[1:] = np.cumsum([len(x) for x in adj])
+    nbr = np.asarray([nb for x in adj for nb, _ in x], dtype=np.int64)
+    return dfs_components_csr(n_contigs, indptr, nbr)
+
+
+class ContigStore(object):
+    """Accepted contigs as one ASCII byte array + offsets (1-based access like the reference's
+    `contigs` list, extension_correction.py:341); strings are only made when asked for."""
+
+    def __init__(self, bases, offs):
+        self.bases = bases
+        self.offs = np.asarray(offs, dtype=np.int64)
+        self._text = None
+
+    def __len__(self):
+        return len(self.offs)            # index 0 unused, like ["buffer"] + contigs
+
+    def __getitem__(self, i):
+        if self._text is None:
+            self._text = self.bases.tobytes().decode()
+        return self._text[self.offs[i - 1]:self.offs[i]]
+
+    def strings(self):
+        return [self[i] for i in range(1, len(self))]
+
+    def gather(self, ids):
+        """(bases, offsets) of the contigs `ids` (1-based), concatenated in that order."""
+        ids = np.asarray(ids, dtype=np.int64)
+        lens = self.offs[ids] - self.offs[ids - 1]
+        out_offs = np.zeros(len(ids) + 1, dtype=np.uint64)
+        out_offs[1:] = np.cumsum(lens)
+        total = int(out_offs[-1])
+        if total == 0:
+            return np.empty(0, dtype=np.uint8), out_offs
+        start = np.repeat(self.offs[ids - 1] - out_offs[:-1].astype(np.int64), lens)
+        return self.bases[start + np.arange(total, dtype=np.int64)], out_offs
+
+
 class Correction(object):
     """Result of the L3 stage (run_correction's in-memory state after :450)."""
-    __slots__ = ("k1", "n_loaded", "sizes", "contigs", "allowed_keys", "allowed_weights", "adj",
+    __slots__ = ("k1", "n_loaded", "sizes", "contigs", "allowed_keys", "allowed_weights", "adj_csr",
                  "component2contig", "comp_of", "n_edges")
+
+    def neighbours(self, contig):
+        """[(neighbour, weight)] of a contig in the reference's dict order."""
+        indptr, nbr, wt = self.adj_csr
+        lo, hi = int(indptr[contig]), int(indptr[contig + 1])
+        return list(zip(nbr[lo:hi].tolist(), wt[lo:hi].tolist()))
 
 
 def correct(ctx, keys, counts, k1, double_stranded, min_weight, min_length, on_device=False,
@@ -93,20 +153,20 @@ def correct(ctx, keys, counts, k1, double_stranded, min_weight, min_length, on_d
     t0 = time.perf_counter()
     n_contigs = cor.sizes["n_contigs"]
     bases, offs = ctx.l3_contigs()
-    text = bases.tobytes().decode()
-    o = offs.tolist()
-    cor.contigs = [None] + [text[o[i]:o[i + 1]] for i in range(n_contigs)]
+    cor.contigs = ContigStore(bases, offs)
     # allowed_kmer_dict (:404-408); left on the device when the caller feeds it straight into L4
     cor.allowed_keys, cor.allowed_weights = ctx.l3_allowed() if fetch_allowed else (None, None)
     ea, eb, ew, efp = ctx.l3_edges()
-    cor.adj = contig_adjacency(n_contigs, ea, eb, ew, efp)
-    cor.component2contig, cor.comp_of = dfs_components(n_contigs, cor.adj)
+    cor.adj_csr = contig_adjacency_csr(n_contigs, ea, eb, ew, efp)
+    cor.component2contig, cor.comp_of = dfs_components_csr(n_contigs, cor.adj_csr[0], cor.adj_csr[1])
     labels = ctx.l3_labels()
     if n_contigs and not np.array_equal(labels[1:], np.asarray(cor.comp_of[1:], dtype=np.uint32)):
         raise _lib.ShnError("internal error: GPU component labels disagree with the DFS partition")
     cor.n_edges = dict((c, 0) for c in cor.component2contig)
-    for x in ea.tolist():
-        cor.n_edges[cor.comp_of[x]] += 1
+    if len(ea):
+        roots, cnt = np.unique(np.asarray(cor.comp_of, dtype=np.int64)[ea.astype(np.int64)],
+                               return_counts=True)
+        cor.n_edges.update(zip(roots.tolist(), cnt.tolist()))
     tm["l3_host_order"] = time.perf_counter() - t0
     return cor
 
@@ -185,27 +245,24 @@ def frontend_in_memory(ctx, keys, counts, k1, mates, paired, min_weight=3, min_l
                   fetch_allowed=False, after_table_build=lambda: upload_reads_early(ctx, mates))
     t0 = time.perf_counter()
     pk = pack_components(cor, partition_size)
-    entries, comp_ids = [], []
+    n_contigs = cor.sizes["n_contigs"]
+    comp_of_contig = np.full(n_contigs + 1, 0xFFFFFFFF, dtype=np.uint32)   # singles stay NONE
     n_comps = 0
     for _, members in pk.big:
         parts = min(-(-len(members) // partition_size), 100)
         block = -(-len(members) // parts)
-        for i, c in enumerate(members):
-            entries.append(cor.contigs[c])
-            comp_ids.append(n_comps + min(i // block, parts - 1))
+        comp_of_contig[members] = n_comps + np.minimum(np.arange(len(members)) // block, parts - 1)
         n_comps += parts
     for group in pk.remaining:
         if not group and len(pk.remaining) > 1 and group is pk.remaining[-1]:
             continue
-        for c in group:
-            entries.append(cor.contigs[c])
-            comp_ids.append(n_comps)
+        comp_of_contig[group] = n_comps
         n_comps += 1
-    bases, offs = contig_arrays(entries)
     tm["pack_host"] = time.perf_counter() - t0
     t0 = time.perf_counter()
-    build_component_map(ctx, bases, offs, np.asarray(comp_ids, dtype=np.uint32), k1,
-                        cor.allowed_keys, cor.allowed_weights)
+    # the accepted contigs and the allowed set are still on the device: no round trip
+    ctx.l4_map_add_l3_contigs(comp_of_contig[1:], True)
+    ctx.l4_map_set_weights(None, None)
     tm["map_build"] = time.perf_counter() - t0
     t0 = time.perf_counter()
     comp_offs, rec_idx, stats = partition_reads(ctx, mates, paired, k1, n_comps, staged=True)
