@@ -12,6 +12,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <thread>
 
 #include "common.cuh"
 #include "selfjoin.cuh"
@@ -1486,13 +1487,26 @@ void shn_l3_run_impl(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
   std::vector<uint32_t>& cand_walk = s->h_cand_walk;
   cand_walk.clear();
   std::vector<uint64_t> cand_off(1, 0);
-  for (uint64_t i = 0; i < n_long; ++i) {
-    uint64_t tot_kmer = (uint64_t)h_long_nl[i] + h_long_nr[i] + 1;
-    uint64_t len = tot_kmer + k1 - 1;
-    if (passes_shape(len, h_long_tot[i], tot_kmer, min_weight, min_length)) {
-      cand_walk.push_back(h_long_idx[i]);
-      cand_off.push_back(cand_off.back() + len);
-    }
+  {
+    // the pow() per walk is evaluated by a few host threads; the order of the candidates is
+    // restored by the serial pass below
+    std::vector<uint8_t> pass(n_long, 0);
+    const unsigned nt = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(8, n_long / 65536));
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; ++t)
+      th.emplace_back([&, t] {
+        for (uint64_t i = n_long * t / nt, e = n_long * (t + 1) / nt; i < e; ++i) {
+          uint64_t tot_kmer = (uint64_t)h_long_nl[i] + h_long_nr[i] + 1;
+          pass[i] = passes_shape(tot_kmer + k1 - 1, h_long_tot[i], tot_kmer, min_weight, min_length);
+        }
+      });
+    for (auto& x : th) x.join();
+    for (uint64_t i = 0; i < n_long; ++i)
+      if (pass[i]) {
+        uint64_t len = (uint64_t)h_long_nl[i] + h_long_nr[i] + k1;
+        cand_walk.push_back(h_long_idx[i]);
+        cand_off.push_back(cand_off.back() + len);
+      }
   }
   const uint64_t n_cand = cand_walk.size();
   const uint64_t cand_bases = cand_off.back();
