@@ -107,6 +107,20 @@ def load():
     return lib
 
 
+def key_words(k1):
+    """uint64 words per packed K1-mer at the C-ABI: 1 for k1 <= 32, 2 (low word first) for k1 = 33."""
+    return 2 if k1 > 32 else 1
+
+
+def shape_keys(flat, k1):
+    """flat uint64 array from the library -> (n,) for one-word keys, (n, 2) for two-word keys."""
+    return flat.reshape(-1, 2) if key_words(k1) == 2 else flat
+
+
+def empty_keys(n, k1):
+    return np.empty((n, 2) if key_words(k1) == 2 else (n,), dtype=np.uint64)
+
+
 def ptr(a):
     """void* of a numpy array / int device pointer / None."""
     if a is None:
@@ -140,8 +154,10 @@ class HostIO(object):
         n, k1 = C.c_uint64(), C.c_int()
         self.call("shn_parse_kmer_file", os.fsencode(path), C.byref(keys), C.byref(counts),
                   C.byref(n), C.byref(k1))
+        kw = key_words(k1.value)
         try:
-            k = np.ctypeslib.as_array(C.cast(keys, u64p), shape=(max(n.value, 1),))[:n.value].copy()
+            k = np.ctypeslib.as_array(C.cast(keys, u64p), shape=(max(n.value, 1) * kw,))[:n.value * kw].copy()
+            k = shape_keys(k, k1.value)
             c = np.ctypeslib.as_array(C.cast(counts, u32p), shape=(max(n.value, 1),))[:n.value].copy()
         finally:
             self.lib.shn_host_free(keys)
@@ -278,7 +294,7 @@ class Context(HostIO):
     def pack_kmers(self, ascii_bytes, n, k1):
         a = np.frombuffer(ascii_bytes, dtype=np.uint8) if not isinstance(ascii_bytes, np.ndarray) \
             else ascii_bytes
-        keys = np.empty(n, dtype=np.uint64)
+        keys = empty_keys(n, k1)
         self.call("shn_pack_kmers", ptr(np.ascontiguousarray(a)), C.c_uint64(n), int(k1), ptr(keys), 0)
         return keys
 
@@ -321,8 +337,9 @@ class Context(HostIO):
         self.call("shn_table_lookup", vp(d_keys), C.c_uint64(n), vp(d_weights), vp(d_found), 1)
 
     def table_dump(self):
-        n = self.table_stats()["n_distinct"]
-        keys = np.empty(n, dtype=np.uint64)
+        st = self.table_stats()
+        n = st["n_distinct"]
+        keys = empty_keys(n, st["k1"])
         w = np.empty(n, dtype=np.uint32)
         idx = np.empty(n, dtype=np.uint32)
         self.call("shn_table_dump", ptr(keys), ptr(w), ptr(idx))
@@ -340,7 +357,7 @@ class Context(HostIO):
 
     def l3_walks(self):
         n = self.l3_sizes()["n_walks"]
-        seed = np.empty(n, dtype=np.uint64)
+        seed = empty_keys(n, self.table_stats()["k1"])
         nl = np.empty(n, dtype=np.uint32)
         nr = np.empty(n, dtype=np.uint32)
         tot = np.empty(n, dtype=np.uint64)
@@ -357,7 +374,7 @@ class Context(HostIO):
 
     def l3_allowed(self):
         n = self.l3_sizes()["n_allowed"]
-        keys = np.empty(n, dtype=np.uint64)
+        keys = empty_keys(n, self.table_stats()["k1"])
         w = np.empty(n, dtype=np.uint32)
         self.call("shn_l3_get_allowed", ptr(keys), ptr(w))
         return keys, w

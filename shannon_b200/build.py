@@ -8,8 +8,13 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "libshannon_b200.so")
-SOURCES = ["api.cu", "table.cu", "l3.cu", "l4.cu", "selfjoin.cu", "synth.cu", "route.cu", "hostio.cpp"]
-HEADERS = ["common.cuh", "table_dev.cuh", "selfjoin.cuh", os.path.join("..", "..", "include", "shannon_b200.h")]
+SOURCES = ["api.cu", "table.cu", "l3.cu", "l4.cu", "selfjoin.cu", "synth.cu", "reads.cu", "route.cu",
+           "hostio.cpp"]
+# translation units that depend on the K1-mer key width: built a second time with -DSHN_WIDE
+# (128-bit keys, K1 = 33) into namespace `wide`; api.cu dispatches on k1
+WIDE_SOURCES = ["table.cu", "l3.cu", "l4.cu", "synth.cu"]
+HEADERS = ["common.cuh", "table_dev.cuh", "selfjoin.cuh", "impls.h", "reads.cuh",
+           os.path.join("..", "..", "include", "shannon_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC,-O3,-pthread", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
@@ -27,13 +32,13 @@ def build(force=False, verbose=False):
     hdrs = [os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__)]
     objs = []
     procs = []
-    for src in SOURCES:
+    for src, extra, tag in [(x, [], "") for x in SOURCES] + [(x, ["-DSHN_WIDE"], ".wide") for x in WIDE_SOURCES]:
         sp = os.path.join(CSRC, src)
-        op = os.path.join(OBJ, src + ".o")
+        op = os.path.join(OBJ, src + tag + ".o")
         objs.append(op)
         if force or _stale(op, [sp] + hdrs):
-            cmd = [NVCC] + FLAGS + ["-x", "cu", "-c", sp, "-o", op]
-            procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
+            cmd = [NVCC] + FLAGS + extra + ["-x", "cu", "-c", sp, "-o", op]
+            procs.append((src + tag, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
     failed = False
     for src, p in procs:
         out = p.communicate()[0].decode()

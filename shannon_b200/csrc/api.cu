@@ -3,7 +3,8 @@
 #include "selfjoin.cuh"
 
 // implemented in the other translation units
-void shn_table_dump_impl(shn_ctx* c, uint64_t* h_keys, uint32_t* h_weights, uint32_t* h_idx);
+#include "impls.h"
+#include "reads.cuh"
 void shn_parse_kmer_file_impl(const char* path, uint64_t** keys_out, uint32_t** counts_out,
                               uint64_t* n_out, int* k1_out);
 void shn_load_fasta_impl(const char* path, int64_t n_fixed, char** bases_out, uint64_t** offs_out,
@@ -14,50 +15,26 @@ void shn_write_fasta_subset_impl(const char* path, int append, const char* bases
 void shn_write_k1mer_windows_impl(const char* path, const char* bases, const uint64_t* offsets,
                                   const uint32_t* contig_ids, uint64_t m, int k1,
                                   const uint32_t* weights, const uint64_t* win_off);
-void shn_table_begin_impl(shn_ctx* c, uint64_t n, int k1, int double_stranded);
-void shn_table_insert_chunk_impl(shn_ctx* c, const uint64_t* d_keys, const uint32_t* d_counts,
-                                 const uint32_t* d_line_idx, uint64_t n, uint64_t first_line,
-                                 int double_stranded);
-void shn_table_finish_impl(shn_ctx* c);
-void shn_l3_run_impl(shn_ctx* c, uint32_t min_weight, uint32_t min_length);
-void shn_l3_get_sizes_impl(shn_ctx* c, shn_l3_sizes* out);
-void shn_l3_get_walks_impl(shn_ctx* c, uint64_t* seed_keys, uint32_t* n_left, uint32_t* n_right,
-                           uint64_t* tot_wt, uint8_t* flags);
-void shn_l3_get_contigs_impl(shn_ctx* c, char* bases, uint64_t* offsets);
-void shn_l3_get_allowed_impl(shn_ctx* c, uint64_t* keys, uint32_t* weights);
-void shn_l3_get_edges_impl(shn_ctx* c, uint32_t* a, uint32_t* b, uint32_t* weight, uint32_t* fp);
-void shn_l3_get_labels_impl(shn_ctx* c, uint32_t* label);
-void shn_l3_allowed_dev(shn_ctx* c, const uint64_t** keys, const uint32_t** weights, uint64_t* n);
-void shn_l4_map_add_contigs_impl(shn_ctx* c, const char* bases, const uint64_t* offsets,
-                                 const uint32_t* comp_of_contig, uint64_t n_contigs, int k1,
-                                 int reset, uint64_t expected_total, int on_device, int is_codes);
-void shn_l3_contigs_dev(shn_ctx* c, const uint8_t** codes, const uint64_t** offs, uint64_t* n,
-                        uint64_t* n_allowed);
-void shn_l4_map_set_weights_impl(shn_ctx* c, const uint64_t* keys, const uint32_t* weights,
-                                 uint64_t n, int on_device);
-void shn_l4_map_window_weights_impl(shn_ctx* c, const char* bases, const uint64_t* offsets,
-                                    uint64_t n_contigs, int k1, uint32_t* h_weights);
-void shn_l4_load_reads_impl(shn_ctx* c, int mate, const char* bases, const uint64_t* offsets,
-                            uint64_t n, int on_device);
-void shn_l4_upload_reads_async_impl(shn_ctx* c, int mate, const char* bases, const uint64_t* offsets,
-                                    uint64_t n);
-void shn_l4_load_reads_staged_impl(shn_ctx* c, int mate);
-void shn_l4_assign_impl(shn_ctx* c, int paired, int k1, uint64_t* n_assign, uint64_t* n_lookups,
-                        uint64_t* n_valid);
-void shn_l4_get_assignments_impl(shn_ctx* c, uint32_t n_comps, uint64_t* h_offs, uint32_t* h_idx);
 void shn_synth_pairs_impl(shn_ctx* c, const uint8_t* tx, const uint64_t* tx_offs, const uint64_t* thr,
                           uint64_t n_tx, uint64_t n_pairs, uint64_t first_pair, uint64_t seed,
                           int read_len, int frag_len, uint32_t err_thr, char* m1, char* m2);
 void shn_revcomp_reads_impl(shn_ctx* c, const char* in, char* out, uint64_t n_reads, int read_len);
-void shn_count_k1mers_impl(shn_ctx* c, const char* const* arrays, const uint64_t* n_reads,
-                           int n_arrays, int read_len, int k1, uint64_t expected_distinct,
-                           uint64_t** keys_dev, uint32_t** counts_dev, uint64_t* n_distinct);
-void shn_count_free(shn_ctx* c);
-void shn_pack_kmers_impl(shn_ctx* c, const char* d_ascii, uint64_t n, int k1, uint64_t* d_keys);
 void shn_route_plan_impl(shn_ctx* c, const uint64_t* d_keys, uint64_t n, uint32_t nranks,
                          uint32_t* d_perm, uint64_t* h_counts);
 void shn_permute_impl(shn_ctx* c, const void* src, const uint32_t* d_perm, uint64_t n, int elem_bytes,
                       int scatter, void* dst);
+
+// K1 <= 32: 64-bit keys (namespace narrow); K1 = 33: 128-bit keys (namespace wide).  Key arrays
+// cross this ABI as 1 resp. 2 uint64 words per key, low word first.
+static inline bool is_wide(int k1) { return k1 > 32; }
+static inline uint64_t key_bytes(int k1) { return is_wide(k1) ? 16 : 8; }
+#define SHN_DISPATCH(k1, call) \
+  do {                         \
+    if (is_wide(k1))           \
+      wide::call;              \
+    else                       \
+      narrow::call;            \
+  } while (0)
 
 static thread_local std::string g_last_error;
 thread_local DevPool* g_shn_pool = nullptr;
@@ -131,6 +108,7 @@ void shn_destroy(shn_ctx* c) {
   shn_l3_free(c);
   shn_l4_free(c);
   shn_count_free(c);
+  shn_reads_free(c);
   c->table.release();
   c->cub_tmp.release();
   c->flush_buf.release();
@@ -300,18 +278,18 @@ int shn_write_k1mer_windows(shn_ctx* c, const char* path, const char* bases, con
 int shn_pack_kmers(shn_ctx* c, const char* ascii, uint64_t n, int k1, uint64_t* keys, int on_device) {
   SHN_API_BEGIN
   bind(c);
-  SHN_CHECK(k1 >= 1 && k1 <= 32, "k1 must be in 1..32");
+  SHN_CHECK(k1 >= 1 && k1 <= 33, "k1 must be in 1..33");
   if (n) {
     DevBuf sa, sk;
     const char* d_ascii = (const char*)InputView::get(c, ascii, n * (uint64_t)k1, on_device, sa);
     uint64_t* d_keys = keys;
     if (!on_device) {
-      sk.reserve(n * 8);
+      sk.reserve(n * key_bytes(k1));
       d_keys = sk.as<uint64_t>();
     }
-    shn_pack_kmers_impl(c, d_ascii, n, k1, d_keys);
+    SHN_DISPATCH(k1, pack_kmers(c, d_ascii, n, k1, d_keys));
     if (!on_device)
-      CUDA_CHECK(cudaMemcpyAsync(keys, d_keys, n * 8, cudaMemcpyDeviceToHost, c->stream));
+      CUDA_CHECK(cudaMemcpyAsync(keys, d_keys, n * key_bytes(k1), cudaMemcpyDeviceToHost, c->stream));
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
   }
   SHN_API_END(c)
@@ -322,15 +300,17 @@ int shn_table_build(shn_ctx* c, const uint64_t* keys, const uint32_t* counts, ui
   SHN_API_BEGIN
   bind(c);
   shn_l3_free(c);
+  SHN_CHECK(k1 >= 1 && k1 <= 33, "k1 must be in 1..33 (K <= 32)");
+  const uint64_t kw = key_bytes(k1) / 8;
   if (on_device || n == 0) {
-    shn_table_build_impl(c, keys, counts, n, k1, double_stranded);
+    SHN_DISPATCH(k1, table_build(c, keys, counts, n, k1, double_stranded, nullptr));
   } else {
     // host input: copy chunk i+1 on the copy stream while chunk i is being inserted
     DevBuf sk, sc;
-    sk.reserve(n * 8);
+    sk.reserve(n * 8 * kw);
     sc.reserve(n * 4);
     if (!c->stream2) CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
-    shn_table_begin_impl(c, n, k1, double_stranded);
+    SHN_DISPATCH(k1, table_begin(c, n, k1, double_stranded));
     const uint64_t chunk = 32ull << 20;
     std::vector<cudaEvent_t> evs;
     {
@@ -341,16 +321,17 @@ int shn_table_build(shn_ctx* c, const uint64_t* keys, const uint32_t* counts, ui
     }
     for (uint64_t lo = 0; lo < n; lo += chunk) {
       const uint64_t m = std::min(chunk, n - lo);
-      CUDA_CHECK(cudaMemcpyAsync(sk.as<uint64_t>() + lo, keys + lo, m * 8, cudaMemcpyHostToDevice, c->stream2));
+      CUDA_CHECK(cudaMemcpyAsync(sk.as<uint64_t>() + lo * kw, keys + lo * kw, m * 8 * kw, cudaMemcpyHostToDevice,
+                                 c->stream2));
       CUDA_CHECK(cudaMemcpyAsync(sc.as<uint32_t>() + lo, counts + lo, m * 4, cudaMemcpyHostToDevice, c->stream2));
       cudaEvent_t ev = c->prof_event();
       CUDA_CHECK(cudaEventRecord(ev, c->stream2));
       CUDA_CHECK(cudaStreamWaitEvent(c->stream, ev, 0));
       evs.push_back(ev);
-      shn_table_insert_chunk_impl(c, sk.as<uint64_t>() + lo, sc.as<uint32_t>() + lo, nullptr, m, lo,
-                                  double_stranded);
+      SHN_DISPATCH(k1, table_insert_chunk(c, sk.as<uint64_t>() + lo * kw, sc.as<uint32_t>() + lo, nullptr,
+                                          m, lo, double_stranded));
     }
-    shn_table_finish_impl(c);
+    SHN_DISPATCH(k1, table_finish(c));
     for (cudaEvent_t ev : evs) c->prof_pool.push_back(ev);
   }
   SHN_API_END(c)
@@ -361,7 +342,7 @@ int shn_table_build_indexed(shn_ctx* c, const uint64_t* keys_dev, const uint32_t
   SHN_API_BEGIN
   bind(c);
   shn_l3_free(c);
-  shn_table_build_impl(c, keys_dev, counts_dev, n, k1, 0, line_idx_dev);
+  SHN_DISPATCH(k1, table_build(c, keys_dev, counts_dev, n, k1, 0, line_idx_dev));
   SHN_API_END(c)
 }
 
@@ -387,7 +368,7 @@ int shn_table_stats(shn_ctx* c, uint64_t* n_distinct, uint64_t* n_lowcomplexity,
   SHN_CHECK(c != nullptr, "null context");
   if (n_distinct) *n_distinct = c->n_distinct;
   if (n_lowcomplexity) *n_lowcomplexity = c->n_lowcomplexity;
-  if (n_slots) *n_slots = c->n_buckets * SHN_BSLOTS;
+  if (n_slots) *n_slots = c->n_buckets * (is_wide(c->k1) ? 2 : 4);
   if (k1) *k1 = c->k1;
   SHN_API_END(c)
 }
@@ -398,7 +379,7 @@ int shn_table_lookup(shn_ctx* c, const uint64_t* keys, uint64_t n, uint32_t* wei
   bind(c);
   if (n) {
     DevBuf sk, sw, sf;
-    const uint64_t* dk = (const uint64_t*)InputView::get(c, keys, n * 8, on_device, sk);
+    const uint64_t* dk = (const uint64_t*)InputView::get(c, keys, n * key_bytes(c->k1), on_device, sk);
     uint32_t* dw = weights;
     uint8_t* df = found;
     if (!on_device) {
@@ -407,7 +388,7 @@ int shn_table_lookup(shn_ctx* c, const uint64_t* keys, uint64_t n, uint32_t* wei
       dw = sw.as<uint32_t>();
       df = sf.as<uint8_t>();
     }
-    shn_table_lookup_impl(c, dk, n, dw, df);
+    SHN_DISPATCH(c->k1, table_lookup(c, dk, n, dw, df));
     if (!on_device) {
       if (weights) CUDA_CHECK(cudaMemcpyAsync(weights, dw, n * 4, cudaMemcpyDeviceToHost, c->stream));
       if (found) CUDA_CHECK(cudaMemcpyAsync(found, df, n, cudaMemcpyDeviceToHost, c->stream));
@@ -420,7 +401,7 @@ int shn_table_lookup(shn_ctx* c, const uint64_t* keys, uint64_t n, uint32_t* wei
 int shn_table_dump(shn_ctx* c, uint64_t* keys, uint32_t* weights, uint32_t* first_idx) {
   SHN_API_BEGIN
   bind(c);
-  shn_table_dump_impl(c, keys, weights, first_idx);
+  SHN_DISPATCH(c->k1, table_dump(c, keys, weights, first_idx));
   SHN_API_END(c)
 }
 
@@ -428,44 +409,44 @@ int shn_table_dump(shn_ctx* c, uint64_t* keys, uint32_t* weights, uint32_t* firs
 int shn_l3_run(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
   SHN_API_BEGIN
   bind(c);
-  shn_l3_run_impl(c, min_weight, min_length);
+  SHN_DISPATCH(c->k1, l3_run(c, min_weight, min_length));
   SHN_API_END(c)
 }
 int shn_l3_get_sizes(shn_ctx* c, shn_l3_sizes* out) {
   SHN_API_BEGIN
   bind(c);
-  shn_l3_get_sizes_impl(c, out);
+  SHN_DISPATCH(c->k1, l3_get_sizes(c, out));
   SHN_API_END(c)
 }
 int shn_l3_get_walks(shn_ctx* c, uint64_t* seed_keys, uint32_t* n_left, uint32_t* n_right,
                      uint64_t* tot_wt, uint8_t* flags) {
   SHN_API_BEGIN
   bind(c);
-  shn_l3_get_walks_impl(c, seed_keys, n_left, n_right, tot_wt, flags);
+  SHN_DISPATCH(c->k1, l3_get_walks(c, seed_keys, n_left, n_right, tot_wt, flags));
   SHN_API_END(c)
 }
 int shn_l3_get_contigs(shn_ctx* c, char* bases, uint64_t* offsets) {
   SHN_API_BEGIN
   bind(c);
-  shn_l3_get_contigs_impl(c, bases, offsets);
+  SHN_DISPATCH(c->k1, l3_get_contigs(c, bases, offsets));
   SHN_API_END(c)
 }
 int shn_l3_get_allowed(shn_ctx* c, uint64_t* keys, uint32_t* weights) {
   SHN_API_BEGIN
   bind(c);
-  shn_l3_get_allowed_impl(c, keys, weights);
+  SHN_DISPATCH(c->k1, l3_get_allowed(c, keys, weights));
   SHN_API_END(c)
 }
 int shn_l3_get_edges(shn_ctx* c, uint32_t* a, uint32_t* b, uint32_t* weight, uint32_t* first_pos_in_b) {
   SHN_API_BEGIN
   bind(c);
-  shn_l3_get_edges_impl(c, a, b, weight, first_pos_in_b);
+  SHN_DISPATCH(c->k1, l3_get_edges(c, a, b, weight, first_pos_in_b));
   SHN_API_END(c)
 }
 int shn_l3_get_labels(shn_ctx* c, uint32_t* label) {
   SHN_API_BEGIN
   bind(c);
-  shn_l3_get_labels_impl(c, label);
+  SHN_DISPATCH(c->k1, l3_get_labels(c, label));
   SHN_API_END(c)
 }
 
@@ -475,8 +456,10 @@ int shn_l4_map_add_contigs(shn_ctx* c, const char* bases, const uint64_t* offset
                            uint64_t expected_total_k1mers) {
   SHN_API_BEGIN
   bind(c);
-  shn_l4_map_add_contigs_impl(c, bases, offsets, comp_of_contig, n_contigs, k1, reset,
-                              expected_total_k1mers, 0, 0);
+  if (reset) c->l4_k1 = k1;
+  SHN_CHECK(k1 == c->l4_k1, "k1 differs from the component map's");
+  SHN_DISPATCH(k1, l4_map_add_contigs(c, bases, offsets, comp_of_contig, n_contigs, k1, reset,
+                                      expected_total_k1mers, 0, 0));
   SHN_API_END(c)
 }
 int shn_l4_map_add_l3_contigs(shn_ctx* c, const uint32_t* comp_of_contig, uint64_t n_contigs, int reset) {
@@ -485,10 +468,11 @@ int shn_l4_map_add_l3_contigs(shn_ctx* c, const uint32_t* comp_of_contig, uint64
   const uint8_t* codes;
   const uint64_t* offs;
   uint64_t n, n_allowed;
-  shn_l3_contigs_dev(c, &codes, &offs, &n, &n_allowed);
+  SHN_DISPATCH(c->k1, l3_contigs_dev(c, &codes, &offs, &n, &n_allowed));
   SHN_CHECK(n == n_contigs, "component id array does not match the number of accepted contigs");
-  shn_l4_map_add_contigs_impl(c, (const char*)codes, offs, comp_of_contig, n, c->k1, reset, n_allowed,
-                              1, 1);
+  if (reset) c->l4_k1 = c->k1;
+  SHN_DISPATCH(c->k1, l4_map_add_contigs(c, (const char*)codes, offs, comp_of_contig, n, c->k1, reset,
+                                         n_allowed, 1, 1));
   SHN_API_END(c)
 }
 int shn_l4_map_set_weights(shn_ctx* c, const uint64_t* dict_keys, const uint32_t* dict_weights,
@@ -499,10 +483,11 @@ int shn_l4_map_set_weights(shn_ctx* c, const uint64_t* dict_keys, const uint32_t
     const uint64_t* dk;
     const uint32_t* dw;
     uint64_t dn;
-    shn_l3_allowed_dev(c, &dk, &dw, &dn);
-    shn_l4_map_set_weights_impl(c, dk, dw, dn, 1);
+    SHN_DISPATCH(c->k1, l3_allowed_dev(c, &dk, &dw, &dn));
+    SHN_CHECK(c->k1 == c->l4_k1, "the allowed set and the component map use different k1");
+    SHN_DISPATCH(c->l4_k1, l4_map_set_weights(c, dk, dw, dn, 1));
   } else {
-    shn_l4_map_set_weights_impl(c, dict_keys, dict_weights, n, 0);
+    SHN_DISPATCH(c->l4_k1, l4_map_set_weights(c, dict_keys, dict_weights, n, 0));
   }
   SHN_API_END(c)
 }
@@ -510,40 +495,42 @@ int shn_l4_map_window_weights(shn_ctx* c, const char* bases, const uint64_t* off
                               uint64_t n_contigs, int k1, uint32_t* weights) {
   SHN_API_BEGIN
   bind(c);
-  shn_l4_map_window_weights_impl(c, bases, offsets, n_contigs, k1, weights);
+  SHN_CHECK(k1 == c->l4_k1, "k1 differs from the component map's");
+  SHN_DISPATCH(k1, l4_map_window_weights(c, bases, offsets, n_contigs, k1, weights));
   SHN_API_END(c)
 }
 int shn_l4_load_reads(shn_ctx* c, int mate, const char* bases, const uint64_t* offsets,
                       uint64_t n_reads, int on_device) {
   SHN_API_BEGIN
   bind(c);
-  shn_l4_load_reads_impl(c, mate, bases, offsets, n_reads, on_device);
+  shn_reads_load(c, mate, bases, offsets, n_reads, on_device);
   SHN_API_END(c)
 }
 int shn_l4_upload_reads_async(shn_ctx* c, int mate, const char* bases, const uint64_t* offsets,
                               uint64_t n_reads) {
   SHN_API_BEGIN
   bind(c);
-  shn_l4_upload_reads_async_impl(c, mate, bases, offsets, n_reads);
+  shn_reads_upload_async(c, mate, bases, offsets, n_reads);
   SHN_API_END(c)
 }
 int shn_l4_load_reads_staged(shn_ctx* c, int mate) {
   SHN_API_BEGIN
   bind(c);
-  shn_l4_load_reads_staged_impl(c, mate);
+  shn_reads_load_staged(c, mate);
   SHN_API_END(c)
 }
 int shn_l4_assign(shn_ctx* c, int paired, int k1, uint64_t* n_assignments, uint64_t* n_lookups,
                   uint64_t* n_valid_records) {
   SHN_API_BEGIN
   bind(c);
-  shn_l4_assign_impl(c, paired, k1, n_assignments, n_lookups, n_valid_records);
+  SHN_CHECK(k1 == c->l4_k1, "k1 differs from the component map's");
+  SHN_DISPATCH(k1, l4_assign(c, paired, k1, n_assignments, n_lookups, n_valid_records));
   SHN_API_END(c)
 }
 int shn_l4_get_assignments(shn_ctx* c, uint32_t n_comps, uint64_t* comp_offsets, uint32_t* record_idx) {
   SHN_API_BEGIN
   bind(c);
-  shn_l4_get_assignments_impl(c, n_comps, comp_offsets, record_idx);
+  SHN_DISPATCH(c->l4_k1, l4_get_assignments(c, n_comps, comp_offsets, record_idx));
   SHN_API_END(c)
 }
 
@@ -571,8 +558,9 @@ int shn_count_k1mers(shn_ctx* c, const char* const* read_arrays_dev, const uint6
                      uint64_t** keys_dev, uint32_t** counts_dev, uint64_t* n_distinct) {
   SHN_API_BEGIN
   bind(c);
-  shn_count_k1mers_impl(c, read_arrays_dev, n_reads, n_arrays, read_len, k1, expected_distinct,
-                        keys_dev, counts_dev, n_distinct);
+  SHN_CHECK(k1 >= 1 && k1 <= 33, "k1 must be in 1..33");
+  SHN_DISPATCH(k1, count_k1mers(c, read_arrays_dev, n_reads, n_arrays, read_len, k1, expected_distinct,
+                                keys_dev, counts_dev, n_distinct));
   SHN_API_END(c)
 }
 

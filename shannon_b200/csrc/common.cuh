@@ -109,29 +109,105 @@ SHN_HD uint64_t shn_ascii_order_key(uint64_t x) {
   return ((x & 0x5555555555555555ull) << 1) | ((x >> 1) & 0x5555555555555555ull);
 }
 
+// ---- the same for K1-mers of 33..64 bases (K = 32..63): two 64-bit words --------------------------
+typedef unsigned __int128 u128;
+
+SHN_HD u128 shn_kmer_mask128(int k) { return k >= 64 ? ~(u128)0 : (((u128)1 << (2 * k)) - 1); }
+SHN_HD u128 shn_revcomp(u128 x, int k) {
+  // reverse-complement both halves as 32-base words, swap them, drop the unused low pairs
+  uint64_t lo = shn_revcomp((uint64_t)x, 32), hi = shn_revcomp((uint64_t)(x >> 64), 32);
+  u128 y = ((u128)lo << 64) | hi;
+  return y >> (128 - 2 * k);
+}
+SHN_HD bool shn_low_complexity(u128 x, int k) {
+  const uint64_t m0 = 0x5555555555555555ull;
+  const uint64_t m1 = 0x5555555555555555ull & shn_kmer_mask(k - 32);
+  uint64_t a = (uint64_t)x, b = (uint64_t)(x >> 64);
+  uint64_t lo0 = a & m0, hi0 = (a >> 1) & m0, lo1 = b & m1, hi1 = (b >> 1) & m1;
+  int nT = SHN_POPC64(hi0 & lo0) + SHN_POPC64(hi1 & lo1);
+  int nC = SHN_POPC64(hi0 & ~lo0) + SHN_POPC64(hi1 & ~lo1);
+  int nG = SHN_POPC64(~hi0 & lo0) + SHN_POPC64(~hi1 & lo1 & m1);
+  int nA = k - nT - nC - nG;
+  int mx = nA > nC ? nA : nC;
+  mx = mx > nG ? mx : nG;
+  mx = mx > nT ? mx : nT;
+  return mx >= k - 2;
+}
+SHN_HD u128 shn_ascii_order_key(u128 x) {
+  return ((u128)shn_ascii_order_key((uint64_t)(x >> 64)) << 64) | shn_ascii_order_key((uint64_t)x);
+}
+SHN_HD uint64_t shn_key_hash(uint64_t x) { return shn_mix64(x); }
+SHN_HD uint64_t shn_key_hash(u128 x) {
+  return shn_mix64((uint64_t)x ^ shn_mix64((uint64_t)(x >> 64) + 0x9E3779B97F4A7C15ull));
+}
+
 // ---------------------------------------------------------------------------------------
-// K1-mer table: open addressing, 64-byte buckets of four 16-byte slots (one DRAM burst per probe),
-// linear probing over buckets; see table_dev.cuh.
+// K1-mer table: open addressing, 64-byte buckets (one DRAM burst per probe), linear probing over
+// buckets; see table_dev.cuh.  Every key-dependent translation unit is compiled twice: once with
+// 64-bit keys (K1 <= 32: four 16-byte slots per bucket) into namespace `narrow`, once with
+// -DSHN_WIDE (K1 = 33..64: two 32-byte slots per bucket, 128-bit keys) into namespace `wide`;
+// api.cu dispatches on k1.  Key arrays cross the C-ABI as SHN_KEY_WORDS uint64 words per key,
+// low word first.
 // ---------------------------------------------------------------------------------------
+static const uint32_t SHN_TRAVERSED = 0x80000000u;
+static const uint32_t SHN_OVERFLOW = 0x40000000u;
+static const uint32_t SHN_WEIGHT_MASK = 0x3FFFFFFFu;
+static const uint32_t SHN_NONE32 = 0xFFFFFFFFu;
+
+#ifdef SHN_WIDE
+#define SHN_NS wide
+#define SHN_KEY_WORDS 2
+#define SHN_BSLOTS 2
+#define SHN_MAX_K1 33 /* contig-overlap words (C = K1-1 bases) must fit 64 bits */
+typedef u128 shn_key_t;
+struct __align__(32) ShnSlot {
+  u128 key;         // all ones when free
+  uint32_t weight;  // as below
+  uint32_t idx;
+  uint64_t pad;
+};
+SHN_HD shn_key_t shn_key_mask(int k) { return shn_kmer_mask128(k); }
+#else
+#define SHN_NS narrow
+#define SHN_KEY_WORDS 1
+#define SHN_BSLOTS 4
+#define SHN_MAX_K1 32
+typedef uint64_t shn_key_t;
 struct __align__(16) ShnSlot {
   uint64_t key;     // SHN_EMPTY_KEY when free
   uint32_t weight;  // sum of counts (30 bits); bit 31 = traversed (walk kernels); bit 30 of the
                     // bucket's slot 0 = an insert walked past this full bucket
-  uint32_t idx;     // first-occurrence index in the input (dict insertion order)
+  uint32_t idx;     // first-occurrence index in the input (dict insertion order); the walks'
+                    // component-local copy re-uses it as the claim stamp of speculative windows
 };
-static const uint32_t SHN_TRAVERSED = 0x80000000u;
-static const uint32_t SHN_OVERFLOW = 0x40000000u;
-static const uint32_t SHN_WEIGHT_MASK = 0x3FFFFFFFu;
-#define SHN_BSLOTS 4
-static const uint32_t SHN_NONE32 = 0xFFFFFFFFu;
+SHN_HD shn_key_t shn_key_mask(int k) { return shn_kmer_mask(k); }
+#endif
+#define SHN_EMPTY ((shn_key_t)~(shn_key_t)0)
 
 struct ShnTableView {
   ShnSlot* slots;      // SHN_BSLOTS * n_buckets
   uint64_t n_buckets;
-  __device__ __forceinline__ uint64_t bucket_of(uint64_t key) const {
-    return __umul64hi(shn_mix64(key), n_buckets);
+  __device__ __forceinline__ uint64_t bucket_of(shn_key_t key) const {
+    return __umul64hi(shn_key_hash(key), n_buckets);
   }
 };
+
+// key arrays at the C-ABI: SHN_KEY_WORDS uint64 per key, low word first
+SHN_HD shn_key_t shn_load_key(const uint64_t* keys, uint64_t i) {
+#ifdef SHN_WIDE
+  return ((u128)keys[2 * i + 1] << 64) | keys[2 * i];
+#else
+  return keys[i];
+#endif
+}
+SHN_HD void shn_store_key(uint64_t* keys, uint64_t i, shn_key_t k) {
+#ifdef SHN_WIDE
+  keys[2 * i] = (uint64_t)k;
+  keys[2 * i + 1] = (uint64_t)(k >> 64);
+#else
+  keys[i] = k;
+#endif
+}
 
 // ---------------------------------------------------------------------------------------
 // device buffers and the context
@@ -252,8 +328,6 @@ struct ProfPending {  // an event pair recorded on the stream, resolved lazily (
   uint64_t launches;
 };
 
-struct L3State;
-struct L4State;
 
 struct shn_ctx {
   int device = 0;
@@ -303,11 +377,18 @@ struct shn_ctx {
   DevBuf table;
   uint64_t n_buckets = 0;
   int k1 = 0;
+  int l4_k1 = 0;  // k1 of the component map (may differ from the table's in a fresh process)
   uint64_t n_distinct = 0, n_lowcomplexity = 0, n_items = 0;
-  L3State* l3 = nullptr;
-  L4State* l4 = nullptr;
+  // stage states, owned by the key-width specific code that created them
+  void* l3 = nullptr;
+  void (*l3_free)(shn_ctx*) = nullptr;
+  void* l4 = nullptr;
+  void (*l4_free)(shn_ctx*) = nullptr;
+  void* count_state = nullptr;
+  void (*count_free)(shn_ctx*) = nullptr;
+  void* reads = nullptr;  // packed reads (reads.cu), independent of the key width
+  void (*reads_free)(shn_ctx*) = nullptr;
 
-  ShnTableView view() const { return ShnTableView{table.as<ShnSlot>(), n_buckets}; }
   void* tmp(uint64_t bytes) {
     cub_tmp.reserve(bytes);
     return cub_tmp.p;
@@ -358,10 +439,26 @@ struct InputView {
   }
 };
 
-// implemented in the individual translation units ------------------------------------------
-void shn_table_build_impl(shn_ctx* c, const uint64_t* d_keys, const uint32_t* d_counts, uint64_t n,
-                          int k1, int double_stranded, const uint32_t* d_line_idx = nullptr);
-void shn_table_lookup_impl(shn_ctx* c, const uint64_t* d_keys, uint64_t n, uint32_t* d_weights,
-                           uint8_t* d_found);
-void shn_l3_free(shn_ctx* c);
-void shn_l4_free(shn_ctx* c);
+// releases the L3 / L4 / counter state of a context, whichever key width created it
+static inline void shn_l3_free(shn_ctx* c) {
+  if (c->l3 && c->l3_free) c->l3_free(c);
+  c->l3 = nullptr;
+}
+static inline void shn_l4_free(shn_ctx* c) {
+  if (c->l4 && c->l4_free) c->l4_free(c);
+  c->l4 = nullptr;
+}
+static inline void shn_reads_free(shn_ctx* c) {
+  if (c->reads && c->reads_free) c->reads_free(c);
+  c->reads = nullptr;
+}
+static inline void shn_count_free(shn_ctx* c) {
+  if (c->count_state && c->count_free) c->count_free(c);
+  c->count_state = nullptr;
+}
+
+namespace SHN_NS {
+static inline ShnTableView table_view(const shn_ctx* c) {
+  return ShnTableView{c->table.as<ShnSlot>(), c->n_buckets};
+}
+}  // namespace SHN_NS

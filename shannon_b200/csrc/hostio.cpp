@@ -54,19 +54,20 @@ unsigned n_threads_for(size_t bytes) {
 
 // one `KMER count` line -> (key, count); returns an error string or nullptr
 const char* parse_kmer_line(const char* b, const char* e, int* k1, uint64_t* key, uint32_t* cnt) {
+  // key: 1 word for k-mers of <= 32 bases, 2 words (low word first) for 33 bases
   while (b < e && is_ws(*b)) ++b;
   const char* t0 = b;
   while (b < e && !is_ws(*b)) ++b;
   int klen = (int)(b - t0);
   if (klen == 0) return "empty line in k-mer file";
-  if (klen > 32) return "k-mer longer than 32 bases (K > 31 is not supported yet)";
+  if (klen > 33) return "k-mer longer than 33 bases (K > 32 is not supported)";
   if (*k1 == 0) *k1 = klen;
   if (klen != *k1) return "k-mers of different lengths in one file";
-  uint64_t x = 0;
+  u128 x = 0;
   for (const char* q = t0; q < b; ++q) {
     uint32_t code = shn_code_of((uint8_t)*q);
     if (code > 3) return "k-mer contains a character outside ACGT";
-    x = (x << 2) | code;
+    x = (x << 2) | (u128)code;
   }
   while (b < e && is_ws(*b)) ++b;
   const char* t1 = b;
@@ -93,7 +94,8 @@ const char* parse_kmer_line(const char* b, const char* e, int* k1, uint64_t* key
       return "k-mer count is not a non-negative integer";
     v = (uint64_t)d;
   }
-  *key = x;
+  key[0] = (uint64_t)x;
+  if (klen > 32) key[1] = (uint64_t)(x >> 64);
   *cnt = (uint32_t)v;
   return nullptr;
 }
@@ -139,13 +141,6 @@ void shn_parse_kmer_file_impl(const char* path, uint64_t** keys_out, uint32_t** 
   std::vector<uint64_t> first(nt + 1, 0);
   for (unsigned t = 0; t < nt; ++t) first[t + 1] = first[t] + lines[t];
   uint64_t n = first[nt];
-  uint64_t* keys = (uint64_t*)malloc(std::max<uint64_t>(n, 1) * 8);
-  uint32_t* counts = (uint32_t*)malloc(std::max<uint64_t>(n, 1) * 4);
-  if (!keys || !counts) {
-    free(keys);
-    free(counts);
-    SHN_FAIL("out of host memory parsing the k-mer file");
-  }
   // k1 from the very first line so that every thread checks against the same length
   int k1 = 0;
   {
@@ -156,6 +151,14 @@ void shn_parse_kmer_file_impl(const char* path, uint64_t** keys_out, uint32_t** 
     const char* t0 = b;
     while (b < e && !is_ws(*b)) ++b;
     k1 = (int)(b - t0);
+  }
+  const uint64_t kw = k1 > 32 ? 2 : 1;
+  uint64_t* keys = (uint64_t*)malloc(std::max<uint64_t>(n, 1) * 8 * kw);
+  uint32_t* counts = (uint32_t*)malloc(std::max<uint64_t>(n, 1) * 4);
+  if (!keys || !counts) {
+    free(keys);
+    free(counts);
+    SHN_FAIL("out of host memory parsing the k-mer file");
   }
   std::vector<std::string> errs(nt);
   {
@@ -169,7 +172,7 @@ void shn_parse_kmer_file_impl(const char* path, uint64_t** keys_out, uint32_t** 
         while (p < e) {
           const char* nl = (const char*)memchr(p, '\n', e - p);
           const char* le = nl ? nl : e;
-          const char* err = parse_kmer_line(p, le, &kk, &keys[i], &counts[i]);
+          const char* err = parse_kmer_line(p, le, &kk, &keys[i * kw], &counts[i]);
           if (err) {
             errs[t] = std::string(err) + " (line " + std::to_string(i + 1) + ")";
             return;

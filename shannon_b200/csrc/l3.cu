@@ -15,8 +15,11 @@
 #include <thread>
 
 #include "common.cuh"
+#include "impls.h"
 #include "selfjoin.cuh"
 #include "table_dev.cuh"
+
+namespace SHN_NS {
 
 struct L3State {
   uint32_t min_weight = 0, min_length = 0;
@@ -52,9 +55,10 @@ __global__ void __launch_bounds__(kBlock)
   uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   unsigned long long mine = 0;
   for (; i < n_slots; i += stride) {
-    uint4 v = __ldg(reinterpret_cast<const uint4*>(slots) + i);
-    bool occ = !(v.x == 0xFFFFFFFFu && v.y == 0xFFFFFFFFu);
-    mine += (occ && (v.z & SHN_WEIGHT_MASK) >= min_weight) ? 1 : 0;
+    shn_key_t key;
+    uint32_t wz, wi;
+    table_load_slot(slots, i, &key, &wz, &wi);
+    mine += (key != SHN_EMPTY && (wz & SHN_WEIGHT_MASK) >= min_weight) ? 1 : 0;
   }
   typedef cub::BlockReduce<unsigned long long, kBlock> BR;
   __shared__ typename BR::TempStorage tmp;
@@ -66,16 +70,16 @@ __global__ void __launch_bounds__(kBlock)
 // weight descending, then first-occurrence index descending (stable ascending sort + pop()).
 __global__ void __launch_bounds__(kBlock)
     seed_emit_kernel(const ShnSlot* __restrict__ slots, uint64_t n_slots, uint32_t min_weight,
-                     uint64_t* __restrict__ skey, uint32_t* __restrict__ sslot,
+                     uint64_t* __restrict__ sortkey, uint32_t* __restrict__ sslot,
                      unsigned long long* cursor) {
   __shared__ unsigned long long block_base;
   __shared__ int warp_off[kBlock / 32];
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  uint4 v = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0, 0);
-  if (i < n_slots) v = __ldg(reinterpret_cast<const uint4*>(slots) + i);
-  bool occ = !(v.x == 0xFFFFFFFFu && v.y == 0xFFFFFFFFu);
-  const uint32_t wt = v.z & SHN_WEIGHT_MASK;
-  bool is_seed = occ && wt >= min_weight;
+  shn_key_t skey = SHN_EMPTY;
+  uint32_t wz = 0, first_idx = 0;
+  if (i < n_slots) table_load_slot(slots, i, &skey, &wz, &first_idx);
+  const uint32_t wt = wz & SHN_WEIGHT_MASK;
+  bool is_seed = skey != SHN_EMPTY && wt >= min_weight;
   unsigned b = __ballot_sync(0xFFFFFFFFu, is_seed);
   int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (lane == 0) warp_off[warp] = __popc(b);
@@ -92,7 +96,7 @@ __global__ void __launch_bounds__(kBlock)
   __syncthreads();
   if (is_seed) {
     uint64_t o = block_base + warp_off[warp] + __popc(b & ((1u << lane) - 1u));
-    skey[o] = ((uint64_t)(~wt) << 32) | (uint64_t)(~v.w);
+    sortkey[o] = ((uint64_t)(~wt) << 32) | (uint64_t)(~first_idx);
     sslot[o] = (uint32_t)i;
   }
 }
@@ -148,14 +152,14 @@ __global__ void __launch_bounds__(kBlock)
     uf_edges_kernel(ShnTableView t, uint32_t* parent, uint64_t n_slots, int k1) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_slots) return;
-  uint64_t key = __ldg(&t.slots[i].key);
-  if (key == SHN_EMPTY_KEY) return;
-  const uint64_t mask = shn_kmer_mask(k1);
-  uint64_t pre = (key << 2) & mask;
+  shn_key_t key = t.slots[i].key;
+  if (key == SHN_EMPTY) return;
+  const shn_key_t mask = shn_key_mask(k1);
+  shn_key_t pre = (key << 2) & mask;
 #pragma unroll
-  for (uint64_t b = 0; b < 4; ++b) {
+  for (int b = 0; b < 4; ++b) {
     uint32_t w;
-    uint64_t s = table_find(t, pre | b, &w);
+    uint64_t s = table_find(t, pre | (shn_key_t)b, &w);
     if (s != ~0ull && s != i) uf_union(parent, (uint32_t)i, (uint32_t)s);
   }
 }
@@ -166,7 +170,7 @@ __global__ void __launch_bounds__(kBlock)
                       uint32_t* __restrict__ is_root) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_slots) return;
-  bool occ = slots[i].key != SHN_EMPTY_KEY;
+  bool occ = slots[i].key != SHN_EMPTY;
   uint32_t root = (uint32_t)i;
   if (occ) root = uf_find_ro(parent, (uint32_t)i);
   is_root[i] = (occ && root == (uint32_t)i) ? 1u : 0u;
@@ -180,7 +184,7 @@ __global__ void __launch_bounds__(kBlock)
                       uint32_t* __restrict__ comp_nodes) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_slots) return;
-  if (slots[i].key == SHN_EMPTY_KEY) return;
+  if (slots[i].key == SHN_EMPTY) return;
   atomicAdd(&comp_nodes[root_id[parent[i]]], 1u);  // parent[i] is the root after flatten
 }
 
@@ -277,8 +281,7 @@ __global__ void __launch_bounds__(kBlock)
     local_clear_kernel(ShnSlot* slots, uint64_t n_slots) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  uint4 v = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u);
-  for (; i < n_slots; i += stride) reinterpret_cast<uint4*>(slots)[i] = v;
+  for (; i < n_slots; i += stride) table_store_empty(slots, i, 0u);  // idx = 0: no claim stamp
 }
 
 __global__ void __launch_bounds__(kBlock)
@@ -289,10 +292,11 @@ __global__ void __launch_bounds__(kBlock)
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int bad = 0;
   if (i < n_slots) {
-    uint4 v = __ldg(reinterpret_cast<const uint4*>(slots) + i);
-    uint64_t key = ((uint64_t)v.y << 32) | v.x;
+    shn_key_t key;
+    uint32_t wz, first_idx;
+    table_load_slot(slots, i, &key, &wz, &first_idx);
     uint32_t loc = SHN_NONE32;
-    if (key != SHN_EMPTY_KEY) {
+    if (key != SHN_EMPTY) {
       uint32_t cid = root_id[parent[i]];
       uint64_t b0 = region_off[cid], nb = region_off[cid + 1] - b0;
       if (nb) {
@@ -303,7 +307,7 @@ __global__ void __launch_bounds__(kBlock)
           bad = 1;
         } else {
           // weight without flags; an overflow flag set meanwhile on this slot must survive
-          atomicAdd(&t.slots[s].weight, v.z & SHN_WEIGHT_MASK);
+          atomicAdd(&t.slots[s].weight, wz & SHN_WEIGHT_MASK);
           loc = (uint32_t)(SHN_BSLOTS * b0 + s);
         }
       }
@@ -357,7 +361,7 @@ __global__ void __launch_bounds__(kWalkBlock, 4) walk_kernel(WalkArgs a) {
   const uint64_t s_begin = a.seed_off[comp], s_end = a.seed_off[comp + 1];
   uint64_t lp = a.log_off[comp];
   const uint64_t le = a.log_off[comp + 1];
-  const uint64_t mask = shn_kmer_mask(a.k1);
+  const shn_key_t mask = shn_key_mask(a.k1);
   const int top = 2 * (a.k1 - 1);
   ShnSlot* slots = a.local;     // slot indices of this kernel are indices into the local table
   const uint64_t r0 = a.region_off[comp];
@@ -373,8 +377,8 @@ __global__ void __launch_bounds__(kWalkBlock, 4) walk_kernel(WalkArgs a) {
   const bool look = tv.n_buckets >= a.lookahead_min_buckets;
   // role of this lane inside a round: level 1 (lanes 0..3), level 2 (lanes 4..19), idle
   const int lvl = lane < 4 ? 1 : ((look && lane < 20) ? 2 : 0);
-  const uint64_t b1 = lvl == 1 ? lane : ((lane - 4) >> 2);  // first appended base
-  const uint64_t b2 = (lane - 4) & 3;                       // second appended base (level 2)
+  const shn_key_t b1 = lvl == 1 ? lane : ((lane - 4) >> 2);  // first appended base
+  const shn_key_t b2 = (lane - 4) & 3;                       // second appended base (level 2)
 
   for (uint64_t base = s_begin; base < s_end; base += 32) {
     // ---- scan 32 seeds of this component (pop order) -------------------------------------
@@ -393,27 +397,29 @@ __global__ void __launch_bounds__(kWalkBlock, 4) walk_kernel(WalkArgs a) {
       const uint32_t slot = __shfl_sync(FULL, my_slot, j);
       const uint32_t rank = __shfl_sync(FULL, my_rank, j);
       // fresh look: an earlier walk of this batch may have traversed it meanwhile (:346)
-      const uint4 v = __ldcg(reinterpret_cast<const uint4*>(slots) + slot);
-      if (v.z & SHN_TRAVERSED) continue;  // warp-uniform
-      const uint64_t seed_key = ((uint64_t)v.y << 32) | v.x;
+      shn_key_t seed_key;
+      uint32_t seed_w, seed_i;
+      table_load_slot(slots, slot, &seed_key, &seed_w, &seed_i);
+      if (seed_w & SHN_TRAVERSED) continue;  // warp-uniform
       if (lane == 0) {
-        slots[slot].weight = v.z | SHN_TRAVERSED;  // traversed.add(start_kmer), :347
+        slots[slot].weight = seed_w | SHN_TRAVERSED;  // traversed.add(start_kmer), :347
         if (lp < le) a.walk_log[lp] = 0xFF;         // the seed's own (unused) log entry
       }
       overflow |= lp >= le;
       const uint64_t my_log = lp;
       ++lp;
       ++traversed;
-      uint64_t tot = v.z & SHN_WEIGHT_MASK;
+      uint64_t tot = seed_w & SHN_WEIGHT_MASK;
       uint32_t n_dir[2] = {0, 0};
       __syncwarp();
 #pragma unroll 1
       for (int dir = 0; dir < 2; ++dir) {  // right extension first, then left (:349-350)
-        uint64_t cur = seed_key;
+        shn_key_t cur = seed_key;
         for (;;) {
           ++rounds;
           // candidate keys in the reference's tie order A,G,C,T = codes 0..3 (:10,229)
-          uint64_t cand = 0, cslot = ~0ull;
+          shn_key_t cand = 0;
+          uint64_t cslot = ~0ull;
           uint32_t wraw = 0;
           int state = 0;       // 1 found, 0 absent, -1 undecided after the two prefetched buckets
           uint64_t nextb = 0;  // where an undecided lane would continue
@@ -474,7 +480,7 @@ __global__ void __launch_bounds__(kWalkBlock, 4) walk_kernel(WalkArgs a) {
           if (s1 == 0) break;  // warp-uniform: no extension
           const int w1 = 3 - (int)((s1 - 1u) & 3u);
           const uint32_t bw1 = (s1 - 1u) >> 2;
-          const uint64_t c1 = __shfl_sync(FULL, cand, w1);
+          const shn_key_t c1 = shfl_key(cand, w1);
           if (lane == w1) slots[cslot].weight = wraw | SHN_TRAVERSED;  // traversed.add(last), :235
           if (lane == 0 && lp < le) a.walk_log[lp] = (uint8_t)w1;
           overflow |= lp >= le;
@@ -512,7 +518,7 @@ __global__ void __launch_bounds__(kWalkBlock, 4) walk_kernel(WalkArgs a) {
           }
           const int w2 = 3 - (int)((s2 - 1u) & 3u);
           const uint32_t bw2 = (s2 - 1u) >> 2;
-          cur = __shfl_sync(FULL, cand, g2 + w2);
+          cur = shfl_key(cand, g2 + w2);
           if (lane == g2 + w2) slots[cslot].weight = wraw | SHN_TRAVERSED;
           if (lane == 0 && lp < le) a.walk_log[lp] = (uint8_t)w2;
           overflow |= lp >= le;
@@ -580,7 +586,7 @@ __global__ void __launch_bounds__(kSpecWarps * 32, 1) walk_spec_kernel(SpecArgs 
   const uint32_t comp = a.comp_order[blockIdx.x];
   const uint64_t s_begin = a.seed_off[comp], s_end = a.seed_off[comp + 1];
   const uint64_t le = a.log_off[comp + 1];
-  const uint64_t mask = shn_kmer_mask(a.k1);
+  const shn_key_t mask = shn_key_mask(a.k1);
   const int top = 2 * (a.k1 - 1);
   ShnSlot* slots = a.local;
   const uint64_t r0 = a.region_off[comp];
@@ -589,8 +595,8 @@ __global__ void __launch_bounds__(kSpecWarps * 32, 1) walk_spec_kernel(SpecArgs 
   uint32_t* my_path_slot = sa.path_slot + ((uint64_t)blockIdx.x * kSpecWarps + warp) * sa.path_cap;
   uint8_t* my_path_base = sa.path_base + ((uint64_t)blockIdx.x * kSpecWarps + warp) * sa.path_cap;
   const int lvl = lane < 4 ? 1 : (lane < 20 ? 2 : 0);
-  const uint64_t b1 = lvl == 1 ? lane : ((lane - 4) >> 2);
-  const uint64_t b2 = (lane - 4) & 3;
+  const shn_key_t b1 = lvl == 1 ? lane : ((lane - 4) >> 2);
+  const shn_key_t b2 = (lane - 4) & 3;
 
   __shared__ uint64_t sh_cursor, sh_cursor_after, sh_lp;
   __shared__ uint32_t sh_win_pos[kSpecWarps], sh_win_slot[kSpecWarps], sh_len[kSpecWarps];
@@ -653,21 +659,23 @@ __global__ void __launch_bounds__(kSpecWarps * 32, 1) walk_spec_kernel(SpecArgs 
       if (lane == 0) old = atomicMax(&slots[seed_slot].idx, stamp);
       old = __shfl_sync(FULL, old, 0);
       if (old < stamp) {
-        const uint4 v = __ldcg(reinterpret_cast<const uint4*>(slots) + seed_slot);
-        const uint64_t seed_key = ((uint64_t)v.y << 32) | v.x;
+        shn_key_t seed_key;
+        uint32_t seed_w, seed_i;
+        table_load_slot(slots, seed_slot, &seed_key, &seed_w, &seed_i);
         if (lane == 0) {
           my_path_slot[0] = seed_slot;
           my_path_base[0] = 0xFF;
         }
         len = 1;
-        tot = v.z & SHN_WEIGHT_MASK;
+        tot = seed_w & SHN_WEIGHT_MASK;
 #pragma unroll 1
         for (int dir = 0; dir < 2; ++dir) {
-          uint64_t cur = seed_key;
+          shn_key_t cur = seed_key;
           bool go = true;
           while (go) {
             ++rounds;
-            uint64_t cand = 0, cslot = ~0ull;
+            shn_key_t cand = 0;
+          uint64_t cslot = ~0ull;
             uint32_t wraw = 0, cstamp = 0;
             int state = 0;
             uint64_t nextb = 0;
@@ -729,7 +737,7 @@ __global__ void __launch_bounds__(kSpecWarps * 32, 1) walk_spec_kernel(SpecArgs 
               if (lane == wl) ok = false;  // an earlier seed got there first: blocked after all
             }
             if (w1 < 0) break;  // no extension in this direction
-            const uint64_t c1 = __shfl_sync(FULL, cand, w1);
+            const shn_key_t c1 = shfl_key(cand, w1);
             const uint32_t c1slot = (uint32_t)__shfl_sync(FULL, (uint32_t)cslot, w1);
             if (lane == 0) {
               if (len < sa.path_cap) {
@@ -778,7 +786,7 @@ __global__ void __launch_bounds__(kSpecWarps * 32, 1) walk_spec_kernel(SpecArgs 
             if (w2 < 0) {
               go = false;  // the walk ends at c1 in this direction
             } else {
-              cur = __shfl_sync(FULL, cand, g2 + w2);
+              cur = shfl_key(cand, g2 + w2);
               const uint32_t c2slot = (uint32_t)__shfl_sync(FULL, (uint32_t)cslot, g2 + w2);
               if (lane == 0 && len < sa.path_cap) {
                 my_path_slot[len] = c2slot;
@@ -874,7 +882,7 @@ __global__ void __launch_bounds__(kBlock)
   if (q < nl) {
     code = walk_log[ls + 1 + nr + (nl - 1 - q)];            // reversed(left_extension)
   } else if (q < (uint64_t)nl + k1) {
-    uint64_t key = slots[w_seed_slot[w]].key;                 // start_kmer
+    shn_key_t key = slots[w_seed_slot[w]].key;                // start_kmer
     code = (uint8_t)((key >> (2 * (k1 - 1 - (int)(q - nl)))) & 3u);
   } else {
     code = walk_log[ls + 1 + (q - nl - k1)];                  // right_extension
@@ -906,6 +914,28 @@ __global__ void __launch_bounds__(kBlock)
   keys[o] = x;
   owner[o] = owner_base + (uint32_t)lo;
   pos[o] = (uint32_t)(g - start);
+}
+
+// K1-mer windows of the accepted contigs as table keys (SHN_KEY_WORDS words each), contig order
+__global__ void __launch_bounds__(kBlock)
+    k1mer_windows_kernel(const uint8_t* __restrict__ codes, const uint64_t* __restrict__ offs,
+                         const uint64_t* __restrict__ ent_off, uint64_t n_contigs, uint64_t total,
+                         int k1, uint64_t* __restrict__ keys) {
+  uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= total) return;
+  uint64_t lo = 0, hi = n_contigs;
+  while (hi - lo > 1) {
+    uint64_t mid = (lo + hi) >> 1;
+    if (__ldg(&offs[mid]) <= g)
+      lo = mid;
+    else
+      hi = mid;
+  }
+  uint64_t start = offs[lo], end = offs[lo + 1];
+  if (g + k1 > end) return;
+  shn_key_t x = 0;
+  for (int j = 0; j < k1; ++j) x = (x << 2) | (shn_key_t)(codes[g + j] & 3u);
+  shn_store_key(keys, ent_off[lo] + (g - start), x);
 }
 
 __global__ void __launch_bounds__(kBlock)
@@ -1019,7 +1049,7 @@ __global__ void __launch_bounds__(kBlock)
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   uint32_t w = 0;
-  uint64_t s = table_find(t, keys[i], &w);
+  uint64_t s = table_find(t, shn_load_key(keys, i), &w);
   if (s == ~0ull) atomicAdd(&counters[0], 1ull);
   w_out[i] = w & SHN_WEIGHT_MASK;
 }
@@ -1115,21 +1145,23 @@ bool passes_shape(uint64_t length, uint64_t tot_wt, uint64_t tot_kmer, uint32_t 
 
 }  // namespace
 
-void shn_l3_free(shn_ctx* c) {
-  delete c->l3;
+static void l3_state_free(shn_ctx* c) {
+  delete static_cast<L3State*>(c->l3);
   c->l3 = nullptr;
 }
 
-void shn_l3_run_impl(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
+void l3_run(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
   SHN_CHECK(c->n_buckets > 0, "no K1-mer table built (call shn_table_build first)");
   shn_l3_free(c);
-  L3State* s = c->l3 = new L3State();
+  L3State* s = new L3State();
+  c->l3 = s;
+  c->l3_free = &l3_state_free;
   s->min_weight = min_weight;
   s->min_length = min_length;
   const int k1 = c->k1;
   const uint64_t n_slots = c->n_buckets * SHN_BSLOTS;
   SHN_CHECK(n_slots < 0xFFFFFFFFull, "table too large for 32-bit slot indices");
-  ShnTableView tv = c->view();
+  ShnTableView tv = table_view(c);
   cudaStream_t st = c->stream;
   unsigned long long h[8];
   const unsigned stream_grid =
@@ -1645,16 +1677,16 @@ void shn_l3_run_impl(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
     exclusive_sum(c, cnt.as<uint64_t>(), off.as<uint64_t>(), n_contigs + 1);
     CUDA_CHECK(cudaMemcpyAsync(&n_allowed, off.as<uint64_t>() + n_contigs, 8, cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaStreamSynchronize(st));
-    s->allowed_keys.reserve(std::max<uint64_t>(n_allowed, 1) * 8);
+    s->allowed_keys.reserve(std::max<uint64_t>(n_allowed, 1) * 8 * SHN_KEY_WORDS);
     s->allowed_w.reserve(std::max<uint64_t>(n_allowed, 1) * 4);
     if (n_allowed) {
       owner.reserve(n_allowed * 4);
       pos.reserve(n_allowed * 4);
       ctr = zero_counters(c);
       ProfScope ps(c, "allowed", 2);
-      window_entries_kernel<<<shn_grid(contig_bases, kBlock), kBlock, 0, st>>>(
+      k1mer_windows_kernel<<<shn_grid(contig_bases, kBlock), kBlock, 0, st>>>(
           s->contig_codes.as<uint8_t>(), s->contig_offs.as<uint64_t>(), off.as<uint64_t>(), n_contigs,
-          contig_bases, k1, 1u, s->allowed_keys.as<uint64_t>(), owner.as<uint32_t>(), pos.as<uint32_t>());
+          contig_bases, k1, s->allowed_keys.as<uint64_t>());
       KERNEL_CHECK();
       allowed_weights_kernel<<<shn_grid(n_allowed, kBlock), kBlock, 0, st>>>(
           tv, s->allowed_keys.as<uint64_t>(), n_allowed, s->allowed_w.as<uint32_t>(), ctr);
@@ -1724,14 +1756,14 @@ void shn_l3_run_impl(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
 namespace {
 L3State* need_l3(shn_ctx* c) {
   SHN_CHECK(c->l3 != nullptr, "shn_l3_run has not been called on this context");
-  return c->l3;
+  return static_cast<L3State*>(c->l3);
 }
 
 __global__ void __launch_bounds__(kBlock)
     seed_keys_kernel(const ShnSlot* __restrict__ slots, const uint32_t* __restrict__ w_slot, uint64_t n,
                      uint64_t* __restrict__ keys) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) keys[i] = slots[w_slot[i]].key;
+  if (i < n) shn_store_key(keys, i, slots[w_slot[i]].key);
 }
 
 __global__ void __launch_bounds__(kBlock)
@@ -1741,10 +1773,10 @@ __global__ void __launch_bounds__(kBlock)
 }
 }  // namespace
 
-void shn_l3_get_sizes_impl(shn_ctx* c, shn_l3_sizes* out) { *out = need_l3(c)->sz; }
+void l3_get_sizes(shn_ctx* c, shn_l3_sizes* out) { *out = need_l3(c)->sz; }
 
 // device-resident accepted contigs (2-bit codes, offsets) for the L4 map
-void shn_l3_contigs_dev(shn_ctx* c, const uint8_t** codes, const uint64_t** offs, uint64_t* n,
+void l3_contigs_dev(shn_ctx* c, const uint8_t** codes, const uint64_t** offs, uint64_t* n,
                         uint64_t* n_allowed) {
   L3State* s = need_l3(c);
   *codes = s->contig_codes.as<uint8_t>();
@@ -1754,14 +1786,14 @@ void shn_l3_contigs_dev(shn_ctx* c, const uint8_t** codes, const uint64_t** offs
 }
 
 // device-resident allowed set (keys, weights) for the L4 map when caller and callee share the ctx
-void shn_l3_allowed_dev(shn_ctx* c, const uint64_t** keys, const uint32_t** weights, uint64_t* n) {
+void l3_allowed_dev(shn_ctx* c, const uint64_t** keys, const uint32_t** weights, uint64_t* n) {
   L3State* s = need_l3(c);
   *keys = s->allowed_keys.as<uint64_t>();
   *weights = s->allowed_w.as<uint32_t>();
   *n = s->sz.n_allowed;
 }
 
-void shn_l3_get_walks_impl(shn_ctx* c, uint64_t* seed_keys, uint32_t* n_left, uint32_t* n_right,
+void l3_get_walks(shn_ctx* c, uint64_t* seed_keys, uint32_t* n_left, uint32_t* n_right,
                            uint64_t* tot_wt, uint8_t* flags) {
   L3State* s = need_l3(c);
   uint64_t n = s->sz.n_walks;
@@ -1769,11 +1801,11 @@ void shn_l3_get_walks_impl(shn_ctx* c, uint64_t* seed_keys, uint32_t* n_left, ui
   cudaStream_t st = c->stream;
   if (seed_keys) {
     DevBuf keys;
-    keys.reserve(n * 8);
-    seed_keys_kernel<<<shn_grid(n, kBlock), kBlock, 0, st>>>(c->view().slots, s->w_seed_slot.as<uint32_t>(),
+    keys.reserve(n * 8 * SHN_KEY_WORDS);
+    seed_keys_kernel<<<shn_grid(n, kBlock), kBlock, 0, st>>>(table_view(c).slots, s->w_seed_slot.as<uint32_t>(),
                                                             n, keys.as<uint64_t>());
     KERNEL_CHECK();
-    CUDA_CHECK(cudaMemcpyAsync(seed_keys, keys.p, n * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaMemcpyAsync(seed_keys, keys.p, n * 8 * SHN_KEY_WORDS, cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaStreamSynchronize(st));
   }
   if (n_left) CUDA_CHECK(cudaMemcpyAsync(n_left, s->w_nl.p, n * 4, cudaMemcpyDeviceToHost, st));
@@ -1791,7 +1823,7 @@ void shn_l3_get_walks_impl(shn_ctx* c, uint64_t* seed_keys, uint32_t* n_left, ui
   }
 }
 
-void shn_l3_get_contigs_impl(shn_ctx* c, char* bases, uint64_t* offsets) {
+void l3_get_contigs(shn_ctx* c, char* bases, uint64_t* offsets) {
   L3State* s = need_l3(c);
   uint64_t nb = s->sz.contig_bases;
   memcpy(offsets, s->h_contig_offs.data(), s->h_contig_offs.size() * 8);
@@ -1805,17 +1837,19 @@ void shn_l3_get_contigs_impl(shn_ctx* c, char* bases, uint64_t* offsets) {
   CUDA_CHECK(cudaStreamSynchronize(c->stream));
 }
 
-void shn_l3_get_allowed_impl(shn_ctx* c, uint64_t* keys, uint32_t* weights) {
+void l3_get_allowed(shn_ctx* c, uint64_t* keys, uint32_t* weights) {
   L3State* s = need_l3(c);
   uint64_t n = s->sz.n_allowed;
   if (n == 0) return;
-  if (keys) CUDA_CHECK(cudaMemcpyAsync(keys, s->allowed_keys.p, n * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (keys)
+    CUDA_CHECK(cudaMemcpyAsync(keys, s->allowed_keys.p, n * 8 * SHN_KEY_WORDS, cudaMemcpyDeviceToHost,
+                               c->stream));
   if (weights)
     CUDA_CHECK(cudaMemcpyAsync(weights, s->allowed_w.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
   CUDA_CHECK(cudaStreamSynchronize(c->stream));
 }
 
-void shn_l3_get_edges_impl(shn_ctx* c, uint32_t* a, uint32_t* b, uint32_t* weight, uint32_t* fp) {
+void l3_get_edges(shn_ctx* c, uint32_t* a, uint32_t* b, uint32_t* weight, uint32_t* fp) {
   L3State* s = need_l3(c);
   uint64_t n = s->edges.n;
   if (n == 0) return;
@@ -1827,9 +1861,11 @@ void shn_l3_get_edges_impl(shn_ctx* c, uint32_t* a, uint32_t* b, uint32_t* weigh
   CUDA_CHECK(cudaStreamSynchronize(st));
 }
 
-void shn_l3_get_labels_impl(shn_ctx* c, uint32_t* label) {
+void l3_get_labels(shn_ctx* c, uint32_t* label) {
   L3State* s = need_l3(c);
   CUDA_CHECK(cudaMemcpyAsync(label, s->labels.p, (s->sz.n_contigs + 1) * 4, cudaMemcpyDeviceToHost,
                              c->stream));
   CUDA_CHECK(cudaStreamSynchronize(c->stream));
 }
+
+}  // namespace SHN_NS

@@ -15,20 +15,25 @@
 #include <cub/cub.cuh>
 
 #include "common.cuh"
+#include "impls.h"
 #include "table_dev.cuh"
 
+#include "reads.cuh"
+
+namespace SHN_NS {
+
+#ifdef SHN_WIDE
+struct __align__(32) CompSlot {
+  u128 key;
+  uint32_t comp0, comp1;
+  uint64_t pad;
+};
+#else
 struct __align__(16) CompSlot {
   uint64_t key;
   uint32_t comp0, comp1;
 };
-
-struct PackedReads {
-  DevBuf words;   // uint64
-  DevBuf woff;    // uint64 [n+1] word offsets
-  DevBuf len;     // uint32 [n]   length, bit 31 = contains a non-ACGT character
-  uint64_t n = 0;
-  uint64_t n_words = 0;
-};
+#endif
 
 struct L4State {
   DevBuf map;       // CompSlot[2*n_buckets]
@@ -36,14 +41,9 @@ struct L4State {
   uint64_t n_buckets = 0;
   int k1 = 0;
   uint64_t n_keys = 0;
-  PackedReads reads[2];
   DevBuf assign;    // uint64 entries (comp << 32 | record), sorted + unique after shn_l4_assign
   uint64_t n_assign = 0;
   DevBuf stage_a, stage_b, stage_c;
-  // reads uploaded ahead of time on the copy stream (overlaps the H2D with the L3 stage)
-  DevBuf up_bases[2], up_offs[2];
-  uint64_t up_n[2] = {0, 0};
-  cudaEvent_t up_done[2] = {nullptr, nullptr};
 };
 
 namespace {
@@ -54,8 +54,8 @@ constexpr uint32_t kLenBad = 0x80000000u;
 struct CompMapView {
   CompSlot* slots;
   uint64_t n_buckets;
-  __device__ __forceinline__ uint64_t bucket_of(uint64_t key) const {
-    return __umul64hi(shn_mix64(key), n_buckets);
+  __device__ __forceinline__ uint64_t bucket_of(shn_key_t key) const {
+    return __umul64hi(shn_key_hash(key), n_buckets);
   }
 };
 
@@ -63,8 +63,13 @@ __global__ void __launch_bounds__(kBlock) map_clear_kernel(CompSlot* slots, uint
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   uint4 v = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
-  for (; i < n; i += stride) {
+  for (; i < n; i += stride) {  // key = EMPTY, comp0 = comp1 = NONE
+#ifdef SHN_WIDE
+    reinterpret_cast<uint4*>(slots)[2 * i] = v;
+    reinterpret_cast<uint4*>(slots)[2 * i + 1] = v;
+#else
     reinterpret_cast<uint4*>(slots)[i] = v;
+#endif
     w[i] = 0;
   }
 }
@@ -85,33 +90,45 @@ __device__ __forceinline__ uint64_t find_segment(const uint64_t* __restrict__ of
 
 // packs bases[p .. p+k) ; returns false if a non-ACGT character is met
 __device__ __forceinline__ bool pack_window(const char* __restrict__ bases, uint64_t p, int k,
-                                            uint64_t* out) {
-  uint64_t x = 0;
+                                            shn_key_t* out) {
+  shn_key_t x = 0;
   bool ok = true;
   for (int j = 0; j < k; ++j) {
     uint32_t code = shn_code_of_strict((uint8_t)__ldg(&bases[p + j]));
     ok &= code < 4;
-    x = (x << 2) | (code & 3u);
+    x = (x << 2) | (shn_key_t)(code & 3u);
   }
   *out = x;
   return ok;
 }
 
-// 32-byte bucket = one 256-bit load; *comps = comp0 | comp1 << 32 of the matching slot
-__device__ __forceinline__ uint64_t map_find(const CompMapView& m, uint64_t key, uint64_t* comps) {
+// bucket of two slots (32 bytes = one 256-bit load for 64-bit keys, 64 bytes for 128-bit keys);
+// *comps = comp0 | comp1 << 32 of the matching slot
+__device__ __forceinline__ uint64_t map_find(const CompMapView& m, shn_key_t key, uint64_t* comps) {
+  if (key == SHN_EMPTY) return ~0ull;
   uint64_t b = m.bucket_of(key);
   for (;;) {
+#ifdef SHN_WIDE
+    uint64_t w[8];
+    shn_ld256_nc(m.slots + 2 * b, w);
+    shn_ld256_nc(m.slots + 2 * b + 1, w + 4);
+    const shn_key_t k0 = ((u128)w[1] << 64) | w[0], k1 = ((u128)w[5] << 64) | w[4];
+    const uint64_t c0 = w[2], c1 = w[6];
+#else
     uint64_t w[4];
     shn_ld256_nc(m.slots + 2 * b, w);
-    if (w[0] == key) {
-      *comps = w[1];
+    const shn_key_t k0 = w[0], k1 = w[2];
+    const uint64_t c0 = w[1], c1 = w[3];
+#endif
+    if (k0 == key) {
+      *comps = c0;
       return 2 * b;
     }
-    if (w[2] == key) {
-      *comps = w[3];
+    if (k1 == key) {
+      *comps = c1;
       return 2 * b + 1;
     }
-    if (w[0] == SHN_EMPTY_KEY || w[2] == SHN_EMPTY_KEY) return ~0ull;
+    if (k0 == SHN_EMPTY || k1 == SHN_EMPTY) return ~0ull;
     b = (b + 1 == m.n_buckets) ? 0 : b + 1;
   }
 }
@@ -128,10 +145,10 @@ __global__ void __launch_bounds__(kBlock)
     uint64_t end = __ldg(&offs[c + 1]);
     uint32_t comp = __ldg(&comp_of[c]);
     if (g + k1 <= end && comp != SHN_NONE32) {  // comp == NONE: contig is not partitioned (single)
-      uint64_t key = 0;
+      shn_key_t key = 0;
       bool okw = true;
       if (is_codes) {
-        for (int j = 0; j < k1; ++j) key = (key << 2) | (uint64_t)((uint8_t)__ldg(&bases[g + j]) & 3u);
+        for (int j = 0; j < k1; ++j) key = (key << 2) | (shn_key_t)((uint8_t)__ldg(&bases[g + j]) & 3u);
       } else {
         okw = pack_window(bases, g, k1, &key);
       }
@@ -144,16 +161,18 @@ __global__ void __launch_bounds__(kBlock)
           CompSlot* s = m.slots + 2 * b;
           const ulonglong2 s0 = __ldcg(reinterpret_cast<const ulonglong2*>(&s[0]));
           const ulonglong2 s1 = __ldcg(reinterpret_cast<const ulonglong2*>(&s[1]));
-          uint64_t k[2] = {s0.x, s1.x};
+#ifdef SHN_WIDE
+          shn_key_t k[2] = {((u128)s0.y << 64) | s0.x, ((u128)s1.y << 64) | s1.x};
+#else
+          shn_key_t k[2] = {s0.x, s1.x};
+#endif
 #pragma unroll
           for (int j = 0; j < 2 && !slot; ++j) {
             if (k[j] == key) {
               slot = &s[j];
-            } else if (k[j] == SHN_EMPTY_KEY) {
-              unsigned long long old =
-                  atomicCAS(reinterpret_cast<unsigned long long*>(&s[j].key),
-                            (unsigned long long)SHN_EMPTY_KEY, (unsigned long long)key);
-              if (old == SHN_EMPTY_KEY) {
+            } else if (k[j] == SHN_EMPTY) {
+              shn_key_t old = shn_cas_key(&s[j].key, SHN_EMPTY, key);
+              if (old == SHN_EMPTY) {
                 n_new = 1;
                 slot = &s[j];
               } else if (old == key) {
@@ -187,7 +206,7 @@ __global__ void __launch_bounds__(kBlock)
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   uint64_t comps;
-  uint64_t slot = map_find(m, keys[i], &comps);
+  uint64_t slot = map_find(m, shn_load_key(keys, i), &comps);
   if (slot != ~0ull) map_w[slot] = weights[i];
 }
 
@@ -210,7 +229,7 @@ __global__ void __launch_bounds__(kBlock)
   uint64_t c = find_segment(offs, n_contigs, g);
   uint64_t start = __ldg(&offs[c]), end = __ldg(&offs[c + 1]);
   if (g + k1 > end) return;
-  uint64_t key;
+  shn_key_t key;
   uint32_t w = 0;
   if (pack_window(bases, g, k1, &key)) {
     uint64_t comps;
@@ -220,65 +239,25 @@ __global__ void __launch_bounds__(kBlock)
   out[win_off[c] + (g - start)] = w;
 }
 
-// ---- read packing -------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock)
-    read_words_kernel(const uint64_t* __restrict__ offs, uint64_t n, uint64_t* __restrict__ nwords) {
-  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  uint64_t len = offs[i + 1] - offs[i];
-  nwords[i] = (len + 31) >> 5;
-}
-
-// 8 lanes per read, one 32-base word per lane and iteration
-__global__ void __launch_bounds__(kBlock)
-    pack_reads_kernel(const char* __restrict__ bases, const uint64_t* __restrict__ offs,
-                      const uint64_t* __restrict__ woff, uint64_t n, uint64_t* __restrict__ words,
-                      uint32_t* __restrict__ len_out) {
-  uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  uint64_t i = t >> 3;
-  int lane8 = (int)(t & 7);
-  bool active = i < n;
-  uint64_t start = 0, len = 0, wbase = 0;
-  if (active) {
-    start = __ldg(&offs[i]);
-    len = __ldg(&offs[i + 1]) - start;
-    wbase = __ldg(&woff[i]);
-  }
-  uint64_t nw = (len + 31) >> 5;
-  bool bad = false;
-  for (uint64_t w = lane8; w < nw; w += 8) {
-    uint64_t x = 0;
-    uint64_t p = start + 32 * w;
-    int cnt = (int)min((uint64_t)32, len - 32 * w);
-    for (int j = 0; j < cnt; ++j) {
-      uint32_t code = shn_code_of_strict((uint8_t)__ldg(&bases[p + j]));
-      bad |= code >= 4;
-      x = (x << 2) | (code & 3u);
-    }
-    x <<= 2 * (32 - cnt);  // left-align a partial last word
-    words[wbase + w] = x;
-  }
-  // OR the bad flags of the 8 lanes of this read
-  unsigned b = __ballot_sync(0xFFFFFFFFu, bad);
-  unsigned grp = (b >> ((threadIdx.x & 31) & ~7)) & 0xFFu;
-  if (active && lane8 == 0) {
-    len_out[i] = (uint32_t)len | (grp ? kLenBad : 0u);
-  }
-}
-
 struct ReadsView {
   const uint64_t* words;
   const uint64_t* woff;
   const uint32_t* len;
 };
 
-__device__ __forceinline__ uint64_t extract_kmer(const uint64_t* __restrict__ words, uint64_t wbase,
-                                                 uint32_t st, int k1) {
+__device__ __forceinline__ shn_key_t extract_kmer(const uint64_t* __restrict__ words, uint64_t wbase,
+                                                  uint32_t st, int k1) {
   uint64_t wi = wbase + (st >> 5);
   int sh = (int)(st & 31);
+#ifdef SHN_WIDE   // 33..64 bases: up to three 32-base words
+  u128 x = (((u128)__ldg(&words[wi]) << 64) | __ldg(&words[wi + 1])) << (2 * sh);
+  if (sh + k1 > 64) x |= (u128)(__ldg(&words[wi + 2]) >> (64 - 2 * sh));
+  return x >> (128 - 2 * k1);
+#else
   uint64_t x = __ldg(&words[wi]) << (2 * sh);
   if (sh + k1 > 32) x |= __ldg(&words[wi + 1]) >> (64 - 2 * sh);
   return x >> (64 - 2 * k1);
+#endif
 }
 
 // number of sampled K1-mers of a read of length len (get_rmers, kmers_for_component.py:186-192)
@@ -327,7 +306,7 @@ __global__ void __launch_bounds__(kBlock)
       uint32_t nsm = second ? ns1 : ns0;
       // offsets 0, k1, 2*k1, ... and the last window (read[-k1:])
       uint32_t st = (si + 1 == nsm) ? len - k1 : si * k1;
-      uint64_t key = extract_kmer(second ? r1.words : r0.words, second ? wb1 : wb0, st, k1);
+      shn_key_t key = extract_kmer(second ? r1.words : r0.words, second ? wb1 : wb0, st, k1);
       uint64_t comps;
       uint64_t slot = map_find(m, key, &comps);
       my_lookups++;
@@ -398,9 +377,18 @@ __global__ void __launch_bounds__(kBlock)
   if (i < n) out[i] = (uint32_t)entries[i];
 }
 
+void l4_state_free(shn_ctx* c) {
+  delete static_cast<L4State*>(c->l4);
+  c->l4 = nullptr;
+}
+
 L4State* l4_of(shn_ctx* c) {
-  if (!c->l4) c->l4 = new L4State();
-  return c->l4;
+  if (c->l4 && c->l4_free != &l4_state_free) shn_l4_free(c);  // state of the other key width
+  if (!c->l4) {
+    c->l4 = new L4State();
+    c->l4_free = &l4_state_free;
+  }
+  return static_cast<L4State*>(c->l4);
 }
 
 CompMapView map_view(L4State* s) { return CompMapView{s->map.as<CompSlot>(), s->n_buckets}; }
@@ -420,18 +408,10 @@ void read_counters(shn_ctx* c, unsigned long long* h, int n) {
 
 }  // namespace
 
-void shn_l4_free(shn_ctx* c) {
-  if (c->l4)
-    for (int m = 0; m < 2; ++m)
-      if (c->l4->up_done[m]) cudaEventDestroy(c->l4->up_done[m]);
-  delete c->l4;
-  c->l4 = nullptr;
-}
-
-void shn_l4_map_add_contigs_impl(shn_ctx* c, const char* bases, const uint64_t* offsets,
+void l4_map_add_contigs(shn_ctx* c, const char* bases, const uint64_t* offsets,
                                  const uint32_t* comp_of_contig, uint64_t n_contigs, int k1,
                                  int reset, uint64_t expected_total, int on_device, int is_codes) {
-  SHN_CHECK(k1 >= 1 && k1 <= 32, "k1 must be in 1..32");
+  SHN_CHECK(k1 >= 1 && k1 <= SHN_MAX_K1, "k1 out of range for this key width");
   L4State* s = l4_of(c);
   if (reset) {
     uint64_t nb = expected_total < 1024 ? 1024 : expected_total;
@@ -480,12 +460,13 @@ void shn_l4_map_add_contigs_impl(shn_ctx* c, const char* bases, const uint64_t* 
   s->n_keys += h[0];
 }
 
-void shn_l4_map_set_weights_impl(shn_ctx* c, const uint64_t* keys, const uint32_t* weights,
+void l4_map_set_weights(shn_ctx* c, const uint64_t* keys, const uint32_t* weights,
                                  uint64_t n, int on_device) {
   L4State* s = l4_of(c);
   SHN_CHECK(s->n_buckets > 0, "component map not initialised");
   if (n == 0) return;
-  const uint64_t* d_keys = (const uint64_t*)InputView::get(c, keys, n * 8, on_device, s->stage_a);
+  const uint64_t* d_keys =
+      (const uint64_t*)InputView::get(c, keys, n * 8 * SHN_KEY_WORDS, on_device, s->stage_a);
   const uint32_t* d_w = (const uint32_t*)InputView::get(c, weights, n * 4, on_device, s->stage_b);
   ProfScope ps(c, "l4_map_set_weights");
   map_set_weights_kernel<<<shn_grid(n, kBlock), kBlock, 0, c->stream>>>(
@@ -494,7 +475,7 @@ void shn_l4_map_set_weights_impl(shn_ctx* c, const uint64_t* keys, const uint32_
   CUDA_CHECK(cudaStreamSynchronize(c->stream));
 }
 
-void shn_l4_map_window_weights_impl(shn_ctx* c, const char* bases, const uint64_t* offsets,
+void l4_map_window_weights(shn_ctx* c, const char* bases, const uint64_t* offsets,
                                     uint64_t n_contigs, int k1, uint32_t* h_weights) {
   L4State* s = l4_of(c);
   SHN_CHECK(s->n_buckets > 0, "component map not initialised");
@@ -531,107 +512,23 @@ void shn_l4_map_window_weights_impl(shn_ctx* c, const char* bases, const uint64_
   CUDA_CHECK(cudaStreamSynchronize(c->stream));
 }
 
-void shn_l4_load_reads_impl(shn_ctx* c, int mate, const char* bases, const uint64_t* offsets,
-                            uint64_t n, int on_device) {
-  SHN_CHECK(mate == 0 || mate == 1, "mate must be 0 or 1");
-  L4State* s = l4_of(c);
-  PackedReads& pr = s->reads[mate];
-  pr.n = n;
-  pr.n_words = 0;
-  if (n == 0) return;
-  SHN_CHECK(n < 0xFFFFFFFFull, "at most 2^32-1 read records per call");
-  uint64_t total = 0;
-  const uint64_t* d_offs;
-  if (on_device) {
-    d_offs = offsets;
-    CUDA_CHECK(cudaMemcpyAsync(&total, offsets + n, 8, cudaMemcpyDeviceToHost, c->stream));
-    CUDA_CHECK(cudaStreamSynchronize(c->stream));
-  } else {
-    total = offsets[n];
-    d_offs = (const uint64_t*)InputView::get(c, offsets, (n + 1) * 8, 0, s->stage_b);
-  }
-  const char* d_bases = (const char*)InputView::get(c, bases, total, on_device, s->stage_a);
-  DevBuf nwords;
-  nwords.reserve((n + 1) * 8);
-  pr.woff.reserve((n + 1) * 8);
-  pr.len.reserve(n * 4);
-  CUDA_CHECK(cudaMemsetAsync(nwords.p, 0, (n + 1) * 8, c->stream));
-  {
-    ProfScope ps(c, "read_word_offsets", 2);
-    read_words_kernel<<<shn_grid(n, kBlock), kBlock, 0, c->stream>>>(d_offs, n, nwords.as<uint64_t>());
-    KERNEL_CHECK();
-    size_t tb = 0;
-    CUDA_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, tb, nwords.as<uint64_t>(), pr.woff.as<uint64_t>(),
-                                             (int64_t)(n + 1), c->stream));
-    CUDA_CHECK(cub::DeviceScan::ExclusiveSum(c->tmp(tb), tb, nwords.as<uint64_t>(),
-                                             pr.woff.as<uint64_t>(), (int64_t)(n + 1), c->stream));
-  }
-  CUDA_CHECK(cudaMemcpyAsync(&pr.n_words, pr.woff.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost,
-                             c->stream));
-  CUDA_CHECK(cudaStreamSynchronize(c->stream));
-  pr.words.reserve((pr.n_words + 1) * 8);  // +1: extract_kmer may touch one word past a read
-  CUDA_CHECK(cudaMemsetAsync(pr.words.as<uint64_t>() + pr.n_words, 0, 8, c->stream));
-  {
-    ProfScope ps(c, "pack_reads");
-    pack_reads_kernel<<<shn_grid(n * 8, kBlock), kBlock, 0, c->stream>>>(
-        d_bases, d_offs, pr.woff.as<uint64_t>(), n, pr.words.as<uint64_t>(), pr.len.as<uint32_t>());
-    KERNEL_CHECK();
-  }
-  CUDA_CHECK(cudaStreamSynchronize(c->stream));
-}
-
-// Starts the host->device copy of one mate file on the context's second stream and returns
-// immediately; shn_l4_load_reads_staged() later waits for it and packs.  With pinned host memory
-// the copy overlaps whatever the main stream does meanwhile (the whole L3 stage in the pipeline).
-void shn_l4_upload_reads_async_impl(shn_ctx* c, int mate, const char* bases, const uint64_t* offsets,
-                                    uint64_t n) {
-  SHN_CHECK(mate == 0 || mate == 1, "mate must be 0 or 1");
-  L4State* s = l4_of(c);
-  if (!c->stream2) CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
-  if (!s->up_done[mate]) CUDA_CHECK(cudaEventCreateWithFlags(&s->up_done[mate], cudaEventDisableTiming));
-  s->up_n[mate] = n;
-  const uint64_t total = n ? offsets[n] : 0;
-  s->up_bases[mate].reserve(std::max<uint64_t>(total, 1));
-  s->up_offs[mate].reserve((n + 1) * 8);
-  // the staging buffers may have been used by kernels still queued on the main stream
-  cudaEvent_t ev = c->prof_event();
-  CUDA_CHECK(cudaEventRecord(ev, c->stream));
-  CUDA_CHECK(cudaStreamWaitEvent(c->stream2, ev, 0));
-  c->prof_pool.push_back(ev);
-  if (total)
-    CUDA_CHECK(cudaMemcpyAsync(s->up_bases[mate].p, bases, total, cudaMemcpyHostToDevice, c->stream2));
-  CUDA_CHECK(cudaMemcpyAsync(s->up_offs[mate].p, offsets, (n + 1) * 8, cudaMemcpyHostToDevice, c->stream2));
-  CUDA_CHECK(cudaEventRecord(s->up_done[mate], c->stream2));
-}
-
-void shn_l4_load_reads_impl(shn_ctx* c, int mate, const char* bases, const uint64_t* offsets,
-                            uint64_t n, int on_device);
-
-void shn_l4_load_reads_staged_impl(shn_ctx* c, int mate) {
-  SHN_CHECK(mate == 0 || mate == 1, "mate must be 0 or 1");
-  L4State* s = l4_of(c);
-  SHN_CHECK(s->up_done[mate] != nullptr, "no upload in flight for this mate");
-  CUDA_CHECK(cudaStreamWaitEvent(c->stream, s->up_done[mate], 0));
-  shn_l4_load_reads_impl(c, mate, s->up_bases[mate].as<char>(), s->up_offs[mate].as<uint64_t>(),
-                         s->up_n[mate], 1);
-}
-
-void shn_l4_assign_impl(shn_ctx* c, int paired, int k1, uint64_t* n_assign, uint64_t* n_lookups,
+void l4_assign(shn_ctx* c, int paired, int k1, uint64_t* n_assign, uint64_t* n_lookups,
                         uint64_t* n_valid) {
   L4State* s = l4_of(c);
   SHN_CHECK(s->n_buckets > 0, "component map not initialised");
   SHN_CHECK(k1 == s->k1, "k1 differs from the component map's");
-  uint64_t n = s->reads[0].n;
-  if (paired) SHN_CHECK(s->reads[1].n == n, "mate files hold different numbers of records");
+  ReadsState* rs = shn_reads_of(c);
+  uint64_t n = rs->reads[0].n;
+  if (paired) SHN_CHECK(rs->reads[1].n == n, "mate files hold different numbers of records");
   s->n_assign = 0;
   *n_assign = *n_lookups = *n_valid = 0;
   if (n == 0) return;
-  ReadsView r0{s->reads[0].words.as<uint64_t>(), s->reads[0].woff.as<uint64_t>(),
-               s->reads[0].len.as<uint32_t>()};
+  ReadsView r0{rs->reads[0].words.as<uint64_t>(), rs->reads[0].woff.as<uint64_t>(),
+               rs->reads[0].len.as<uint32_t>()};
   ReadsView r1 = r0;
   if (paired)
-    r1 = ReadsView{s->reads[1].words.as<uint64_t>(), s->reads[1].woff.as<uint64_t>(),
-                   s->reads[1].len.as<uint32_t>()};
+    r1 = ReadsView{rs->reads[1].words.as<uint64_t>(), rs->reads[1].woff.as<uint64_t>(),
+                   rs->reads[1].len.as<uint32_t>()};
   uint64_t cap = std::max<uint64_t>(2 * n, 1024);
   unsigned long long h[4];
   for (int attempt = 0;; ++attempt) {
@@ -675,7 +572,7 @@ void shn_l4_assign_impl(shn_ctx* c, int paired, int k1, uint64_t* n_assign, uint
   *n_assign = m;
 }
 
-void shn_l4_get_assignments_impl(shn_ctx* c, uint32_t n_comps, uint64_t* h_offs, uint32_t* h_idx) {
+void l4_get_assignments(shn_ctx* c, uint32_t n_comps, uint64_t* h_offs, uint32_t* h_idx) {
   L4State* s = l4_of(c);
   uint64_t m = s->n_assign;
   DevBuf offs, idx;
@@ -694,3 +591,5 @@ void shn_l4_get_assignments_impl(shn_ctx* c, uint32_t n_comps, uint64_t* h_offs,
                              c->stream));
   CUDA_CHECK(cudaStreamSynchronize(c->stream));
 }
+
+}  // namespace SHN_NS

@@ -5,8 +5,10 @@
 #include <cub/cub.cuh>
 
 #include "common.cuh"
+#include "impls.h"
 #include "table_dev.cuh"
 
+#ifndef SHN_WIDE  // the generators do not depend on the key width: compiled once
 namespace {
 
 constexpr int kBlock = 256;
@@ -72,86 +74,6 @@ __global__ void __launch_bounds__(kBlock)
   out[g] = o;
 }
 
-// one thread per window; counters: [0]=new keys [1]=table full
-__global__ void __launch_bounds__(kBlock)
-    count_windows_kernel(ShnTableView t, const char* __restrict__ reads, uint64_t n_reads,
-                         int read_len, int k1, unsigned long long* counters) {
-  const int wins = read_len - k1 + 1;
-  uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  int n_new = 0, full = 0;
-  if (g < n_reads * (uint64_t)wins) {
-    uint64_t r = g / wins;
-    int w = (int)(g - r * wins);
-    const char* p = reads + r * read_len + w;
-    uint64_t key = 0;
-    bool ok = true;
-    for (int j = 0; j < k1; ++j) {
-      uint32_t code = shn_code_of_strict((uint8_t)__ldg(&p[j]));
-      ok &= code < 4;
-      key = (key << 2) | (code & 3u);
-    }
-    if (ok) {
-      uint64_t slot = table_upsert_slot(t, key, &n_new);
-      if (slot == ~0ull)
-        full = 1;
-      else
-        atomicAdd(&t.slots[slot].weight, 1u);
-    }
-  }
-  int t_new = __syncthreads_count(n_new), t_full = __syncthreads_count(full);
-  if (threadIdx.x == 0) {
-    if (t_new) atomicAdd(&counters[0], (unsigned long long)t_new);
-    if (t_full) atomicAdd(&counters[1], (unsigned long long)t_full);
-  }
-}
-
-__global__ void __launch_bounds__(kBlock)
-    count_clear_kernel(ShnSlot* slots, uint64_t n_slots) {
-  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  uint4 v = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u);
-  for (; i < n_slots; i += stride) reinterpret_cast<uint4*>(slots)[i] = v;
-}
-
-// compaction of occupied slots into (ascii-order sort key, count), block-aggregated append
-__global__ void __launch_bounds__(kBlock)
-    count_compact_kernel(const ShnSlot* __restrict__ slots, uint64_t n_slots,
-                         uint64_t* __restrict__ skeys, uint32_t* __restrict__ counts,
-                         unsigned long long* cursor) {
-  __shared__ unsigned long long block_base;
-  __shared__ int warp_off[kBlock / 32];
-  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  uint4 v = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0, 0);
-  if (i < n_slots) v = __ldg(reinterpret_cast<const uint4*>(slots) + i);
-  uint64_t key = ((uint64_t)v.y << 32) | v.x;
-  bool occ = key != SHN_EMPTY_KEY;
-  unsigned b = __ballot_sync(0xFFFFFFFFu, occ);
-  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (lane == 0) warp_off[warp] = __popc(b);
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int tot = 0;
-    for (int w = 0; w < kBlock / 32; ++w) {
-      int c = warp_off[w];
-      warp_off[w] = tot;
-      tot += c;
-    }
-    block_base = tot ? atomicAdd(cursor, (unsigned long long)tot) : 0ull;
-  }
-  __syncthreads();
-  if (occ) {
-    uint64_t o = block_base + warp_off[warp] + __popc(b & ((1u << lane) - 1u));
-    skeys[o] = shn_ascii_order_key(key);
-    counts[o] = v.z & SHN_WEIGHT_MASK;
-  }
-}
-
-__global__ void __launch_bounds__(kBlock)
-    unorder_keys_kernel(uint64_t* __restrict__ keys, uint64_t n) {
-  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) keys[i] = shn_ascii_order_key(keys[i]);  // the pair swap is an involution
-}
-
 }  // namespace
 
 void shn_synth_pairs_impl(shn_ctx* c, const uint8_t* tx, const uint64_t* tx_offs, const uint64_t* thr,
@@ -173,26 +95,135 @@ void shn_revcomp_reads_impl(shn_ctx* c, const char* in, char* out, uint64_t n_re
   KERNEL_CHECK();
 }
 
-struct CountState {
-  DevBuf keys, counts;
-};
-static std::map<shn_ctx*, CountState*> g_count_state;
+#endif  // !SHN_WIDE
 
-void shn_count_free(shn_ctx* c) {
-  auto it = g_count_state.find(c);
-  if (it != g_count_state.end()) {
-    delete it->second;
-    g_count_state.erase(it);
+namespace SHN_NS {
+namespace {
+
+constexpr int kCBlock = 256;
+
+// one thread per window; counters: [0]=new keys [1]=table full
+__global__ void __launch_bounds__(kCBlock)
+    count_windows_kernel(ShnTableView t, const char* __restrict__ reads, uint64_t n_reads,
+                         int read_len, int k1, unsigned long long* counters) {
+  const int wins = read_len - k1 + 1;
+  uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int n_new = 0, full = 0;
+  if (g < n_reads * (uint64_t)wins) {
+    uint64_t r = g / wins;
+    int w = (int)(g - r * wins);
+    const char* p = reads + r * read_len + w;
+    shn_key_t key = 0;
+    bool ok = true;
+    for (int j = 0; j < k1; ++j) {
+      uint32_t code = shn_code_of_strict((uint8_t)__ldg(&p[j]));
+      ok &= code < 4;
+      key = (key << 2) | (shn_key_t)(code & 3u);
+    }
+    if (ok && key != SHN_EMPTY) {  // (the all-T K1-mer of 32/64 bases is the table's empty marker;
+                                   //  it is low-complexity and dropped by load_kmers anyway)
+      uint64_t slot = table_upsert_slot(t, key, &n_new);
+      if (slot == ~0ull)
+        full = 1;
+      else
+        atomicAdd(&t.slots[slot].weight, 1u);
+    }
+  }
+  int t_new = __syncthreads_count(n_new), t_full = __syncthreads_count(full);
+  if (threadIdx.x == 0) {
+    if (t_new) atomicAdd(&counters[0], (unsigned long long)t_new);
+    if (t_full) atomicAdd(&counters[1], (unsigned long long)t_full);
   }
 }
 
-void shn_count_k1mers_impl(shn_ctx* c, const char* const* arrays, const uint64_t* n_reads,
-                           int n_arrays, int read_len, int k1, uint64_t expected_distinct,
-                           uint64_t** keys_dev, uint32_t** counts_dev, uint64_t* n_distinct) {
-  SHN_CHECK(k1 >= 1 && k1 <= 32 && read_len >= k1, "bad k1 / read length");
+__global__ void __launch_bounds__(kCBlock) count_clear_kernel(ShnSlot* slots, uint64_t n_slots) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (; i < n_slots; i += stride) table_store_empty(slots, i, 0u);
+}
+
+// compaction of occupied slots: ASCII-order sort words of the key, count, running index
+__global__ void __launch_bounds__(kCBlock)
+    count_compact_kernel(const ShnSlot* __restrict__ slots, uint64_t n_slots,
+                         uint64_t* __restrict__ ord_lo, uint64_t* __restrict__ ord_hi,
+                         uint32_t* __restrict__ counts, uint32_t* __restrict__ iota,
+                         unsigned long long* cursor) {
+  __shared__ unsigned long long block_base;
+  __shared__ int warp_off[kCBlock / 32];
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  shn_key_t key = SHN_EMPTY;
+  uint32_t wz = 0, wi = 0;
+  if (i < n_slots) table_load_slot(slots, i, &key, &wz, &wi);
+  bool occ = key != SHN_EMPTY;
+  unsigned b = __ballot_sync(0xFFFFFFFFu, occ);
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) warp_off[warp] = __popc(b);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int tot = 0;
+    for (int w = 0; w < kCBlock / 32; ++w) {
+      int c = warp_off[w];
+      warp_off[w] = tot;
+      tot += c;
+    }
+    block_base = tot ? atomicAdd(cursor, (unsigned long long)tot) : 0ull;
+  }
+  __syncthreads();
+  if (occ) {
+    uint64_t o = block_base + warp_off[warp] + __popc(b & ((1u << lane) - 1u));
+    shn_key_t ok = shn_ascii_order_key(key);
+    ord_lo[o] = (uint64_t)ok;
+#ifdef SHN_WIDE
+    ord_hi[o] = (uint64_t)(ok >> 64);
+#endif
+    counts[o] = wz & SHN_WEIGHT_MASK;
+    iota[o] = (uint32_t)o;
+  }
+}
+
+__global__ void __launch_bounds__(kCBlock)
+    gather_u64_kernel(const uint64_t* __restrict__ src, const uint32_t* __restrict__ perm, uint64_t n,
+                      uint64_t* __restrict__ dst) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[perm[i]];
+}
+
+// final order: keys back in table code order (the pair swap is an involution), counts permuted
+__global__ void __launch_bounds__(kCBlock)
+    count_emit_kernel(const uint64_t* __restrict__ ord_lo, const uint64_t* __restrict__ ord_hi,
+                      const uint32_t* __restrict__ counts, const uint32_t* __restrict__ perm, uint64_t n,
+                      uint64_t* __restrict__ keys_out, uint32_t* __restrict__ counts_out) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t p = perm[i];
+#ifdef SHN_WIDE
+  shn_key_t k = ((u128)ord_hi[p] << 64) | ord_lo[p];
+#else
+  shn_key_t k = ord_lo[p];
+#endif
+  shn_store_key(keys_out, i, shn_ascii_order_key(k));
+  counts_out[i] = counts[p];
+}
+
+struct CountState {
+  DevBuf keys, counts;
+};
+
+void count_state_free(shn_ctx* c) {
+  delete static_cast<CountState*>(c->count_state);
+  c->count_state = nullptr;
+}
+
+}  // namespace
+
+void count_k1mers(shn_ctx* c, const char* const* arrays, const uint64_t* n_reads, int n_arrays,
+                  int read_len, int k1, uint64_t expected_distinct, uint64_t** keys_dev,
+                  uint32_t** counts_dev, uint64_t* n_distinct) {
+  SHN_CHECK(k1 >= 1 && k1 <= SHN_MAX_K1 && read_len >= k1, "bad k1 / read length");
   uint64_t total_windows = 0;
   for (int a = 0; a < n_arrays; ++a) total_windows += n_reads[a] * (uint64_t)(read_len - k1 + 1);
-  uint64_t nb = std::max<uint64_t>(256, (std::min(expected_distinct, total_windows) + 1) / 2);
+  uint64_t nb = std::max<uint64_t>(256, (2 * std::min(expected_distinct, total_windows) + SHN_BSLOTS - 1) /
+                                            SHN_BSLOTS);
   DevBuf table;
   table.reserve(nb * SHN_BSLOTS * sizeof(ShnSlot));
   ShnTableView view{table.as<ShnSlot>(), nb};
@@ -202,16 +233,16 @@ void shn_count_k1mers_impl(shn_ctx* c, const char* const* arrays, const uint64_t
   {
     ProfScope ps(c, "count_clear");
     unsigned grid =
-        (unsigned)std::min<uint64_t>((nb * SHN_BSLOTS + kBlock - 1) / kBlock, (uint64_t)c->sm_count * 32);
-    count_clear_kernel<<<grid, kBlock, 0, c->stream>>>(view.slots, nb * SHN_BSLOTS);
+        (unsigned)std::min<uint64_t>((nb * SHN_BSLOTS + kCBlock - 1) / kCBlock, (uint64_t)c->sm_count * 32);
+    count_clear_kernel<<<grid, kCBlock, 0, c->stream>>>(view.slots, nb * SHN_BSLOTS);
     KERNEL_CHECK();
   }
   for (int a = 0; a < n_arrays; ++a) {
     uint64_t nw = n_reads[a] * (uint64_t)(read_len - k1 + 1);
     if (nw == 0) continue;
     ProfScope ps(c, "count_windows");
-    count_windows_kernel<<<shn_grid(nw, kBlock), kBlock, 0, c->stream>>>(view, arrays[a], n_reads[a],
-                                                                         read_len, k1, ctr);
+    count_windows_kernel<<<shn_grid(nw, kCBlock), kCBlock, 0, c->stream>>>(view, arrays[a], n_reads[a],
+                                                                           read_len, k1, ctr);
     KERNEL_CHECK();
   }
   unsigned long long h[2];
@@ -219,31 +250,64 @@ void shn_count_k1mers_impl(shn_ctx* c, const char* const* arrays, const uint64_t
   CUDA_CHECK(cudaStreamSynchronize(c->stream));
   SHN_CHECK(h[1] == 0, "k-mer counting table full: raise expected_distinct");
   uint64_t n = h[0];
-  CountState*& st = g_count_state[c];
-  if (!st) st = new CountState();
-  DevBuf skeys, cnt;
-  skeys.reserve(std::max<uint64_t>(n, 1) * 8);
-  cnt.reserve(std::max<uint64_t>(n, 1) * 4);
-  st->keys.reserve(std::max<uint64_t>(n, 1) * 8);
-  st->counts.reserve(std::max<uint64_t>(n, 1) * 4);
+  SHN_CHECK(n < 0xFFFFFFFFull, "more than 2^32-1 distinct K1-mers");
+  if (c->count_state && c->count_free != &count_state_free) shn_count_free(c);
+  if (!c->count_state) {
+    c->count_state = new CountState();
+    c->count_free = &count_state_free;
+  }
+  CountState* st = static_cast<CountState*>(c->count_state);
+  const uint64_t n1 = std::max<uint64_t>(n, 1);
+  st->keys.reserve(n1 * 8 * SHN_KEY_WORDS);
+  st->counts.reserve(n1 * 4);
   if (n) {
+    DevBuf ord_lo, ord_hi, cnt, iota, lo_s, perm;
+    ord_lo.reserve(n1 * 8);
+    ord_hi.reserve(n1 * 8);
+    cnt.reserve(n1 * 4);
+    iota.reserve(n1 * 4);
+    lo_s.reserve(n1 * 8);
+    perm.reserve(n1 * 4);
     CUDA_CHECK(cudaMemsetAsync(ctr, 0, 8, c->stream));
     {
       ProfScope ps(c, "count_compact");
-      count_compact_kernel<<<shn_grid(nb * SHN_BSLOTS, kBlock), kBlock, 0, c->stream>>>(
-          view.slots, nb * SHN_BSLOTS, skeys.as<uint64_t>(), cnt.as<uint32_t>(), ctr);
+      count_compact_kernel<<<shn_grid(nb * SHN_BSLOTS, kCBlock), kCBlock, 0, c->stream>>>(
+          view.slots, nb * SHN_BSLOTS, ord_lo.as<uint64_t>(), ord_hi.as<uint64_t>(), cnt.as<uint32_t>(),
+          iota.as<uint32_t>(), ctr);
       KERNEL_CHECK();
     }
-    ProfScope ps(c, "count_sort", 2);
+    ProfScope ps(c, "count_sort", 4);
+    // LSD radix over the ASCII-order key: low word first, then (stable) the high word
     size_t tb = 0;
-    CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, tb, skeys.as<uint64_t>(), st->keys.as<uint64_t>(),
-                                               cnt.as<uint32_t>(), st->counts.as<uint32_t>(), (int64_t)n,
-                                               0, 2 * k1, c->stream));
-    CUDA_CHECK(cub::DeviceRadixSort::SortPairs(c->tmp(tb), tb, skeys.as<uint64_t>(),
-                                               st->keys.as<uint64_t>(), cnt.as<uint32_t>(),
-                                               st->counts.as<uint32_t>(), (int64_t)n, 0, 2 * k1,
-                                               c->stream));
-    unorder_keys_kernel<<<shn_grid(n, kBlock), kBlock, 0, c->stream>>>(st->keys.as<uint64_t>(), n);
+    const int lo_bits = k1 > 32 ? 64 : 2 * k1;
+    CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, tb, ord_lo.as<uint64_t>(), lo_s.as<uint64_t>(),
+                                               iota.as<uint32_t>(), perm.as<uint32_t>(), (int64_t)n, 0,
+                                               lo_bits, c->stream));
+    CUDA_CHECK(cub::DeviceRadixSort::SortPairs(c->tmp(tb), tb, ord_lo.as<uint64_t>(), lo_s.as<uint64_t>(),
+                                               iota.as<uint32_t>(), perm.as<uint32_t>(), (int64_t)n, 0,
+                                               lo_bits, c->stream));
+    uint32_t* final_perm = perm.as<uint32_t>();
+#ifdef SHN_WIDE
+    DevBuf hi_g, hi_s, perm2;
+    hi_g.reserve(n1 * 8);
+    hi_s.reserve(n1 * 8);
+    perm2.reserve(n1 * 4);
+    gather_u64_kernel<<<shn_grid(n, kCBlock), kCBlock, 0, c->stream>>>(ord_hi.as<uint64_t>(),
+                                                                     perm.as<uint32_t>(), n,
+                                                                     hi_g.as<uint64_t>());
+    KERNEL_CHECK();
+    tb = 0;
+    CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, tb, hi_g.as<uint64_t>(), hi_s.as<uint64_t>(),
+                                               perm.as<uint32_t>(), perm2.as<uint32_t>(), (int64_t)n, 0,
+                                               2 * (k1 - 32), c->stream));
+    CUDA_CHECK(cub::DeviceRadixSort::SortPairs(c->tmp(tb), tb, hi_g.as<uint64_t>(), hi_s.as<uint64_t>(),
+                                               perm.as<uint32_t>(), perm2.as<uint32_t>(), (int64_t)n, 0,
+                                               2 * (k1 - 32), c->stream));
+    final_perm = perm2.as<uint32_t>();
+#endif
+    count_emit_kernel<<<shn_grid(n, kCBlock), kCBlock, 0, c->stream>>>(
+        ord_lo.as<uint64_t>(), ord_hi.as<uint64_t>(), cnt.as<uint32_t>(), final_perm, n,
+        st->keys.as<uint64_t>(), st->counts.as<uint32_t>());
     KERNEL_CHECK();
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
   }
@@ -251,3 +315,5 @@ void shn_count_k1mers_impl(shn_ctx* c, const char* const* arrays, const uint64_t
   *counts_dev = st->counts.as<uint32_t>();
   *n_distinct = n;
 }
+
+}  // namespace SHN_NS

@@ -1,17 +1,20 @@
 // a1/a2: K1-mer -> weight table (load_kmers + lowComplexity, extension_correction.py:202-221,
-// 142-149) as an open-addressing hash table in HBM.
+// 142-149) as an open-addressing hash table in HBM.  Compiled twice (common.cuh): 64-bit keys into
+// namespace `narrow`, 128-bit keys (-DSHN_WIDE) into namespace `wide`.
 //
-// Layout: 64-byte buckets of four 16-byte slots {key u64, weight u32, first_idx u32}; a probe
-// moves one 64-byte DRAM burst.  Bucket = mulhi(mix64(key), n_buckets), linear probing over
-// buckets with an overflow flag per bucket (table_dev.cuh).  Load factor <= 0.5.
+// Layout: 64-byte buckets {key, weight u32, first_idx u32} x 4 (2 for wide keys); a probe moves
+// one 64-byte DRAM burst.  Bucket = mulhi(hash(key), n_buckets), linear probing over buckets with
+// an overflow flag per bucket (table_dev.cuh).  Load factor <= 0.5.
 //
 // Algorithmic bytes: insert = 8 B key + 4 B count streamed + one bucket
 // read-modify-write (2 x 64 B) = 140 B per input line; lookup = 8 B + 64 B + 5 B out = 77 B.
 #include <cub/cub.cuh>
 
 #include "common.cuh"
+#include "impls.h"
 #include "table_dev.cuh"
 
+namespace SHN_NS {
 namespace {
 
 constexpr int kBlock = 256;
@@ -19,13 +22,8 @@ constexpr int kBlock = 256;
 __global__ void __launch_bounds__(kBlock) table_clear_kernel(ShnSlot* slots, uint64_t n_slots) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  // one 16-byte store per slot, fully coalesced
-  uint4 v;
-  v.x = 0xFFFFFFFFu;
-  v.y = 0xFFFFFFFFu;  // key = EMPTY
-  v.z = 0u;           // weight
-  v.w = 0xFFFFFFFFu;  // first_idx = +inf for atomicMin
-  for (; i < n_slots; i += stride) reinterpret_cast<uint4*>(slots)[i] = v;
+  // key = EMPTY, weight = 0, first_idx = +inf for atomicMin; coalesced 16/32-byte stores
+  for (; i < n_slots; i += stride) table_store_empty(slots, i, 0xFFFFFFFFu);
 }
 
 // counters: [0]=new keys [1]=low-complexity lines [3]=bad key / index overflow
@@ -37,18 +35,18 @@ __global__ void __launch_bounds__(kBlock)
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int n_new = 0, n_low = 0, n_bad = 0;
   if (i < n) {
-    uint64_t key = keys[i];
+    shn_key_t key = shn_load_key(keys, i);
     uint32_t w = counts[i];
     // explicit line indices (sharded build: the global input line of every routed key)
     uint64_t base_idx = line_idx ? (uint64_t)line_idx[i] : (ds ? 2 * (first_line + i) : first_line + i);
-    if ((key & ~shn_kmer_mask(k1)) || base_idx + 1 >= 0xFFFFFFFFull || w >= SHN_WEIGHT_MASK) {
+    if ((key & ~shn_key_mask(k1)) || base_idx + 1 >= 0xFFFFFFFFull || w >= SHN_WEIGHT_MASK) {
       n_bad = 1;
     } else if (shn_low_complexity(key, k1)) {  // rc(kmer) is low-complexity iff kmer is
       n_low = 1;
     } else {
       const int reps = ds ? 2 : 1;
       for (int r = 0; r < reps; ++r) {
-        uint64_t kk = r == 0 ? key : shn_revcomp(key, k1);
+        shn_key_t kk = r == 0 ? key : shn_revcomp(key, k1);
         uint64_t slot = table_upsert_slot(t, kk, &n_new);
         if (slot == ~0ull) {
           n_bad = 1;
@@ -77,7 +75,7 @@ __global__ void __launch_bounds__(kBlock)
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   uint32_t wraw = 0;
-  uint64_t slot = table_find(t, keys[i], &wraw);
+  uint64_t slot = table_find(t, shn_load_key(keys, i), &wraw);
   uint32_t w = slot == ~0ull ? 0u : (wraw & SHN_WEIGHT_MASK);
   uint8_t f = slot == ~0ull ? 0 : 1;
   if (weights) weights[i] = w;
@@ -86,18 +84,31 @@ __global__ void __launch_bounds__(kBlock)
 
 struct OccupiedSlot {
   const ShnSlot* slots;
-  __device__ bool operator()(uint64_t i) const { return slots[i].key != SHN_EMPTY_KEY; }
+  __device__ bool operator()(uint64_t i) const { return slots[i].key != SHN_EMPTY; }
 };
 
 __global__ void __launch_bounds__(kBlock)
     table_dump_gather_kernel(const ShnSlot* __restrict__ slots, const uint64_t* __restrict__ sel,
-                             uint64_t n, uint64_t* keys, uint32_t* weights, uint32_t* idx) {
+                             uint64_t n, uint64_t* keys, uint32_t* weights, uint32_t* idx,
+                             uint32_t* order) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   ShnSlot s = slots[sel[i]];
-  keys[i] = s.key;
+  shn_store_key(keys, i, s.key);
   weights[i] = s.weight & SHN_WEIGHT_MASK;
   idx[i] = s.idx;
+  order[i] = (uint32_t)i;
+}
+
+__global__ void __launch_bounds__(kBlock)
+    table_dump_permute_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ weights,
+                              const uint32_t* __restrict__ order, uint64_t n, uint64_t* keys_out,
+                              uint32_t* weights_out) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t o = order[i];
+  shn_store_key(keys_out, i, shn_load_key(keys, o));
+  weights_out[i] = weights[o];
 }
 
 __global__ void __launch_bounds__(kBlock)
@@ -107,13 +118,13 @@ __global__ void __launch_bounds__(kBlock)
   int bad = 0;
   if (i < n) {
     const char* p = ascii + i * (uint64_t)k1;
-    uint64_t x = 0;
+    shn_key_t x = 0;
     for (int j = 0; j < k1; ++j) {
       uint32_t code = shn_code_of((uint8_t)__ldg(&p[j]));  // kmer.upper(), :214
       bad |= code > 3;
-      x = (x << 2) | (code & 3u);
+      x = (x << 2) | (shn_key_t)(code & 3u);
     }
-    keys[i] = x;
+    shn_store_key(keys, i, x);
   }
   int tot = __syncthreads_count(bad);
   if (threadIdx.x == 0 && tot) atomicAdd(&counters[0], (unsigned long long)tot);
@@ -121,7 +132,7 @@ __global__ void __launch_bounds__(kBlock)
 
 }  // namespace
 
-void shn_pack_kmers_impl(shn_ctx* c, const char* d_ascii, uint64_t n, int k1, uint64_t* d_keys) {
+void pack_kmers(shn_ctx* c, const char* d_ascii, uint64_t n, int k1, uint64_t* d_keys) {
   c->counters.reserve(64 * sizeof(unsigned long long));
   unsigned long long* ctr = c->counters.as<unsigned long long>();
   CUDA_CHECK(cudaMemsetAsync(ctr, 0, 8, c->stream));
@@ -138,12 +149,12 @@ void shn_pack_kmers_impl(shn_ctx* c, const char* d_ascii, uint64_t n, int k1, ui
 
 // The build in three parts so that a host-resident input can be copied in chunks on the copy
 // stream while earlier chunks are being inserted (shn_table_build, api.cu).
-void shn_table_begin_impl(shn_ctx* c, uint64_t n, int k1, int double_stranded) {
-  SHN_CHECK(k1 >= 1 && k1 <= 32, "k1 must be in 1..32 (K <= 31); wider keys are not built yet");
+void table_begin(shn_ctx* c, uint64_t n, int k1, int double_stranded) {
+  SHN_CHECK(k1 >= 1 && k1 <= SHN_MAX_K1 && (SHN_KEY_WORDS == 1 || k1 > 32), "k1 out of range for this key width");
   uint64_t items = n * (double_stranded ? 2 : 1);
   SHN_CHECK(items < 0xFFFFFFFEull, "more than 2^32-2 input K1-mers per table");
-  // slots >= 2 * items  (load factor <= 0.5)  => buckets >= items / 2 (4 slots each)
-  uint64_t n_buckets = items < 1024 ? 256 : (items + 1) / 2;
+  // slots >= 2 * items  (load factor <= 0.5)
+  uint64_t n_buckets = items < 1024 ? 1024 / SHN_BSLOTS : (2 * items + SHN_BSLOTS - 1) / SHN_BSLOTS;
   c->table.reserve(n_buckets * SHN_BSLOTS * sizeof(ShnSlot));
   c->n_buckets = n_buckets;
   c->k1 = k1;
@@ -159,18 +170,18 @@ void shn_table_begin_impl(shn_ctx* c, uint64_t n, int k1, int double_stranded) {
 }
 
 // lines [first_line, first_line + n) of the input; d_keys/d_counts point at this chunk
-void shn_table_insert_chunk_impl(shn_ctx* c, const uint64_t* d_keys, const uint32_t* d_counts,
-                                 const uint32_t* d_line_idx, uint64_t n, uint64_t first_line,
-                                 int double_stranded) {
+void table_insert_chunk(shn_ctx* c, const uint64_t* d_keys, const uint32_t* d_counts,
+                        const uint32_t* d_line_idx, uint64_t n, uint64_t first_line,
+                        int double_stranded) {
   if (n == 0) return;
   ProfScope ps(c, "table_insert");
   table_insert_kernel<<<shn_grid(n, kBlock), kBlock, 0, c->stream>>>(
-      c->view(), d_keys, d_counts, d_line_idx, n, first_line, c->k1, double_stranded,
+      table_view(c), d_keys, d_counts, d_line_idx, n, first_line, c->k1, double_stranded,
       c->counters.as<unsigned long long>());
   KERNEL_CHECK();
 }
 
-void shn_table_finish_impl(shn_ctx* c) {
+void table_finish(shn_ctx* c) {
   unsigned long long h[4];
   CUDA_CHECK(cudaMemcpyAsync(h, c->counters.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
   CUDA_CHECK(cudaStreamSynchronize(c->stream));
@@ -179,38 +190,41 @@ void shn_table_finish_impl(shn_ctx* c) {
   c->n_lowcomplexity = h[1];
 }
 
-void shn_table_build_impl(shn_ctx* c, const uint64_t* d_keys, const uint32_t* d_counts, uint64_t n,
-                          int k1, int double_stranded, const uint32_t* d_line_idx) {
+void table_build(shn_ctx* c, const uint64_t* d_keys, const uint32_t* d_counts, uint64_t n, int k1,
+                 int double_stranded, const uint32_t* d_line_idx) {
   SHN_CHECK(!(double_stranded && d_line_idx), "explicit line indices exclude double_stranded");
-  shn_table_begin_impl(c, n, k1, double_stranded);
-  shn_table_insert_chunk_impl(c, d_keys, d_counts, d_line_idx, n, 0, double_stranded);
-  shn_table_finish_impl(c);
+  table_begin(c, n, k1, double_stranded);
+  table_insert_chunk(c, d_keys, d_counts, d_line_idx, n, 0, double_stranded);
+  table_finish(c);
 }
 
-void shn_table_lookup_impl(shn_ctx* c, const uint64_t* d_keys, uint64_t n, uint32_t* d_weights,
-                           uint8_t* d_found) {
+void table_lookup(shn_ctx* c, const uint64_t* d_keys, uint64_t n, uint32_t* d_weights,
+                  uint8_t* d_found) {
   SHN_CHECK(c->n_buckets > 0, "no table built");
   if (n == 0) return;
   ProfScope ps(c, "table_lookup");
-  table_lookup_kernel<<<shn_grid(n, kBlock), kBlock, 0, c->stream>>>(c->view(), d_keys, n, d_weights,
-                                                                     d_found);
+  table_lookup_kernel<<<shn_grid(n, kBlock), kBlock, 0, c->stream>>>(table_view(c), d_keys, n,
+                                                                     d_weights, d_found);
   KERNEL_CHECK();
 }
 
-// dump sorted by first-occurrence index --------------------------------------------------
-void shn_table_dump_impl(shn_ctx* c, uint64_t* h_keys, uint32_t* h_weights, uint32_t* h_idx) {
+// dump sorted by first-occurrence index ------------------------------------------------------
+void table_dump(shn_ctx* c, uint64_t* h_keys, uint32_t* h_weights, uint32_t* h_idx) {
   SHN_CHECK(c->n_buckets > 0, "no table built");
   uint64_t n_slots = c->n_buckets * SHN_BSLOTS, n = c->n_distinct;
   if (n == 0) return;
-  DevBuf sel, nsel, keys, w, idx, keys2, w2, idx2;
+  const uint64_t kb = 8 * SHN_KEY_WORDS;
+  DevBuf sel, nsel, keys, w, idx, order, keys2, w2, idx2, order2;
   sel.reserve(n * 8);
   nsel.reserve(8);
-  keys.reserve(n * 8);
+  keys.reserve(n * kb);
   w.reserve(n * 4);
   idx.reserve(n * 4);
-  keys2.reserve(n * 8);
+  order.reserve(n * 4);
+  keys2.reserve(n * kb);
   w2.reserve(n * 4);
   idx2.reserve(n * 4);
+  order2.reserve(n * 4);
   cub::CountingInputIterator<uint64_t> it(0);
   OccupiedSlot pred{c->table.as<ShnSlot>()};
   size_t tb = 0;
@@ -221,25 +235,24 @@ void shn_table_dump_impl(shn_ctx* c, uint64_t* h_keys, uint32_t* h_weights, uint
                                    (int)n_slots, pred, c->stream));
   table_dump_gather_kernel<<<shn_grid(n, kBlock), kBlock, 0, c->stream>>>(
       c->table.as<ShnSlot>(), sel.as<uint64_t>(), n, keys.as<uint64_t>(), w.as<uint32_t>(),
-      idx.as<uint32_t>());
+      idx.as<uint32_t>(), order.as<uint32_t>());
   KERNEL_CHECK();
-  // sort by idx: two passes (keys, then weights) sharing the same sort key
+  // sort the permutation by first-occurrence index, then permute keys and weights
   tb = 0;
   CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, tb, idx.as<uint32_t>(), idx2.as<uint32_t>(),
-                                             keys.as<uint64_t>(), keys2.as<uint64_t>(), (int)n, 0, 32,
+                                             order.as<uint32_t>(), order2.as<uint32_t>(), (int)n, 0, 32,
                                              c->stream));
   CUDA_CHECK(cub::DeviceRadixSort::SortPairs(c->tmp(tb), tb, idx.as<uint32_t>(), idx2.as<uint32_t>(),
-                                             keys.as<uint64_t>(), keys2.as<uint64_t>(), (int)n, 0, 32,
+                                             order.as<uint32_t>(), order2.as<uint32_t>(), (int)n, 0, 32,
                                              c->stream));
-  tb = 0;
-  CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, tb, idx.as<uint32_t>(), idx2.as<uint32_t>(),
-                                             w.as<uint32_t>(), w2.as<uint32_t>(), (int)n, 0, 32,
-                                             c->stream));
-  CUDA_CHECK(cub::DeviceRadixSort::SortPairs(c->tmp(tb), tb, idx.as<uint32_t>(), idx2.as<uint32_t>(),
-                                             w.as<uint32_t>(), w2.as<uint32_t>(), (int)n, 0, 32,
-                                             c->stream));
-  CUDA_CHECK(cudaMemcpyAsync(h_keys, keys2.p, n * 8, cudaMemcpyDeviceToHost, c->stream));
+  table_dump_permute_kernel<<<shn_grid(n, kBlock), kBlock, 0, c->stream>>>(
+      keys.as<uint64_t>(), w.as<uint32_t>(), order2.as<uint32_t>(), n, keys2.as<uint64_t>(),
+      w2.as<uint32_t>());
+  KERNEL_CHECK();
+  CUDA_CHECK(cudaMemcpyAsync(h_keys, keys2.p, n * kb, cudaMemcpyDeviceToHost, c->stream));
   CUDA_CHECK(cudaMemcpyAsync(h_weights, w2.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
   CUDA_CHECK(cudaMemcpyAsync(h_idx, idx2.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
   CUDA_CHECK(cudaStreamSynchronize(c->stream));
 }
+
+}  // namespace SHN_NS

@@ -12,7 +12,7 @@ import numpy as np
 
 from . import _lib
 from .pipeline import (contig_adjacency, correct, decode_kmers, dfs_components,  # noqa: F401
-                       pack_components)
+                       encode_kmer, keys_array, keys_as_ints, pack_components)
 
 _default_ctx = None
 
@@ -25,13 +25,6 @@ def get_context(device=None):
             device = int(os.environ.get("SHANNON_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
         _default_ctx = _lib.Context(device)
     return _default_ctx
-
-
-def encode_kmer(s):
-    x = 0
-    for ch in s:
-        x = (x << 2) | "AGCT".index(ch)
-    return x
 
 
 class AllowedKmerDict(Mapping):
@@ -48,7 +41,7 @@ class AllowedKmerDict(Mapping):
 
     def _idx(self):
         if self._index is None:
-            self._index = dict(zip(self.keys_packed.tolist(), self.weights.tolist()))
+            self._index = dict(zip(keys_as_ints(self.keys_packed), self.weights.tolist()))
         return self._index
 
     def __len__(self):
@@ -67,7 +60,7 @@ class AllowedKmerDict(Mapping):
         return self._idx()[encode_kmer(kmer)]
 
     def clear(self):  # shannon.py:469
-        self.keys_packed = np.empty(0, dtype=np.uint64)
+        self.keys_packed = self.keys_packed[:0]
         self.weights = np.empty(0, dtype=np.uint32)
         self._index = None
 

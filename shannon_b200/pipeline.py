@@ -10,11 +10,42 @@ _CODE_TO_ASCII = np.frombuffer(b"AGCT", dtype=np.uint8)
 
 
 def decode_kmers(keys, k1):
-    """uint64 packed keys -> (n, k1) uint8 ASCII matrix."""
+    """packed keys ((n,) uint64, or (n, 2) uint64 low word first for k1 = 33) -> (n, k1) uint8
+    ASCII matrix."""
     keys = np.asarray(keys, dtype=np.uint64)
-    shifts = (2 * (k1 - 1 - np.arange(k1))).astype(np.uint64)
-    codes = ((keys[:, None] >> shifts[None, :]) & np.uint64(3)).astype(np.uint8)
-    return _CODE_TO_ASCII[codes]
+    shifts = 2 * (k1 - 1 - np.arange(k1))
+    if keys.ndim == 1:
+        codes = (keys[:, None] >> shifts.astype(np.uint64)[None, :]) & np.uint64(3)
+    else:
+        word = (shifts >= 64).astype(np.int64)                  # pairs never straddle a word
+        sh = (shifts - 64 * word).astype(np.uint64)
+        codes = (keys[:, word] >> sh[None, :]) & np.uint64(3)
+    return _CODE_TO_ASCII[codes.astype(np.uint8)]
+
+
+def encode_kmer(s):
+    """str -> packed integer key (arbitrary precision), A=0 G=1 C=2 T=3, first base most significant."""
+    x = 0
+    for ch in s:
+        x = (x << 2) | "AGCT".index(ch)
+    return x
+
+
+def keys_array(values, k1):
+    """list of integer keys -> array in the layout the library uses ((n,) or (n, 2) uint64)."""
+    if k1 <= 32:
+        return np.asarray(values, dtype=np.uint64).reshape(-1)
+    lo = np.asarray([v & 0xFFFFFFFFFFFFFFFF for v in values], dtype=np.uint64)
+    hi = np.asarray([v >> 64 for v in values], dtype=np.uint64)
+    return np.stack([lo, hi], axis=1) if len(values) else np.empty((0, 2), dtype=np.uint64)
+
+
+def keys_as_ints(keys):
+    """array of packed keys -> list of Python ints."""
+    keys = np.asarray(keys, dtype=np.uint64)
+    if keys.ndim == 1:
+        return keys.tolist()
+    return [(int(h) << 64) | int(l) for l, h in keys.tolist()]
 
 
 def contig_adjacency_csr(n_contigs, a, b, w, fp):

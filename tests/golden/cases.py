@@ -52,6 +52,14 @@ CASES = {
                            "run": {"inMem": True, "partition_size": 2, "min_length": 50}},
     "synth_pe_dflag": {"K": 24, "input": ("synth", 8, 800, 11), "rc_double": False,
                        "run": {"double_stranded_load": True, "ec_inMem": False}},
+    # key-width boundaries: K1 = 32 fills one 64-bit word, K1 = 33 (shannon.py's largest -K, 32)
+    # needs two words per key
+    "synth_pe_k31": {"K": 31, "input": ("synth", 10, 1200, 17), "run": {"partition_size": 2}},
+    "synth_pe_k32": {"K": 32, "input": ("synth", 12, 1500, 13), "run": {}},
+    "synth_se_k32_inmem": {"K": 32, "input": ("synth_se", 10, 1500, 19),
+                           "run": {"inMem": True, "partition_size": 1, "min_length": 60}},
+    "repeat_rich_k32": {"K": 32, "input": ("repeat", 9, 500, 60, 220, 4),
+                        "run": {"min_weight": 2, "min_length": 40, "partition_size": 2}},
 }
 for _s in range(6):
     CASES["repeat_rich_%d" % _s] = {

@@ -1,7 +1,7 @@
 """Generates tests/golden/*.json.gz by running the REAL reference (from /root/reference via
 oracle/ref_loader.py) -- run in the build container only:
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py [case names ...]      (default: all cases)
 
 Each fixture holds the inputs (read sequences; k1mer.dict_org is re-derived with the
 deterministic stand-in counter and pinned by sha256), the run parameters, and everything the
@@ -37,7 +37,10 @@ def export_samples():
 
 def main():
     export_samples()
+    only = sys.argv[1:]
     for name, spec in CASES.items():
+        if only and name not in only:
+            continue
         work = tempfile.mkdtemp(prefix="golden_")
         seqs1, seqs2 = case_inputs(spec)
         case = helpers.make_case(work, spec["K"], seqs1, seqs2,

@@ -63,6 +63,29 @@ def test_parse_kmer_file_matches_oracle_loader(workdir):
     assert ec.decode_kmers(keys[:5], 25).tobytes().decode() == "".join(k for k, _ in lines[:5])
 
 
+def test_parse_kmer_file_two_word_keys(workdir):
+    """K = 32 (shannon.py's largest -K): 33-base k-mers come back as (n, 2) uint64, low word first."""
+    s1, s2 = helpers.synthetic_seqs(4, 200, 9)
+    case = helpers.make_case(workdir, 32, s1, s2)
+    keys, counts, k1 = _lib.HostIO().parse_kmer_file(case.k1mer_org)
+    with open(case.k1mer_org) as f:
+        lines = [l.split() for l in f]
+    assert k1 == 33 and keys.shape == (len(lines), 2) and keys.dtype == np.uint64
+    assert ec.keys_as_ints(keys) == [ec.encode_kmer(k) for k, _ in lines]
+    assert np.array_equal(ec.keys_array(ec.keys_as_ints(keys), 33), keys)
+    assert [int(c) for _, c in lines] == counts.tolist()
+    txt = ec.decode_kmers(keys, 33).tobytes().decode()
+    assert [txt[i:i + 33] for i in range(0, len(txt), 33)] == [k for k, _ in lines]
+    d = ec.AllowedKmerDict(keys[:50], counts[:50], 33)
+    assert dict(d) == dict((k, int(c)) for k, c in lines[:50])
+    assert d.get(lines[7][0]) == int(lines[7][1]) and d.get("A" * 33, 0) == 0
+    p = os.path.join(workdir, "k34")
+    with open(p, "w") as f:
+        f.write("A" * 34 + "\t1\n")
+    with pytest.raises(_lib.ShnError):
+        _lib.HostIO().parse_kmer_file(p)
+
+
 def test_load_fasta_quirks(workdir):
     io = _lib.HostIO()
     p = os.path.join(workdir, "r.fa")

@@ -24,8 +24,9 @@ def ctx():
     c.close()
 
 
-def _enc(kmers):
-    return np.asarray([ec.encode_kmer(k) for k in kmers], dtype=np.uint64)
+def _enc(kmers, k1=None):
+    kmers = list(kmers)
+    return ec.keys_array([ec.encode_kmer(k) for k in kmers], k1 or len(kmers[0]))
 
 
 def _dec(keys, k1):
@@ -39,11 +40,18 @@ def _case(workdir, kind, seed):
     if kind == "synth":
         s1, s2 = helpers.synthetic_seqs(10, 1200, seed)
         return helpers.make_case(workdir, 24, s1, s2), 3, 75
+    if kind in ("synth31", "synth32"):      # K1 = 32: full 64-bit keys; K1 = 33: two-word keys
+        s1, s2 = helpers.synthetic_seqs(10, 1200, seed)
+        return helpers.make_case(workdir, int(kind[-2:]), s1, s2), 3, 75
+    if kind == "repeat32":
+        reads = cases.repeat_rich_reads(seed, 600, 60, 220, 5)
+        return helpers.make_case(workdir, 32, reads), 2, 45
     reads = cases.repeat_rich_reads(seed, 500, 40, 200, 5)
     return helpers.make_case(workdir, [8, 10, 12, 15][seed % 4], reads), 2, 25
 
 
-CASES = [("synth", 1), ("synth", 2), ("repeat", 0), ("repeat", 1), ("repeat", 2), ("repeat", 3)]
+CASES = [("synth", 1), ("synth", 2), ("repeat", 0), ("repeat", 1), ("repeat", 2), ("repeat", 3),
+         ("synth31", 5), ("synth32", 6), ("repeat32", 7), ("repeat32", 8)]
 
 
 # ---- a1/a2 ---------------------------------------------------------------------------------
@@ -69,7 +77,19 @@ def test_table_build_equals_load_kmers(ctx, workdir, kind, seed, ds):
     w, f = ctx.table_lookup(gk)
     assert f.all() and np.array_equal(w, gw)
     rng = np.random.default_rng(seed)
-    probe = rng.integers(0, 1 << (2 * k1), size=5000, dtype=np.uint64)
+    if k1 <= 32:
+        probe = rng.integers(0, (1 << (2 * k1)) - 1, size=5000, dtype=np.uint64, endpoint=True)
+    else:
+        probe = np.stack([rng.integers(0, (1 << 64) - 1, size=5000, dtype=np.uint64, endpoint=True),
+                          rng.integers(0, 4, size=5000, dtype=np.uint64)], axis=1)
+    # half of the probes: one-base mutations of present keys (near misses in the same word)
+    mut = gk[rng.integers(0, len(gk), size=2500)].copy()
+    if k1 <= 32:
+        mut ^= np.uint64(1) << rng.integers(0, 2 * k1, size=2500).astype(np.uint64)
+    else:
+        bit = rng.integers(0, 2 * k1, size=2500)
+        mut[np.arange(2500), bit // 64] ^= np.uint64(1) << (bit % 64).astype(np.uint64)
+    probe = np.concatenate([probe, mut])
     w, f = ctx.table_lookup(probe)
     exp = [kmers.get(s) for s in _dec(probe, k1)]
     assert f.tolist() == [int(e is not None) for e in exp]
@@ -94,8 +114,24 @@ def test_pack_and_lowcomplexity_edge_cases(ctx):
     ctx.table_build(np.concatenate([keys, keys[:1]]), np.asarray([4, 9, 6], np.uint32), 32, False)
     gk, gw, gi = ctx.table_dump()
     assert _dec(gk, 32) == ks and gw.tolist() == [10, 9] and gi.tolist() == [0, 1]
-    w, f = ctx.table_lookup(np.asarray([ec.encode_kmer(so.reverse_complement(ks[0]))], np.uint64))
+    w, f = ctx.table_lookup(_enc([so.reverse_complement(ks[0])]))
     assert f.tolist() == [0]
+    # k1 = 33: two words per key; keys that differ only in the high word are distinct
+    ks = ["A" + "ACGTTGCAACGTTGCAACGTTGCAACGTTGCA", "G" + "ACGTTGCAACGTTGCAACGTTGCAACGTTGCA",
+          "T" * 32 + "G", "TGCA" * 8 + "C"]
+    assert [so.low_complexity(k) for k in ks] == [False, False, True, False]
+    keys = ctx.pack_kmers("".join(ks).encode(), 4, 33)
+    assert keys.shape == (4, 2) and np.array_equal(keys, _enc(ks))
+    ctx.table_build(np.concatenate([keys, keys[1:2]]), np.asarray([4, 9, 6, 2, 5], np.uint32), 33, False)
+    gk, gw, gi = ctx.table_dump()
+    assert _dec(gk, 33) == [ks[0], ks[1], ks[3]] and gw.tolist() == [4, 14, 2] and gi.tolist() == [0, 1, 3]
+    w, f = ctx.table_lookup(_enc(["C" + ks[0][1:], ks[1], so.reverse_complement(ks[3])]))
+    assert f.tolist() == [0, 1, 0] and w.tolist() == [0, 14, 0]
+    ctx.table_build(keys, np.arange(1, 5, dtype=np.uint32), 33, True)      # + reverse complements
+    w, f = ctx.table_lookup(_enc([so.reverse_complement(ks[3]), so.reverse_complement(ks[0])]))
+    assert f.tolist() == [1, 1] and w.tolist() == [4, 1]
+    with pytest.raises(_lib.ShnError):
+        ctx.pack_kmers(b"A" * 34, 1, 34)
     # empty input
     ctx.table_build(np.empty(0, np.uint64), np.empty(0, np.uint32), 25, False)
     assert ctx.table_stats()["n_distinct"] == 0
@@ -152,16 +188,19 @@ def test_l3_stages_equal_oracle(ctx, workdir, kind, seed, spec, monkeypatch):
 
 
 # ---- a10-a12 ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("K", [24, 32])
 @pytest.mark.parametrize("paired", [False, True])
-def test_l4_assign_equals_oracle(ctx, workdir, paired):
+def test_l4_assign_equals_oracle(ctx, workdir, paired, K):
     s1, s2 = helpers.synthetic_seqs(10, 1200, 4)
     # ragged + dirty reads: short, exactly K1, K1+1, with N, lower case, empty mate
-    s1[5], s2[5] = s1[5][:25], s2[5][:26]
+    s1[5], s2[5] = s1[5][:K + 1], s2[5][:K + 2]
     s1[6] = s1[6][:10]
     s1[7] = s1[7][:40] + "N" + s1[7][41:]
     s2[8] = s2[8].lower()
     s1[9] = s1[9][:57]
-    case = helpers.make_case(workdir, 24, s1, s2 if paired else None)
+    s2[10] = s2[10][:2 * (K + 1)]
+    s1[11] = s1[11][:2 * (K + 1) + 1]
+    case = helpers.make_case(workdir, K, s1, s2 if paired else None)
     out = case.outdir("o")
     res = so.run_correction(case.k1mer_org, out + "/k", 3, 75, False, out, 500, True, True)
     k1 = res.k1
@@ -208,7 +247,7 @@ def test_l4_assign_equals_oracle(ctx, workdir, paired):
     assert nvalid == exp_valid and nlook == exp_look
     assert sum(len(e) for e in exp) == na > 0
     # window weights (a12)
-    ak = np.asarray([ec.encode_kmer(k) for k in res.allowed_kmer_dict], np.uint64)
+    ak = _enc(res.allowed_kmer_dict, k1)
     ctx.l4_map_set_weights(ak, np.asarray(list(res.allowed_kmer_dict.values()), np.uint32))
     ww, woff = ctx.l4_map_window_weights(np.frombuffer(text.encode(), np.uint8), offs, k1)
     expw = [res.allowed_kmer_dict.get(c[p:p + k1], 0) for c, _ in entries
