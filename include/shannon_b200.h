@@ -19,8 +19,13 @@
  *  - getters are two-phase: call shn_*_sizes first, then pass buffers of at least that size.
  *  - 2-bit base code: A=0, G=1, C=2, T=3 (the reference's successor tie order BASES =
  *    ['A','G','C','T'], extension_correction.py:10; complement = 3 - code).  A K1-mer is
- *    packed into a uint64 with its FIRST base in the most significant used pair:
- *    key = sum_i code[i] << 2*(k1-1-i), 1 <= k1 <= 32.
+ *    packed with its FIRST base in the most significant used pair:
+ *    key = sum_i code[i] << 2*(k1-1-i).  1 <= k1 <= 32: one uint64 per key.  k1 = 33 (K = 32,
+ *    the largest -K shannon.py accepts): the key is a 66-bit number carried as TWO uint64 words per
+ *    key, low word first (keys[2*i] = bits 0..63, keys[2*i+1] = bits 64..65); every `keys`
+ *    array below then holds 2*n words.  The library is compiled once per key width and dispatches
+ *    on k1.  The hash-routing calls (shn_route_plan / shn_table_build_indexed) take one-word keys
+ *    only.
  */
 #ifndef SHANNON_B200_H
 #define SHANNON_B200_H
