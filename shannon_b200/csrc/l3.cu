@@ -148,20 +148,30 @@ __device__ __forceinline__ void uf_union(uint32_t* parent, uint32_t a, uint32_t 
 // Measured: bound by the random 4-byte accesses of the union-find (two finds + CAS per link), not
 // by the table probes -- issuing the four bucket loads together (more registers, half the
 // occupancy) was 11 % slower.
+// The probes also yield the neighbour masks the walks prune their probes with (layout of the aux
+// word: see "greedy walks" below): successor bit b of x = (x[1:] . b) exists, OR-ed by x's own
+// thread; predecessor bit f of y = (f . y[:-1]) exists, OR-ed by the thread of that predecessor.
 __global__ void __launch_bounds__(kBlock)
-    uf_edges_kernel(ShnTableView t, uint32_t* parent, uint64_t n_slots, int k1) {
+    uf_edges_kernel(ShnTableView t, uint32_t* parent, uint64_t n_slots, int k1, uint32_t* aux) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_slots) return;
   shn_key_t key = t.slots[i].key;
   if (key == SHN_EMPTY) return;
   const shn_key_t mask = shn_key_mask(k1);
   shn_key_t pre = (key << 2) & mask;
+  const uint32_t first = (uint32_t)(key >> (2 * (k1 - 1))) & 3u;
+  uint32_t sm = 0;
 #pragma unroll
   for (int b = 0; b < 4; ++b) {
     uint32_t w;
     uint64_t s = table_find(t, pre | (shn_key_t)b, &w);
-    if (s != ~0ull && s != i) uf_union(parent, (uint32_t)i, (uint32_t)s);
+    if (s != ~0ull) {
+      sm |= 1u << b;
+      atomicOr(&aux[s], 1u << (28 + first));
+      if (s != i) uf_union(parent, (uint32_t)i, (uint32_t)s);
+    }
   }
+  if (sm) atomicOr(&aux[i], sm << 24);
 }
 
 // parent[i] <- root for occupied slots; roots get flag 1
@@ -206,14 +216,6 @@ __global__ void __launch_bounds__(kBlock)
                       uint32_t* __restrict__ dst) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = src[idx[i]];
-}
-
-// dst[i] = table[src[idx[i]]]
-__global__ void __launch_bounds__(kBlock)
-    gather2_u32_kernel(const uint32_t* __restrict__ table, const uint32_t* __restrict__ src,
-                       const uint32_t* __restrict__ idx, uint64_t n, uint32_t* __restrict__ dst) {
-  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) dst[i] = table[src[idx[i]]];
 }
 
 __global__ void __launch_bounds__(kBlock)
@@ -263,73 +265,30 @@ __global__ void __launch_bounds__(kBlock)
   tot[i] = w_tot[w];
 }
 
-// ---- component-local copy of the table for the walks ------------------------------------------
-// The walks of one component only ever touch that component's K1-mers.  In the global table those
-// are scattered over the whole multi-GB allocation (every probe = TLB miss + DRAM round trip); here
-// they are re-hashed into one contiguous region per component (load 0.5), so the component that
-// ends up on the critical path works out of a few tens of MB that stay resident in the 126 MB L2.
-__global__ void __launch_bounds__(kBlock)
-    region_size_kernel(const uint32_t* __restrict__ comp_nodes, const uint32_t* __restrict__ comp_seeds,
-                       uint32_t n_comps, uint64_t* __restrict__ nb) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i > n_comps) return;
-  // only components that own a seed are ever walked
-  nb[i] = (i < n_comps && comp_seeds[i] > 0) ? ((uint64_t)comp_nodes[i] + 1) / 2 + 1 : 0;
-}
-
-__global__ void __launch_bounds__(kBlock)
-    local_clear_kernel(ShnSlot* slots, uint64_t n_slots) {
-  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (; i < n_slots; i += stride) table_store_empty(slots, i, 0u);  // idx = 0: no claim stamp
-}
-
-__global__ void __launch_bounds__(kBlock)
-    repack_kernel(const ShnSlot* __restrict__ slots, uint64_t n_slots,
-                  const uint32_t* __restrict__ parent, const uint32_t* __restrict__ root_id,
-                  const uint64_t* __restrict__ region_off, ShnSlot* local,
-                  uint32_t* __restrict__ local_of, unsigned long long* counters) {
-  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  int bad = 0;
-  if (i < n_slots) {
-    shn_key_t key;
-    uint32_t wz, first_idx;
-    table_load_slot(slots, i, &key, &wz, &first_idx);
-    uint32_t loc = SHN_NONE32;
-    if (key != SHN_EMPTY) {
-      uint32_t cid = root_id[parent[i]];
-      uint64_t b0 = region_off[cid], nb = region_off[cid + 1] - b0;
-      if (nb) {
-        ShnTableView t{local + SHN_BSLOTS * b0, nb};
-        int is_new = 0;
-        uint64_t s = table_upsert_slot(t, key, &is_new);
-        if (s == ~0ull || !is_new) {
-          bad = 1;
-        } else {
-          // weight without flags; an overflow flag set meanwhile on this slot must survive
-          atomicAdd(&t.slots[s].weight, wz & SHN_WEIGHT_MASK);
-          loc = (uint32_t)(SHN_BSLOTS * b0 + s);
-        }
-      }
-    }
-    local_of[i] = loc;
-  }
-  int tot = __syncthreads_count(bad);
-  if (threadIdx.x == 0 && tot) atomicAdd(&counters[0], (unsigned long long)tot);
-}
-
 // ---- greedy walks -----------------------------------------------------------------------
+// The walks read the K1-mer table in place (keys and weights never change) and keep everything
+// that does change in one 32-bit word per slot, `aux`:
+//   bits 31..28  predecessor mask: bit f = K1-mer (f . x[:-1]) exists      } written by
+//   bits 27..24  successor mask:   bit b = K1-mer (x[1:] . b) exists        } uf_edges_kernel
+//   bit  23      traversed (extension_correction.py:235,347)
+//   bits 22..0   claim stamp of the speculative walks (0 = unclaimed)
+// The masks prune the probes: of the four successors (predecessors) of the current K1-mer only
+// the existing ones are fetched (1.2 on average), and only their children are probed blind for
+// the second step of a round.
+constexpr int kAuxSuccShift = 24;
+constexpr uint32_t kAuxTraversed = 1u << 23;
+constexpr uint32_t kAuxStampMask = 0x007FFFFFu;
+
 struct WalkArgs {
-  ShnSlot* local;               // component-local table (all regions)
-  const uint64_t* region_off;   // [n_comps+1] first bucket of every component's region
-  uint64_t lookahead_min_buckets;  // walk_kernel: regions below this size walk without look-ahead
+  ShnTableView tv;              // the K1-mer table (read only)
+  uint32_t* aux;                // [n_slots]
+  uint32_t lookahead;           // walk_kernel: 0 = one step per round (no second-level probes)
   int k1;
   uint32_t n_comps;
-  const uint32_t* comp_order;   // components sorted by seed count (descending)
+  const uint32_t* comp_order;   // components sorted by node count (descending)
   const uint64_t* seed_off;     // [n_comps+1] into ranks_by_comp
   const uint32_t* ranks_by_comp;  // seed ranks grouped by component, ascending inside a group
   const uint32_t* slots_by_comp;  // table slot of the same seeds
-  const uint32_t* seed_slot;    // by rank
   const uint64_t* log_off;      // [n_comps+1] into walk_log
   uint8_t* walk_log;
   // per seed rank outputs
@@ -338,21 +297,77 @@ struct WalkArgs {
   uint32_t* nr;
   uint64_t* totwt;
   uint64_t* logstart;
-  unsigned long long* counters;  // [0]=traversed [1]=max rounds of a warp [2]=log overflow
-  unsigned long long* trace;     // optional: per warp {end time ns, rounds, seeds} (SHN_WALK_TRACE)
+  unsigned long long* counters;  // [0]=traversed [1]=max rounds of a warp [2]=log overflow [3]=windows
+  unsigned long long* trace;     // optional: per warp {end time ns, rounds, cycles} (SHN_WALK_TRACE)
 };
 
-// One WARP per component.  Seeds are scanned 32 at a time (one coalesced load of the slot
-// indices, one gather of the traversed flags, a ballot).  A walk advances TWO K1-mers per memory
-// round trip: lanes 0..3 probe the four successors (predecessors) c_b of the current node and, in
-// the same round, lanes 4..19 probe the sixteen second-level nodes succ(c_b, b'); after the
-// first arg-max picks c_w the second step is decided from lanes 4+4w..7+4w, whose traversed
-// flags are still exact except for c_w itself (marked after the fetch; compared by key).  The
-// arg-max keeps the reference's tie order A,G,C,T.  The kernel is bound by the dependent-probe
-// latency of the longest component, not by issue slots or bandwidth.
-constexpr int kWalkBlock = 128;
+// aux words of the SHN_BSLOTS slots of bucket b, in the same memory round as the bucket itself
+struct AuxQuad {
+  uint32_t v[SHN_BSLOTS];
+};
+__device__ __forceinline__ void aux_load_bucket(const uint32_t* aux, uint64_t b, AuxQuad* q) {
+#ifdef SHN_WIDE
+  const uint2 t = __ldcg(reinterpret_cast<const uint2*>(aux) + b);
+  q->v[0] = t.x;
+  q->v[1] = t.y;
+#else
+  const uint4 t = __ldcg(reinterpret_cast<const uint4*>(aux) + b);
+  q->v[0] = t.x;
+  q->v[1] = t.y;
+  q->v[2] = t.z;
+  q->v[3] = t.w;
+#endif
+}
+__device__ __forceinline__ uint32_t aux_pick(const AuxQuad& q, int j) {
+  uint32_t r = q.v[0];
+#pragma unroll
+  for (int t = 1; t < SHN_BSLOTS; ++t) r = j == t ? q.v[t] : r;
+  return r;
+}
 
-__global__ void __launch_bounds__(kWalkBlock, 4) walk_kernel(WalkArgs a) {
+// One probe of the walks: the candidate's home bucket + its aux words are already loaded.
+// state: 1 found (slot, raw weight word, aux word), 0 absent, -1 continues in bucket *nextb.
+__device__ __forceinline__ int walk_resolve(const ShnTableView& tv, const ShnBucket& bk, const AuxQuad& aq,
+                                            shn_key_t cand, uint64_t hb, uint64_t* cslot, uint32_t* wraw,
+                                            uint32_t* caux, uint64_t* nextb) {
+  int jj = 0;
+  const int state = table_match_bucket(bk, cand, &jj, wraw);
+  *nextb = (hb + 1 == tv.n_buckets) ? 0 : hb + 1;
+  if (state == 1) {
+    *cslot = SHN_BSLOTS * hb + jj;
+    *caux = aux_pick(aq, jj);
+  }
+  return state;
+}
+// the rare continuation of a probe sequence (the key was displaced from its home bucket)
+__device__ __forceinline__ int walk_chase(const ShnTableView& tv, const uint32_t* aux, shn_key_t cand,
+                                          uint64_t* cslot, uint32_t* wraw, uint32_t* caux, uint64_t* nextb) {
+  for (;;) {
+    ShnBucket bk;
+    AuxQuad aq;
+    table_load_bucket(tv, *nextb, &bk);
+    aux_load_bucket(aux, *nextb, &aq);
+    const uint64_t hb = *nextb;
+    const int state = walk_resolve(tv, bk, aq, cand, hb, cslot, wraw, caux, nextb);
+    if (state >= 0) return state;
+  }
+}
+
+// One WARP per component.  Seeds are scanned 32 at a time (one coalesced load of the slot
+// indices, one gather of the aux words, a ballot).  A walk advances TWO K1-mers per memory round
+// trip: lanes 0..3 probe the existing successors (predecessors) c_b of the current node and, in the
+// same round, lanes 4..19 probe the second-level nodes succ(c_b, b'); after the first arg-max
+// picks c_w the second step is decided from lanes 4+4w..7+4w, whose traversed flags are still
+// exact except for c_w itself (marked after the fetch; compared by key).  The arg-max keeps the
+// reference's tie order A,G,C,T.  The kernel is bound by the dependent chain of one round
+// (~1 DRAM round trip + ~250 instructions), not by issue slots or bandwidth.
+constexpr int kWalkBlock = 128;
+#ifndef SHN_WALK_BLOCKS_PER_SM
+#define SHN_WALK_BLOCKS_PER_SM 8
+#endif
+constexpr int kWalkBlocksPerSM = SHN_WALK_BLOCKS_PER_SM;  // 8 -> 64 registers: co-resident with speculative CTAs
+
+__global__ void __launch_bounds__(kWalkBlock, kWalkBlocksPerSM) walk_kernel(WalkArgs a) {
   const unsigned FULL = 0xFFFFFFFFu;
   const int lane = threadIdx.x & 31;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -363,18 +378,13 @@ __global__ void __launch_bounds__(kWalkBlock, 4) walk_kernel(WalkArgs a) {
   const uint64_t le = a.log_off[comp + 1];
   const shn_key_t mask = shn_key_mask(a.k1);
   const int top = 2 * (a.k1 - 1);
-  ShnSlot* slots = a.local;     // slot indices of this kernel are indices into the local table
-  const uint64_t r0 = a.region_off[comp];
-  const ShnTableView tv{a.local + SHN_BSLOTS * r0, a.region_off[comp + 1] - r0};
-  const uint64_t slot_base = SHN_BSLOTS * r0;
+  const ShnTableView tv = a.tv;
+  uint32_t* aux = a.aux;
   unsigned long long rounds = 0, traversed = 0;
   long long mem_cycles = 0, t_begin = clock64();
   const bool tracing = a.trace != nullptr;
   bool overflow = false;
-  // Small components finish long before the large ones: they skip the second-level prefetch (one
-  // step per round, 4 instead of 20 probes) and leave the DRAM bandwidth to the components whose
-  // latency is the critical path.
-  const bool look = tv.n_buckets >= a.lookahead_min_buckets;
+  const bool look = a.lookahead != 0;
   // role of this lane inside a round: level 1 (lanes 0..3), level 2 (lanes 4..19), idle
   const int lvl = lane < 4 ? 1 : ((look && lane < 20) ? 2 : 0);
   const shn_key_t b1 = lvl == 1 ? lane : ((lane - 4) >> 2);  // first appended base
@@ -384,26 +394,27 @@ __global__ void __launch_bounds__(kWalkBlock, 4) walk_kernel(WalkArgs a) {
     // ---- scan 32 seeds of this component (pop order) -------------------------------------
     const uint64_t si = base + lane;
     const bool have = si < s_end;
-    uint32_t my_rank = 0, my_slot = 0, my_w = SHN_TRAVERSED;
+    uint32_t my_rank = 0, my_slot = 0, my_aux = kAuxTraversed;
     if (have) {
       my_rank = a.ranks_by_comp[si];
       my_slot = a.slots_by_comp[si];
-      my_w = __ldcg(&slots[my_slot].weight);
+      my_aux = __ldcg(&aux[my_slot]);
     }
-    unsigned pending = __ballot_sync(FULL, have && !(my_w & SHN_TRAVERSED));
+    unsigned pending = __ballot_sync(FULL, have && !(my_aux & kAuxTraversed));
     while (pending) {
       const int j = __ffs(pending) - 1;
       pending &= pending - 1;
       const uint32_t slot = __shfl_sync(FULL, my_slot, j);
       const uint32_t rank = __shfl_sync(FULL, my_rank, j);
       // fresh look: an earlier walk of this batch may have traversed it meanwhile (:346)
+      const uint32_t seed_aux = __ldcg(&aux[slot]);
+      if (seed_aux & kAuxTraversed) continue;  // warp-uniform
       shn_key_t seed_key;
       uint32_t seed_w, seed_i;
-      table_load_slot(slots, slot, &seed_key, &seed_w, &seed_i);
-      if (seed_w & SHN_TRAVERSED) continue;  // warp-uniform
+      table_load_slot(tv.slots, slot, &seed_key, &seed_w, &seed_i);
       if (lane == 0) {
-        slots[slot].weight = seed_w | SHN_TRAVERSED;  // traversed.add(start_kmer), :347
-        if (lp < le) a.walk_log[lp] = 0xFF;         // the seed's own (unused) log entry
+        aux[slot] = seed_aux | kAuxTraversed;      // traversed.add(start_kmer), :347
+        if (lp < le) a.walk_log[lp] = 0xFF;        // the seed's own (unused) log entry
       }
       overflow |= lp >= le;
       const uint64_t my_log = lp;
@@ -415,16 +426,19 @@ __global__ void __launch_bounds__(kWalkBlock, 4) walk_kernel(WalkArgs a) {
 #pragma unroll 1
       for (int dir = 0; dir < 2; ++dir) {  // right extension first, then left (:349-350)
         shn_key_t cur = seed_key;
+        uint32_t cur_aux = seed_aux;  // neighbour masks of `cur`
         for (;;) {
+          const uint32_t cm = (cur_aux >> (kAuxSuccShift + 4 * dir)) & 0xFu;
+          if (cm == 0) break;  // warp-uniform: dead end
           ++rounds;
+          const bool act = lvl != 0 && ((cm >> (int)b1) & 1u);
           // candidate keys in the reference's tie order A,G,C,T = codes 0..3 (:10,229)
           shn_key_t cand = 0;
           uint64_t cslot = ~0ull;
-          uint32_t wraw = 0;
-          int state = 0;       // 1 found, 0 absent, -1 undecided after the two prefetched buckets
+          uint32_t wraw = 0, caux = 0;
+          int state = 0;       // 1 found, 0 absent, -1 undecided after the home bucket
           uint64_t nextb = 0;  // where an undecided lane would continue
-          long long tm0 = 0;
-          if (lvl) {
+          if (act) {
             if (dir == 0) {
               cand = ((cur << 2) & mask) | b1;
               if (lvl == 2) cand = ((cand << 2) & mask) | b2;
@@ -432,45 +446,23 @@ __global__ void __launch_bounds__(kWalkBlock, 4) walk_kernel(WalkArgs a) {
               cand = (cur >> 2) | (b1 << top);
               if (lvl == 2) cand = (cand >> 2) | (b2 << top);
             }
-            // home bucket and its successor in the same memory round
-            uint64_t hb = tv.bucket_of(cand);
-            uint64_t hb1 = (hb + 1 == tv.n_buckets) ? 0 : hb + 1;
-            ShnBucket bk0, bk1;
+            const uint64_t hb = tv.bucket_of(cand);
+            ShnBucket bk0;
+            AuxQuad aq0;
+            long long tm0 = 0;
             if (tracing) tm0 = clock64();
             table_load_bucket(tv, hb, &bk0);
-            // the first decision must not wait for a second round trip: its four lanes also
-            // prefetch the next bucket of the probe sequence (6.5 % of probes continue)
-            if (lvl == 1) table_load_bucket(tv, hb1, &bk1);
+            aux_load_bucket(aux, hb, &aq0);
             if (tracing) {  // wait for the data here so the cycles are attributed to memory
-              volatile uint64_t sink = bk0.w[0] ^ bk0.w[4] ^ (lvl == 1 ? bk1.w[0] ^ bk1.w[4] : 0ull);
+              volatile uint64_t sink = bk0.w[0] ^ bk0.w[4] ^ aq0.v[0];
               (void)sink;
               mem_cycles += clock64() - tm0;
             }
-            int jj = 0;
-            state = table_match_bucket(bk0, cand, &jj, &wraw);
-            nextb = hb1;
-            if (state == 1) {
-              cslot = slot_base + SHN_BSLOTS * hb + jj;
-            } else if (state < 0 && lvl == 1) {
-              state = table_match_bucket(bk1, cand, &jj, &wraw);
-              if (state == 1) cslot = slot_base + SHN_BSLOTS * hb1 + jj;
-              nextb = (hb1 + 1 == tv.n_buckets) ? 0 : hb1 + 1;
-            }
+            state = walk_resolve(tv, bk0, aq0, cand, hb, &cslot, &wraw, &caux, &nextb);
           }
           // only the lanes a decision actually depends on pay for longer probe sequences
-          if (lvl == 1 && state < 0) {
-            ShnTableView t2 = tv;
-            for (;;) {
-              ShnBucket bk;
-              table_load_bucket(t2, nextb, &bk);
-              int jj = 0;
-              state = table_match_bucket(bk, cand, &jj, &wraw);
-              if (state == 1) cslot = slot_base + SHN_BSLOTS * nextb + jj;
-              if (state >= 0) break;
-              nextb = (nextb + 1 == t2.n_buckets) ? 0 : nextb + 1;
-            }
-          }
-          bool ok = cslot != ~0ull && !(wraw & SHN_TRAVERSED);
+          if (lvl == 1 && state < 0) state = walk_chase(tv, aux, cand, &cslot, &wraw, &caux, &nextb);
+          bool ok = state == 1 && !(caux & kAuxTraversed);
           // ---- first step: arg-max weight over lanes 0..3, first of equals wins (:159-166) ---
           // score = (weight, 3 - code) + 1 in 32 bits (weights are < 2^30 - 1), 0 = no candidate
           uint32_t score = ok ? ((((wraw & SHN_WEIGHT_MASK) << 2) | (uint32_t)(3 - (lane & 3))) + 1u) : 0u;
@@ -480,8 +472,9 @@ __global__ void __launch_bounds__(kWalkBlock, 4) walk_kernel(WalkArgs a) {
           if (s1 == 0) break;  // warp-uniform: no extension
           const int w1 = 3 - (int)((s1 - 1u) & 3u);
           const uint32_t bw1 = (s1 - 1u) >> 2;
-          const shn_key_t c1 = shfl_key(cand, w1);
-          if (lane == w1) slots[cslot].weight = wraw | SHN_TRAVERSED;  // traversed.add(last), :235
+          const shn_key_t c1 = dir == 0 ? (((cur << 2) & mask) | (shn_key_t)w1)
+                                        : ((cur >> 2) | ((shn_key_t)w1 << top));
+          if (lane == w1) aux[cslot] = caux | kAuxTraversed;  // traversed.add(last), :235
           if (lane == 0 && lp < le) a.walk_log[lp] = (uint8_t)w1;
           overflow |= lp >= le;
           ++lp;
@@ -490,22 +483,15 @@ __global__ void __launch_bounds__(kWalkBlock, 4) walk_kernel(WalkArgs a) {
           ++n_dir[dir];
           if (!look) {  // warp-uniform: no prefetched level, continue from c1
             cur = c1;
+            cur_aux = __shfl_sync(FULL, caux, w1);
             __syncwarp();
             continue;
           }
           // ---- second step from the prefetched level: group 4+4*w1; c1 is traversed by now ---
           const int g2 = 4 + 4 * w1;
           if (lane >= g2 && lane < g2 + 4 && state < 0) {
-            for (;;) {
-              ShnBucket bk;
-              table_load_bucket(tv, nextb, &bk);
-              int jj = 0;
-              state = table_match_bucket(bk, cand, &jj, &wraw);
-              if (state == 1) cslot = slot_base + SHN_BSLOTS * nextb + jj;
-              if (state >= 0) break;
-              nextb = (nextb + 1 == tv.n_buckets) ? 0 : nextb + 1;
-            }
-            ok = cslot != ~0ull && !(wraw & SHN_TRAVERSED);
+            state = walk_chase(tv, aux, cand, &cslot, &wraw, &caux, &nextb);
+            ok = state == 1 && !(caux & kAuxTraversed);
           }
           ok = ok && cand != c1;
           score = ok ? ((((wraw & SHN_WEIGHT_MASK) << 2) | (uint32_t)(3 - (lane & 3))) + 1u) : 0u;
@@ -518,8 +504,9 @@ __global__ void __launch_bounds__(kWalkBlock, 4) walk_kernel(WalkArgs a) {
           }
           const int w2 = 3 - (int)((s2 - 1u) & 3u);
           const uint32_t bw2 = (s2 - 1u) >> 2;
-          cur = shfl_key(cand, g2 + w2);
-          if (lane == g2 + w2) slots[cslot].weight = wraw | SHN_TRAVERSED;
+          cur = dir == 0 ? (((c1 << 2) & mask) | (shn_key_t)w2) : ((c1 >> 2) | ((shn_key_t)w2 << top));
+          cur_aux = __shfl_sync(FULL, caux, g2 + w2);
+          if (lane == g2 + w2) aux[cslot] = caux | kAuxTraversed;
           if (lane == 0 && lp < le) a.walk_log[lp] = (uint8_t)w2;
           overflow |= lp >= le;
           ++lp;
@@ -558,8 +545,9 @@ __global__ void __launch_bounds__(kWalkBlock, 4) walk_kernel(WalkArgs a) {
 // dependent probe rounds).  Large components are therefore given a CTA of kSpecWarps warps that
 // run the next kSpecWarps untraversed seeds of the pop order CONCURRENTLY and commit them IN ORDER
 // ("deterministic reservations"):
-//   * every walk of a window carries a stamp = 0xFFFFFFFF - seed position (earlier seed = larger
-//     stamp) and claims a K1-mer with atomicMax on the slot's (otherwise unused) idx word;
+//   * every walk of a window carries a stamp = kSpecWarps - its position in the window (earlier
+//     seed = larger stamp) and claims a K1-mer with atomicMax on the slot's aux word (stamp in the
+//     low bits; the bits above it are the same for every claimant of an untraversed slot);
 //   * a candidate is blocked for a walk iff it is committed-traversed or stamped by an EARLIER
 //     seed (or by the walk itself); stamps of later seeds are ignored and overwritten (stolen);
 //   * after the window every walk re-reads its path: it is intact iff every slot still carries its
@@ -568,8 +556,13 @@ __global__ void __launch_bounds__(kWalkBlock, 4) walk_kernel(WalkArgs a) {
 //     final; nothing it examined-and-rejected can matter): those are
 //     committed (traversed bits, log, metas); the others clear their stamps and are retried in
 //     the next window, which starts at the first uncommitted seed.  The first walk of a window is
-//     always intact, so every window makes progress.
+//     always intact, so every window makes progress.  After a window every untraversed slot is
+//     back to stamp 0, so stamps only ever order the walks of one window.
 constexpr int kSpecWarps = 16;
+#ifndef SHN_SPEC_CTAS_PER_SM
+#define SHN_SPEC_CTAS_PER_SM 2
+#endif
+constexpr int kSpecCtasPerSM = SHN_SPEC_CTAS_PER_SM;  // 2 -> 64 registers
 
 struct SpecArgs {
   WalkArgs w;
@@ -578,7 +571,7 @@ struct SpecArgs {
   uint64_t path_cap;
 };
 
-__global__ void __launch_bounds__(kSpecWarps * 32, 1) walk_spec_kernel(SpecArgs sa) {
+__global__ void __launch_bounds__(kSpecWarps * 32, kSpecCtasPerSM) walk_spec_kernel(SpecArgs sa) {
   const WalkArgs& a = sa.w;
   const unsigned FULL = 0xFFFFFFFFu;
   const int lane = threadIdx.x & 31;
@@ -588,10 +581,8 @@ __global__ void __launch_bounds__(kSpecWarps * 32, 1) walk_spec_kernel(SpecArgs 
   const uint64_t le = a.log_off[comp + 1];
   const shn_key_t mask = shn_key_mask(a.k1);
   const int top = 2 * (a.k1 - 1);
-  ShnSlot* slots = a.local;
-  const uint64_t r0 = a.region_off[comp];
-  const ShnTableView tv{a.local + SHN_BSLOTS * r0, a.region_off[comp + 1] - r0};
-  const uint64_t slot_base = SHN_BSLOTS * r0;
+  const ShnTableView tv = a.tv;
+  uint32_t* aux = a.aux;
   uint32_t* my_path_slot = sa.path_slot + ((uint64_t)blockIdx.x * kSpecWarps + warp) * sa.path_cap;
   uint8_t* my_path_base = sa.path_base + ((uint64_t)blockIdx.x * kSpecWarps + warp) * sa.path_cap;
   const int lvl = lane < 4 ? 1 : (lane < 20 ? 2 : 0);
@@ -606,7 +597,7 @@ __global__ void __launch_bounds__(kSpecWarps * 32, 1) walk_spec_kernel(SpecArgs 
     sh_cursor = s_begin;
     sh_lp = a.log_off[comp];
   }
-  unsigned long long rounds = 0, traversed = 0, windows = 0;
+  unsigned long long rounds = 0, traversed = 0, windows = 0, n_commit = 0, n_retry = 0;
   bool overflow = false;
   __syncthreads();
 
@@ -617,12 +608,12 @@ __global__ void __launch_bounds__(kSpecWarps * 32, 1) walk_spec_kernel(SpecArgs 
       uint64_t pos = sh_cursor;
       while (n < kSpecWarps && pos < s_end) {
         const uint64_t si = pos + lane;
-        uint32_t slot = 0, wv = SHN_TRAVERSED;
+        uint32_t slot = 0, av = kAuxTraversed;
         if (si < s_end) {
           slot = a.slots_by_comp[si];
-          wv = __ldcg(&slots[slot].weight);
+          av = __ldcg(&aux[slot]);
         }
-        unsigned fresh = __ballot_sync(FULL, si < s_end && !(wv & SHN_TRAVERSED));
+        unsigned fresh = __ballot_sync(FULL, si < s_end && !(av & kAuxTraversed));
         uint64_t consumed = min((uint64_t)32, s_end - pos);
         while (fresh && n < kSpecWarps) {
           const int j = __ffs(fresh) - 1;
@@ -650,36 +641,47 @@ __global__ void __launch_bounds__(kSpecWarps * 32, 1) walk_spec_kernel(SpecArgs 
     // ---- 2. speculative walks -----------------------------------------------------------------
     uint32_t len = 0, n_dir[2] = {0, 0};
     uint64_t tot = 0;
-    uint32_t stamp = 0;
+    const uint32_t stamp = (uint32_t)(kSpecWarps - warp);  // earlier seed = larger stamp
     if (warp < (int)win_n) {
-      stamp = 0xFFFFFFFFu - sh_win_pos[warp];
       const uint32_t seed_slot = sh_win_slot[warp];
+      const uint32_t seed_aux = __ldcg(&aux[seed_slot]);
       // claim the seed; an earlier walk of this window may already hold it
       uint32_t old = 0;
-      if (lane == 0) old = atomicMax(&slots[seed_slot].idx, stamp);
+      if (lane == 0) old = atomicMax(&aux[seed_slot], (seed_aux & ~kAuxStampMask) | stamp);
       old = __shfl_sync(FULL, old, 0);
-      if (old < stamp) {
+      if ((old & kAuxStampMask) < stamp) {
         shn_key_t seed_key;
         uint32_t seed_w, seed_i;
-        table_load_slot(slots, seed_slot, &seed_key, &seed_w, &seed_i);
+        table_load_slot(tv.slots, seed_slot, &seed_key, &seed_w, &seed_i);
         if (lane == 0) {
           my_path_slot[0] = seed_slot;
           my_path_base[0] = 0xFF;
         }
         len = 1;
         tot = seed_w & SHN_WEIGHT_MASK;
+        // Claims are OPTIMISTIC: the atomicMax of a step is issued and the walk moves on; its
+        // result is looked at one round later, under the latency of the next probes.  A claim
+        // that lost against an earlier seed leaves that seed's stamp in the slot, so the walk can
+        // never pass the intact check below; it is abandoned as soon as the loss is seen.
+        uint32_t pend1 = 0, pend2 = 0;
+        bool poisoned = false;
 #pragma unroll 1
-        for (int dir = 0; dir < 2; ++dir) {
+        for (int dir = 0; dir < 2 && !poisoned; ++dir) {
           shn_key_t cur = seed_key;
-          bool go = true;
-          while (go) {
+          uint32_t cur_aux = seed_aux;
+          for (;;) {
+            const uint32_t cm = (cur_aux >> (kAuxSuccShift + 4 * dir)) & 0xFu;
+            if (cm == 0) break;  // dead end
             ++rounds;
+            const bool act = lvl != 0 && ((cm >> (int)b1) & 1u);
             shn_key_t cand = 0;
-          uint64_t cslot = ~0ull;
-            uint32_t wraw = 0, cstamp = 0;
+            uint64_t cslot = ~0ull, hb = 0;
+            uint32_t wraw = 0, caux = 0;
             int state = 0;
             uint64_t nextb = 0;
-            if (lvl) {
+            ShnBucket bk0;
+            AuxQuad aq0;
+            if (act) {
               if (dir == 0) {
                 cand = ((cur << 2) & mask) | b1;
                 if (lvl == 2) cand = ((cand << 2) & mask) | b2;
@@ -687,63 +689,37 @@ __global__ void __launch_bounds__(kSpecWarps * 32, 1) walk_spec_kernel(SpecArgs 
                 cand = (cur >> 2) | (b1 << top);
                 if (lvl == 2) cand = (cand >> 2) | (b2 << top);
               }
-              uint64_t hb = tv.bucket_of(cand);
-              uint64_t hb1 = (hb + 1 == tv.n_buckets) ? 0 : hb + 1;
-              ShnBucket bk0, bk1;
+              hb = tv.bucket_of(cand);
               table_load_bucket(tv, hb, &bk0);
-              if (lvl == 1) table_load_bucket(tv, hb1, &bk1);
-              int jj = 0;
-              state = table_match_bucket2(bk0, cand, &jj, &wraw, &cstamp);
-              nextb = hb1;
-              if (state == 1) {
-                cslot = slot_base + SHN_BSLOTS * hb + jj;
-              } else if (state < 0 && lvl == 1) {
-                state = table_match_bucket2(bk1, cand, &jj, &wraw, &cstamp);
-                if (state == 1) cslot = slot_base + SHN_BSLOTS * hb1 + jj;
-                nextb = (hb1 + 1 == tv.n_buckets) ? 0 : hb1 + 1;
-              }
+              aux_load_bucket(aux, hb, &aq0);
             }
-            if (lvl == 1 && state < 0) {
-              for (;;) {
-                ShnBucket bk;
-                table_load_bucket(tv, nextb, &bk);
-                int jj = 0;
-                state = table_match_bucket2(bk, cand, &jj, &wraw, &cstamp);
-                if (state == 1) cslot = slot_base + SHN_BSLOTS * nextb + jj;
-                if (state >= 0) break;
-                nextb = (nextb + 1 == tv.n_buckets) ? 0 : nextb + 1;
-              }
-            }
-            // blocked: committed-traversed, or stamped by an earlier seed or by this walk
-            bool ok = cslot != ~0ull && !(wraw & SHN_TRAVERSED) && cstamp < stamp;
-            // ---- first step (re-decided if the claim loses a race against an earlier seed) -----
-            int w1 = -1;
-            uint32_t bw1 = 0;
-            for (;;) {
-              uint32_t score = ok ? ((((wraw & SHN_WEIGHT_MASK) << 2) | (uint32_t)(3 - (lane & 3))) + 1u) : 0u;
-              uint32_t m = max(score, __shfl_xor_sync(FULL, score, 1));
-              m = max(m, __shfl_xor_sync(FULL, m, 2));
-              const uint32_t s1 = __shfl_sync(FULL, m, 0);
-              if (s1 == 0) break;
-              const int wl = 3 - (int)((s1 - 1u) & 3u);
-              uint32_t o = 0;
-              if (lane == wl) o = atomicMax(&slots[cslot].idx, stamp);
-              o = __shfl_sync(FULL, o, wl);
-              if (o < stamp) {
-                w1 = wl;
-                bw1 = (s1 - 1u) >> 2;
+            {  // the claims of the previous round, by now usually back from L2
+              const bool lost = (pend1 & kAuxStampMask) >= stamp || (pend2 & kAuxStampMask) >= stamp;
+              pend1 = pend2 = 0;
+              if (__any_sync(FULL, lost)) {
+                poisoned = true;
                 break;
               }
-              if (lane == wl) ok = false;  // an earlier seed got there first: blocked after all
             }
-            if (w1 < 0) break;  // no extension in this direction
-            const shn_key_t c1 = shfl_key(cand, w1);
+            if (act) state = walk_resolve(tv, bk0, aq0, cand, hb, &cslot, &wraw, &caux, &nextb);
+            if (lvl == 1 && state < 0) state = walk_chase(tv, aux, cand, &cslot, &wraw, &caux, &nextb);
+            // blocked: committed-traversed, or stamped by an earlier seed or by this walk
+            bool ok = state == 1 && !(caux & kAuxTraversed) && (caux & kAuxStampMask) < stamp;
+            // ---- first step ------------------------------------------------------------------
+            uint32_t score = ok ? ((((wraw & SHN_WEIGHT_MASK) << 2) | (uint32_t)(3 - (lane & 3))) + 1u) : 0u;
+            uint32_t m = max(score, __shfl_xor_sync(FULL, score, 1));
+            m = max(m, __shfl_xor_sync(FULL, m, 2));
+            const uint32_t s1 = __shfl_sync(FULL, m, 0);
+            if (s1 == 0) break;  // no extension in this direction
+            const int w1 = 3 - (int)((s1 - 1u) & 3u);
+            const uint32_t bw1 = (s1 - 1u) >> 2;
+            if (lane == w1) pend1 = atomicMax(&aux[cslot], (caux & ~kAuxStampMask) | stamp);
+            const shn_key_t c1 = dir == 0 ? (((cur << 2) & mask) | (shn_key_t)w1)
+                                          : ((cur >> 2) | ((shn_key_t)w1 << top));
             const uint32_t c1slot = (uint32_t)__shfl_sync(FULL, (uint32_t)cslot, w1);
-            if (lane == 0) {
-              if (len < sa.path_cap) {
-                my_path_slot[len] = c1slot;
-                my_path_base[len] = (uint8_t)w1;
-              }
+            if (lane == 0 && len < sa.path_cap) {
+              my_path_slot[len] = c1slot;
+              my_path_base[len] = (uint8_t)w1;
             }
             overflow |= len >= sa.path_cap;
             ++len;
@@ -752,51 +728,29 @@ __global__ void __launch_bounds__(kSpecWarps * 32, 1) walk_spec_kernel(SpecArgs 
             // ---- second step from the prefetched level ---------------------------------------
             const int g2 = 4 + 4 * w1;
             if (lane >= g2 && lane < g2 + 4 && state < 0) {
-              for (;;) {
-                ShnBucket bk;
-                table_load_bucket(tv, nextb, &bk);
-                int jj = 0;
-                state = table_match_bucket2(bk, cand, &jj, &wraw, &cstamp);
-                if (state == 1) cslot = slot_base + SHN_BSLOTS * nextb + jj;
-                if (state >= 0) break;
-                nextb = (nextb + 1 == tv.n_buckets) ? 0 : nextb + 1;
-              }
-              ok = cslot != ~0ull && !(wraw & SHN_TRAVERSED) && cstamp < stamp;
+              state = walk_chase(tv, aux, cand, &cslot, &wraw, &caux, &nextb);
+              ok = state == 1 && !(caux & kAuxTraversed) && (caux & kAuxStampMask) < stamp;
             }
             ok = ok && cand != c1;
-            int w2 = -1;
-            uint32_t bw2 = 0;
-            for (;;) {
-              uint32_t score = ok ? ((((wraw & SHN_WEIGHT_MASK) << 2) | (uint32_t)(3 - (lane & 3))) + 1u) : 0u;
-              uint32_t m = max(score, __shfl_xor_sync(FULL, score, 1));
-              m = max(m, __shfl_xor_sync(FULL, m, 2));
-              const uint32_t s2 = __shfl_sync(FULL, m, g2);
-              if (s2 == 0) break;
-              const int wl = 3 - (int)((s2 - 1u) & 3u);
-              uint32_t o = 0;
-              if (lane == g2 + wl) o = atomicMax(&slots[cslot].idx, stamp);
-              o = __shfl_sync(FULL, o, g2 + wl);
-              if (o < stamp) {
-                w2 = wl;
-                bw2 = (s2 - 1u) >> 2;
-                break;
-              }
-              if (lane == g2 + wl) ok = false;
+            score = ok ? ((((wraw & SHN_WEIGHT_MASK) << 2) | (uint32_t)(3 - (lane & 3))) + 1u) : 0u;
+            m = max(score, __shfl_xor_sync(FULL, score, 1));
+            m = max(m, __shfl_xor_sync(FULL, m, 2));
+            const uint32_t s2 = __shfl_sync(FULL, m, g2);
+            if (s2 == 0) break;  // the walk ends at c1 in this direction
+            const int w2 = 3 - (int)((s2 - 1u) & 3u);
+            const uint32_t bw2 = (s2 - 1u) >> 2;
+            if (lane == g2 + w2) pend2 = atomicMax(&aux[cslot], (caux & ~kAuxStampMask) | stamp);
+            cur = dir == 0 ? (((c1 << 2) & mask) | (shn_key_t)w2) : ((c1 >> 2) | ((shn_key_t)w2 << top));
+            cur_aux = __shfl_sync(FULL, caux, g2 + w2);
+            const uint32_t c2slot = (uint32_t)__shfl_sync(FULL, (uint32_t)cslot, g2 + w2);
+            if (lane == 0 && len < sa.path_cap) {
+              my_path_slot[len] = c2slot;
+              my_path_base[len] = (uint8_t)w2;
             }
-            if (w2 < 0) {
-              go = false;  // the walk ends at c1 in this direction
-            } else {
-              cur = shfl_key(cand, g2 + w2);
-              const uint32_t c2slot = (uint32_t)__shfl_sync(FULL, (uint32_t)cslot, g2 + w2);
-              if (lane == 0 && len < sa.path_cap) {
-                my_path_slot[len] = c2slot;
-                my_path_base[len] = (uint8_t)w2;
-              }
-              overflow |= len >= sa.path_cap;
-              ++len;
-              tot += bw2;
-              ++n_dir[dir];
-            }
+            overflow |= len >= sa.path_cap;
+            ++len;
+            tot += bw2;
+            ++n_dir[dir];
             __syncwarp();
           }
         }
@@ -808,13 +762,16 @@ __global__ void __launch_bounds__(kSpecWarps * 32, 1) walk_spec_kernel(SpecArgs 
     // ---- 3. is my path intact? ------------------------------------------------------------------
     if (warp < (int)win_n) {
       bool mine = true;
-      for (uint32_t e = lane; e < len; e += 32) mine &= __ldcg(&slots[my_path_slot[e]].idx) == stamp;
+      for (uint32_t e = lane; e < len; e += 32)
+        mine &= (__ldcg(&aux[my_path_slot[e]]) & kAuxStampMask) == stamp;
       mine = __all_sync(FULL, mine);
       if (lane == 0) sh_intact[warp] = mine ? 1u : 0u;
     }
     __syncthreads();
     uint32_t P = 0;
     while (P < win_n && sh_intact[P]) ++P;
+    n_commit += P;
+    n_retry += win_n - P;
 
     // ---- 4. commit the intact prefix in order, roll the rest back ---------------------------
     if (warp < (int)win_n) {
@@ -822,7 +779,7 @@ __global__ void __launch_bounds__(kSpecWarps * 32, 1) walk_spec_kernel(SpecArgs 
         uint64_t off = sh_lp;
         for (int q = 0; q < warp; ++q) off += sh_len[q];
         for (uint32_t e = lane; e < len; e += 32) {
-          atomicOr(&slots[my_path_slot[e]].weight, SHN_TRAVERSED);
+          atomicOr(&aux[my_path_slot[e]], kAuxTraversed);
           if (off + e < le) a.walk_log[off + e] = my_path_base[e];
         }
         overflow |= off + len > le;
@@ -836,7 +793,11 @@ __global__ void __launch_bounds__(kSpecWarps * 32, 1) walk_spec_kernel(SpecArgs 
         }
         traversed += len;
       } else {
-        for (uint32_t e = lane; e < len; e += 32) atomicCAS(&slots[my_path_slot[e]].idx, stamp, 0u);
+        for (uint32_t e = lane; e < len; e += 32) {
+          uint32_t* p = &aux[my_path_slot[e]];
+          const uint32_t v = __ldcg(p);  // only the stamp bits change: the CAS fails iff stolen
+          if ((v & kAuxStampMask) == stamp) atomicCAS(p, v, v & ~kAuxStampMask);
+        }
       }
     }
     __syncthreads();
@@ -853,6 +814,13 @@ __global__ void __launch_bounds__(kSpecWarps * 32, 1) walk_spec_kernel(SpecArgs 
     if (warp == 0) atomicMax(&a.counters[1], rounds);
     if (overflow) atomicAdd(&a.counters[2], 1ull);
     if (warp == 0) atomicAdd(&a.counters[3], windows);
+    if (warp == 0 && a.trace) {
+      unsigned long long tns;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tns));
+      a.trace[3 * (uint64_t)blockIdx.x] = tns;
+      a.trace[3 * (uint64_t)blockIdx.x + 1] = (windows << 32) | rounds;
+      a.trace[3 * (uint64_t)blockIdx.x + 2] = (n_commit << 32) | n_retry;
+    }
   }
 }
 
@@ -1212,9 +1180,13 @@ void l3_run(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
     uf_init_kernel<<<stream_grid, kBlock, 0, st>>>(parent.as<uint32_t>(), n_slots);
     KERNEL_CHECK();
   }
+  DevBuf aux;  // per slot: neighbour masks | traversed | claim stamp (see "greedy walks")
+  aux.reserve(n_slots * 4);
   {
-    ProfScope ps(c, "uf_edges");
-    uf_edges_kernel<<<shn_grid(n_slots, kBlock), kBlock, 0, st>>>(tv, parent.as<uint32_t>(), n_slots, k1);
+    ProfScope ps(c, "uf_edges", 2);
+    CUDA_CHECK(cudaMemsetAsync(aux.p, 0, n_slots * 4, st));
+    uf_edges_kernel<<<shn_grid(n_slots, kBlock), kBlock, 0, st>>>(tv, parent.as<uint32_t>(), n_slots, k1,
+                                                                 aux.as<uint32_t>());
     KERNEL_CHECK();
   }
   {
@@ -1268,38 +1240,14 @@ void l3_run(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
                                                seed_comp_s.as<uint32_t>(), rank_in.as<uint32_t>(),
                                                ranks_by_comp.as<uint32_t>(), (int64_t)n_seeds, 0, bits, st));
   }
-  // component-local copy of the table (regions of the components that own seeds)
-  DevBuf region_nb, region_off, local, local_of, slots_by_comp;
-  region_nb.reserve(((uint64_t)n_comps + 1) * 8);
-  region_off.reserve(((uint64_t)n_comps + 1) * 8);
+  // table slots of the seeds, grouped like ranks_by_comp
+  DevBuf slots_by_comp;
   slots_by_comp.reserve(std::max<uint64_t>(n_seeds, 1) * 4);
-  uint64_t local_buckets = 0;
   if (n_seeds) {
-    ProfScope ps(c, "repack", 5);
-    region_size_kernel<<<shn_grid((uint64_t)n_comps + 1, kBlock), kBlock, 0, st>>>(
-        comp_nodes.as<uint32_t>(), comp_seeds.as<uint32_t>(), n_comps, region_nb.as<uint64_t>());
+    ProfScope ps(c, "seed_group");
+    gather_u32_kernel<<<shn_grid(n_seeds, kBlock), kBlock, 0, st>>>(
+        seed_slot.as<uint32_t>(), ranks_by_comp.as<uint32_t>(), n_seeds, slots_by_comp.as<uint32_t>());
     KERNEL_CHECK();
-    exclusive_sum(c, region_nb.as<uint64_t>(), region_off.as<uint64_t>(), (uint64_t)n_comps + 1);
-    CUDA_CHECK(cudaMemcpyAsync(&local_buckets, region_off.as<uint64_t>() + n_comps, 8,
-                               cudaMemcpyDeviceToHost, st));
-    CUDA_CHECK(cudaStreamSynchronize(st));
-    SHN_CHECK(local_buckets * SHN_BSLOTS < 0xFFFFFFFFull, "component-local table too large");
-    local.reserve(std::max<uint64_t>(local_buckets, 1) * SHN_BSLOTS * sizeof(ShnSlot));
-    local_of.reserve(n_slots * 4);
-    local_clear_kernel<<<stream_grid, kBlock, 0, st>>>(local.as<ShnSlot>(), local_buckets * SHN_BSLOTS);
-    KERNEL_CHECK();
-    ctr = zero_counters(c);
-    repack_kernel<<<shn_grid(n_slots, kBlock), kBlock, 0, st>>>(
-        tv.slots, n_slots, parent.as<uint32_t>(), root_id.as<uint32_t>(), region_off.as<uint64_t>(),
-        local.as<ShnSlot>(), local_of.as<uint32_t>(), ctr);
-    KERNEL_CHECK();
-    gather2_u32_kernel<<<shn_grid(n_seeds, kBlock), kBlock, 0, st>>>(
-        local_of.as<uint32_t>(), seed_slot.as<uint32_t>(), ranks_by_comp.as<uint32_t>(), n_seeds,
-        slots_by_comp.as<uint32_t>());
-    KERNEL_CHECK();
-    read_counters(c, h, 1);
-    SHN_CHECK(h[0] == 0, "internal error: component-local table repack failed");
-    local_of.release();
   }
   parent.release();
   root_id.release();
@@ -1346,11 +1294,11 @@ void l3_run(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
   ctr = zero_counters(c);
   if (n_active) {
     WalkArgs a;
-    a.local = local.as<ShnSlot>();
-    a.region_off = region_off.as<uint64_t>();
+    a.tv = tv;
+    a.aux = aux.as<uint32_t>();
     {
-      const char* envl = getenv("SHN_LOOKAHEAD_MIN_NODES");
-      a.lookahead_min_buckets = (envl ? strtoull(envl, nullptr, 10) : 0ull) / 2;
+      const char* envl = getenv("SHN_NO_LOOKAHEAD");
+      a.lookahead = envl ? 0u : 1u;
     }
     a.k1 = k1;
     a.n_comps = n_active;
@@ -1358,7 +1306,6 @@ void l3_run(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
     a.seed_off = seed_off.as<uint64_t>();
     a.ranks_by_comp = ranks_by_comp.as<uint32_t>();
     a.slots_by_comp = slots_by_comp.as<uint32_t>();
-    a.seed_slot = seed_slot.as<uint32_t>();
     a.log_off = log_off.as<uint64_t>();
     a.walk_log = s->walk_log.as<uint8_t>();
     a.started = started.as<uint8_t>();
@@ -1432,6 +1379,7 @@ void l3_run(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
       std::vector<unsigned long long> tr;
       d2h(c, tr, trace.p, (uint64_t)n_active * 3);
       unsigned long long t_min = ~0ull, t_max = 0, r_sum = 0;
+      for (uint32_t w = 0; w < n_spec; ++w) t_min = std::min(t_min, tr[3 * w]);
       for (uint32_t w = n_spec; w < n_active; ++w) {
         t_min = std::min(t_min, tr[3 * w]);
         t_max = std::max(t_max, tr[3 * w]);
@@ -1446,6 +1394,17 @@ void l3_run(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
               "[walk trace] warps=%u total_rounds=%llu  finish-time spread (ms after the first warp "
               "finished): p50=%.1f p90=%.1f p99=%.1f max=%.1f\n",
               n_active, r_sum, pct(0.5), pct(0.9), pct(0.99), pct(1.0));
+      {
+        std::vector<uint32_t> top;
+        d2h(c, top, work_s.p, std::min<uint32_t>(n_active, 4096));
+        for (uint32_t w = 0; w < n_spec; ++w)
+          if (w < 24 || w % 16 == 0 || w + 1 == n_spec)
+            fprintf(stderr,
+                    "[walk trace] spec comp #%u: nodes=%u windows=%llu rounds(warp0)=%llu committed=%llu "
+                    "retried=%llu end=+%.1f ms\n",
+                    w, top[w], tr[3 * w + 1] >> 32, tr[3 * w + 1] & 0xFFFFFFFFull, tr[3 * w + 2] >> 32,
+                    tr[3 * w + 2] & 0xFFFFFFFFull, (tr[3 * w] - t_min) / 1e6);
+      }
       for (uint32_t w = n_spec; w < std::min<uint32_t>(n_active, n_spec + 6); ++w)
         fprintf(stderr, "[walk trace] largest component #%u: rounds=%llu seeds=%llu end=+%.1f ms\n", w,
                 tr[3 * w + 1], tr[3 * w + 2], (tr[3 * w] - t_min) / 1e6);
