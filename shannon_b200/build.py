@@ -27,6 +27,10 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+# e.g. SHN_NVCC_DEFINES="-DSHN_SPEC_DEBUG" python -m shannon_b200.build  (debug builds only)
+EXTRA_DEFINES = os.environ.get("SHN_NVCC_DEFINES", "").split()
+
+
 def build(force=False, verbose=False):
     os.makedirs(OBJ, exist_ok=True)
     hdrs = [os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__)]
@@ -37,7 +41,7 @@ def build(force=False, verbose=False):
         op = os.path.join(OBJ, src + tag + ".o")
         objs.append(op)
         if force or _stale(op, [sp] + hdrs):
-            cmd = [NVCC] + FLAGS + extra + ["-x", "cu", "-c", sp, "-o", op]
+            cmd = [NVCC] + FLAGS + EXTRA_DEFINES + extra + ["-x", "cu", "-c", sp, "-o", op]
             procs.append((src + tag, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
     failed = False
     for src, p in procs:

@@ -101,6 +101,25 @@ __global__ void __launch_bounds__(kBlock)
   }
 }
 
+// ---- the idx word of every slot doubles as the walks' scratch word -----------------------------
+// (first-occurrence index, needed again by shn_table_dump and the next shn_l3_run, is parked in a
+// side array for the duration of the walks)
+__global__ void __launch_bounds__(kBlock)
+    idx_park_kernel(ShnSlot* slots, uint64_t n_slots, uint32_t* __restrict__ saved) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (; i < n_slots; i += stride) {
+    saved[i] = slots[i].idx;
+    slots[i].idx = 0;
+  }
+}
+__global__ void __launch_bounds__(kBlock)
+    idx_unpark_kernel(ShnSlot* slots, uint64_t n_slots, const uint32_t* __restrict__ saved) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (; i < n_slots; i += stride) slots[i].idx = saved[i];
+}
+
 // ---- raw components: lock-free union-find over table slots ---------------------------------
 __global__ void __launch_bounds__(kBlock) uf_init_kernel(uint32_t* parent, uint64_t n) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -152,7 +171,7 @@ __device__ __forceinline__ void uf_union(uint32_t* parent, uint32_t a, uint32_t 
 // word: see "greedy walks" below): successor bit b of x = (x[1:] . b) exists, OR-ed by x's own
 // thread; predecessor bit f of y = (f . y[:-1]) exists, OR-ed by the thread of that predecessor.
 __global__ void __launch_bounds__(kBlock)
-    uf_edges_kernel(ShnTableView t, uint32_t* parent, uint64_t n_slots, int k1, uint32_t* aux) {
+    uf_edges_kernel(ShnTableView t, uint32_t* parent, uint64_t n_slots, int k1) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_slots) return;
   shn_key_t key = t.slots[i].key;
@@ -167,11 +186,11 @@ __global__ void __launch_bounds__(kBlock)
     uint64_t s = table_find(t, pre | (shn_key_t)b, &w);
     if (s != ~0ull) {
       sm |= 1u << b;
-      atomicOr(&aux[s], 1u << (28 + first));
+      atomicOr(&t.slots[s].idx, 1u << (28 + first));  // the bucket of s was just read: an L2 hit
       if (s != i) uf_union(parent, (uint32_t)i, (uint32_t)s);
     }
   }
-  if (sm) atomicOr(&aux[i], sm << 24);
+  if (sm) atomicOr(&t.slots[i].idx, sm << 24);
 }
 
 // parent[i] <- root for occupied slots; roots get flag 1
@@ -196,6 +215,24 @@ __global__ void __launch_bounds__(kBlock)
   if (i >= n_slots) return;
   if (slots[i].key == SHN_EMPTY) return;
   atomicAdd(&comp_nodes[root_id[parent[i]]], 1u);  // parent[i] is the root after flatten
+}
+
+// the same with a block-private histogram in shared memory (n_comps * 4 bytes of dynamic smem):
+// 10^8 atomics on a few thousand counters serialise in L2, shared-memory atomics do not
+__global__ void __launch_bounds__(kBlock)
+    comp_count_smem_kernel(const ShnSlot* __restrict__ slots, const uint32_t* __restrict__ parent,
+                           const uint32_t* __restrict__ root_id, uint64_t n_slots, uint32_t n_comps,
+                           uint32_t* __restrict__ comp_nodes) {
+  extern __shared__ uint32_t hist[];
+  for (uint32_t k = threadIdx.x; k < n_comps; k += blockDim.x) hist[k] = 0;
+  __syncthreads();
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (; i < n_slots; i += stride)
+    if (slots[i].key != SHN_EMPTY) atomicAdd(&hist[root_id[parent[i]]], 1u);
+  __syncthreads();
+  for (uint32_t k = threadIdx.x; k < n_comps; k += blockDim.x)
+    if (hist[k]) atomicAdd(&comp_nodes[k], hist[k]);
 }
 
 __global__ void __launch_bounds__(kBlock)
@@ -280,8 +317,7 @@ constexpr uint32_t kAuxTraversed = 1u << 23;
 constexpr uint32_t kAuxStampMask = 0x007FFFFFu;
 
 struct WalkArgs {
-  ShnTableView tv;              // the K1-mer table (read only)
-  uint32_t* aux;                // [n_slots]
+  ShnTableView tv;              // the K1-mer table; the walks only write the idx (= aux) words
   uint32_t lookahead;           // walk_kernel: 0 = one step per round (no second-level probes)
   int k1;
   uint32_t n_comps;
@@ -301,54 +337,25 @@ struct WalkArgs {
   unsigned long long* trace;     // optional: per warp {end time ns, rounds, cycles} (SHN_WALK_TRACE)
 };
 
-// aux words of the SHN_BSLOTS slots of bucket b, in the same memory round as the bucket itself
-struct AuxQuad {
-  uint32_t v[SHN_BSLOTS];
-};
-__device__ __forceinline__ void aux_load_bucket(const uint32_t* aux, uint64_t b, AuxQuad* q) {
-#ifdef SHN_WIDE
-  const uint2 t = __ldcg(reinterpret_cast<const uint2*>(aux) + b);
-  q->v[0] = t.x;
-  q->v[1] = t.y;
-#else
-  const uint4 t = __ldcg(reinterpret_cast<const uint4*>(aux) + b);
-  q->v[0] = t.x;
-  q->v[1] = t.y;
-  q->v[2] = t.z;
-  q->v[3] = t.w;
-#endif
-}
-__device__ __forceinline__ uint32_t aux_pick(const AuxQuad& q, int j) {
-  uint32_t r = q.v[0];
-#pragma unroll
-  for (int t = 1; t < SHN_BSLOTS; ++t) r = j == t ? q.v[t] : r;
-  return r;
-}
-
-// One probe of the walks: the candidate's home bucket + its aux words are already loaded.
+// One probe of the walks: the candidate's home bucket is already loaded.
 // state: 1 found (slot, raw weight word, aux word), 0 absent, -1 continues in bucket *nextb.
-__device__ __forceinline__ int walk_resolve(const ShnTableView& tv, const ShnBucket& bk, const AuxQuad& aq,
-                                            shn_key_t cand, uint64_t hb, uint64_t* cslot, uint32_t* wraw,
-                                            uint32_t* caux, uint64_t* nextb) {
+__device__ __forceinline__ int walk_resolve(const ShnTableView& tv, const ShnBucket& bk, shn_key_t cand,
+                                            uint64_t hb, uint64_t* cslot, uint32_t* wraw, uint32_t* caux,
+                                            uint64_t* nextb) {
   int jj = 0;
-  const int state = table_match_bucket(bk, cand, &jj, wraw);
+  const int state = table_match_bucket2(bk, cand, &jj, wraw, caux);
   *nextb = (hb + 1 == tv.n_buckets) ? 0 : hb + 1;
-  if (state == 1) {
-    *cslot = SHN_BSLOTS * hb + jj;
-    *caux = aux_pick(aq, jj);
-  }
+  if (state == 1) *cslot = SHN_BSLOTS * hb + jj;
   return state;
 }
 // the rare continuation of a probe sequence (the key was displaced from its home bucket)
-__device__ __forceinline__ int walk_chase(const ShnTableView& tv, const uint32_t* aux, shn_key_t cand,
-                                          uint64_t* cslot, uint32_t* wraw, uint32_t* caux, uint64_t* nextb) {
+__device__ __forceinline__ int walk_chase(const ShnTableView& tv, shn_key_t cand, uint64_t* cslot,
+                                          uint32_t* wraw, uint32_t* caux, uint64_t* nextb) {
   for (;;) {
     ShnBucket bk;
-    AuxQuad aq;
     table_load_bucket(tv, *nextb, &bk);
-    aux_load_bucket(aux, *nextb, &aq);
     const uint64_t hb = *nextb;
-    const int state = walk_resolve(tv, bk, aq, cand, hb, cslot, wraw, caux, nextb);
+    const int state = walk_resolve(tv, bk, cand, hb, cslot, wraw, caux, nextb);
     if (state >= 0) return state;
   }
 }
@@ -379,7 +386,6 @@ __global__ void __launch_bounds__(kWalkBlock, kWalkBlocksPerSM) walk_kernel(Walk
   const shn_key_t mask = shn_key_mask(a.k1);
   const int top = 2 * (a.k1 - 1);
   const ShnTableView tv = a.tv;
-  uint32_t* aux = a.aux;
   unsigned long long rounds = 0, traversed = 0;
   long long mem_cycles = 0, t_begin = clock64();
   const bool tracing = a.trace != nullptr;
@@ -398,7 +404,7 @@ __global__ void __launch_bounds__(kWalkBlock, kWalkBlocksPerSM) walk_kernel(Walk
     if (have) {
       my_rank = a.ranks_by_comp[si];
       my_slot = a.slots_by_comp[si];
-      my_aux = __ldcg(&aux[my_slot]);
+      my_aux = __ldcg(&tv.slots[my_slot].idx);
     }
     unsigned pending = __ballot_sync(FULL, have && !(my_aux & kAuxTraversed));
     while (pending) {
@@ -407,13 +413,13 @@ __global__ void __launch_bounds__(kWalkBlock, kWalkBlocksPerSM) walk_kernel(Walk
       const uint32_t slot = __shfl_sync(FULL, my_slot, j);
       const uint32_t rank = __shfl_sync(FULL, my_rank, j);
       // fresh look: an earlier walk of this batch may have traversed it meanwhile (:346)
-      const uint32_t seed_aux = __ldcg(&aux[slot]);
+      const uint32_t seed_aux = __ldcg(&tv.slots[slot].idx);
       if (seed_aux & kAuxTraversed) continue;  // warp-uniform
       shn_key_t seed_key;
       uint32_t seed_w, seed_i;
       table_load_slot(tv.slots, slot, &seed_key, &seed_w, &seed_i);
       if (lane == 0) {
-        aux[slot] = seed_aux | kAuxTraversed;      // traversed.add(start_kmer), :347
+        tv.slots[slot].idx = seed_aux | kAuxTraversed;      // traversed.add(start_kmer), :347
         if (lp < le) a.walk_log[lp] = 0xFF;        // the seed's own (unused) log entry
       }
       overflow |= lp >= le;
@@ -448,20 +454,18 @@ __global__ void __launch_bounds__(kWalkBlock, kWalkBlocksPerSM) walk_kernel(Walk
             }
             const uint64_t hb = tv.bucket_of(cand);
             ShnBucket bk0;
-            AuxQuad aq0;
             long long tm0 = 0;
             if (tracing) tm0 = clock64();
             table_load_bucket(tv, hb, &bk0);
-            aux_load_bucket(aux, hb, &aq0);
             if (tracing) {  // wait for the data here so the cycles are attributed to memory
-              volatile uint64_t sink = bk0.w[0] ^ bk0.w[4] ^ aq0.v[0];
+              volatile uint64_t sink = bk0.w[0] ^ bk0.w[4];
               (void)sink;
               mem_cycles += clock64() - tm0;
             }
-            state = walk_resolve(tv, bk0, aq0, cand, hb, &cslot, &wraw, &caux, &nextb);
+            state = walk_resolve(tv, bk0, cand, hb, &cslot, &wraw, &caux, &nextb);
           }
           // only the lanes a decision actually depends on pay for longer probe sequences
-          if (lvl == 1 && state < 0) state = walk_chase(tv, aux, cand, &cslot, &wraw, &caux, &nextb);
+          if (lvl == 1 && state < 0) state = walk_chase(tv, cand, &cslot, &wraw, &caux, &nextb);
           bool ok = state == 1 && !(caux & kAuxTraversed);
           // ---- first step: arg-max weight over lanes 0..3, first of equals wins (:159-166) ---
           // score = (weight, 3 - code) + 1 in 32 bits (weights are < 2^30 - 1), 0 = no candidate
@@ -474,7 +478,7 @@ __global__ void __launch_bounds__(kWalkBlock, kWalkBlocksPerSM) walk_kernel(Walk
           const uint32_t bw1 = (s1 - 1u) >> 2;
           const shn_key_t c1 = dir == 0 ? (((cur << 2) & mask) | (shn_key_t)w1)
                                         : ((cur >> 2) | ((shn_key_t)w1 << top));
-          if (lane == w1) aux[cslot] = caux | kAuxTraversed;  // traversed.add(last), :235
+          if (lane == w1) tv.slots[cslot].idx = caux | kAuxTraversed;  // traversed.add(last), :235
           if (lane == 0 && lp < le) a.walk_log[lp] = (uint8_t)w1;
           overflow |= lp >= le;
           ++lp;
@@ -490,7 +494,7 @@ __global__ void __launch_bounds__(kWalkBlock, kWalkBlocksPerSM) walk_kernel(Walk
           // ---- second step from the prefetched level: group 4+4*w1; c1 is traversed by now ---
           const int g2 = 4 + 4 * w1;
           if (lane >= g2 && lane < g2 + 4 && state < 0) {
-            state = walk_chase(tv, aux, cand, &cslot, &wraw, &caux, &nextb);
+            state = walk_chase(tv, cand, &cslot, &wraw, &caux, &nextb);
             ok = state == 1 && !(caux & kAuxTraversed);
           }
           ok = ok && cand != c1;
@@ -506,7 +510,7 @@ __global__ void __launch_bounds__(kWalkBlock, kWalkBlocksPerSM) walk_kernel(Walk
           const uint32_t bw2 = (s2 - 1u) >> 2;
           cur = dir == 0 ? (((c1 << 2) & mask) | (shn_key_t)w2) : ((c1 >> 2) | ((shn_key_t)w2 << top));
           cur_aux = __shfl_sync(FULL, caux, g2 + w2);
-          if (lane == g2 + w2) aux[cslot] = caux | kAuxTraversed;
+          if (lane == g2 + w2) tv.slots[cslot].idx = caux | kAuxTraversed;
           if (lane == 0 && lp < le) a.walk_log[lp] = (uint8_t)w2;
           overflow |= lp >= le;
           ++lp;
@@ -582,7 +586,6 @@ __global__ void __launch_bounds__(kSpecWarps * 32, kSpecCtasPerSM) walk_spec_ker
   const shn_key_t mask = shn_key_mask(a.k1);
   const int top = 2 * (a.k1 - 1);
   const ShnTableView tv = a.tv;
-  uint32_t* aux = a.aux;
   uint32_t* my_path_slot = sa.path_slot + ((uint64_t)blockIdx.x * kSpecWarps + warp) * sa.path_cap;
   uint8_t* my_path_base = sa.path_base + ((uint64_t)blockIdx.x * kSpecWarps + warp) * sa.path_cap;
   const int lvl = lane < 4 ? 1 : (lane < 20 ? 2 : 0);
@@ -611,7 +614,7 @@ __global__ void __launch_bounds__(kSpecWarps * 32, kSpecCtasPerSM) walk_spec_ker
         uint32_t slot = 0, av = kAuxTraversed;
         if (si < s_end) {
           slot = a.slots_by_comp[si];
-          av = __ldcg(&aux[slot]);
+          av = __ldcg(&tv.slots[slot].idx);
         }
         unsigned fresh = __ballot_sync(FULL, si < s_end && !(av & kAuxTraversed));
         uint64_t consumed = min((uint64_t)32, s_end - pos);
@@ -644,10 +647,10 @@ __global__ void __launch_bounds__(kSpecWarps * 32, kSpecCtasPerSM) walk_spec_ker
     const uint32_t stamp = (uint32_t)(kSpecWarps - warp);  // earlier seed = larger stamp
     if (warp < (int)win_n) {
       const uint32_t seed_slot = sh_win_slot[warp];
-      const uint32_t seed_aux = __ldcg(&aux[seed_slot]);
+      const uint32_t seed_aux = __ldcg(&tv.slots[seed_slot].idx);
       // claim the seed; an earlier walk of this window may already hold it
       uint32_t old = 0;
-      if (lane == 0) old = atomicMax(&aux[seed_slot], (seed_aux & ~kAuxStampMask) | stamp);
+      if (lane == 0) old = atomicMax(&tv.slots[seed_slot].idx, (seed_aux & ~kAuxStampMask) | stamp);
       old = __shfl_sync(FULL, old, 0);
       if ((old & kAuxStampMask) < stamp) {
         shn_key_t seed_key;
@@ -680,7 +683,6 @@ __global__ void __launch_bounds__(kSpecWarps * 32, kSpecCtasPerSM) walk_spec_ker
             int state = 0;
             uint64_t nextb = 0;
             ShnBucket bk0;
-            AuxQuad aq0;
             if (act) {
               if (dir == 0) {
                 cand = ((cur << 2) & mask) | b1;
@@ -691,8 +693,7 @@ __global__ void __launch_bounds__(kSpecWarps * 32, kSpecCtasPerSM) walk_spec_ker
               }
               hb = tv.bucket_of(cand);
               table_load_bucket(tv, hb, &bk0);
-              aux_load_bucket(aux, hb, &aq0);
-            }
+              }
             {  // the claims of the previous round, by now usually back from L2
               const bool lost = (pend1 & kAuxStampMask) >= stamp || (pend2 & kAuxStampMask) >= stamp;
               pend1 = pend2 = 0;
@@ -701,8 +702,8 @@ __global__ void __launch_bounds__(kSpecWarps * 32, kSpecCtasPerSM) walk_spec_ker
                 break;
               }
             }
-            if (act) state = walk_resolve(tv, bk0, aq0, cand, hb, &cslot, &wraw, &caux, &nextb);
-            if (lvl == 1 && state < 0) state = walk_chase(tv, aux, cand, &cslot, &wraw, &caux, &nextb);
+            if (act) state = walk_resolve(tv, bk0, cand, hb, &cslot, &wraw, &caux, &nextb);
+            if (lvl == 1 && state < 0) state = walk_chase(tv, cand, &cslot, &wraw, &caux, &nextb);
             // blocked: committed-traversed, or stamped by an earlier seed or by this walk
             bool ok = state == 1 && !(caux & kAuxTraversed) && (caux & kAuxStampMask) < stamp;
             // ---- first step ------------------------------------------------------------------
@@ -713,7 +714,7 @@ __global__ void __launch_bounds__(kSpecWarps * 32, kSpecCtasPerSM) walk_spec_ker
             if (s1 == 0) break;  // no extension in this direction
             const int w1 = 3 - (int)((s1 - 1u) & 3u);
             const uint32_t bw1 = (s1 - 1u) >> 2;
-            if (lane == w1) pend1 = atomicMax(&aux[cslot], (caux & ~kAuxStampMask) | stamp);
+            if (lane == w1) pend1 = atomicMax(&tv.slots[cslot].idx, (caux & ~kAuxStampMask) | stamp);
             const shn_key_t c1 = dir == 0 ? (((cur << 2) & mask) | (shn_key_t)w1)
                                           : ((cur >> 2) | ((shn_key_t)w1 << top));
             const uint32_t c1slot = (uint32_t)__shfl_sync(FULL, (uint32_t)cslot, w1);
@@ -728,7 +729,7 @@ __global__ void __launch_bounds__(kSpecWarps * 32, kSpecCtasPerSM) walk_spec_ker
             // ---- second step from the prefetched level ---------------------------------------
             const int g2 = 4 + 4 * w1;
             if (lane >= g2 && lane < g2 + 4 && state < 0) {
-              state = walk_chase(tv, aux, cand, &cslot, &wraw, &caux, &nextb);
+              state = walk_chase(tv, cand, &cslot, &wraw, &caux, &nextb);
               ok = state == 1 && !(caux & kAuxTraversed) && (caux & kAuxStampMask) < stamp;
             }
             ok = ok && cand != c1;
@@ -739,7 +740,7 @@ __global__ void __launch_bounds__(kSpecWarps * 32, kSpecCtasPerSM) walk_spec_ker
             if (s2 == 0) break;  // the walk ends at c1 in this direction
             const int w2 = 3 - (int)((s2 - 1u) & 3u);
             const uint32_t bw2 = (s2 - 1u) >> 2;
-            if (lane == g2 + w2) pend2 = atomicMax(&aux[cslot], (caux & ~kAuxStampMask) | stamp);
+            if (lane == g2 + w2) pend2 = atomicMax(&tv.slots[cslot].idx, (caux & ~kAuxStampMask) | stamp);
             cur = dir == 0 ? (((c1 << 2) & mask) | (shn_key_t)w2) : ((c1 >> 2) | ((shn_key_t)w2 << top));
             cur_aux = __shfl_sync(FULL, caux, g2 + w2);
             const uint32_t c2slot = (uint32_t)__shfl_sync(FULL, (uint32_t)cslot, g2 + w2);
@@ -763,7 +764,7 @@ __global__ void __launch_bounds__(kSpecWarps * 32, kSpecCtasPerSM) walk_spec_ker
     if (warp < (int)win_n) {
       bool mine = true;
       for (uint32_t e = lane; e < len; e += 32)
-        mine &= (__ldcg(&aux[my_path_slot[e]]) & kAuxStampMask) == stamp;
+        mine &= (__ldcg(&tv.slots[my_path_slot[e]].idx) & kAuxStampMask) == stamp;
       mine = __all_sync(FULL, mine);
       if (lane == 0) sh_intact[warp] = mine ? 1u : 0u;
     }
@@ -779,7 +780,7 @@ __global__ void __launch_bounds__(kSpecWarps * 32, kSpecCtasPerSM) walk_spec_ker
         uint64_t off = sh_lp;
         for (int q = 0; q < warp; ++q) off += sh_len[q];
         for (uint32_t e = lane; e < len; e += 32) {
-          atomicOr(&aux[my_path_slot[e]], kAuxTraversed);
+          atomicOr(&tv.slots[my_path_slot[e]].idx, kAuxTraversed);
           if (off + e < le) a.walk_log[off + e] = my_path_base[e];
         }
         overflow |= off + len > le;
@@ -794,7 +795,7 @@ __global__ void __launch_bounds__(kSpecWarps * 32, kSpecCtasPerSM) walk_spec_ker
         traversed += len;
       } else {
         for (uint32_t e = lane; e < len; e += 32) {
-          uint32_t* p = &aux[my_path_slot[e]];
+          uint32_t* p = &tv.slots[my_path_slot[e]].idx;
           const uint32_t v = __ldcg(p);  // only the stamp bits change: the CAS fails iff stolen
           if ((v & kAuxStampMask) == stamp) atomicCAS(p, v, v & ~kAuxStampMask);
         }
@@ -1180,13 +1181,33 @@ void l3_run(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
     uf_init_kernel<<<stream_grid, kBlock, 0, st>>>(parent.as<uint32_t>(), n_slots);
     KERNEL_CHECK();
   }
-  DevBuf aux;  // per slot: neighbour masks | traversed | claim stamp (see "greedy walks")
-  aux.reserve(n_slots * 4);
+  // from here until the walks are done the idx words of the table hold the walks' aux words
+  struct IdxParking {
+    shn_ctx* c;
+    ShnSlot* slots;
+    uint64_t n_slots;
+    unsigned grid;
+    DevBuf saved;
+    bool parked = false;
+    void unpark() {
+      if (!parked) return;
+      parked = false;
+      idx_unpark_kernel<<<grid, kBlock, 0, c->stream>>>(slots, n_slots, saved.as<uint32_t>());
+      cudaStreamSynchronize(c->stream);
+      saved.release();
+    }
+    ~IdxParking() { unpark(); }  // also on the error paths: the table must stay usable
+  } parking{c, tv.slots, n_slots, stream_grid};
+  parking.saved.reserve(n_slots * 4);
   {
-    ProfScope ps(c, "uf_edges", 2);
-    CUDA_CHECK(cudaMemsetAsync(aux.p, 0, n_slots * 4, st));
-    uf_edges_kernel<<<shn_grid(n_slots, kBlock), kBlock, 0, st>>>(tv, parent.as<uint32_t>(), n_slots, k1,
-                                                                 aux.as<uint32_t>());
+    ProfScope ps(c, "idx_park");
+    idx_park_kernel<<<stream_grid, kBlock, 0, st>>>(tv.slots, n_slots, parking.saved.as<uint32_t>());
+    KERNEL_CHECK();
+    parking.parked = true;
+  }
+  {
+    ProfScope ps(c, "uf_edges");
+    uf_edges_kernel<<<shn_grid(n_slots, kBlock), kBlock, 0, st>>>(tv, parent.as<uint32_t>(), n_slots, k1);
     KERNEL_CHECK();
   }
   {
@@ -1215,8 +1236,14 @@ void l3_run(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
   CUDA_CHECK(cudaMemsetAsync(comp_seeds.p, 0, ((uint64_t)n_comps + 1) * 4, st));
   {
     ProfScope ps(c, "comp_count");
-    comp_count_kernel<<<shn_grid(n_slots, kBlock), kBlock, 0, st>>>(
-        tv.slots, parent.as<uint32_t>(), root_id.as<uint32_t>(), n_slots, comp_nodes.as<uint32_t>());
+    if (n_comps && (uint64_t)n_comps * 4 <= 40 * 1024) {
+      comp_count_smem_kernel<<<c->sm_count * 8, kBlock, (size_t)n_comps * 4, st>>>(
+          tv.slots, parent.as<uint32_t>(), root_id.as<uint32_t>(), n_slots, n_comps,
+          comp_nodes.as<uint32_t>());
+    } else {
+      comp_count_kernel<<<shn_grid(n_slots, kBlock), kBlock, 0, st>>>(
+          tv.slots, parent.as<uint32_t>(), root_id.as<uint32_t>(), n_slots, comp_nodes.as<uint32_t>());
+    }
     KERNEL_CHECK();
   }
   DevBuf seed_comp, rank_in, seed_comp_s, ranks_by_comp;
@@ -1295,7 +1322,6 @@ void l3_run(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
   if (n_active) {
     WalkArgs a;
     a.tv = tv;
-    a.aux = aux.as<uint32_t>();
     {
       const char* envl = getenv("SHN_NO_LOOKAHEAD");
       a.lookahead = envl ? 0u : 1u;
@@ -1334,8 +1360,9 @@ void l3_run(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
       const char* envb = getenv("SHN_SPEC_SCRATCH_GB");
       const uint64_t budget = (envb ? strtoull(envb, nullptr, 10) : 16ull) << 30;  // scratch for the paths
       path_cap = peek ? top[0] : 0;
-      // one speculative CTA per SM at most: beyond that the windows only burn probe bandwidth
-      while (n_spec < peek && n_spec < (uint32_t)c->sm_count && top[n_spec] >= min_nodes &&
+      const char* envc = getenv("SHN_SPEC_MAX_COMPS");
+      const uint32_t max_spec = envc ? (uint32_t)strtoul(envc, nullptr, 10) : (uint32_t)c->sm_count;
+      while (n_spec < peek && n_spec < max_spec && top[n_spec] >= min_nodes &&
              (uint64_t)(n_spec + 1) * kSpecWarps * path_cap * 5 <= budget)
         ++n_spec;
     }
@@ -1409,6 +1436,11 @@ void l3_run(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
         fprintf(stderr, "[walk trace] largest component #%u: rounds=%llu seeds=%llu end=+%.1f ms\n", w,
                 tr[3 * w + 1], tr[3 * w + 2], (tr[3 * w] - t_min) / 1e6);
     }
+  }
+  {
+    ProfScope ps(c, "idx_unpark");
+    parking.unpark();
+    CUDA_CHECK(cudaGetLastError());
   }
   read_counters(c, h, 4);
   SHN_CHECK(h[2] == 0, "internal error: walk log overflow (component node count mismatch)");

@@ -47,14 +47,13 @@ __global__ void __launch_bounds__(kBlock)
       const int reps = ds ? 2 : 1;
       for (int r = 0; r < reps; ++r) {
         shn_key_t kk = r == 0 ? key : shn_revcomp(key, k1);
-        uint64_t slot = table_upsert_slot(t, kk, &n_new);
+        uint32_t old = 0;
+        uint64_t slot = table_insert_add(t, kk, w, (uint32_t)(base_idx + r), &n_new, &old);
         if (slot == ~0ull) {
           n_bad = 1;
           break;
         }
-        uint32_t old = atomicAdd(&t.slots[slot].weight, w);
-        if ((uint64_t)(old & SHN_WEIGHT_MASK) + w >= (uint64_t)SHN_WEIGHT_MASK) n_bad = 1;
-        atomicMin(&t.slots[slot].idx, (uint32_t)(base_idx + r));
+        if ((uint64_t)old + w >= (uint64_t)SHN_WEIGHT_MASK) n_bad = 1;
       }
     }
   }

@@ -158,6 +158,55 @@ __device__ __forceinline__ uint64_t table_upsert_slot(const ShnTableView& t, shn
   return ~0ull;
 }
 
+// Insert (key, +w, min idx) in one pass.  64-bit keys: a NEW key is published with a single
+// 128-bit CAS of the whole slot {key, w, idx} against the pristine pattern {EMPTY, 0, 0xFFFFFFFF}
+// (one atomic round trip instead of CAS + add + min); only a key that is already present takes
+// the add/min path.  Returns the slot (~0: table full); *old_w = weight before this insert.
+__device__ __forceinline__ uint64_t table_insert_add(const ShnTableView& t, shn_key_t key, uint32_t w,
+                                                     uint32_t idx, int* is_new, uint32_t* old_w) {
+#ifdef SHN_WIDE
+  uint64_t slot = table_upsert_slot(t, key, is_new);
+  if (slot == ~0ull) return slot;
+  *old_w = atomicAdd(&t.slots[slot].weight, w) & SHN_WEIGHT_MASK;
+  atomicMin(&t.slots[slot].idx, idx);
+  return slot;
+#else
+  const u128 pristine = ((u128)0xFFFFFFFF00000000ull << 64) | (u128)SHN_EMPTY_KEY;
+  const u128 fresh = ((u128)(((uint64_t)idx << 32) | w) << 64) | (u128)key;
+  uint64_t b = t.bucket_of(key);
+  for (uint64_t probes = 0; probes < t.n_buckets; ++probes) {
+    ShnSlot* s = t.slots + SHN_BSLOTS * b;
+    ShnBucket bk;
+    table_load_bucket(t, b, &bk);
+    uint64_t hit = ~0ull;
+#pragma unroll
+    for (int j = 0; j < SHN_BSLOTS; ++j) {
+      if (hit != ~0ull) continue;
+      shn_key_t cur = bk.key(j);
+      if (cur == SHN_EMPTY) {
+        const u128 old = shn_cas128(reinterpret_cast<u128*>(&s[j]), pristine, fresh);
+        if (old == pristine) {
+          *is_new += 1;
+          *old_w = 0;
+          return SHN_BSLOTS * b + j;
+        }
+        cur = (shn_key_t)old;  // somebody else took the slot meanwhile
+      }
+      if (cur == key) hit = SHN_BSLOTS * b + j;
+    }
+    if (hit != ~0ull) {
+      *old_w = atomicAdd(&t.slots[hit].weight, w) & SHN_WEIGHT_MASK;
+      atomicMin(&t.slots[hit].idx, idx);
+      return hit;
+    }
+    // every slot holds another key: leave the trail marker for lookups, then move on
+    if (!(bk.weight(0) & SHN_OVERFLOW)) atomicOr(&s[0].weight, SHN_OVERFLOW);
+    b = (b + 1 == t.n_buckets) ? 0 : b + 1;
+  }
+  return ~0ull;
+#endif
+}
+
 // slot initialisation pattern: key = all ones, weight = 0, idx = `idx0`
 __device__ __forceinline__ void table_store_empty(ShnSlot* slots, uint64_t s, uint32_t idx0) {
 #ifdef SHN_WIDE
