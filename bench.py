@@ -47,6 +47,7 @@ def parse_args():
     ap.add_argument("--pairs", type=int, default=10_000_000, help="read pairs per GPU")
     ap.add_argument("--transcripts", type=int, default=5000, help="transcripts per GPU")
     ap.add_argument("--seed", type=int, default=1234 + 2)
+    ap.add_argument("--K", type=int, default=24, help="k-mer size (K1 = K+1; 32 -> 128-bit keys)")
     ap.add_argument("--sample-pairs", type=int, default=None)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -160,7 +161,7 @@ class Workload(object):
         self.host = {
             "r1": ctx.d2h(ctx.pinned_empty(nb, np.uint8), self.d_r1),
             "r2": ctx.d2h(ctx.pinned_empty(nb, np.uint8), self.d_r2),
-            "keys": ctx.d2h(ctx.pinned_empty(self.n_kmers, np.uint64), self.d_keys),
+            "keys": ctx.d2h(ctx.pinned_empty(self.n_kmers * (2 if K1 > 32 else 1), np.uint64), self.d_keys),
             "counts": ctx.d2h(ctx.pinned_empty(self.n_kmers, np.uint32), self.d_counts),
         }
         return sum(a.nbytes for a in self.host.values()) + self.h_offs.nbytes * 2
@@ -172,6 +173,8 @@ def run_step(ctx, wl, on_device):
         keys, counts = wl.d_keys, wl.d_counts
     else:
         keys, counts = wl.host["keys"], wl.host["counts"]
+        if K1 > 32:
+            keys = keys.reshape(-1, 2)
     cor, comp_offs, rec_idx, stats = pipeline.frontend_in_memory(
         ctx, keys, counts, K1, wl.mates(on_device), True, 3, 75, 500, on_device, wl.n_kmers)
     # what comes back to the host: the partition, the contigs and the contig graph
@@ -262,7 +265,9 @@ def workload_config(args, n_gpus):
 
 
 def main():
+    global K, K1
     args = parse_args()
+    K, K1 = args.K, args.K + 1
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -379,7 +384,7 @@ def main():
 
     # ---- N > 1: the hash-sharded K1-mer table (all-to-all over NVLink) as a lookup service ------
     dist_table = None
-    if world > 1:
+    if world > 1 and K1 <= 32:   # the hash-routed table carries one-word keys
         from shannon_b200 import dist as sdist
         ops = sdist.GpuOps(ctx, local_rank)
         tab = sdist.ShardedKmerTable(ops)
