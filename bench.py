@@ -453,7 +453,7 @@ def main():
                                               if "l4_assign" in prof else None),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu, "dist_table": dist_table,
-            "kernels": kern[:14],
+            "kernels": kern[:int(os.environ.get("SHN_BENCH_KERNELS", "14"))],
             "kernel_ms_per_step": step_kernel_ms,
             "host_ms_per_step": ms_per_step - step_kernel_ms,
             "workload_stats": dict((k, int(v)) for k, v in stats.items() if k != "host_timings_ms"),

@@ -357,8 +357,15 @@ struct shn_ctx {
   void prof_resolve() {
     if (prof_pending.empty()) return;
     cudaStreamSynchronize(stream);
+    const bool gaps = getenv("SHN_PROF_GAPS") != nullptr;  // GPU-idle time in front of each scope
+    cudaEvent_t prev = nullptr;
     for (auto& p : prof_pending) {
       float ms = 0;
+      if (gaps && prev) {
+        cudaEventElapsedTime(&ms, prev, p.e0);
+        if (ms > 0) prof[std::string("gap<") + p.name].ms += ms;
+      }
+      prev = p.e1;
       cudaEventElapsedTime(&ms, p.e0, p.e1);
       ProfEntry& e = prof[p.name];
       e.ms += ms;

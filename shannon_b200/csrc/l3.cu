@@ -547,9 +547,9 @@ __global__ void __launch_bounds__(kWalkBlock, kWalkBlocksPerSM) walk_kernel(Walk
 // ---- speculative windowed walks for the large components ------------------------------------
 // The serial replay of one component is the critical path of the whole stage (latency of ~10^5
 // dependent probe rounds).  Large components are therefore given a CTA of kSpecWarps warps that
-// run the next kSpecWarps untraversed seeds of the pop order CONCURRENTLY and commit them IN ORDER
+// run the next kSpecWindow untraversed seeds of the pop order CONCURRENTLY and commit them IN ORDER
 // ("deterministic reservations"):
-//   * every walk of a window carries a stamp = kSpecWarps - its position in the window (earlier
+//   * every walk of a window carries a stamp = kSpecWindow - its position in the window (earlier
 //     seed = larger stamp) and claims a K1-mer with atomicMax on the slot's aux word (stamp in the
 //     low bits; the bits above it are the same for every claimant of an untraversed slot);
 //   * a candidate is blocked for a walk iff it is committed-traversed or stamped by an EARLIER
@@ -561,8 +561,21 @@ __global__ void __launch_bounds__(kWalkBlock, kWalkBlocksPerSM) walk_kernel(Walk
 //     committed (traversed bits, log, metas); the others clear their stamps and are retried in
 //     the next window, which starts at the first uncommitted seed.  The first walk of a window is
 //     always intact, so every window makes progress.  After a window every untraversed slot is
-//     back to stamp 0, so stamps only ever order the walks of one window.
+//     back to stamp 0, so stamps only ever order the walks of one window;
+//   * most seeds of a window lie on a chain that an earlier seed of the same window walks over.
+//     Such a walk is not a misspeculation: if its SEED ends up stamped by a committed earlier walk
+//     the sequential loop would have found the seed traversed and skipped it (:346), so the walk is
+//     dropped (SKIP) and the prefix goes on.  Its other, phantom claims may have blocked later
+//     walks, so every walk records which window positions ever blocked it and commits only if all
+//     of them committed.
 constexpr int kSpecWarps = 16;
+#ifndef SHN_SPEC_WINDOW
+#define SHN_SPEC_WINDOW 32
+#endif
+// Seeds per window.  The warps of the CTA pull the window's seeds from a shared counter, so one long
+// walk occupies one warp while the others work through the many short ones (98 % of the seeds of a
+// large component are found traversed, or are taken by an earlier walk of the same window).
+constexpr int kSpecWindow = SHN_SPEC_WINDOW;
 #ifndef SHN_SPEC_CTAS_PER_SM
 #define SHN_SPEC_CTAS_PER_SM 2
 #endif
@@ -570,9 +583,9 @@ constexpr int kSpecCtasPerSM = SHN_SPEC_CTAS_PER_SM;  // 2 -> 64 registers
 
 struct SpecArgs {
   WalkArgs w;
-  uint32_t* path_slot;  // [n_spec * kSpecWarps * path_cap]
+  uint32_t* path_slot;       // per component: kSpecWindow buffers of (node count) entries
   uint8_t* path_base;
-  uint64_t path_cap;
+  const uint64_t* path_off;  // [n_spec + 1] first entry of every component's buffers
 };
 
 __global__ void __launch_bounds__(kSpecWarps * 32, kSpecCtasPerSM) walk_spec_kernel(SpecArgs sa) {
@@ -586,16 +599,22 @@ __global__ void __launch_bounds__(kSpecWarps * 32, kSpecCtasPerSM) walk_spec_ker
   const shn_key_t mask = shn_key_mask(a.k1);
   const int top = 2 * (a.k1 - 1);
   const ShnTableView tv = a.tv;
-  uint32_t* my_path_slot = sa.path_slot + ((uint64_t)blockIdx.x * kSpecWarps + warp) * sa.path_cap;
-  uint8_t* my_path_base = sa.path_base + ((uint64_t)blockIdx.x * kSpecWarps + warp) * sa.path_cap;
+  const uint64_t path_cap = (sa.path_off[blockIdx.x + 1] - sa.path_off[blockIdx.x]) / kSpecWindow;
+  uint32_t* const cta_path_slot = sa.path_slot + sa.path_off[blockIdx.x];
+  uint8_t* const cta_path_base = sa.path_base + sa.path_off[blockIdx.x];
   const int lvl = lane < 4 ? 1 : (lane < 20 ? 2 : 0);
   const shn_key_t b1 = lvl == 1 ? lane : ((lane - 4) >> 2);
   const shn_key_t b2 = (lane - 4) & 3;
 
   __shared__ uint64_t sh_cursor, sh_cursor_after, sh_lp;
-  __shared__ uint32_t sh_win_pos[kSpecWarps], sh_win_slot[kSpecWarps], sh_len[kSpecWarps];
-  __shared__ uint32_t sh_intact[kSpecWarps];
-  __shared__ uint32_t sh_win_n;
+  __shared__ uint32_t sh_win_pos[kSpecWindow], sh_win_slot[kSpecWindow], sh_len[kSpecWindow];
+  __shared__ uint32_t sh_nr[kSpecWindow], sh_nl[kSpecWindow], sh_intact[kSpecWindow];
+  __shared__ unsigned long long sh_tot[kSpecWindow];
+  __shared__ unsigned long long sh_block[kSpecWindow];  // window positions whose stamps blocked this walk
+  __shared__ uint32_t sh_thief[kSpecWindow];            // position holding this walk's seed (or none)
+  __shared__ uint32_t sh_status[kSpecWindow];           // 1 commit, 2 skip
+  __shared__ uint64_t sh_off[kSpecWindow];
+  __shared__ uint32_t sh_win_n, sh_next, sh_P;
   if (threadIdx.x == 0) {
     sh_cursor = s_begin;
     sh_lp = a.log_off[comp];
@@ -609,7 +628,7 @@ __global__ void __launch_bounds__(kSpecWarps * 32, kSpecCtasPerSM) walk_spec_ker
     if (warp == 0) {
       uint32_t n = 0;
       uint64_t pos = sh_cursor;
-      while (n < kSpecWarps && pos < s_end) {
+      while (n < (uint32_t)kSpecWindow && pos < s_end) {
         const uint64_t si = pos + lane;
         uint32_t slot = 0, av = kAuxTraversed;
         if (si < s_end) {
@@ -618,7 +637,7 @@ __global__ void __launch_bounds__(kSpecWarps * 32, kSpecCtasPerSM) walk_spec_ker
         }
         unsigned fresh = __ballot_sync(FULL, si < s_end && !(av & kAuxTraversed));
         uint64_t consumed = min((uint64_t)32, s_end - pos);
-        while (fresh && n < kSpecWarps) {
+        while (fresh && n < (uint32_t)kSpecWindow) {
           const int j = __ffs(fresh) - 1;
           fresh &= fresh - 1;
           const uint32_t sj = __shfl_sync(FULL, slot, j);
@@ -627,12 +646,13 @@ __global__ void __launch_bounds__(kSpecWarps * 32, kSpecCtasPerSM) walk_spec_ker
             sh_win_slot[n] = sj;
           }
           ++n;
-          if (n == kSpecWarps) consumed = j + 1;
+          if (n == (uint32_t)kSpecWindow) consumed = j + 1;
         }
         pos += consumed;
       }
       if (lane == 0) {
         sh_win_n = n;
+        sh_next = 0;
         sh_cursor_after = pos;
       }
     }
@@ -641,12 +661,19 @@ __global__ void __launch_bounds__(kSpecWarps * 32, kSpecCtasPerSM) walk_spec_ker
     if (win_n == 0) break;
     ++windows;
 
-    // ---- 2. speculative walks -----------------------------------------------------------------
-    uint32_t len = 0, n_dir[2] = {0, 0};
-    uint64_t tot = 0;
-    const uint32_t stamp = (uint32_t)(kSpecWarps - warp);  // earlier seed = larger stamp
-    if (warp < (int)win_n) {
-      const uint32_t seed_slot = sh_win_slot[warp];
+    // ---- 2. speculative walks: every warp pulls window slots until none is left ----------------
+    for (;;) {
+      uint32_t ws = 0;
+      if (lane == 0) ws = atomicAdd(&sh_next, 1u);
+      ws = __shfl_sync(FULL, ws, 0);
+      if (ws >= win_n) break;
+      uint32_t* my_path_slot = cta_path_slot + (uint64_t)ws * path_cap;
+      uint8_t* my_path_base = cta_path_base + (uint64_t)ws * path_cap;
+      uint32_t len = 0, n_dir[2] = {0, 0};
+      uint64_t tot = 0;
+      unsigned long long bl = 0;  // per lane: positions of earlier walks whose stamps blocked a candidate
+      const uint32_t stamp = (uint32_t)kSpecWindow - ws;  // earlier seed = larger stamp
+      const uint32_t seed_slot = sh_win_slot[ws];
       const uint32_t seed_aux = __ldcg(&tv.slots[seed_slot].idx);
       // claim the seed; an earlier walk of this window may already hold it
       uint32_t old = 0;
@@ -693,7 +720,7 @@ __global__ void __launch_bounds__(kSpecWarps * 32, kSpecCtasPerSM) walk_spec_ker
               }
               hb = tv.bucket_of(cand);
               table_load_bucket(tv, hb, &bk0);
-              }
+            }
             {  // the claims of the previous round, by now usually back from L2
               const bool lost = (pend1 & kAuxStampMask) >= stamp || (pend2 & kAuxStampMask) >= stamp;
               pend1 = pend2 = 0;
@@ -706,6 +733,8 @@ __global__ void __launch_bounds__(kSpecWarps * 32, kSpecCtasPerSM) walk_spec_ker
             if (lvl == 1 && state < 0) state = walk_chase(tv, cand, &cslot, &wraw, &caux, &nextb);
             // blocked: committed-traversed, or stamped by an earlier seed or by this walk
             bool ok = state == 1 && !(caux & kAuxTraversed) && (caux & kAuxStampMask) < stamp;
+            if (lvl == 1 && state == 1 && !(caux & kAuxTraversed) && (caux & kAuxStampMask) > stamp)
+              bl |= 1ull << ((uint32_t)kSpecWindow - (caux & kAuxStampMask));
             // ---- first step ------------------------------------------------------------------
             uint32_t score = ok ? ((((wraw & SHN_WEIGHT_MASK) << 2) | (uint32_t)(3 - (lane & 3))) + 1u) : 0u;
             uint32_t m = max(score, __shfl_xor_sync(FULL, score, 1));
@@ -718,11 +747,11 @@ __global__ void __launch_bounds__(kSpecWarps * 32, kSpecCtasPerSM) walk_spec_ker
             const shn_key_t c1 = dir == 0 ? (((cur << 2) & mask) | (shn_key_t)w1)
                                           : ((cur >> 2) | ((shn_key_t)w1 << top));
             const uint32_t c1slot = (uint32_t)__shfl_sync(FULL, (uint32_t)cslot, w1);
-            if (lane == 0 && len < sa.path_cap) {
+            if (lane == 0 && len < path_cap) {
               my_path_slot[len] = c1slot;
               my_path_base[len] = (uint8_t)w1;
             }
-            overflow |= len >= sa.path_cap;
+            overflow |= len >= path_cap;
             ++len;
             tot += bw1;
             ++n_dir[dir];
@@ -733,6 +762,9 @@ __global__ void __launch_bounds__(kSpecWarps * 32, kSpecCtasPerSM) walk_spec_ker
               ok = state == 1 && !(caux & kAuxTraversed) && (caux & kAuxStampMask) < stamp;
             }
             ok = ok && cand != c1;
+            if (lane >= g2 && lane < g2 + 4 && state == 1 && !(caux & kAuxTraversed) &&
+                (caux & kAuxStampMask) > stamp)
+              bl |= 1ull << ((uint32_t)kSpecWindow - (caux & kAuxStampMask));
             score = ok ? ((((wraw & SHN_WEIGHT_MASK) << 2) | (uint32_t)(3 - (lane & 3))) + 1u) : 0u;
             m = max(score, __shfl_xor_sync(FULL, score, 1));
             m = max(m, __shfl_xor_sync(FULL, m, 2));
@@ -744,11 +776,11 @@ __global__ void __launch_bounds__(kSpecWarps * 32, kSpecCtasPerSM) walk_spec_ker
             cur = dir == 0 ? (((c1 << 2) & mask) | (shn_key_t)w2) : ((c1 >> 2) | ((shn_key_t)w2 << top));
             cur_aux = __shfl_sync(FULL, caux, g2 + w2);
             const uint32_t c2slot = (uint32_t)__shfl_sync(FULL, (uint32_t)cslot, g2 + w2);
-            if (lane == 0 && len < sa.path_cap) {
+            if (lane == 0 && len < path_cap) {
               my_path_slot[len] = c2slot;
               my_path_base[len] = (uint8_t)w2;
             }
-            overflow |= len >= sa.path_cap;
+            overflow |= len >= path_cap;
             ++len;
             tot += bw2;
             ++n_dir[dir];
@@ -756,70 +788,104 @@ __global__ void __launch_bounds__(kSpecWarps * 32, kSpecCtasPerSM) walk_spec_ker
           }
         }
       }
-      if (lane == 0) sh_len[warp] = len;
+      const unsigned blo = __reduce_or_sync(FULL, (unsigned)bl);
+      const unsigned bhi = __reduce_or_sync(FULL, (unsigned)(bl >> 32));
+      if (lane == 0) {
+        sh_len[ws] = len;
+        sh_nr[ws] = n_dir[0];
+        sh_nl[ws] = n_dir[1];
+        sh_tot[ws] = tot;
+        sh_block[ws] = ((unsigned long long)bhi << 32) | blo;
+      }
     }
     __syncthreads();  // all claims of the window are in L2
 
-    // ---- 3. is my path intact? ------------------------------------------------------------------
-    if (warp < (int)win_n) {
+    // ---- 3. which paths are intact, and who holds the seeds? -----------------------------------
+    for (uint32_t ws = warp; ws < win_n; ws += kSpecWarps) {
+      const uint32_t len = sh_len[ws], stamp = (uint32_t)kSpecWindow - ws;
+      const uint32_t* ps = cta_path_slot + (uint64_t)ws * path_cap;
       bool mine = true;
       for (uint32_t e = lane; e < len; e += 32)
-        mine &= (__ldcg(&tv.slots[my_path_slot[e]].idx) & kAuxStampMask) == stamp;
+        mine &= (__ldcg(&tv.slots[ps[e]].idx) & kAuxStampMask) == stamp;
       mine = __all_sync(FULL, mine);
-      if (lane == 0) sh_intact[warp] = mine ? 1u : 0u;
+      if (lane == 0) {
+        sh_intact[ws] = (mine && len) ? 1u : 0u;
+        const uint32_t sst = __ldcg(&tv.slots[sh_win_slot[ws]].idx) & kAuxStampMask;
+        sh_thief[ws] = (sst > stamp && sst <= (uint32_t)kSpecWindow) ? (uint32_t)kSpecWindow - sst : 0xFFFFFFFFu;
+      }
     }
     __syncthreads();
-    uint32_t P = 0;
-    while (P < win_n && sh_intact[P]) ++P;
-    n_commit += P;
-    n_retry += win_n - P;
+    if (threadIdx.x == 0) {
+      // in pop order: COMMIT = intact and never blocked by anything but committed walks;
+      // SKIP = the seed belongs to a committed earlier walk (the sequential loop finds it traversed);
+      // anything else ends the prefix and is retried
+      uint32_t P = 0;
+      uint64_t off = sh_lp;
+      unsigned long long committed = 0;
+      for (; P < win_n; ++P) {
+        uint32_t st = 0;
+        if (sh_intact[P] && (sh_block[P] & ~committed) == 0) st = 1;
+        else if (sh_thief[P] != 0xFFFFFFFFu && ((committed >> sh_thief[P]) & 1ull)) st = 2;
+        if (st == 0) break;
+        sh_status[P] = st;
+        if (st == 1) {
+          committed |= 1ull << P;
+          sh_off[P] = off;
+          off += sh_len[P];
+        }
+      }
+      sh_P = P;
+      sh_lp = off;
+      sh_cursor = P < win_n ? s_begin + sh_win_pos[P] : sh_cursor_after;
+    }
+    __syncthreads();
+    const uint32_t P = sh_P;
+    if (warp == 0) {
+      n_commit += P;
+      n_retry += win_n - P;
+    }
 
     // ---- 4. commit the intact prefix in order, roll the rest back ---------------------------
-    if (warp < (int)win_n) {
-      if ((uint32_t)warp < P) {
-        uint64_t off = sh_lp;
-        for (int q = 0; q < warp; ++q) off += sh_len[q];
+    for (uint32_t ws = warp; ws < win_n; ws += kSpecWarps) {
+      const uint32_t len = sh_len[ws], stamp = (uint32_t)kSpecWindow - ws;
+      const uint32_t* ps = cta_path_slot + (uint64_t)ws * path_cap;
+      const uint8_t* pb = cta_path_base + (uint64_t)ws * path_cap;
+      if (ws < P && sh_status[ws] == 1) {
+        const uint64_t off = sh_off[ws];
         for (uint32_t e = lane; e < len; e += 32) {
-          atomicOr(&tv.slots[my_path_slot[e]].idx, kAuxTraversed);
-          if (off + e < le) a.walk_log[off + e] = my_path_base[e];
+          atomicOr(&tv.slots[ps[e]].idx, kAuxTraversed);
+          if (off + e < le) a.walk_log[off + e] = pb[e];
         }
         overflow |= off + len > le;
         if (lane == 0 && len) {
-          const uint32_t rank = a.ranks_by_comp[s_begin + sh_win_pos[warp]];
+          const uint32_t rank = a.ranks_by_comp[s_begin + sh_win_pos[ws]];
           a.started[rank] = 1;
-          a.nr[rank] = n_dir[0];
-          a.nl[rank] = n_dir[1];
-          a.totwt[rank] = tot;
+          a.nr[rank] = sh_nr[ws];
+          a.nl[rank] = sh_nl[ws];
+          a.totwt[rank] = sh_tot[ws];
           a.logstart[rank] = off;
         }
         traversed += len;
       } else {
         for (uint32_t e = lane; e < len; e += 32) {
-          uint32_t* p = &tv.slots[my_path_slot[e]].idx;
+          uint32_t* p = &tv.slots[ps[e]].idx;
           const uint32_t v = __ldcg(p);  // only the stamp bits change: the CAS fails iff stolen
           if ((v & kAuxStampMask) == stamp) atomicCAS(p, v, v & ~kAuxStampMask);
         }
       }
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-      uint64_t add = 0;
-      for (uint32_t q = 0; q < P; ++q) add += sh_len[q];
-      sh_lp += add;
-      sh_cursor = P < win_n ? s_begin + sh_win_pos[P] : sh_cursor_after;
-    }
-    __syncthreads();
   }
   if (lane == 0) {
     atomicAdd(&a.counters[0], traversed);
-    if (warp == 0) atomicMax(&a.counters[1], rounds);
+    atomicMax(&a.counters[1], rounds);
     if (overflow) atomicAdd(&a.counters[2], 1ull);
     if (warp == 0) atomicAdd(&a.counters[3], windows);
     if (warp == 0 && a.trace) {
       unsigned long long tns;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tns));
       a.trace[3 * (uint64_t)blockIdx.x] = tns;
-      a.trace[3 * (uint64_t)blockIdx.x + 1] = (windows << 32) | rounds;
+      a.trace[3 * (uint64_t)blockIdx.x + 1] = (windows << 32) | (rounds & 0xFFFFFFFFull);
       a.trace[3 * (uint64_t)blockIdx.x + 2] = (n_commit << 32) | n_retry;
     }
   }
@@ -1350,23 +1416,24 @@ void l3_run(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
     // large components: speculative windows (one CTA each); the rest: one warp each, on a second
     // stream so that both kernels share the GPU
     uint32_t n_spec = 0;
-    uint64_t path_cap = 0;
+    std::vector<uint64_t> h_path_off(1, 0);
     {
-      const uint32_t peek = std::min<uint32_t>(n_active, 4096);
+      const uint32_t peek = std::min<uint32_t>(n_active, 1u << 16);
       std::vector<uint32_t> top;
       d2h(c, top, work_s.p, peek);
       const char* env = getenv("SHN_SPEC_MIN_NODES");
       const uint64_t min_nodes = env ? strtoull(env, nullptr, 10) : 60000ull;
       const char* envb = getenv("SHN_SPEC_SCRATCH_GB");
-      const uint64_t budget = (envb ? strtoull(envb, nullptr, 10) : 16ull) << 30;  // scratch for the paths
-      path_cap = peek ? top[0] : 0;
+      const uint64_t budget = (envb ? strtoull(envb, nullptr, 10) : 32ull) << 30;  // scratch for the paths
       const char* envc = getenv("SHN_SPEC_MAX_COMPS");
       const uint32_t max_spec = envc ? (uint32_t)strtoul(envc, nullptr, 10) : (uint32_t)c->sm_count;
       while (n_spec < peek && n_spec < max_spec && top[n_spec] >= min_nodes &&
-             (uint64_t)(n_spec + 1) * kSpecWarps * path_cap * 5 <= budget)
+             (h_path_off.back() + (uint64_t)kSpecWindow * top[n_spec]) * 5 <= budget) {
+        h_path_off.push_back(h_path_off.back() + (uint64_t)kSpecWindow * top[n_spec]);
         ++n_spec;
+      }
     }
-    DevBuf path_slot, path_base;
+    DevBuf path_slot, path_base, path_off;
     cudaEvent_t ev_fork = c->prof_event(), ev_join = c->prof_event();
     {
       ProfScope ps(c, "walk", 2);
@@ -1379,11 +1446,12 @@ void l3_run(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
         SpecArgs sa;
         sa.w = a;
         sa.w.n_comps = n_spec;
-        sa.path_cap = path_cap;
-        path_slot.reserve((uint64_t)n_spec * kSpecWarps * path_cap * 4);
-        path_base.reserve((uint64_t)n_spec * kSpecWarps * path_cap);
+        path_slot.reserve(h_path_off.back() * 4);
+        path_base.reserve(h_path_off.back());
+        h2d(c, path_off, h_path_off);
         sa.path_slot = path_slot.as<uint32_t>();
         sa.path_base = path_base.as<uint8_t>();
+        sa.path_off = path_off.as<uint64_t>();
         walk_spec_kernel<<<n_spec, kSpecWarps * 32, 0, st>>>(sa);
         KERNEL_CHECK();
       }
