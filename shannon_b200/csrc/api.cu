@@ -122,6 +122,8 @@ void shn_destroy(shn_ctx* c) {
   cudaStreamSynchronize(c->stream);
   c->pool.trim();
   if (c->stream2) cudaStreamDestroy(c->stream2);
+  if (c->stream3) cudaStreamDestroy(c->stream3);
+  if (c->stream4) cudaStreamDestroy(c->stream4);
   cudaStreamDestroy(c->stream);
   g_shn_pool = nullptr;
   delete c;

@@ -333,7 +333,8 @@ struct shn_ctx {
   int device = 0;
   int sm_count = 0;
   cudaStream_t stream = nullptr;
-  cudaStream_t stream2 = nullptr;  // second stream of the walk stage (created on demand)
+  cudaStream_t stream2 = nullptr;  // asynchronous uploads (created on demand)
+  cudaStream_t stream3 = nullptr, stream4 = nullptr;  // side streams of the walk stage (created on demand)
   std::string last_error;
   cudaEvent_t t0 = nullptr, t1 = nullptr;
   // profiling

@@ -568,7 +568,9 @@ __global__ void __launch_bounds__(kWalkBlock, kWalkBlocksPerSM) walk_kernel(Walk
 //     dropped (SKIP) and the prefix goes on.  Its other, phantom claims may have blocked later
 //     walks, so every walk records which window positions ever blocked it and commits only if all
 //     of them committed.
-constexpr int kSpecWarps = 16;
+// Warps per CTA: 16 for the largest components (their serial chain is the critical path), 8 for
+// the next tier (half the resident-warp budget per component, so three times as many components
+// can walk speculatively at once); see l3_run.
 #ifndef SHN_SPEC_WINDOW
 #define SHN_SPEC_WINDOW 32
 #endif
@@ -579,7 +581,7 @@ constexpr int kSpecWindow = SHN_SPEC_WINDOW;
 #ifndef SHN_SPEC_CTAS_PER_SM
 #define SHN_SPEC_CTAS_PER_SM 2
 #endif
-constexpr int kSpecCtasPerSM = SHN_SPEC_CTAS_PER_SM;  // 2 -> 64 registers
+constexpr int kSpecCtasPerSM = SHN_SPEC_CTAS_PER_SM;  // x 16 warps: 64 registers per thread
 
 struct SpecArgs {
   WalkArgs w;
@@ -588,7 +590,8 @@ struct SpecArgs {
   const uint64_t* path_off;  // [n_spec + 1] first entry of every component's buffers
 };
 
-__global__ void __launch_bounds__(kSpecWarps * 32, kSpecCtasPerSM) walk_spec_kernel(SpecArgs sa) {
+template <int kSpecWarps>
+__global__ void __launch_bounds__(kSpecWarps * 32, kSpecCtasPerSM * 16 / kSpecWarps) walk_spec_kernel(SpecArgs sa) {
   const WalkArgs& a = sa.w;
   const unsigned FULL = 0xFFFFFFFFu;
   const int lane = threadIdx.x & 31;
@@ -1426,7 +1429,7 @@ void l3_run(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
       const char* envb = getenv("SHN_SPEC_SCRATCH_GB");
       const uint64_t budget = (envb ? strtoull(envb, nullptr, 10) : 32ull) << 30;  // scratch for the paths
       const char* envc = getenv("SHN_SPEC_MAX_COMPS");
-      const uint32_t max_spec = envc ? (uint32_t)strtoul(envc, nullptr, 10) : (uint32_t)c->sm_count;
+      const uint32_t max_spec = envc ? (uint32_t)strtoul(envc, nullptr, 10) : 3u * (uint32_t)c->sm_count;
       while (n_spec < peek && n_spec < max_spec && top[n_spec] >= min_nodes &&
              (h_path_off.back() + (uint64_t)kSpecWindow * top[n_spec]) * 5 <= budget) {
         h_path_off.push_back(h_path_off.back() + (uint64_t)kSpecWindow * top[n_spec]);
@@ -1434,13 +1437,13 @@ void l3_run(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
       }
     }
     DevBuf path_slot, path_base, path_off;
-    cudaEvent_t ev_fork = c->prof_event(), ev_join = c->prof_event();
+    cudaEvent_t ev_fork = c->prof_event(), ev_join = c->prof_event(), ev_join3 = c->prof_event();
     {
       ProfScope ps(c, "walk", 2);
+      CUDA_CHECK(cudaEventRecord(ev_fork, st));
       if (n_spec < n_active) {
-        if (!c->stream2) CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
-        CUDA_CHECK(cudaEventRecord(ev_fork, st));
-        CUDA_CHECK(cudaStreamWaitEvent(c->stream2, ev_fork, 0));
+        if (!c->stream3) CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking));
+        CUDA_CHECK(cudaStreamWaitEvent(c->stream3, ev_fork, 0));
       }
       if (n_spec) {
         SpecArgs sa;
@@ -1452,23 +1455,44 @@ void l3_run(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
         sa.path_slot = path_slot.as<uint32_t>();
         sa.path_base = path_base.as<uint8_t>();
         sa.path_off = path_off.as<uint64_t>();
-        walk_spec_kernel<<<n_spec, kSpecWarps * 32, 0, st>>>(sa);
-        KERNEL_CHECK();
+        const char* envt = getenv("SHN_SPEC_TIER16");
+        const uint32_t n16 =
+            std::min<uint32_t>(n_spec, envt ? (uint32_t)strtoul(envt, nullptr, 10) : (uint32_t)c->sm_count / 4u);
+        if (n16) {
+          SpecArgs t = sa;
+          t.w.n_comps = n16;
+          walk_spec_kernel<16><<<n16, 16 * 32, 0, st>>>(t);
+          KERNEL_CHECK();
+        }
+        if (n_spec > n16) {  // second tier on its own stream: all three kernels share the GPU
+          if (!c->stream4) CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream4, cudaStreamNonBlocking));
+          CUDA_CHECK(cudaStreamWaitEvent(c->stream4, ev_fork, 0));
+          SpecArgs t = sa;
+          t.w.comp_order = a.comp_order + n16;
+          t.w.n_comps = n_spec - n16;
+          t.path_off = sa.path_off + n16;
+          if (t.w.trace) t.w.trace += 3 * (uint64_t)n16;
+          walk_spec_kernel<8><<<n_spec - n16, 8 * 32, 0, c->stream4>>>(t);
+          KERNEL_CHECK();
+          CUDA_CHECK(cudaEventRecord(ev_join3, c->stream4));
+          CUDA_CHECK(cudaStreamWaitEvent(st, ev_join3, 0));
+        }
       }
       if (n_spec < n_active) {
         WalkArgs b = a;
         b.comp_order = a.comp_order + n_spec;
         b.n_comps = n_active - n_spec;
         if (b.trace) b.trace += 3 * (uint64_t)n_spec;
-        walk_kernel<<<shn_grid((uint64_t)b.n_comps * 32, kWalkBlock), kWalkBlock, 0, c->stream2>>>(b);
+        walk_kernel<<<shn_grid((uint64_t)b.n_comps * 32, kWalkBlock), kWalkBlock, 0, c->stream3>>>(b);
         KERNEL_CHECK();
-        CUDA_CHECK(cudaEventRecord(ev_join, c->stream2));
+        CUDA_CHECK(cudaEventRecord(ev_join, c->stream3));
         CUDA_CHECK(cudaStreamWaitEvent(st, ev_join, 0));
       }
     }
     CUDA_CHECK(cudaStreamSynchronize(st));
     c->prof_pool.push_back(ev_fork);
     c->prof_pool.push_back(ev_join);
+    c->prof_pool.push_back(ev_join3);
     s->sz.n_spec_comps = n_spec;
     if (want_trace) {  // when does each component's warp finish? (tail = critical path)
       std::vector<unsigned long long> tr;
@@ -1668,21 +1692,32 @@ void l3_run(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
                                                                         n_cand, seg_off.as<uint64_t>());
       KERNEL_CHECK();
       CUDA_CHECK(cudaMemcpyAsync(st_b.p, st_a.p, n_cand, cudaMemcpyDeviceToDevice, st));
-      for (uint64_t r_in_block = 0;; ++r_in_block) {
+      // kDupBatch rounds per host round trip; rounds after convergence only copy the statuses
+      constexpr int kDupBatch = 4;
+      for (uint64_t r_in_block = 0;; r_in_block += kDupBatch) {
         ctr = zero_counters(c);
         {
-          ProfScope ps(c, "dup_round");
-          dup_round_kernel<<<shn_grid(hi - lo, kBlock), kBlock, 0, st>>>(
-              seg_off.as<uint64_t>(), pt.lo.as<uint32_t>(), pt.count.as<uint32_t>(),
-              pt.max_i.as<uint32_t>(), pt.covered.as<uint32_t>(), d_cand_off.as<uint64_t>(), lo, hi,
-              st_a.as<uint8_t>(), st_b.as<uint8_t>(), dupf.as<uint8_t>(), ctr);
-          KERNEL_CHECK();
+          ProfScope ps(c, "dup_round", kDupBatch);
+          for (int g = 0; g < kDupBatch; ++g) {
+            dup_round_kernel<<<shn_grid(hi - lo, kBlock), kBlock, 0, st>>>(
+                seg_off.as<uint64_t>(), pt.lo.as<uint32_t>(), pt.count.as<uint32_t>(),
+                pt.max_i.as<uint32_t>(), pt.covered.as<uint32_t>(), d_cand_off.as<uint64_t>(), lo, hi,
+                st_a.as<uint8_t>(), st_b.as<uint8_t>(), dupf.as<uint8_t>(), ctr + g);
+            KERNEL_CHECK();
+            std::swap(st_a.p, st_b.p);
+            std::swap(st_a.bytes, st_b.bytes);
+          }
         }
-        ++rounds;
-        read_counters(c, h, 1);
-        std::swap(st_a.p, st_b.p);
-        std::swap(st_a.bytes, st_b.bytes);
-        if (h[0] == 0) break;
+        read_counters(c, h, kDupBatch);
+        bool done = false;
+        for (int g = 0; g < kDupBatch; ++g) {
+          ++rounds;
+          if (h[g] == 0) {
+            done = true;
+            break;
+          }
+        }
+        if (done) break;
         SHN_CHECK(r_in_block <= hi - lo + 1, "internal error: duplicate filter does not converge");
       }
       // both buffers agree outside [lo, hi); make them agree inside as well

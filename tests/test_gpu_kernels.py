@@ -144,6 +144,7 @@ def test_l3_stages_equal_oracle(ctx, workdir, kind, seed, spec, monkeypatch):
     # spec=True forces the speculative windowed walk kernel (normally only used for components
     # with >= 60 k K1-mers) onto every component
     monkeypatch.setenv("SHN_SPEC_MIN_NODES", "1" if spec else "1000000000")
+    monkeypatch.setenv("SHN_SPEC_TIER16", "2")   # first two components: 16-warp CTAs, the rest: 8-warp CTAs
     case, min_weight, min_length = _case(workdir, kind, seed)
     out = case.outdir("o")
     res = so.run_correction(case.k1mer_org, out + "/k", min_weight, min_length, False, out, 2,
