@@ -148,18 +148,31 @@ __device__ __forceinline__ uint32_t uf_find_ro(const uint32_t* parent, uint32_t 
   return x;
 }
 
+// Rem's algorithm with splicing, lock-free (CAS): the two find paths are climbed together, always
+// on the side whose parent has the larger index, and every node passed is re-pointed at the other
+// side's (smaller) parent; the climb stops as soon as the paths meet instead of walking both to
+// their roots.  Parents always have smaller indices than their children, so the forest stays
+// acyclic under any interleaving, and the root of a finished set is its minimum slot index.
 __device__ __forceinline__ void uf_union(uint32_t* parent, uint32_t a, uint32_t b) {
-  for (;;) {
-    a = uf_find(parent, a);
-    b = uf_find(parent, b);
-    if (a == b) return;
-    if (a < b) {
+  uint32_t pa = __ldcg(&parent[a]), pb = __ldcg(&parent[b]);
+  while (pa != pb) {
+    if (pa < pb) {  // climb on the side with the larger parent
       uint32_t t = a;
       a = b;
       b = t;
+      t = pa;
+      pa = pb;
+      pb = t;
     }
-    // link the larger root under the smaller one: the final root is the minimum slot index
-    if (atomicCAS(&parent[a], a, b) == a) return;
+    if (a == pa) {  // a is a root: link it under the other side
+      const uint32_t old = atomicCAS(&parent[a], a, pb);
+      if (old == a) return;
+      pa = old;  // somebody linked it first
+      continue;
+    }
+    atomicCAS(&parent[a], pa, pb);  // splice (harmless if it fails: the entry only ever decreases)
+    a = pa;
+    pa = __ldcg(&parent[a]);
   }
 }
 
