@@ -397,6 +397,11 @@ def main():
         counts_all = [None] * world
         dist.all_gather_object(counts_all, n_k)
         first_line = sum(counts_all[:rank])
+        # first all-to-all of the process sets up NCCL's point-to-point channels: keep that out of
+        # the build time
+        wu_in = torch.zeros(world, dtype=torch.int64, device="cuda")
+        wu_out = torch.empty(world, dtype=torch.int64, device="cuda")
+        dist.all_to_all_single(wu_out, wu_in)
         barrier()
         t0 = time.perf_counter()
         tab.build(tk, tc, first_line, K1)
