@@ -175,10 +175,10 @@ SHN_HD shn_key_t shn_key_mask(int k) { return shn_kmer_mask128(k); }
 typedef uint64_t shn_key_t;
 struct __align__(16) ShnSlot {
   uint64_t key;     // SHN_EMPTY_KEY when free
-  uint32_t weight;  // sum of counts (30 bits); bit 31 = traversed (walk kernels); bit 30 of the
-                    // bucket's slot 0 = an insert walked past this full bucket
-  uint32_t idx;     // first-occurrence index in the input (dict insertion order); the walks'
-                    // component-local copy re-uses it as the claim stamp of speculative windows
+  uint32_t weight;  // sum of counts (30 bits); bit 30 of the bucket's slot 0 = an insert walked
+                    // past this full bucket
+  uint32_t idx;     // first-occurrence index in the input (dict insertion order); parked in a side
+                    // array during shn_l3_run, when the word is the walks' aux word (l3.cu)
 };
 SHN_HD shn_key_t shn_key_mask(int k) { return shn_kmer_mask(k); }
 #endif
