@@ -163,7 +163,7 @@ class Correction(object):
 
 
 def correct(ctx, keys, counts, k1, double_stranded, min_weight, min_length, on_device=False,
-            n=None, timings=None, fetch_allowed=True, after_table_build=None):
+            n=None, timings=None, fetch_allowed=True, after_table_build=None, after_l3_run=None):
     """load_kmers .. DFS (extension_correction.py:317-450) on the GPU.  keys/counts: host numpy
     arrays, or device pointers with on_device=True and n given."""
     import time
@@ -181,6 +181,8 @@ def correct(ctx, keys, counts, k1, double_stranded, min_weight, min_length, on_d
     t0 = time.perf_counter()
     cor.sizes = ctx.l3_run(min_weight, min_length)
     tm["l3_run"] = time.perf_counter() - t0
+    if after_l3_run is not None:
+        after_l3_run()           # e.g. queue the read packing: it runs under the host-side ordering
     t0 = time.perf_counter()
     n_contigs = cor.sizes["n_contigs"]
     bases, offs = ctx.l3_contigs()
@@ -251,14 +253,20 @@ def upload_reads_early(ctx, mates):
             ctx.l4_upload_reads_async(m, bases, offs)
 
 
-def partition_reads(ctx, mates, paired, k1, n_comps, staged=False):
-    """get_comps over all records (kmers_for_component.py:322-423).  mates: list of
-    (bases, offsets, n, on_device).  Returns (comp_offsets, record_idx, stats)."""
+def load_reads(ctx, mates, staged=False):
+    """2-bit packing of the read files on the device (asynchronous on the context's stream)."""
     for m, (bases, offs, n, on_dev) in enumerate(mates):
         if staged and not on_dev:
             ctx.l4_load_reads_staged(m)
         else:
             ctx.l4_load_reads(m, bases, offs, n=n, on_device=on_dev)
+
+
+def partition_reads(ctx, mates, paired, k1, n_comps, staged=False, loaded=False):
+    """get_comps over all records (kmers_for_component.py:322-423).  mates: list of
+    (bases, offsets, n, on_device).  Returns (comp_offsets, record_idx, stats)."""
+    if not loaded:
+        load_reads(ctx, mates, staged)
     n_assign, n_lookups, n_valid = ctx.l4_assign(paired, k1)
     comp_offs, rec_idx = ctx.l4_assignments(n_comps, n_assign)
     return comp_offs.astype(np.int64), rec_idx, {"assignments": n_assign, "lookups": n_lookups,
@@ -272,8 +280,10 @@ def frontend_in_memory(ctx, keys, counts, k1, mates, paired, min_weight=3, min_l
     the gpmetis stand-in."""
     import time
     tm = {}
+    loaded = []   # set once the read packing has been queued (under the host-side ordering)
     cor = correct(ctx, keys, counts, k1, False, min_weight, min_length, on_device, n_kmers, tm,
-                  fetch_allowed=False, after_table_build=lambda: upload_reads_early(ctx, mates))
+                  fetch_allowed=False, after_table_build=lambda: upload_reads_early(ctx, mates),
+                  after_l3_run=lambda: loaded.append(load_reads(ctx, mates, staged=True)))
     t0 = time.perf_counter()
     pk = pack_components(cor, partition_size)
     n_contigs = cor.sizes["n_contigs"]
@@ -296,7 +306,7 @@ def frontend_in_memory(ctx, keys, counts, k1, mates, paired, min_weight=3, min_l
     ctx.l4_map_set_weights(None, None)
     tm["map_build"] = time.perf_counter() - t0
     t0 = time.perf_counter()
-    comp_offs, rec_idx, stats = partition_reads(ctx, mates, paired, k1, n_comps, staged=True)
+    comp_offs, rec_idx, stats = partition_reads(ctx, mates, paired, k1, n_comps, staged=True, loaded=bool(loaded))
     tm["partition_reads"] = time.perf_counter() - t0
     stats["host_timings_ms"] = dict((k, 1000.0 * v) for k, v in tm.items())
     stats.update(cor.sizes)
