@@ -188,7 +188,10 @@ __global__ void __launch_bounds__(kBlock)
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_slots) return;
   shn_key_t key = t.slots[i].key;
-  if (key == SHN_EMPTY) return;
+  if (key == SHN_EMPTY) {
+    parent[i] = SHN_NONE32;  // the later passes tell free slots from the parent array alone
+    return;
+  }
   const shn_key_t mask = shn_key_mask(k1);
   shn_key_t pre = (key << 2) & mask;
   const uint32_t first = (uint32_t)(key >> (2 * (k1 - 1))) & 3u;
@@ -206,43 +209,44 @@ __global__ void __launch_bounds__(kBlock)
   if (sm) atomicOr(&t.slots[i].idx, sm << 24);
 }
 
-// parent[i] <- root for occupied slots; roots get flag 1
+// parent[i] <- root for occupied slots; roots get flag 1 (free slots: parent = SHN_NONE32)
 __global__ void __launch_bounds__(kBlock)
-    uf_flatten_kernel(const ShnSlot* __restrict__ slots, uint32_t* parent, uint64_t n_slots,
-                      uint32_t* __restrict__ is_root) {
+    uf_flatten_kernel(uint32_t* parent, uint64_t n_slots, uint32_t* __restrict__ is_root) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_slots) return;
-  bool occ = slots[i].key != SHN_EMPTY;
+  const uint32_t p = __ldcg(&parent[i]);
+  const bool occ = p != SHN_NONE32;
   uint32_t root = (uint32_t)i;
-  if (occ) root = uf_find_ro(parent, (uint32_t)i);
+  if (occ && p != (uint32_t)i) root = uf_find_ro(parent, p);
   is_root[i] = (occ && root == (uint32_t)i) ? 1u : 0u;
-  if (occ && root != (uint32_t)i) parent[i] = root;
+  if (occ && root != p) parent[i] = root;
 }
 
 // comp id of every occupied slot + node count per component
 __global__ void __launch_bounds__(kBlock)
-    comp_count_kernel(const ShnSlot* __restrict__ slots, const uint32_t* __restrict__ parent,
-                      const uint32_t* __restrict__ root_id, uint64_t n_slots,
-                      uint32_t* __restrict__ comp_nodes) {
+    comp_count_kernel(const uint32_t* __restrict__ parent, const uint32_t* __restrict__ root_id,
+                      uint64_t n_slots, uint32_t* __restrict__ comp_nodes) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_slots) return;
-  if (slots[i].key == SHN_EMPTY) return;
-  atomicAdd(&comp_nodes[root_id[parent[i]]], 1u);  // parent[i] is the root after flatten
+  const uint32_t p = parent[i];  // the root after flatten
+  if (p == SHN_NONE32) return;
+  atomicAdd(&comp_nodes[root_id[p]], 1u);
 }
 
 // the same with a block-private histogram in shared memory (n_comps * 4 bytes of dynamic smem):
 // 10^8 atomics on a few thousand counters serialise in L2, shared-memory atomics do not
 __global__ void __launch_bounds__(kBlock)
-    comp_count_smem_kernel(const ShnSlot* __restrict__ slots, const uint32_t* __restrict__ parent,
-                           const uint32_t* __restrict__ root_id, uint64_t n_slots, uint32_t n_comps,
-                           uint32_t* __restrict__ comp_nodes) {
+    comp_count_smem_kernel(const uint32_t* __restrict__ parent, const uint32_t* __restrict__ root_id,
+                           uint64_t n_slots, uint32_t n_comps, uint32_t* __restrict__ comp_nodes) {
   extern __shared__ uint32_t hist[];
   for (uint32_t k = threadIdx.x; k < n_comps; k += blockDim.x) hist[k] = 0;
   __syncthreads();
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (; i < n_slots; i += stride)
-    if (slots[i].key != SHN_EMPTY) atomicAdd(&hist[root_id[parent[i]]], 1u);
+  for (; i < n_slots; i += stride) {
+    const uint32_t p = parent[i];
+    if (p != SHN_NONE32) atomicAdd(&hist[root_id[p]], 1u);
+  }
   __syncthreads();
   for (uint32_t k = threadIdx.x; k < n_comps; k += blockDim.x)
     if (hist[k]) atomicAdd(&comp_nodes[k], hist[k]);
@@ -1295,8 +1299,8 @@ void l3_run(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
   {
     ProfScope ps(c, "uf_flatten");
     CUDA_CHECK(cudaMemsetAsync(root_flag.as<uint32_t>() + n_slots, 0, 4, st));
-    uf_flatten_kernel<<<shn_grid(n_slots, kBlock), kBlock, 0, st>>>(tv.slots, parent.as<uint32_t>(),
-                                                                   n_slots, root_flag.as<uint32_t>());
+    uf_flatten_kernel<<<shn_grid(n_slots, kBlock), kBlock, 0, st>>>(parent.as<uint32_t>(), n_slots,
+                                                                   root_flag.as<uint32_t>());
     KERNEL_CHECK();
   }
   uint32_t n_comps = 0;
@@ -1320,11 +1324,10 @@ void l3_run(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
     ProfScope ps(c, "comp_count");
     if (n_comps && (uint64_t)n_comps * 4 <= 40 * 1024) {
       comp_count_smem_kernel<<<c->sm_count * 8, kBlock, (size_t)n_comps * 4, st>>>(
-          tv.slots, parent.as<uint32_t>(), root_id.as<uint32_t>(), n_slots, n_comps,
-          comp_nodes.as<uint32_t>());
+          parent.as<uint32_t>(), root_id.as<uint32_t>(), n_slots, n_comps, comp_nodes.as<uint32_t>());
     } else {
       comp_count_kernel<<<shn_grid(n_slots, kBlock), kBlock, 0, st>>>(
-          tv.slots, parent.as<uint32_t>(), root_id.as<uint32_t>(), n_slots, comp_nodes.as<uint32_t>());
+          parent.as<uint32_t>(), root_id.as<uint32_t>(), n_slots, comp_nodes.as<uint32_t>());
     }
     KERNEL_CHECK();
   }

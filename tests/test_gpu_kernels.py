@@ -152,7 +152,11 @@ def test_l3_stages_equal_oracle(ctx, workdir, kind, seed, spec, monkeypatch):
     k1 = res.k1
     keys, counts, _ = ctx.parse_kmer_file(case.k1mer_org)
     ctx.table_build(keys, counts, k1, False)
+    dump_before = ctx.table_dump()
     sz = ctx.l3_run(min_weight, min_length)
+    # the walks borrow the first-occurrence word of every slot: the table must come back unchanged
+    for x, y in zip(dump_before, ctx.table_dump()):
+        assert np.array_equal(x, y)
     # walks, in pop order
     seed_k, nl, nr, tot, flags = ctx.l3_walks()
     exp = res.walks
