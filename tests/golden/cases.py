@@ -40,6 +40,26 @@ def repeat_rich_reads(seed, n_reads, read_len, genome_len, n_genomes):
     return reads
 
 
+def degenerate_reads(kind):
+    """Inputs on which (almost) nothing survives: the front end must still leave the reference's
+    (empty) files behind."""
+    rnd = random.Random(5)
+
+    def rand(n):
+        return "".join(rnd.choice("ACGT") for _ in range(n))
+    if kind == "low_cov":                 # every K1-mer has weight 1-2: no seed
+        return [rand(100) for _ in range(40)]
+    if kind == "lowcomplexity":           # homopolymer reads: (nearly) every K1-mer is filtered
+        return ["A" * 100] * 30 + ["T" * 60 + "A" * 40] * 10
+    if kind == "short_reads":             # walks shorter than min_length
+        return [rand(30) for _ in range(200)] * 4
+    if kind == "one_read":                # one contig, a single component of size 1
+        return [rand(100)] * 50
+    if kind == "with_N":                  # every read is dropped by the read partition
+        return [rand(50) + "N" + rand(49) for _ in range(20)] * 5
+    raise ValueError(kind)
+
+
 CASES = {
     # BASELINE.json config 1 (bundled single-end sample; FASTA twin of the fastq, no Quorum)
     "sample_se": {"K": 24, "input": ("sample_se",), "run": {}},
@@ -61,6 +81,8 @@ CASES = {
     "repeat_rich_k32": {"K": 32, "input": ("repeat", 9, 500, 60, 220, 4),
                         "run": {"min_weight": 2, "min_length": 40, "partition_size": 2}},
 }
+for _k in ("low_cov", "lowcomplexity", "short_reads", "one_read", "with_N"):
+    CASES["degenerate_" + _k] = {"K": 24, "input": ("degenerate", _k), "run": {}}
 for _s in range(6):
     CASES["repeat_rich_%d" % _s] = {
         "K": [8, 10, 12, 15][_s % 4], "input": ("repeat", _s, 400, 40, 160, 4),
@@ -83,6 +105,8 @@ def case_inputs(spec):
         return helpers.synthetic_seqs(ntx, npairs, seed)[0], None
     if kind == "repeat":
         return repeat_rich_reads(*spec["input"][1:]), None
+    if kind == "degenerate":
+        return degenerate_reads(spec["input"][1]), None
     raise ValueError(kind)
 
 
