@@ -131,3 +131,79 @@ def shard_range(n, rank, world):
     base, rem = divmod(n, world)
     lo = rank * base + min(rank, rem)
     return lo, lo + base + (1 if rank < rem else 0)
+
+
+# ---- read partition sharded by record range (second regime) ---------------------
+def _bcast_array(a, src, device, group=None):
+    """numpy array of rank `src` -> the same array on every rank (tensor broadcast; the shape and
+    dtype travel as a small object first)."""
+    meta = [None if a is None else (a.shape, a.dtype.str)]
+    dist.broadcast_object_list(meta, src=src, group=group)
+    shape, dtype = meta[0]
+    if dist.get_rank(group) != src:
+        a = np.empty(shape, dtype=np.dtype(dtype))
+    t = torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1))
+    if device is not None:
+        t = t.to(device)
+    if t.numel():
+        dist.broadcast(t, src=src, group=group)
+    return t.cpu().numpy().view(np.dtype(dtype)).reshape(shape)
+
+
+def merge_partitions(per_rank, n_comps):
+    """[(comp_offsets, record_idx)] in rank order -> one (comp_offsets, record_idx): inside every
+    component the records of rank 0 come first, then rank 1, ...  Ranks own ascending contiguous
+    record ranges, so this is the global input order the reference appends reads in
+    (kmers_for_component.py:345-351)."""
+    sizes = np.stack([np.diff(np.asarray(o, dtype=np.int64)) for o, _ in per_rank])  # [world, n_comps]
+    total = sizes.sum(axis=0)
+    goff = np.zeros(n_comps + 1, dtype=np.int64)
+    goff[1:] = np.cumsum(total)
+    before = np.cumsum(sizes, axis=0) - sizes                                        # earlier ranks
+    out = np.empty(int(goff[-1]), dtype=np.uint32)
+    for r, (offs, idx) in enumerate(per_rank):
+        offs = np.asarray(offs, dtype=np.int64)
+        n = int(offs[-1])
+        if n == 0:
+            continue
+        comp_of_entry = np.repeat(np.arange(n_comps, dtype=np.int64), sizes[r])
+        dst = goff[comp_of_entry] + before[r][comp_of_entry] + (np.arange(n, dtype=np.int64) - offs[comp_of_entry])
+        out[dst] = np.asarray(idx[:n], dtype=np.uint32)
+    return goff, out
+
+
+def partition_reads_sharded(ctx, mates, paired, k1, contigs=None, n_comps=None, src=0, device=None,
+                            group=None):
+    """K1-mer -> component map replicated on every rank, reads sharded by record range, no
+    communication during the lookups.
+
+    mates : [(bases uint8, offsets uint64)] host arrays of the WHOLE read files on every rank
+            (each rank packs and looks up only its own record range)
+    contigs : on rank `src` (bases uint8 ASCII, offsets uint64, comp_of_contig uint32), the
+            contigs of the partition and their component ids (SHN none = 0xFFFFFFFF is skipped);
+            ignored elsewhere
+    Returns (comp_offsets int64, record_idx uint32) on rank `src` -- identical to
+    pipeline.partition_reads on one GPU -- and (None, None) on the other ranks."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    cb, co, cc = contigs if rank == src else (None, None, None)
+    cb = _bcast_array(cb, src, device, group)
+    co = _bcast_array(co, src, device, group)
+    cc = _bcast_array(cc, src, device, group)
+    nc = [n_comps]
+    dist.broadcast_object_list(nc, src=src, group=group)
+    n_comps = int(nc[0])
+    lens = np.diff(co.astype(np.int64))
+    ctx.l4_map_add_contigs(cb, co, cc, k1, True, int(np.maximum(lens - k1 + 1, 0).sum()))
+    n_rec = len(mates[0][1]) - 1
+    lo, hi = shard_range(n_rec, rank, world)
+    for m, (bases, offs) in enumerate(mates):
+        o = np.asarray(offs, dtype=np.uint64)
+        ctx.l4_load_reads(m, bases[int(o[lo]):int(o[hi])], o[lo:hi + 1] - o[lo])
+    n_assign, _, _ = ctx.l4_assign(paired, k1)
+    offs, idx = ctx.l4_assignments(n_comps, n_assign)
+    idx = idx.astype(np.uint32) + np.uint32(lo)
+    gathered = [None] * world if rank == src else None
+    dist.gather_object((offs.astype(np.int64), idx), gathered, dst=src, group=group)
+    if rank != src:
+        return None, None
+    return merge_partitions(gathered, n_comps)

@@ -77,3 +77,49 @@ def test_sharded_table_two_gpus(tmp_path):
     world = 2
     mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     assert sorted(os.listdir(tmp_path)) == ["ok0", "ok1"]
+
+
+def _partition_worker(rank, world, port, out_dir):
+    import dist_testlib
+    from shannon_b200 import _lib
+    from shannon_b200 import dist as sdist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        contigs, n_comps, mates = dist_testlib.partition_case(seed=4, n_tx=12, n_pairs=20000)
+        ctx = _lib.Context(rank)
+        offs, idx = sdist.partition_reads_sharded(ctx, mates, True, 25,
+                                                  contigs if rank == 0 else None,
+                                                  n_comps if rank == 0 else None,
+                                                  device=torch.device("cuda", rank))
+        if rank == 0:
+            # the same partition on one GPU over all the records, and the oracle's loop
+            lens = np.diff(contigs[1].astype(np.int64))
+            ctx.l4_map_add_contigs(contigs[0], contigs[1], contigs[2], 25, True,
+                                   int(np.maximum(lens - 24, 0).sum()))
+            for m, (b, o) in enumerate(mates):
+                ctx.l4_load_reads(m, b, o)
+            na, _, _ = ctx.l4_assign(True, 25)
+            eo, ei = ctx.l4_assignments(n_comps, na)
+            assert offs.tolist() == eo.astype(np.int64).tolist() and np.array_equal(idx, ei) and na > 5000
+            ref = dist_testlib.OracleL4Ctx()
+            ref.l4_map_add_contigs(contigs[0], contigs[1], contigs[2], 25, True, 10 ** 9)
+            for m, (b, o) in enumerate(mates):
+                ref.l4_load_reads(m, b, o)
+            assert ref.l4_assign(True, 25)[0] == na
+            ro, ri = ref.l4_assignments(n_comps, na)
+            assert ro.tolist() == eo.tolist() and ri.tolist() == ei.tolist()
+        ctx.close()
+        open(os.path.join(out_dir, "pok%d" % rank), "w").close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_read_partition_two_gpus(tmp_path):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    world = 2
+    mp.spawn(_partition_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert sorted(os.listdir(tmp_path)) == ["pok0", "pok1"]

@@ -98,3 +98,47 @@ def test_owner_hash_is_independent_of_bucket_hash():
     assert np.bincount(own, minlength=8).min() > 200000 / 8 * 0.9
     hi = (synth.mix64(keys[own == 3]) >> np.uint64(54)).astype(np.int64)      # top 10 bits
     assert np.bincount(hi, minlength=1024).min() > 0
+
+
+def _partition_worker(rank, world, port, out_dir):
+    import dist_testlib
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        contigs, n_comps, mates = dist_testlib.partition_case()
+        ctx = dist_testlib.OracleL4Ctx()
+        offs, idx = sdist.partition_reads_sharded(ctx, mates, True, 25,
+                                                  contigs if rank == 0 else None,
+                                                  n_comps if rank == 0 else None)
+        if rank == 0:
+            # one "rank" over all the records = the reference's own loop order
+            ref = dist_testlib.OracleL4Ctx()
+            ref.l4_map_add_contigs(contigs[0], contigs[1], contigs[2], 25, True, 10 ** 9)
+            for m, (b, o) in enumerate(mates):
+                ref.l4_load_reads(m, b, o)
+            na, _, _ = ref.l4_assign(True, 25)
+            eo, ei = ref.l4_assignments(n_comps, na)
+            assert offs.tolist() == eo.tolist() and idx.tolist() == ei.tolist() and na > 100
+        else:
+            assert offs is None and idx is None
+        open(os.path.join(out_dir, "ok%d" % rank), "w").close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_read_partition_equals_single_rank(tmp_path, world):
+    """Reads sharded by record range against a replicated component map: the merged
+    per-component lists are the single-rank lists, in input order."""
+    mp.spawn(_partition_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert sorted(os.listdir(tmp_path)) == ["ok%d" % r for r in range(world)]
+
+
+def test_merge_partitions_orders_by_rank_inside_components():
+    a = (np.array([0, 2, 2, 5]), np.array([1, 3, 0, 2, 4], dtype=np.uint32))
+    b = (np.array([0, 1, 3, 3]), np.array([10, 11, 12], dtype=np.uint32))
+    offs, idx = sdist.merge_partitions([a, b], 3)
+    assert offs.tolist() == [0, 3, 5, 8] and idx.tolist() == [1, 3, 10, 11, 12, 0, 2, 4]
+    offs, idx = sdist.merge_partitions([(np.zeros(4, np.int64), np.zeros(0, np.uint32))] * 2, 3)
+    assert offs.tolist() == [0, 0, 0, 0] and len(idx) == 0
