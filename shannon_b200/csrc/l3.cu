@@ -1455,7 +1455,7 @@ void l3_run(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
     DevBuf path_slot, path_base, path_off;
     cudaEvent_t ev_fork = c->prof_event(), ev_join = c->prof_event(), ev_join3 = c->prof_event();
     {
-      ProfScope ps(c, "walk", 2);
+      ProfScope ps(c, "walk", (n_spec ? 2 : 0) + (n_spec < n_active ? 1 : 0));  // upper bound: two tiers
       CUDA_CHECK(cudaEventRecord(ev_fork, st));
       if (n_spec < n_active) {
         if (!c->stream3) CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking));
