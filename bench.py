@@ -365,7 +365,22 @@ def main():
 
     # ---- e2e: same step through the C-ABI with host buffers ----------------------------------
     e2e = None
-    if not args.no_e2e:
+    e2e_ok = not args.no_e2e
+    if e2e_ok:
+        # every rank pins its own copy of the inputs: do not drive the box out of host memory
+        need = world * (2 * wl.n_records * READ_LEN + 12 * wl.n_kmers * (2 if K1 > 32 else 1))
+        try:
+            import psutil
+            avail = psutil.virtual_memory().available
+        except Exception:
+            avail = None
+        flag = torch.tensor([1 if (avail is None or need < 0.6 * avail) else 0], device="cuda")
+        if world > 1:
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        e2e_ok = bool(flag.item())
+        if not e2e_ok and rank == 0:
+            sys.stderr.write("bench: e2e leg skipped, %d GB of pinned host buffers do not fit\n" % (need >> 30))
+    if e2e_ok:
         h2d_bytes = wl.stage_host()
         run_step(ctx, wl, False)
         barrier()
