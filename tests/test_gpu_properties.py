@@ -133,3 +133,40 @@ def test_speculative_walks_equal_serial_walks_at_scale(run, monkeypatch):
         for x, y in zip(walks, results[0][1]):
             assert np.array_equal(x, y)
         assert np.array_equal(bases, results[0][2][0]) and np.array_equal(offs, results[0][2][1])
+
+
+def test_speculative_walks_equal_serial_walks_wide_keys(monkeypatch):
+    """Same check for K = 32 (128-bit keys, two slots per bucket) at 300 k read pairs: the serial
+    one-warp replay, both speculative tiers on every component, and the default mix agree on every
+    walk and every contig."""
+    ctx = _lib.Context(0)
+    try:
+        n_pairs, n_tx, seed, k1 = 300000, 150, 91, 33
+        tx = synth.make_transcripts(n_tx, seed)
+        codes, offs = synth.pack_transcripts(tx)
+        thr = synth.expression_thresholds(len(tx), [len(t) for t in tx], True)
+        d_tx, d_off, d_thr = ctx.to_device(codes), ctx.to_device(offs), ctx.to_device(thr)
+        n_rec = 2 * n_pairs
+        d1, d2 = ctx.dev_alloc(n_rec * L), ctx.dev_alloc(n_rec * L)
+        half = n_pairs * L
+        ctx.synth_pairs(d_tx, d_off, d_thr, len(tx), n_pairs, 0, seed, L, 300, synth.ERR_THRESHOLD_24,
+                        d1, d2 + half)
+        ctx.revcomp_reads(d2 + half, d1 + half, n_pairs, L)
+        ctx.revcomp_reads(d1, d2, n_pairs, L)
+        dk, dc, nk = ctx.count_k1mers([d1, d2], [n_rec, n_rec], L, k1, 2 * n_rec * (L - k1 + 1) // 3)
+        results = []
+        for min_nodes, tier16 in (("1000000000", "0"), ("1", "3"), ("20000", "1")):
+            monkeypatch.setenv("SHN_SPEC_MIN_NODES", min_nodes)
+            monkeypatch.setenv("SHN_SPEC_TIER16", tier16)
+            ctx.table_build(dk, dc, k1, False, on_device=True, n=nk)
+            sz = ctx.l3_run(3, 75)
+            results.append((sz, ctx.l3_walks(), ctx.l3_contigs()))
+        assert results[0][0]["n_spec_comps"] == 0 and results[1][0]["n_spec_comps"] > 3
+        assert results[0][0]["n_contigs"] > 50 and results[0][1][0].shape[1] == 2
+        for sz, walks, (bases, offs_c) in results[1:]:
+            assert sz["n_traversed"] == results[0][0]["n_traversed"]
+            for x, y in zip(walks, results[0][1]):
+                assert np.array_equal(x, y)
+            assert np.array_equal(bases, results[0][2][0]) and np.array_equal(offs_c, results[0][2][1])
+    finally:
+        ctx.close()
