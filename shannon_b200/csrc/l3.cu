@@ -307,16 +307,46 @@ __global__ void __launch_bounds__(kBlock)
   is_long[w] = ((uint64_t)nl + nr + (uint64_t)k1 >= (uint64_t)min_length) ? 1 : 0;  // len(contig)
 }
 
+// a5 on the device: the hyperbola test (extension_correction.py:356-361) in doubles.  The device
+// pow() may differ from the host libm in the last bits, so a walk whose two sides are closer than
+// tol_rel (1e-9, relative) is not decided here: flag 2 = the host evaluates it with the
+// reference's own expression (passes_shape).  flag 1 = passes, 0 = fails.
 __global__ void __launch_bounds__(kBlock)
-    gather_long_kernel(const uint32_t* __restrict__ idx, uint64_t n, const uint32_t* __restrict__ w_nl,
-                       const uint32_t* __restrict__ w_nr, const uint64_t* __restrict__ w_tot,
-                       uint32_t* __restrict__ nl, uint32_t* __restrict__ nr, uint64_t* __restrict__ tot) {
-  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  uint32_t w = idx[i];
-  nl[i] = w_nl[w];
-  nr[i] = w_nr[w];
-  tot[i] = w_tot[w];
+    shape_kernel(const uint32_t* __restrict__ w_nl, const uint32_t* __restrict__ w_nr,
+                 const uint64_t* __restrict__ w_tot, uint64_t n_walks, int k1, uint32_t min_weight,
+                 uint32_t min_length, double tol_rel, uint8_t* __restrict__ flag,
+                 unsigned long long* counters) {
+  uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= n_walks) return;
+  const uint64_t tot_kmer = (uint64_t)w_nl[w] + w_nr[w] + 1;
+  const uint64_t length = tot_kmer + (uint64_t)k1 - 1;
+  uint8_t f = 0;
+  if (length >= min_length) {
+    const double avg_wt = (double)w_tot[w] / (double)(tot_kmer > 1 ? tot_kmer : 1);
+    const double lhs = (double)length * pow(avg_wt, 0.25);
+    const double rhs = (double)(2ull * min_length) * pow((double)min_weight, 0.25);
+    const double tol = tol_rel * rhs;
+    if (lhs > rhs + tol) f = 1;
+    else if (lhs >= rhs - tol) {
+      f = 2;
+      atomicAdd(&counters[0], 1ull);
+    }
+  }
+  flag[w] = f;
+}
+
+__global__ void __launch_bounds__(kBlock)
+    cand_len_kernel(const uint32_t* __restrict__ cand_walk, uint64_t n_cand,
+                    const uint32_t* __restrict__ w_nl, const uint32_t* __restrict__ w_nr, int k1,
+                    uint64_t* __restrict__ len) {
+  uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j > n_cand) return;
+  uint64_t v = 0;
+  if (j < n_cand) {
+    const uint32_t w = cand_walk[j];
+    v = (uint64_t)w_nl[w] + w_nr[w] + (uint64_t)k1;
+  }
+  len[j] = v;
 }
 
 // ---- greedy walks -----------------------------------------------------------------------
@@ -1556,15 +1586,18 @@ void l3_run(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
   s->sz.walk_rounds = h[1];
   s->sz.spec_windows = h[3];
 
-  // started walks in pop order (device compaction), then the walks long enough to matter
-  uint64_t n_walks = 0, n_long = 0;
-  std::vector<uint32_t> h_long_idx, h_long_nl, h_long_nr;
-  std::vector<uint64_t> h_long_tot;
+  // started walks in pop order (device compaction), then a5: the walks that pass the length +
+  // hyperbola filter, in pop order ("candidates")
+  uint64_t n_walks = 0, n_cand = 0;
+  std::vector<uint32_t>& cand_walk = s->h_cand_walk;
+  cand_walk.clear();
+  std::vector<uint64_t> cand_off(1, 0);
+  DevBuf d_cand_walk, d_cand_off, cand_codes;
   if (n_seeds) {
     DevBuf sel, nsel;
     sel.reserve(n_seeds * 4);
     nsel.reserve(8);
-    ProfScope ps(c, "walk_compact", 6);
+    ProfScope ps(c, "walk_compact", 8);
     cub::CountingInputIterator<uint32_t> it(0);
     size_t tb = 0;
     CUDA_CHECK(cub::DeviceSelect::Flagged(nullptr, tb, it, started.as<uint8_t>(), sel.as<uint32_t>(),
@@ -1580,72 +1613,70 @@ void l3_run(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
     s->w_totwt.reserve(nw1 * 8);
     s->w_logstart.reserve(nw1 * 8);
     if (n_walks) {
-      DevBuf is_long, long_idx, l_nl, l_nr, l_tot;
+      DevBuf is_long, shape;
       is_long.reserve(n_walks);
-      long_idx.reserve(n_walks * 4);
+      shape.reserve(n_walks);
+      d_cand_walk.reserve(n_walks * 4);
       gather_walks_kernel<<<shn_grid(n_walks, kBlock), kBlock, 0, st>>>(
           sel.as<uint32_t>(), n_walks, seed_slot.as<uint32_t>(), nl_r.as<uint32_t>(),
           nr_r.as<uint32_t>(), tot_r.as<uint64_t>(), ls_r.as<uint64_t>(), k1, min_length,
           s->w_seed_slot.as<uint32_t>(), s->w_nl.as<uint32_t>(), s->w_nr.as<uint32_t>(),
           s->w_totwt.as<uint64_t>(), s->w_logstart.as<uint64_t>(), is_long.as<uint8_t>());
       KERNEL_CHECK();
-      tb = 0;
-      CUDA_CHECK(cub::DeviceSelect::Flagged(nullptr, tb, it, is_long.as<uint8_t>(), long_idx.as<uint32_t>(),
-                                            nsel.as<uint64_t>(), (int64_t)n_walks, st));
-      CUDA_CHECK(cub::DeviceSelect::Flagged(c->tmp(tb), tb, it, is_long.as<uint8_t>(),
-                                            long_idx.as<uint32_t>(), nsel.as<uint64_t>(),
-                                            (int64_t)n_walks, st));
-      CUDA_CHECK(cudaMemcpyAsync(&n_long, nsel.p, 8, cudaMemcpyDeviceToHost, st));
-      CUDA_CHECK(cudaStreamSynchronize(st));
-      if (n_long) {
-        l_nl.reserve(n_long * 4);
-        l_nr.reserve(n_long * 4);
-        l_tot.reserve(n_long * 8);
-        gather_long_kernel<<<shn_grid(n_long, kBlock), kBlock, 0, st>>>(
-            long_idx.as<uint32_t>(), n_long, s->w_nl.as<uint32_t>(), s->w_nr.as<uint32_t>(),
-            s->w_totwt.as<uint64_t>(), l_nl.as<uint32_t>(), l_nr.as<uint32_t>(), l_tot.as<uint64_t>());
-        KERNEL_CHECK();
-        d2h(c, h_long_idx, long_idx.p, n_long);
-        d2h(c, h_long_nl, l_nl.p, n_long);
-        d2h(c, h_long_nr, l_nr.p, n_long);
-        d2h(c, h_long_tot, l_tot.p, n_long);
+      const char* envs = getenv("SHN_SHAPE_TOL");  // tests: a huge tolerance sends every walk to the host
+      const double shape_tol = envs ? strtod(envs, nullptr) : 1e-9;
+      ctr = zero_counters(c);
+      shape_kernel<<<shn_grid(n_walks, kBlock), kBlock, 0, st>>>(
+          s->w_nl.as<uint32_t>(), s->w_nr.as<uint32_t>(), s->w_totwt.as<uint64_t>(), n_walks, k1,
+          min_weight, min_length, shape_tol, shape.as<uint8_t>(), ctr);
+      KERNEL_CHECK();
+      read_counters(c, h, 1);
+      if (h[0]) {
+        // borderline walks: decided on the host with the reference's expression and libm's pow
+        std::vector<uint8_t> h_shape;
+        std::vector<uint32_t> h_nl, h_nr;
+        std::vector<uint64_t> h_tot;
+        d2h(c, h_shape, shape.p, n_walks);
+        d2h(c, h_nl, s->w_nl.p, n_walks);
+        d2h(c, h_nr, s->w_nr.p, n_walks);
+        d2h(c, h_tot, s->w_totwt.p, n_walks);
+        for (uint64_t w = 0; w < n_walks; ++w)
+          if (h_shape[w] == 2) {
+            const uint64_t tot_kmer = (uint64_t)h_nl[w] + h_nr[w] + 1;
+            h_shape[w] = passes_shape(tot_kmer + k1 - 1, h_tot[w], tot_kmer, min_weight, min_length) ? 1 : 0;
+          }
+        CUDA_CHECK(cudaMemcpyAsync(shape.p, h_shape.data(), n_walks, cudaMemcpyHostToDevice, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
       }
+      tb = 0;
+      CUDA_CHECK(cub::DeviceSelect::Flagged(nullptr, tb, it, shape.as<uint8_t>(), d_cand_walk.as<uint32_t>(),
+                                            nsel.as<uint64_t>(), (int64_t)n_walks, st));
+      CUDA_CHECK(cub::DeviceSelect::Flagged(c->tmp(tb), tb, it, shape.as<uint8_t>(),
+                                            d_cand_walk.as<uint32_t>(), nsel.as<uint64_t>(),
+                                            (int64_t)n_walks, st));
+      CUDA_CHECK(cudaMemcpyAsync(&n_cand, nsel.p, 8, cudaMemcpyDeviceToHost, st));
+      CUDA_CHECK(cudaStreamSynchronize(st));
+      DevBuf cand_len;
+      cand_len.reserve((n_cand + 1) * 8);
+      d_cand_off.reserve((n_cand + 1) * 8);
+      cand_len_kernel<<<shn_grid(n_cand + 1, kBlock), kBlock, 0, st>>>(
+          d_cand_walk.as<uint32_t>(), n_cand, s->w_nl.as<uint32_t>(), s->w_nr.as<uint32_t>(), k1,
+          cand_len.as<uint64_t>());
+      KERNEL_CHECK();
+      exclusive_sum(c, cand_len.as<uint64_t>(), d_cand_off.as<uint64_t>(), n_cand + 1);
+      d2h(c, cand_walk, d_cand_walk.p, n_cand);
+      d2h(c, cand_off, d_cand_off.p, n_cand + 1);
     }
   }
-  s->sz.n_walks = n_walks;
-
-  // ---- a5: length + hyperbola filter (host doubles, same expression as the reference) -------
-  std::vector<uint32_t>& cand_walk = s->h_cand_walk;
-  cand_walk.clear();
-  std::vector<uint64_t> cand_off(1, 0);
-  {
-    // the pow() per walk is evaluated by a few host threads; the order of the candidates is
-    // restored by the serial pass below
-    std::vector<uint8_t> pass(n_long, 0);
-    const unsigned nt = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(8, n_long / 65536));
-    std::vector<std::thread> th;
-    for (unsigned t = 0; t < nt; ++t)
-      th.emplace_back([&, t] {
-        for (uint64_t i = n_long * t / nt, e = n_long * (t + 1) / nt; i < e; ++i) {
-          uint64_t tot_kmer = (uint64_t)h_long_nl[i] + h_long_nr[i] + 1;
-          pass[i] = passes_shape(tot_kmer + k1 - 1, h_long_tot[i], tot_kmer, min_weight, min_length);
-        }
-      });
-    for (auto& x : th) x.join();
-    for (uint64_t i = 0; i < n_long; ++i)
-      if (pass[i]) {
-        uint64_t len = (uint64_t)h_long_nl[i] + h_long_nr[i] + k1;
-        cand_walk.push_back(h_long_idx[i]);
-        cand_off.push_back(cand_off.back() + len);
-      }
+  if (d_cand_walk.p == nullptr) d_cand_walk.reserve(4);
+  if (d_cand_off.p == nullptr) {
+    d_cand_off.reserve(8);
+    CUDA_CHECK(cudaMemsetAsync(d_cand_off.p, 0, 8, st));
   }
-  const uint64_t n_cand = cand_walk.size();
+  s->sz.n_walks = n_walks;
   const uint64_t cand_bases = cand_off.back();
   s->sz.n_candidates = n_cand;
 
-  DevBuf d_cand_walk, d_cand_off, cand_codes;
-  h2d(c, d_cand_walk, cand_walk);
-  h2d(c, d_cand_off, cand_off);
   cand_codes.reserve(std::max<uint64_t>(cand_bases, 1));
   if (cand_bases) {
     ProfScope ps(c, "assemble");
