@@ -11,6 +11,7 @@
 #include <cub/cub.cuh>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <thread>
 
@@ -273,6 +274,13 @@ __global__ void __launch_bounds__(kBlock)
 }
 
 __global__ void __launch_bounds__(kBlock)
+    gather_u64_kernel(const uint64_t* __restrict__ src, const uint32_t* __restrict__ idx, uint64_t n,
+                      uint64_t* __restrict__ dst) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[idx[i]];
+}
+
+__global__ void __launch_bounds__(kBlock)
     comp_work_kernel(const uint32_t* __restrict__ comp_nodes, const uint32_t* __restrict__ comp_seeds,
                      uint32_t n_comps, uint32_t* __restrict__ work, uint32_t* __restrict__ ids,
                      unsigned long long* counters) {
@@ -315,7 +323,7 @@ __global__ void __launch_bounds__(kBlock)
     shape_kernel(const uint32_t* __restrict__ w_nl, const uint32_t* __restrict__ w_nr,
                  const uint64_t* __restrict__ w_tot, uint64_t n_walks, int k1, uint32_t min_weight,
                  uint32_t min_length, double tol_rel, uint8_t* __restrict__ flag,
-                 unsigned long long* counters) {
+                 uint32_t* __restrict__ borderline, unsigned long long* counters) {
   uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= n_walks) return;
   const uint64_t tot_kmer = (uint64_t)w_nl[w] + w_nr[w] + 1;
@@ -329,10 +337,17 @@ __global__ void __launch_bounds__(kBlock)
     if (lhs > rhs + tol) f = 1;
     else if (lhs >= rhs - tol) {
       f = 2;
-      atomicAdd(&counters[0], 1ull);
+      borderline[atomicAdd(&counters[0], 1ull)] = (uint32_t)w;  // at most n_walks entries
     }
   }
   flag[w] = f;
+}
+
+__global__ void __launch_bounds__(kBlock)
+    patch_flags_kernel(const uint32_t* __restrict__ idx, const uint8_t* __restrict__ val, uint64_t n,
+                       uint8_t* __restrict__ flag) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) flag[idx[i]] = val[i];
 }
 
 __global__ void __launch_bounds__(kBlock)
@@ -1235,7 +1250,19 @@ static void l3_state_free(shn_ctx* c) {
   c->l3 = nullptr;
 }
 
+struct HostTrace {  // SHN_HOST_TRACE=1: wall-clock marks of l3_run's host side on stderr
+  bool on = getenv("SHN_HOST_TRACE") != nullptr;
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  void mark(const char* what) {
+    if (!on) return;
+    auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[l3 host] %-28s +%.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  }
+};
+
 void l3_run(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
+  HostTrace ht;
   SHN_CHECK(c->n_buckets > 0, "no K1-mer table built (call shn_table_build first)");
   shn_l3_free(c);
   L3State* s = new L3State();
@@ -1586,6 +1613,7 @@ void l3_run(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
   s->sz.walk_rounds = h[1];
   s->sz.spec_windows = h[3];
 
+  ht.mark("walks done");
   // started walks in pop order (device compaction), then a5: the walks that pass the length +
   // hyperbola filter, in pop order ("candidates")
   uint64_t n_walks = 0, n_cand = 0;
@@ -1612,6 +1640,7 @@ void l3_run(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
     s->w_nr.reserve(nw1 * 4);
     s->w_totwt.reserve(nw1 * 8);
     s->w_logstart.reserve(nw1 * 8);
+    ht.mark("select started");
     if (n_walks) {
       DevBuf is_long, shape;
       is_long.reserve(n_walks);
@@ -1623,31 +1652,50 @@ void l3_run(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
           s->w_seed_slot.as<uint32_t>(), s->w_nl.as<uint32_t>(), s->w_nr.as<uint32_t>(),
           s->w_totwt.as<uint64_t>(), s->w_logstart.as<uint64_t>(), is_long.as<uint8_t>());
       KERNEL_CHECK();
+      ht.mark("gather_walks launched");
       const char* envs = getenv("SHN_SHAPE_TOL");  // tests: a huge tolerance sends every walk to the host
       const double shape_tol = envs ? strtod(envs, nullptr) : 1e-9;
+      DevBuf borderline;
+      borderline.reserve(n_walks * 4);
       ctr = zero_counters(c);
       shape_kernel<<<shn_grid(n_walks, kBlock), kBlock, 0, st>>>(
           s->w_nl.as<uint32_t>(), s->w_nr.as<uint32_t>(), s->w_totwt.as<uint64_t>(), n_walks, k1,
-          min_weight, min_length, shape_tol, shape.as<uint8_t>(), ctr);
+          min_weight, min_length, shape_tol, shape.as<uint8_t>(), borderline.as<uint32_t>(), ctr);
       KERNEL_CHECK();
       read_counters(c, h, 1);
       if (h[0]) {
-        // borderline walks: decided on the host with the reference's expression and libm's pow
-        std::vector<uint8_t> h_shape;
+        // borderline walks (a handful): decided on the host with the reference's expression and
+        // libm's pow, then patched into the flags
+        const uint64_t nb = h[0];
+        DevBuf b_nl, b_nr, b_tot, b_val;
+        b_nl.reserve(nb * 4);
+        b_nr.reserve(nb * 4);
+        b_tot.reserve(nb * 8);
+        b_val.reserve(nb);
+        gather_u32_kernel<<<shn_grid(nb, kBlock), kBlock, 0, st>>>(s->w_nl.as<uint32_t>(),
+                                                                  borderline.as<uint32_t>(), nb, b_nl.as<uint32_t>());
+        gather_u32_kernel<<<shn_grid(nb, kBlock), kBlock, 0, st>>>(s->w_nr.as<uint32_t>(),
+                                                                  borderline.as<uint32_t>(), nb, b_nr.as<uint32_t>());
+        gather_u64_kernel<<<shn_grid(nb, kBlock), kBlock, 0, st>>>(s->w_totwt.as<uint64_t>(),
+                                                                  borderline.as<uint32_t>(), nb, b_tot.as<uint64_t>());
+        KERNEL_CHECK();
         std::vector<uint32_t> h_nl, h_nr;
         std::vector<uint64_t> h_tot;
-        d2h(c, h_shape, shape.p, n_walks);
-        d2h(c, h_nl, s->w_nl.p, n_walks);
-        d2h(c, h_nr, s->w_nr.p, n_walks);
-        d2h(c, h_tot, s->w_totwt.p, n_walks);
-        for (uint64_t w = 0; w < n_walks; ++w)
-          if (h_shape[w] == 2) {
-            const uint64_t tot_kmer = (uint64_t)h_nl[w] + h_nr[w] + 1;
-            h_shape[w] = passes_shape(tot_kmer + k1 - 1, h_tot[w], tot_kmer, min_weight, min_length) ? 1 : 0;
-          }
-        CUDA_CHECK(cudaMemcpyAsync(shape.p, h_shape.data(), n_walks, cudaMemcpyHostToDevice, st));
-        CUDA_CHECK(cudaStreamSynchronize(st));
+        d2h(c, h_nl, b_nl.p, nb);
+        d2h(c, h_nr, b_nr.p, nb);
+        d2h(c, h_tot, b_tot.p, nb);
+        std::vector<uint8_t> h_val(nb);
+        for (uint64_t i = 0; i < nb; ++i) {
+          const uint64_t tot_kmer = (uint64_t)h_nl[i] + h_nr[i] + 1;
+          h_val[i] = passes_shape(tot_kmer + k1 - 1, h_tot[i], tot_kmer, min_weight, min_length) ? 1 : 0;
+        }
+        CUDA_CHECK(cudaMemcpyAsync(b_val.p, h_val.data(), nb, cudaMemcpyHostToDevice, st));
+        patch_flags_kernel<<<shn_grid(nb, kBlock), kBlock, 0, st>>>(borderline.as<uint32_t>(),
+                                                                   b_val.as<uint8_t>(), nb, shape.as<uint8_t>());
+        KERNEL_CHECK();
+        CUDA_CHECK(cudaStreamSynchronize(st));  // h_val goes out of scope
       }
+      ht.mark("shape filter");
       tb = 0;
       CUDA_CHECK(cub::DeviceSelect::Flagged(nullptr, tb, it, shape.as<uint8_t>(), d_cand_walk.as<uint32_t>(),
                                             nsel.as<uint64_t>(), (int64_t)n_walks, st));
@@ -1656,6 +1704,7 @@ void l3_run(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
                                             (int64_t)n_walks, st));
       CUDA_CHECK(cudaMemcpyAsync(&n_cand, nsel.p, 8, cudaMemcpyDeviceToHost, st));
       CUDA_CHECK(cudaStreamSynchronize(st));
+      ht.mark("select candidates");
       DevBuf cand_len;
       cand_len.reserve((n_cand + 1) * 8);
       d_cand_off.reserve((n_cand + 1) * 8);
@@ -1668,6 +1717,7 @@ void l3_run(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
       d2h(c, cand_off, d_cand_off.p, n_cand + 1);
     }
   }
+  ht.mark("cand offsets + d2h");
   if (d_cand_walk.p == nullptr) d_cand_walk.reserve(4);
   if (d_cand_off.p == nullptr) {
     d_cand_off.reserve(8);
@@ -1678,6 +1728,7 @@ void l3_run(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
   s->sz.n_candidates = n_cand;
 
   cand_codes.reserve(std::max<uint64_t>(cand_bases, 1));
+  ht.mark("before assemble");
   if (cand_bases) {
     ProfScope ps(c, "assemble");
     assemble_kernel<<<shn_grid(cand_bases, kBlock), kBlock, 0, st>>>(
