@@ -255,6 +255,17 @@ class Context(HostIO):
         self._pinned.append(p.value)
         return arr
 
+    def pinned_scratch(self, name, n, dtype):
+        """View of a cached page-locked buffer (grown on demand, re-used by the next call with
+        the same name: consume the contents before calling again)."""
+        dtype = np.dtype(dtype)
+        cache = self.__dict__.setdefault("_pinned_cache", {})
+        buf = cache.get(name)
+        need = max(int(n), 1) * dtype.itemsize
+        if buf is None or buf.nbytes < need:
+            buf = cache[name] = self.pinned_empty(need + need // 2, np.uint8)
+        return buf[:int(n) * dtype.itemsize].view(dtype)
+
     def sync(self):
         self.call("shn_sync")
 
@@ -448,9 +459,14 @@ class Context(HostIO):
         self.call("shn_l4_assign", int(bool(paired)), int(k1), C.byref(na), C.byref(nl), C.byref(nv))
         return na.value, nl.value, nv.value
 
-    def l4_assignments(self, n_comps, n_assign):
+    def l4_assignments(self, n_comps, n_assign, pinned=False):
+        """pinned=True: record_idx is a view of a cached page-locked buffer (valid until the next
+        call), which makes the device-to-host copy of large partitions several times faster."""
         offs = np.empty(n_comps + 1, dtype=np.uint64)
-        idx = np.empty(max(n_assign, 1), dtype=np.uint32)
+        if pinned:
+            idx = self.pinned_scratch("l4_assignments", max(n_assign, 1), np.uint32)
+        else:
+            idx = np.empty(max(n_assign, 1), dtype=np.uint32)
         self.call("shn_l4_get_assignments", C.c_uint32(n_comps), ptr(offs), ptr(idx))
         return offs, idx[:n_assign]
 

@@ -1314,6 +1314,7 @@ void l3_run(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
     CUDA_CHECK(cudaStreamSynchronize(st));
   }
 
+  ht.mark("seeds sorted");
   // ---- raw components of the successor graph ------------------------------------------------
   DevBuf parent, root_flag, root_id;
   parent.reserve(n_slots * 4);
@@ -1450,6 +1451,7 @@ void l3_run(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
     n_active = (uint32_t)h[0];
   }
 
+  ht.mark("components + seed groups");
   // ---- a4: greedy walks -----------------------------------------------------------------------
   const uint64_t n_nodes = c->n_distinct;
   s->walk_log.reserve(std::max<uint64_t>(n_nodes, 1));
@@ -1738,6 +1740,7 @@ void l3_run(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
     KERNEL_CHECK();
   }
 
+  ht.mark("assembled candidates");
   // ---- a6: duplicate filter ------------------------------------------------------------------
   std::vector<uint8_t> h_status(n_cand, 1);
   std::vector<uint8_t> h_dup(n_cand, 0);
@@ -1857,6 +1860,7 @@ void l3_run(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
   }
   cand_codes.release();
 
+  ht.mark("duplicate filter + accepted contigs");
   // ---- a7: allowed K1-mers with weights, in contig order ------------------------------------
   uint64_t n_allowed = 0;
   if (n_contigs) {
@@ -1889,6 +1893,7 @@ void l3_run(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
   }
   s->sz.n_allowed = n_allowed;
 
+  ht.mark("allowed set");
   // ---- a8: contig C-mer graph (C = K1-1) --------------------------------------------------------
   const int C = k1 - 1;
   s->labels.reserve((n_contigs + 1) * 4);
@@ -1925,6 +1930,7 @@ void l3_run(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
   }
   s->sz.n_edges = s->edges.n;
 
+  ht.mark("contig graph");
   // ---- a9: components of the contig graph (label = minimum contig index) ----------------------
   if (s->edges.n) {
     ProfScope ps(c, "contig_components", 2);
@@ -1942,6 +1948,7 @@ void l3_run(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
     }
   }
   CUDA_CHECK(cudaStreamSynchronize(st));
+  ht.mark("contig components (end)");
 }
 
 // ---- getters -----------------------------------------------------------------------------------

@@ -262,13 +262,13 @@ def load_reads(ctx, mates, staged=False):
             ctx.l4_load_reads(m, bases, offs, n=n, on_device=on_dev)
 
 
-def partition_reads(ctx, mates, paired, k1, n_comps, staged=False, loaded=False):
+def partition_reads(ctx, mates, paired, k1, n_comps, staged=False, loaded=False, pinned=False):
     """get_comps over all records (kmers_for_component.py:322-423).  mates: list of
     (bases, offsets, n, on_device).  Returns (comp_offsets, record_idx, stats)."""
     if not loaded:
         load_reads(ctx, mates, staged)
     n_assign, n_lookups, n_valid = ctx.l4_assign(paired, k1)
-    comp_offs, rec_idx = ctx.l4_assignments(n_comps, n_assign)
+    comp_offs, rec_idx = ctx.l4_assignments(n_comps, n_assign, pinned=pinned)
     return comp_offs.astype(np.int64), rec_idx, {"assignments": n_assign, "lookups": n_lookups,
                                                   "valid_records": n_valid}
 
@@ -277,7 +277,8 @@ def frontend_in_memory(ctx, keys, counts, k1, mates, paired, min_weight=3, min_l
                        partition_size=500, on_device=False, n_kmers=None):
     """Whole hot path without files: what shannon.py:459+467 compute, for bench.py.  Oversized
     components (more than partition_size contigs) are split into contiguous blocks, the rule of
-    the gpmetis stand-in."""
+    the gpmetis stand-in.  The returned record_idx is a view of a page-locked buffer that the
+    next call re-uses: copy it to keep it."""
     import time
     tm = {}
     loaded = []   # set once the read packing has been queued (under the host-side ordering)
@@ -306,7 +307,8 @@ def frontend_in_memory(ctx, keys, counts, k1, mates, paired, min_weight=3, min_l
     ctx.l4_map_set_weights(None, None)
     tm["map_build"] = time.perf_counter() - t0
     t0 = time.perf_counter()
-    comp_offs, rec_idx, stats = partition_reads(ctx, mates, paired, k1, n_comps, staged=True, loaded=bool(loaded))
+    comp_offs, rec_idx, stats = partition_reads(ctx, mates, paired, k1, n_comps, staged=True, loaded=bool(loaded),
+                                                pinned=True)
     tm["partition_reads"] = time.perf_counter() - t0
     stats["host_timings_ms"] = dict((k, 1000.0 * v) for k, v in tm.items())
     stats.update(cor.sizes)

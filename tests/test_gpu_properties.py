@@ -36,7 +36,7 @@ def run():
             ctx, dk, dc, K1, mates, True, 3, 75, 500, True, nk)
         walks = ctx.l3_walks()
         allowed = ctx.l3_allowed()
-        out.append((cor, comp_offs, rec_idx, stats, walks, allowed))
+        out.append((cor, comp_offs, rec_idx.copy(), stats, walks, allowed))   # rec_idx: view of a re-used pinned buffer
     reads = (ctx.d2h(np.empty((n_rec, L), np.uint8), d1), ctx.d2h(np.empty((n_rec, L), np.uint8), d2))
     keys = ctx.d2h(np.empty(nk, np.uint64), dk)
     counts = ctx.d2h(np.empty(nk, np.uint32), dc)
