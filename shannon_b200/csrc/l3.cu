@@ -1794,7 +1794,7 @@ void l3_run(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
       KERNEL_CHECK();
       CUDA_CHECK(cudaMemcpyAsync(st_b.p, st_a.p, n_cand, cudaMemcpyDeviceToDevice, st));
       // kDupBatch rounds per host round trip; rounds after convergence only copy the statuses
-      constexpr int kDupBatch = 4;
+      constexpr int kDupBatch = 8;
       for (uint64_t r_in_block = 0;; r_in_block += kDupBatch) {
         ctr = zero_counters(c);
         {
