@@ -1380,7 +1380,9 @@ void l3_run(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
   CUDA_CHECK(cudaMemsetAsync(comp_seeds.p, 0, ((uint64_t)n_comps + 1) * 4, st));
   {
     ProfScope ps(c, "comp_count");
-    if (n_comps && (uint64_t)n_comps * 4 <= 40 * 1024) {
+    const char* envh = getenv("SHN_COMP_HIST_MAX_BYTES");  // tests: 0 forces the global-atomics variant
+    const uint64_t hist_max = envh ? strtoull(envh, nullptr, 10) : 40ull * 1024;
+    if (n_comps && (uint64_t)n_comps * 4 <= hist_max) {
       comp_count_smem_kernel<<<c->sm_count * 8, kBlock, (size_t)n_comps * 4, st>>>(
           parent.as<uint32_t>(), root_id.as<uint32_t>(), n_slots, n_comps, comp_nodes.as<uint32_t>());
     } else {

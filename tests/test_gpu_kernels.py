@@ -147,6 +147,8 @@ def test_l3_stages_equal_oracle(ctx, workdir, kind, seed, spec, monkeypatch):
     monkeypatch.setenv("SHN_SPEC_TIER16", "2")   # first two components: 16-warp CTAs, the rest: 8-warp CTAs
     # hyperbola filter: decided on the device, or (borderline walks; here: all) by the host's libm
     monkeypatch.setenv("SHN_SHAPE_TOL", "1e9" if spec else "1e-9")
+    # component sizes: block-private shared-memory histogram, or global atomics (many components)
+    monkeypatch.setenv("SHN_COMP_HIST_MAX_BYTES", "0" if spec else "40960")
     case, min_weight, min_length = _case(workdir, kind, seed)
     out = case.outdir("o")
     res = so.run_correction(case.k1mer_org, out + "/k", min_weight, min_length, False, out, 2,
