@@ -18,7 +18,28 @@ __global__ void __launch_bounds__(kBlock)
   nwords[i] = (len + 31) >> 5;
 }
 
-// 8 lanes per read, one 32-base word per lane and iteration
+// Eight ASCII bases (first base in the lowest byte of w) -> 16 bits, first base most significant;
+// *bad is set if any byte is not one of "ACGT" (upper case only).  SWAR over the 64-bit word:
+// with x = bits 2..1 of a byte, A,C,T,G = 0,1,2,3 and the code (A0 G1 C2 T3) is
+// hi = bit1 ^ bit2, lo = bit2; the byte is valid iff it equals 'A' + 6*lo + 2*hi + 11*(hi&lo).
+__device__ __forceinline__ uint64_t pack8(uint64_t w, bool* bad) {
+  const uint64_t ones = 0x0101010101010101ull;
+  const uint64_t b1 = (w >> 1) & ones, b2 = (w >> 2) & ones;
+  const uint64_t hi = b1 ^ b2, lo = b2;
+  const uint64_t expect = 0x4141414141414141ull + 6ull * lo + 2ull * hi + 11ull * (hi & lo);
+  *bad |= expect != w;
+  uint64_t c = (hi << 1) | lo;
+  // byte 0 (first base) to the top, then squeeze the eight 2-bit codes together
+  c = ((uint64_t)__byte_perm((uint32_t)c, 0, 0x0123) << 32) | (uint64_t)__byte_perm((uint32_t)(c >> 32), 0, 0x0123);
+  c = (c | (c >> 6)) & 0x000F000F000F000Full;
+  c = (c | (c >> 12)) & 0x000000FF000000FFull;
+  c = (c | (c >> 24)) & 0xFFFFull;
+  return c;
+}
+
+// 8 lanes per read, one 32-base word per lane and iteration.  The 32 bytes of a word are fetched
+// with five aligned 8-byte loads and funnel shifts (reads start at arbitrary byte offsets); the
+// aligned loads never leave the allocation (256-byte granular), bytes past the read count as 'A'.
 __global__ void __launch_bounds__(kBlock)
     pack_reads_kernel(const char* __restrict__ bases, const uint64_t* __restrict__ offs,
                       const uint64_t* __restrict__ woff, uint64_t n, uint64_t* __restrict__ words,
@@ -36,15 +57,22 @@ __global__ void __launch_bounds__(kBlock)
   uint64_t nw = (len + 31) >> 5;
   bool bad = false;
   for (uint64_t w = lane8; w < nw; w += 8) {
+    const int cnt = (int)min((uint64_t)32, len - 32 * w);
+    const uint64_t addr = (uint64_t)(uintptr_t)bases + start + 32 * w;
+    const uint64_t* q = reinterpret_cast<const uint64_t*>(addr & ~7ull);
+    const int off = (int)(addr & 7);
+    uint64_t v[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) v[k] = (8 * k < off + cnt) ? __ldg(q + k) : 0ull;
     uint64_t x = 0;
-    uint64_t p = start + 32 * w;
-    int cnt = (int)min((uint64_t)32, len - 32 * w);
-    for (int j = 0; j < cnt; ++j) {
-      uint32_t code = shn_code_of_strict((uint8_t)__ldg(&bases[p + j]));
-      bad |= code >= 4;
-      x = (x << 2) | (code & 3u);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      uint64_t g = off ? ((v[k] >> (8 * off)) | (v[k + 1] << (64 - 8 * off))) : v[k];
+      const int nb = min(max(cnt - 8 * k, 0), 8);
+      const uint64_t m = nb == 8 ? ~0ull : ((1ull << (8 * nb)) - 1ull);
+      g = (g & m) | (0x4141414141414141ull & ~m);  // past the end: 'A' = code 0 = left-aligned word
+      x = (x << 16) | pack8(g, &bad);
     }
-    x <<= 2 * (32 - cnt);  // left-align a partial last word
     words[wbase + w] = x;
   }
   // OR the bad flags of the 8 lanes of this read
@@ -120,7 +148,8 @@ void shn_reads_load(shn_ctx* c, int mate, const char* bases, const uint64_t* off
         d_bases, d_offs, pr.woff.as<uint64_t>(), n, pr.words.as<uint64_t>(), pr.len.as<uint32_t>());
     KERNEL_CHECK();
   }
-  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  // no synchronisation here: the copies of the inputs completed before the size round trip above,
+  // and the packing itself runs under whatever the host does next
 }
 
 // Starts the host->device copy of one mate file on the context's second stream and returns
