@@ -1522,6 +1522,19 @@ void l3_run(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
         if (!c->stream3) CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking));
         CUDA_CHECK(cudaStreamWaitEvent(c->stream3, ev_fork, 0));
       }
+      bool serial_launched = false;
+      auto launch_serial = [&]() {
+        if (serial_launched || n_spec >= n_active) return;
+        serial_launched = true;
+        WalkArgs b = a;
+        b.comp_order = a.comp_order + n_spec;
+        b.n_comps = n_active - n_spec;
+        if (b.trace) b.trace += 3 * (uint64_t)n_spec;
+        walk_kernel<<<shn_grid((uint64_t)b.n_comps * 32, kWalkBlock), kWalkBlock, 0, c->stream3>>>(b);
+        KERNEL_CHECK();
+        CUDA_CHECK(cudaEventRecord(ev_join, c->stream3));
+        CUDA_CHECK(cudaStreamWaitEvent(st, ev_join, 0));
+      };
       if (n_spec) {
         SpecArgs sa;
         sa.w = a;
@@ -1541,6 +1554,9 @@ void l3_run(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
           walk_spec_kernel<16><<<n16, 16 * 32, 0, st>>>(t);
           KERNEL_CHECK();
         }
+        // Launch order = block scheduling order: the 16-warp CTAs and the one-warp components hold
+        // the long serial chains and must start at once; the short 8-warp CTAs fill what is left.
+        if (!getenv("SHN_WALK_SERIAL_LAST")) launch_serial();
         if (n_spec > n16) {  // second tier on its own stream: all three kernels share the GPU
           if (!c->stream4) CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream4, cudaStreamNonBlocking));
           CUDA_CHECK(cudaStreamWaitEvent(c->stream4, ev_fork, 0));
@@ -1555,16 +1571,7 @@ void l3_run(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
           CUDA_CHECK(cudaStreamWaitEvent(st, ev_join3, 0));
         }
       }
-      if (n_spec < n_active) {
-        WalkArgs b = a;
-        b.comp_order = a.comp_order + n_spec;
-        b.n_comps = n_active - n_spec;
-        if (b.trace) b.trace += 3 * (uint64_t)n_spec;
-        walk_kernel<<<shn_grid((uint64_t)b.n_comps * 32, kWalkBlock), kWalkBlock, 0, c->stream3>>>(b);
-        KERNEL_CHECK();
-        CUDA_CHECK(cudaEventRecord(ev_join, c->stream3));
-        CUDA_CHECK(cudaStreamWaitEvent(st, ev_join, 0));
-      }
+      launch_serial();
     }
     CUDA_CHECK(cudaStreamSynchronize(st));
     c->prof_pool.push_back(ev_fork);
