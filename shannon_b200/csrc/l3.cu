@@ -1506,7 +1506,7 @@ void l3_run(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
       const char* envb = getenv("SHN_SPEC_SCRATCH_GB");
       const uint64_t budget = (envb ? strtoull(envb, nullptr, 10) : 32ull) << 30;  // scratch for the paths
       const char* envc = getenv("SHN_SPEC_MAX_COMPS");
-      const uint32_t max_spec = envc ? (uint32_t)strtoul(envc, nullptr, 10) : 3u * (uint32_t)c->sm_count;
+      const uint32_t max_spec = envc ? (uint32_t)strtoul(envc, nullptr, 10) : 4u * (uint32_t)c->sm_count;
       while (n_spec < peek && n_spec < max_spec && top[n_spec] >= min_nodes &&
              (h_path_off.back() + (uint64_t)kSpecWindow * top[n_spec]) * 5 <= budget) {
         h_path_off.push_back(h_path_off.back() + (uint64_t)kSpecWindow * top[n_spec]);
