@@ -165,8 +165,19 @@ __device__ __forceinline__ uint64_t table_upsert_slot(const ShnTableView& t, shn
 __device__ __forceinline__ uint64_t table_insert_add(const ShnTableView& t, shn_key_t key, uint32_t w,
                                                      uint32_t idx, int* is_new, uint32_t* old_w) {
 #ifdef SHN_WIDE
+  // 128-bit keys: the key is claimed with a 128-bit CAS; a freshly claimed slot then gets its
+  // {weight, idx} pair with ONE 64-bit CAS against the pristine {0, 0xFFFFFFFF} (it fails only if a
+  // duplicate line or an overflow marker got there first: then add/min as for a present key)
+  const int before = *is_new;
   uint64_t slot = table_upsert_slot(t, key, is_new);
   if (slot == ~0ull) return slot;
+  if (*is_new != before) {
+    unsigned long long* wi = reinterpret_cast<unsigned long long*>(&t.slots[slot].weight);
+    if (atomicCAS(wi, 0xFFFFFFFF00000000ull, ((unsigned long long)idx << 32) | w) == 0xFFFFFFFF00000000ull) {
+      *old_w = 0;
+      return slot;
+    }
+  }
   *old_w = atomicAdd(&t.slots[slot].weight, w) & SHN_WEIGHT_MASK;
   atomicMin(&t.slots[slot].idx, idx);
   return slot;
