@@ -3,6 +3,7 @@ symbol the header declares, the native host IO, the host-side contig ordering (a
 DFS) and the closed forms the kernels implement, all against the oracle.  No GPU compute."""
 import os
 import re
+import sys
 
 import numpy as np
 import pytest
@@ -246,3 +247,19 @@ def test_synth_generator_is_deterministic_and_strand_consistent():
     assert np.array_equal(a[0][30:], b[0]) and np.array_equal(a[1][30:], b[1])
     r1, r2 = synth.rc_double(a[0], a[1])
     assert r1.shape == (100, 100) and bytes(r2[0]).decode() == helpers.rc_str(bytes(a[0][0]).decode())
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """bench.py --impl reference runs on the host cores without a GPU and prints one JSON line with
+    the keys the driver reads."""
+    import json
+    import subprocess
+    out = subprocess.run([sys.executable, os.path.join(helpers.ROOT, "bench.py"), "--impl", "reference",
+                          "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "reads_partitioned_per_sec"
+    assert line["value"] > 0 and line["higher_is_better"] is True and line["n_gpus"] == 1
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] == 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert line["e2e"]["value"] == line["value"] and "workload" in line["config"]
