@@ -129,7 +129,10 @@ int shn_table_dump(shn_ctx* ctx, uint64_t* keys, uint32_t* weights, uint32_t* fi
 
 /* ---- a3-a9: seeds, greedy walks, shape filter, duplicate filter, contig graph ------------ */
 /* run_correction's seed loop and accept logic (extension_correction.py:334-397) on the table
- * built by shn_table_build.  After it returns, the getters below are valid. */
+ * built by shn_table_build.  After it returns, the getters below are valid.  The table itself is
+ * left exactly as it was (keys and weights are never written; the first-occurrence words are
+ * borrowed by the walks and restored before the call returns, also when it fails), so lookups,
+ * shn_table_dump and further shn_l3_run calls see the same table. */
 int shn_l3_run(shn_ctx* ctx, uint32_t min_weight, uint32_t min_length);
 typedef struct shn_l3_sizes {
   uint64_t n_seeds;        /* K1-mers with weight >= min_weight */
