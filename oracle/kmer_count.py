@@ -31,6 +31,49 @@ def count_k1mers(fasta_paths, k1):
     return counts
 
 
+def count_k1mers_numpy(fasta_paths, k1):
+    """Same result as count_k1mers (checked in tests/test_cpu_host_logic.py), vectorised with numpy
+    for the large fixtures (k1 <= 32): returns (kmers as an (n, k1) uint8 ASCII matrix in ascending
+    ASCII order, counts)."""
+    import numpy as np
+    assert k1 <= 32
+    code = np.full(256, 4, dtype=np.uint8)
+    for i, ch in enumerate(b"ACGT"):          # ASCII order = integer order of the packed word
+        code[ch] = i
+    by_len = {}
+    for path in fasta_paths:
+        with open(path, "rb") as f:
+            for line in f:
+                if line.startswith(b">"):
+                    continue
+                s = line.strip()
+                if len(s) >= k1:
+                    by_len.setdefault(len(s), []).append(s)
+    chunks = []
+    for L, seqs in by_len.items():
+        a = code[np.frombuffer(b"".join(seqs), dtype=np.uint8).reshape(len(seqs), L)]
+        nw = L - k1 + 1
+        key = np.zeros((len(seqs), nw), dtype=np.uint64)
+        bad = np.zeros((len(seqs), nw), dtype=bool)
+        for j in range(k1):
+            col = a[:, j:j + nw]
+            bad |= col > 3
+            key = (key << np.uint64(2)) | (col & 3).astype(np.uint64)
+        chunks.append(key[~bad])
+    allk = np.concatenate(chunks) if chunks else np.empty(0, dtype=np.uint64)
+    keys, counts = np.unique(allk, return_counts=True)
+    shifts = (2 * (k1 - 1 - np.arange(k1))).astype(np.uint64)
+    mat = np.frombuffer(b"ACGT", dtype=np.uint8)[((keys[:, None] >> shifts[None, :]) & np.uint64(3)).astype(np.uint8)]
+    return mat, counts
+
+
+def write_dict_numpy(mat, counts, out_path):
+    k1 = mat.shape[1] if len(mat) else 0
+    txt = mat.tobytes().decode()
+    with open(out_path, "w") as f:
+        f.write("".join("%s\t%d\n" % (txt[i * k1:(i + 1) * k1], c) for i, c in enumerate(counts.tolist())))
+
+
 def write_dict(counts, out_path, min_count=1):
     with open(out_path, "w") as f:
         for km in sorted(counts):

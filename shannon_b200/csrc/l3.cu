@@ -673,7 +673,7 @@ __global__ void __launch_bounds__(kSpecWarps * 32, kSpecCtasPerSM * 16 / kSpecWa
 
   __shared__ uint64_t sh_cursor, sh_cursor_after, sh_lp;
   __shared__ uint32_t sh_win_pos[kSpecWindow], sh_win_slot[kSpecWindow], sh_len[kSpecWindow];
-  __shared__ uint32_t sh_nr[kSpecWindow], sh_nl[kSpecWindow], sh_intact[kSpecWindow];
+  __shared__ uint32_t sh_nr[kSpecWindow], sh_nl[kSpecWindow], sh_intact[kSpecWindow], sh_poison[kSpecWindow];
   __shared__ unsigned long long sh_tot[kSpecWindow];
   __shared__ unsigned long long sh_block[kSpecWindow];  // window positions whose stamps blocked this walk
   __shared__ uint32_t sh_thief[kSpecWindow];            // position holding this walk's seed (or none)
@@ -834,7 +834,10 @@ __global__ void __launch_bounds__(kSpecWarps * 32, kSpecCtasPerSM * 16 / kSpecWa
             m = max(score, __shfl_xor_sync(FULL, score, 1));
             m = max(m, __shfl_xor_sync(FULL, m, 2));
             const uint32_t s2 = __shfl_sync(FULL, m, g2);
-            if (s2 == 0) break;  // the walk ends at c1 in this direction
+            if (s2 == 0) {  // the walk ends at c1 in this direction
+              __syncwarp();  // the claim on c1 is ordered before the first probes of the other direction
+              break;
+            }
             const int w2 = 3 - (int)((s2 - 1u) & 3u);
             const uint32_t bw2 = (s2 - 1u) >> 2;
             if (lane == g2 + w2) pend2 = atomicMax(&tv.slots[cslot].idx, (caux & ~kAuxStampMask) | stamp);
@@ -852,6 +855,12 @@ __global__ void __launch_bounds__(kSpecWarps * 32, kSpecCtasPerSM * 16 / kSpecWa
             __syncwarp();
           }
         }
+        // claims still pending when the walk ended, and walks abandoned after a lost claim: never
+        // committed from this window, whatever the stamps on the path say
+        poisoned |= __any_sync(FULL, (pend1 & kAuxStampMask) >= stamp || (pend2 & kAuxStampMask) >= stamp) != 0;
+        if (lane == 0) sh_poison[ws] = poisoned ? 1u : 0u;
+      } else if (lane == 0) {
+        sh_poison[ws] = 0u;
       }
       const unsigned blo = __reduce_or_sync(FULL, (unsigned)bl);
       const unsigned bhi = __reduce_or_sync(FULL, (unsigned)(bl >> 32));
@@ -874,7 +883,7 @@ __global__ void __launch_bounds__(kSpecWarps * 32, kSpecCtasPerSM * 16 / kSpecWa
         mine &= (__ldcg(&tv.slots[ps[e]].idx) & kAuxStampMask) == stamp;
       mine = __all_sync(FULL, mine);
       if (lane == 0) {
-        sh_intact[ws] = (mine && len) ? 1u : 0u;
+        sh_intact[ws] = (mine && len && !sh_poison[ws]) ? 1u : 0u;
         const uint32_t sst = __ldcg(&tv.slots[sh_win_slot[ws]].idx) & kAuxStampMask;
         sh_thief[ws] = (sst > stamp && sst <= (uint32_t)kSpecWindow) ? (uint32_t)kSpecWindow - sst : 0xFFFFFFFFu;
       }

@@ -134,12 +134,13 @@ __device__ __forceinline__ uint64_t map_find(const CompMapView& m, shn_key_t key
 }
 
 // counters: [0]=new keys [1]=non-ACGT windows [2]=more than two components for a K1-mer
+// [3]=windows equal to the free-slot marker (poly-T of 32 / 64 bases)
 __global__ void __launch_bounds__(kBlock)
     map_add_kernel(CompMapView m, const char* __restrict__ bases, const uint64_t* __restrict__ offs,
                    const uint32_t* __restrict__ comp_of, uint64_t n_contigs, uint64_t total_bases,
                    int k1, int is_codes, unsigned long long* counters) {
   uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  int n_new = 0, n_bad = 0, n_over = 0;
+  int n_new = 0, n_bad = 0, n_over = 0, n_empty = 0;
   if (g < total_bases) {
     uint64_t c = find_segment(offs, n_contigs, g);
     uint64_t end = __ldg(&offs[c + 1]);
@@ -154,6 +155,8 @@ __global__ void __launch_bounds__(kBlock)
       }
       if (!okw) {
         n_bad = 1;
+      } else if (key == SHN_EMPTY) {
+        n_empty = 1;  // the all-T K1-mer of 32 (64) bases is the table's free-slot marker
       } else {
         uint64_t b = m.bucket_of(key);
         CompSlot* slot = nullptr;
@@ -191,11 +194,12 @@ __global__ void __launch_bounds__(kBlock)
     }
   }
   int t_new = __syncthreads_count(n_new), t_bad = __syncthreads_count(n_bad),
-      t_over = __syncthreads_count(n_over);
+      t_over = __syncthreads_count(n_over), t_empty = __syncthreads_count(n_empty);
   if (threadIdx.x == 0) {
     if (t_new) atomicAdd(&counters[0], (unsigned long long)t_new);
     if (t_bad) atomicAdd(&counters[1], (unsigned long long)t_bad);
     if (t_over) atomicAdd(&counters[2], (unsigned long long)t_over);
+    if (t_empty) atomicAdd(&counters[3], (unsigned long long)t_empty);
   }
 }
 
@@ -453,10 +457,12 @@ void l4_map_add_contigs(shn_ctx* c, const char* bases, const uint64_t* offsets,
         map_view(s), d_bases, d_offs, d_comp, n_contigs, total, k1, is_codes, ctr);
     KERNEL_CHECK();
   }
-  unsigned long long h[3];
-  read_counters(c, h, 3);
+  unsigned long long h[4];
+  read_counters(c, h, 4);
   SHN_CHECK(h[1] == 0, "contig contains a character outside ACGT");
   SHN_CHECK(h[2] == 0, "a K1-mer belongs to more than two components (unsupported)");
+  SHN_CHECK(h[3] == 0, "a contig holds the poly-T K1-mer of 32 (64) bases, which the component map cannot store "
+                       "(low-complexity: never produced by extension_correction)");
   s->n_keys += h[0];
 }
 

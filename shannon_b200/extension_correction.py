@@ -110,38 +110,23 @@ def run_correction(infile, outfile, min_weight, min_length, double_stranded,
     f_log.write(str(time.asctime()) + ": " + "After dfs " + "\n")
     f_log.write(str(time.asctime()) + ": " + "After Edges Loaded " + "\n")
 
+    # file packing of :458-513 (singles / METIS graphs of oversized components / remaining files)
     d = comp_directory_name
-    new_comp_num = 1
-    remaining_file_curr_size = 0
-    remaining_file_num = 1
-    single_contig_index = 0
-    single_contigs = open(d + "/reconstructed_single_contigs.fasta", 'w')
-    non_comp_contigs = open(d + "/remaining_contigs" + str(remaining_file_num) + ".txt", 'w')
-    for component, members in component2contig.items():
-        if len(members) == 1:
-            single_contigs.write('>Single_' + str(single_contig_index) + '\n' + contigs[members[0]] + '\n')
-            single_contig_index += 1
-            continue
-        if len(members) > comp_size_threshold:
-            code = dict((c, i + 1) for i, c in enumerate(members))
-            with open(d + "/component" + str(new_comp_num) + ".txt", 'w') as f:
-                f.write(str(len(members)) + "\t" + str(n_edges[component]) + "\t" + "001" + "\n")
-                for c in members:
-                    f.write("".join(str(code[nb]) + "\t" + str(wt) + "\t"
-                                    for nb, wt in cor.neighbours(c)) + "\n")
-            with open(d + "/component" + str(new_comp_num) + "contigs" + ".txt", 'w') as f:
-                f.write("".join(contigs[c] + "\n" for c in members))
-            new_comp_num += 1
-        else:
-            non_comp_contigs.write("".join(contigs[c] + "\n" for c in members))
-            remaining_file_curr_size += len(members)
-            if remaining_file_curr_size > comp_size_threshold:
-                remaining_file_num += 1
-                non_comp_contigs.close()
-                non_comp_contigs = open(d + "/remaining_contigs" + str(remaining_file_num) + ".txt", 'w')
-                remaining_file_curr_size = 0
-    single_contigs.close()
-    non_comp_contigs.close()
+    pk = pack_components(cor, comp_size_threshold)
+    with open(d + "/reconstructed_single_contigs.fasta", 'w') as f:
+        f.write("".join('>Single_' + str(j) + '\n' + contigs[c] + '\n' for j, c in enumerate(pk.singles)))
+    for n, (component, members) in enumerate(pk.big):
+        code = dict((c, i + 1) for i, c in enumerate(members))
+        with open(d + "/component" + str(n + 1) + ".txt", 'w') as f:
+            f.write(str(len(members)) + "\t" + str(n_edges[component]) + "\t" + "001" + "\n")
+            for c in members:
+                f.write("".join(str(code[nb]) + "\t" + str(wt) + "\t"
+                                for nb, wt in cor.neighbours(c)) + "\n")
+        with open(d + "/component" + str(n + 1) + "contigs" + ".txt", 'w') as f:
+            f.write("".join(contigs[c] + "\n" for c in members))
+    for m, group in enumerate(pk.remaining):
+        with open(d + "/remaining_contigs" + str(m + 1) + ".txt", 'w') as f:
+            f.write("".join(contigs[c] + "\n" for c in group))
     f_log.write(str(time.asctime()) + ": " + "Metis Input File Created " + "\n")
     f_log.write("{:s}: Read-loader in background process joinig back.".format(time.asctime()) + "\n")
     reads = []

@@ -63,6 +63,10 @@ def degenerate_reads(kind):
 CASES = {
     # BASELINE.json config 1 (bundled single-end sample; FASTA twin of the fastq, no Quorum)
     "sample_se": {"K": 24, "input": ("sample_se",), "run": {}},
+    # BASELINE.json config 1 as literally written: the sequence lines of Samples/SE_reads.fastq
+    # (= PE_read_1.fastq ++ PE_read_2.fastq, 5 000 x 100 bp, many N; checked by make_golden.py
+    # against the fastq itself) in single-end mode, no Quorum (absent: SURVEY 8c)
+    "sample_se_fastq": {"K": 24, "input": ("sample_se_fastq",), "run": {}},
     # BASELINE.json config 2 (bundled paired-end sample, double-stranded RC doubling)
     "sample_pe": {"K": 24, "input": ("sample_pe",), "run": {}},
     "synth_pe_default": {"K": 24, "input": ("synth", 12, 1500, 1), "run": {}},
@@ -78,6 +82,10 @@ CASES = {
     "synth_pe_k32": {"K": 32, "input": ("synth", 12, 1500, 13), "run": {}},
     "synth_se_k32_inmem": {"K": 32, "input": ("synth_se", 10, 1500, 19),
                            "run": {"inMem": True, "partition_size": 1, "min_length": 60}},
+    # raw K1-mer components of 10^5..10^6 nodes: the default speculative walk tiers (>= 60 000
+    # nodes) fire without any environment override.  Stored as digests (sha256 per output).
+    "synth_pe_big": {"K": 24, "input": ("synth", 10, 80000, 23), "run": {}, "digest": True,
+                     "fast_count": True},
     "repeat_rich_k32": {"K": 32, "input": ("repeat", 9, 500, 60, 220, 4),
                         "run": {"min_weight": 2, "min_length": 40, "partition_size": 2}},
 }
@@ -95,6 +103,8 @@ def case_inputs(spec):
     kind = spec["input"][0]
     if kind == "sample_se":
         return sample_seqs("SE_read"), None
+    if kind == "sample_se_fastq":
+        return sample_seqs("PE_read_1") + sample_seqs("PE_read_2"), None
     if kind == "sample_pe":
         return sample_seqs("PE_read_1"), sample_seqs("PE_read_2")
     if kind == "synth":
@@ -108,6 +118,18 @@ def case_inputs(spec):
     if kind == "degenerate":
         return degenerate_reads(spec["input"][1]), None
     raise ValueError(kind)
+
+
+def digest(data):
+    import hashlib
+    if isinstance(data, str):
+        data = data.encode()
+    return hashlib.sha256(data).hexdigest()
+
+
+def digest_allowed(allowed):
+    """sha256 over the sorted `KMER\tweight` lines of an allowed_kmer_dict."""
+    return digest("".join("%s\t%d\n" % kv for kv in sorted(allowed.items())))
 
 
 def load_golden(name):

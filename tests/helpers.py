@@ -48,8 +48,9 @@ class Case(object):
         return d
 
 
-def make_case(workdir, K, seqs1, seqs2=None, double_stranded=True):
-    """RC-double the reads like shannon.py:395-424 and count (K+1)-mers with the stand-in."""
+def make_case(workdir, K, seqs1, seqs2=None, double_stranded=True, fast_count=False):
+    """RC-double the reads like shannon.py:395-424 and count (K+1)-mers with the stand-in
+    (fast_count: its numpy twin, for the large fixtures)."""
     case = Case(workdir, K, seqs2 is not None)
     if seqs2 is None:
         reads = seqs1 + [rc_str(s) for s in seqs1] if double_stranded else list(seqs1)
@@ -67,7 +68,10 @@ def make_case(workdir, K, seqs1, seqs2=None, double_stranded=True):
         write_reads(p1, r1)
         write_reads(p2, r2)
         case.reads_files = [p1, p2]
-    kmer_count.write_dict(kmer_count.count_k1mers(case.reads_files, K + 1), case.k1mer_org)
+    if fast_count:
+        kmer_count.write_dict_numpy(*kmer_count.count_k1mers_numpy(case.reads_files, K + 1), case.k1mer_org)
+    else:
+        kmer_count.write_dict(kmer_count.count_k1mers(case.reads_files, K + 1), case.k1mer_org)
     return case
 
 
@@ -161,11 +165,28 @@ def check_against_golden(ec_fn, kfc_fn, name, workdir, label):
     spec = cases.CASES[name]
     gold = cases.load_golden(name)
     seqs1, seqs2 = cases.case_inputs(spec)
-    case = make_case(workdir, spec["K"], seqs1, seqs2, double_stranded=spec.get("rc_double", True))
+    case = make_case(workdir, spec["K"], seqs1, seqs2, double_stranded=spec.get("rc_double", True),
+                     fast_count=spec.get("fast_count", False))
     with open(case.k1mer_org, "rb") as f:
         assert hashlib.sha256(f.read()).hexdigest() == gold["k1mer_dict_org_sha256"], \
             "input k1mer.dict_org differs from the one the golden was generated from"
     out, allowed, reads, ret = run_frontend(ec_fn, kfc_fn, case, "run", **spec["run"])
+    if gold.get("digest"):      # large fixture: sha256 of every output
+        assert len(allowed) == gold["n_allowed"], label + ": allowed_kmer_dict size differs from golden"
+        assert cases.digest_allowed(dict(allowed)) == gold["allowed_sha256"], label + ": allowed_kmer_dict"
+        assert list(reads) == []
+        snap = snapshot(out)
+        assert sorted(snap) == sorted(gold["files_sha256"]), label + ": file set differs"
+        for k, v in snap.items():
+            if k.endswith("algo_input/k1mer.dict"):
+                v = b"".join(sorted(v.splitlines(True)))
+            assert cases.digest(v) == gold["files_sha256"][k], label + ": file %s differs from golden" % k
+        cb, new_comps, cw, rps = normalise_ret(ret)
+        got = {"components_broken": dict((str(k), v) for k, v in cb.items()),
+               "new_comps": new_comps, "contig_weights": cw, "rps": rps}
+        assert cases.digest(json.dumps(json.loads(json.dumps(got)), sort_keys=True)) == gold["ret_sha256"], \
+            label + ": return value differs from golden"
+        return case, out
     assert allowed == gold["allowed_kmer_dict"], label + ": allowed_kmer_dict differs from golden"
     assert list(reads) == []
     snap = snapshot(out)
