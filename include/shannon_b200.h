@@ -52,7 +52,12 @@ int shn_host_alloc_pinned(shn_ctx* ctx, uint64_t bytes, void** hptr);
 int shn_host_free_pinned(shn_ctx* ctx, void* hptr);
 int shn_memcpy_h2d(shn_ctx* ctx, void* dst_dev, const void* src_host, uint64_t bytes);
 int shn_memcpy_d2h(shn_ctx* ctx, void* dst_host, const void* src_dev, uint64_t bytes);
+int shn_memcpy_d2d(shn_ctx* ctx, void* dst_dev, const void* src_dev, uint64_t bytes); /* asynchronous */
 int shn_sync(shn_ctx* ctx);
+/* Issue all further work of ctx on the caller's CUDA stream (cudaStream_t; NULL = back to the
+ * context's own stream).  The sharded path runs the library and torch.distributed's NCCL calls on
+ * one stream, so no host synchronisation separates kernels from collectives. */
+int shn_use_stream(shn_ctx* ctx, void* cuda_stream);
 /* CUDA-event stopwatch on the ctx stream (the stream every kernel of this library runs on). */
 int shn_timer_start(shn_ctx* ctx);
 int shn_timer_stop(shn_ctx* ctx, float* elapsed_ms);
@@ -150,6 +155,27 @@ typedef struct shn_l3_sizes {
   uint64_t spec_windows;   /* windows those components needed */
 } shn_l3_sizes;
 int shn_l3_get_sizes(shn_ctx* ctx, shn_l3_sizes* out);
+/* The same in two phases, for the sharded path:
+ *   shn_l3_walks  = seeds, raw K1-mer components, greedy walks, length + hyperbola terms, candidate
+ *                   contigs (extension_correction.py:334-356) -- needs only this context's table,
+ *                   which must hold COMPLETE components of the K1-mer successor graph;
+ *   shn_l3_filter = duplicate_check in acceptance order, allowed set, contig C-mer graph and its
+ *                   components (:358-450) on this context's own candidates (external == 0) or on
+ *                   candidates merged from all ranks in global pop order (external != 0: device
+ *                   pointers, one base code per byte, n_cand+1 offsets).  allow_missing != 0:
+ *                   allowed K1-mers absent from this context's table get weight 0 (their owner rank
+ *                   supplies it: shn_l3_allowed_copy / all-reduce / shn_l3_set_allowed_weights).
+ * shn_l3_run == shn_l3_walks + shn_l3_filter(NULL, NULL, 0, 0, 0). */
+int shn_l3_walks(shn_ctx* ctx, uint32_t min_weight, uint32_t min_length);
+int shn_l3_cand_sizes(shn_ctx* ctx, uint64_t* n_candidates, uint64_t* n_bases);
+/* candidates of shn_l3_walks in pop order: weight and first-occurrence index of the seed (the pop
+ * order key: weight descending, index descending), offsets, base codes.  Device pointers. */
+int shn_l3_cand_export(shn_ctx* ctx, uint32_t* seed_weight_dev, uint32_t* seed_first_idx_dev,
+                       uint64_t* offsets_dev, uint8_t* codes_dev);
+int shn_l3_filter(shn_ctx* ctx, const uint8_t* codes_dev, const uint64_t* offsets_dev, uint64_t n_cand,
+                  int external, int allow_missing);
+int shn_l3_allowed_copy(shn_ctx* ctx, uint64_t* keys_dev, uint32_t* weights_dev);
+int shn_l3_set_allowed_weights(shn_ctx* ctx, const uint32_t* weights_dev);
 /* Per started walk, in pop order: seed key, steps to the left/right, sum of weights, and flags
  * bit0 = passes length+hyperbola, bit1 = duplicate_check() true (only evaluated when bit0),
  * bit2 = accepted. */
@@ -209,6 +235,44 @@ int shn_l4_assign(shn_ctx* ctx, int paired, int k1, uint64_t* n_assignments, uin
 /* comp_offsets: n_comps+1 prefix offsets into record_idx (record indices ascending per comp). */
 int shn_l4_get_assignments(shn_ctx* ctx, uint32_t n_comps, uint64_t* comp_offsets,
                            uint32_t* record_idx);
+
+/* ---- e: the path on hash-sharded tables, one shard per rank (shannon_b200/dist.py drives the
+ * exchanges with torch.distributed all_to_all_single on the same stream) -------------------------
+ * Records on the wire have the size of a table slot (16 bytes for k1 <= 32, 32 bytes for k1 = 33):
+ * {key (1 or 2 words), payload u64 [, pad u64]}.  Lines and table entries carry payload =
+ * global input line << 30 | weight, successor queries the asking component.  owner(K1-mer) = hash
+ * of its minimizer (the 11-mer with the smallest hash), so most successor edges are rank-local.
+ * Every routing call is made twice: with send_dev == NULL it writes the number of records per
+ * destination rank to counts_host; with a send buffer of sum(counts) records it reads counts_host
+ * back and fills the buffer contiguously per destination (order inside a destination is free: the
+ * records carry their global line).  All pointers are device pointers unless named *_host. */
+/* load_kmers' lines (extension_correction.py:209-219) of this rank's slice of k1mer.dict_org:
+ * line i is global line first_line + i; double_stranded emits the reverse complement as line 2i+1. */
+int shn_route_lines(shn_ctx* ctx, const uint64_t* keys_dev, const uint32_t* counts_dev, uint64_t n,
+                    uint64_t first_line, int double_stranded, int k1, uint32_t nranks,
+                    uint64_t* counts_host, void* send_dev);
+/* shn_table_build from received records: first-occurrence index = rank of the record's global line
+ * among the received ones (order-preserving); gline_sorted_dev[i] = global line of local index i. */
+int shn_table_build_records(shn_ctx* ctx, const void* recs_dev, uint64_t n, int k1,
+                            uint64_t* gline_sorted_dev);
+/* connected components of the successor graph restricted to this shard (lock-free union-find). */
+int shn_cc_local(shn_ctx* ctx, uint64_t* n_local_components);
+/* successor candidates owned by other ranks: {successor key, gid_base + my local component}. */
+int shn_cc_cross(shn_ctx* ctx, uint32_t nranks, uint32_t rank, uint64_t gid_base, uint64_t* counts_host,
+                 void* send_dev);
+/* received queries -> edges (asking component | my component << 32) for the keys this shard holds;
+ * edges_dev has room for n entries. */
+int shn_cc_resolve(shn_ctx* ctx, const void* recs_dev, uint64_t n, uint64_t gid_base, uint64_t* edges_dev,
+                   uint64_t* n_edges);
+/* components of the graph whose nodes are the local components of all ranks (all-gathered edges). */
+int shn_cc_merge(shn_ctx* ctx, const uint64_t* edges_dev, uint64_t n_edges, uint64_t n_super,
+                 uint64_t* n_final_components);
+/* sizes_dev[f] = K1-mers of this shard in final component f (n_final entries, zeroed here). */
+int shn_cc_sizes(shn_ctx* ctx, uint64_t gid_base, uint64_t* sizes_dev);
+/* every table entry {key, global line << 30 | weight} to owner_of_final[its component]. */
+int shn_cc_route(shn_ctx* ctx, const uint32_t* owner_of_final_dev, uint64_t gid_base,
+                 const uint64_t* gline_dev, uint32_t nranks, uint64_t* counts_host, void* send_dev);
+int shn_cc_free(shn_ctx* ctx);
 
 /* ---- f1/f2 (inputs of the path): RC doubling, K1-mer counting, synthetic reads ---------- */
 /* Generates n_pairs synthetic read pairs on the device (twin of shannon_b200/synth.py::

@@ -42,6 +42,24 @@ SIGNATURES = {
     "shn_memcpy_h2d": (C.c_int, [vp, vp, vp, C.c_uint64]),
     "shn_memcpy_d2h": (C.c_int, [vp, vp, vp, C.c_uint64]),
     "shn_sync": (C.c_int, [vp]),
+    "shn_memcpy_d2d": (C.c_int, [vp, vp, vp, C.c_uint64]),
+    "shn_use_stream": (C.c_int, [vp, vp]),
+    "shn_l3_walks": (C.c_int, [vp, C.c_uint32, C.c_uint32]),
+    "shn_l3_cand_sizes": (C.c_int, [vp, u64p, u64p]),
+    "shn_l3_cand_export": (C.c_int, [vp, vp, vp, vp, vp]),
+    "shn_l3_filter": (C.c_int, [vp, vp, vp, C.c_uint64, C.c_int, C.c_int]),
+    "shn_l3_allowed_copy": (C.c_int, [vp, vp, vp]),
+    "shn_l3_set_allowed_weights": (C.c_int, [vp, vp]),
+    "shn_route_lines": (C.c_int, [vp, vp, vp, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_uint32,
+                                  u64p, vp]),
+    "shn_table_build_records": (C.c_int, [vp, vp, C.c_uint64, C.c_int, vp]),
+    "shn_cc_local": (C.c_int, [vp, u64p]),
+    "shn_cc_cross": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_uint64, u64p, vp]),
+    "shn_cc_resolve": (C.c_int, [vp, vp, C.c_uint64, C.c_uint64, vp, u64p]),
+    "shn_cc_merge": (C.c_int, [vp, vp, C.c_uint64, C.c_uint64, u64p]),
+    "shn_cc_sizes": (C.c_int, [vp, C.c_uint64, vp]),
+    "shn_cc_route": (C.c_int, [vp, vp, C.c_uint64, vp, C.c_uint32, u64p, vp]),
+    "shn_cc_free": (C.c_int, [vp]),
     "shn_timer_start": (C.c_int, [vp]),
     "shn_timer_stop": (C.c_int, [vp, C.POINTER(C.c_float)]),
     "shn_prof_enable": (C.c_int, [vp, C.c_int]),
@@ -269,6 +287,14 @@ class Context(HostIO):
     def sync(self):
         self.call("shn_sync")
 
+    def use_stream(self, cuda_stream):
+        """cuda_stream: raw cudaStream_t as int (torch.cuda.current_stream().cuda_stream), 0/None =
+        the context's own stream."""
+        self.call("shn_use_stream", vp(cuda_stream or None))
+
+    def d2d(self, d_dst, d_src, nbytes):
+        self.call("shn_memcpy_d2d", vp(d_dst), vp(d_src), C.c_uint64(int(nbytes)))
+
     def timer_start(self):
         self.call("shn_timer_start")
 
@@ -360,6 +386,76 @@ class Context(HostIO):
     def l3_run(self, min_weight, min_length):
         self.call("shn_l3_run", C.c_uint32(min_weight), C.c_uint32(min_length))
         return self.l3_sizes()
+
+    # the two phases of l3_run and the candidate exchange of the sharded path (device pointers)
+    def l3_walks_phase(self, min_weight, min_length):
+        self.call("shn_l3_walks", C.c_uint32(min_weight), C.c_uint32(min_length))
+
+    def l3_cand_sizes(self):
+        n, nb = C.c_uint64(), C.c_uint64()
+        self.call("shn_l3_cand_sizes", C.byref(n), C.byref(nb))
+        return n.value, nb.value
+
+    def l3_cand_export(self, d_weight, d_first_idx, d_offs, d_codes):
+        self.call("shn_l3_cand_export", vp(d_weight), vp(d_first_idx), vp(d_offs), vp(d_codes))
+
+    def l3_filter_phase(self, d_codes=None, d_offs=None, n_cand=0, external=False, allow_missing=False):
+        self.call("shn_l3_filter", vp(d_codes or None), vp(d_offs or None), C.c_uint64(int(n_cand)),
+                  int(bool(external)), int(bool(allow_missing)))
+        return self.l3_sizes()
+
+    def l3_allowed_copy(self, d_keys, d_weights):
+        self.call("shn_l3_allowed_copy", vp(d_keys or None), vp(d_weights or None))
+
+    def l3_set_allowed_weights(self, d_weights):
+        self.call("shn_l3_set_allowed_weights", vp(d_weights or None))
+
+    # ---- sharded tables ------------------------------------------------------------------------
+    def _route(self, name, nranks, counts, d_send, *args):
+        arr = (C.c_uint64 * nranks)(*([0] * nranks if counts is None else [int(x) for x in counts]))
+        self.call(name, *args, arr, vp(d_send or None))
+        return [int(x) for x in arr]
+
+    def route_lines(self, d_keys, d_counts, n, first_line, double_stranded, k1, nranks, counts=None,
+                    d_send=None):
+        return self._route("shn_route_lines", nranks, counts, d_send, vp(d_keys or None),
+                           vp(d_counts or None), C.c_uint64(int(n)), C.c_uint64(int(first_line)),
+                           int(bool(double_stranded)), int(k1), C.c_uint32(nranks))
+
+    def table_build_records(self, d_recs, n, k1, d_gline_sorted):
+        self.call("shn_table_build_records", vp(d_recs or None), C.c_uint64(int(n)), int(k1),
+                  vp(d_gline_sorted or None))
+
+    def cc_local(self):
+        n = C.c_uint64()
+        self.call("shn_cc_local", C.byref(n))
+        return n.value
+
+    def cc_cross(self, nranks, rank, gid_base, counts=None, d_send=None):
+        return self._route("shn_cc_cross", nranks, counts, d_send, C.c_uint32(nranks), C.c_uint32(rank),
+                           C.c_uint64(int(gid_base)))
+
+    def cc_resolve(self, d_recs, n, gid_base, d_edges):
+        ne = C.c_uint64()
+        self.call("shn_cc_resolve", vp(d_recs or None), C.c_uint64(int(n)), C.c_uint64(int(gid_base)),
+                  vp(d_edges or None), C.byref(ne))
+        return ne.value
+
+    def cc_merge(self, d_edges, n_edges, n_super):
+        nf = C.c_uint64()
+        self.call("shn_cc_merge", vp(d_edges or None), C.c_uint64(int(n_edges)), C.c_uint64(int(n_super)),
+                  C.byref(nf))
+        return nf.value
+
+    def cc_sizes(self, gid_base, d_sizes):
+        self.call("shn_cc_sizes", C.c_uint64(int(gid_base)), vp(d_sizes))
+
+    def cc_route(self, d_owner_of_final, gid_base, d_gline, nranks, counts=None, d_send=None):
+        return self._route("shn_cc_route", nranks, counts, d_send, vp(d_owner_of_final),
+                           C.c_uint64(int(gid_base)), vp(d_gline or None), C.c_uint32(nranks))
+
+    def cc_free(self):
+        self.call("shn_cc_free")
 
     def l3_sizes(self):
         s = L3Sizes()

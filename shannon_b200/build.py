@@ -9,11 +9,11 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "libshannon_b200.so")
 SOURCES = ["api.cu", "table.cu", "l3.cu", "l4.cu", "selfjoin.cu", "synth.cu", "reads.cu", "route.cu",
-           "hostio.cpp"]
+           "shard.cu", "hostio.cpp"]
 # translation units that depend on the K1-mer key width: built a second time with -DSHN_WIDE
 # (128-bit keys, K1 = 33) into namespace `wide`; api.cu dispatches on k1
-WIDE_SOURCES = ["table.cu", "l3.cu", "l4.cu", "synth.cu"]
-HEADERS = ["common.cuh", "table_dev.cuh", "selfjoin.cuh", "impls.h", "reads.cuh",
+WIDE_SOURCES = ["table.cu", "l3.cu", "l4.cu", "synth.cu", "shard.cu"]
+HEADERS = ["common.cuh", "table_dev.cuh", "selfjoin.cuh", "impls.h", "reads.cuh", "uf_dev.cuh",
            os.path.join("..", "..", "include", "shannon_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

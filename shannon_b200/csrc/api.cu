@@ -92,6 +92,7 @@ int shn_create(int device, shn_ctx** out) {
   CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
   c->sm_count = prop.multiProcessorCount;
   CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  c->own_stream = c->stream;
   CUDA_CHECK(cudaEventCreate(&c->t0));
   CUDA_CHECK(cudaEventCreate(&c->t1));
   CUDA_CHECK(cudaEventCreate(&c->p0));
@@ -109,6 +110,7 @@ void shn_destroy(shn_ctx* c) {
   shn_l4_free(c);
   shn_count_free(c);
   shn_reads_free(c);
+  shn_shard_free(c);
   c->table.release();
   c->cub_tmp.release();
   c->flush_buf.release();
@@ -124,7 +126,7 @@ void shn_destroy(shn_ctx* c) {
   if (c->stream2) cudaStreamDestroy(c->stream2);
   if (c->stream3) cudaStreamDestroy(c->stream3);
   if (c->stream4) cudaStreamDestroy(c->stream4);
-  cudaStreamDestroy(c->stream);
+  cudaStreamDestroy(c->own_stream);
   g_shn_pool = nullptr;
   delete c;
 }
@@ -192,6 +194,20 @@ int shn_sync(shn_ctx* c) {
   SHN_API_BEGIN
   bind(c);
   CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  SHN_API_END(c)
+}
+int shn_use_stream(shn_ctx* c, void* stream) {
+  SHN_API_BEGIN
+  bind(c);
+  CUDA_CHECK(cudaStreamSynchronize(c->stream));  // nothing of the old stream is left in flight
+  c->prof_resolve();
+  c->stream = stream ? static_cast<cudaStream_t>(stream) : c->own_stream;
+  SHN_API_END(c)
+}
+int shn_memcpy_d2d(shn_ctx* c, void* dst, const void* src, uint64_t bytes) {
+  SHN_API_BEGIN
+  bind(c);
+  if (bytes) CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, c->stream));
   SHN_API_END(c)
 }
 int shn_timer_start(shn_ctx* c) {
@@ -449,6 +465,116 @@ int shn_l3_get_labels(shn_ctx* c, uint32_t* label) {
   SHN_API_BEGIN
   bind(c);
   SHN_DISPATCH(c->k1, l3_get_labels(c, label));
+  SHN_API_END(c)
+}
+
+int shn_l3_walks(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
+  SHN_API_BEGIN
+  bind(c);
+  SHN_DISPATCH(c->k1, l3_walks(c, min_weight, min_length));
+  SHN_API_END(c)
+}
+int shn_l3_cand_sizes(shn_ctx* c, uint64_t* n_cand, uint64_t* n_bases) {
+  SHN_API_BEGIN
+  bind(c);
+  SHN_DISPATCH(c->k1, l3_cand_sizes(c, n_cand, n_bases));
+  SHN_API_END(c)
+}
+int shn_l3_cand_export(shn_ctx* c, uint32_t* weight_dev, uint32_t* first_idx_dev, uint64_t* offs_dev,
+                       uint8_t* codes_dev) {
+  SHN_API_BEGIN
+  bind(c);
+  SHN_DISPATCH(c->k1, l3_cand_export(c, weight_dev, first_idx_dev, offs_dev, codes_dev));
+  SHN_API_END(c)
+}
+int shn_l3_filter(shn_ctx* c, const uint8_t* codes_dev, const uint64_t* offs_dev, uint64_t n_cand,
+                  int external, int allow_missing) {
+  SHN_API_BEGIN
+  bind(c);
+  SHN_DISPATCH(c->k1, l3_filter(c, codes_dev, offs_dev, n_cand, external, allow_missing));
+  SHN_API_END(c)
+}
+int shn_l3_allowed_copy(shn_ctx* c, uint64_t* keys_dev, uint32_t* weights_dev) {
+  SHN_API_BEGIN
+  bind(c);
+  const uint64_t* dk;
+  const uint32_t* dw;
+  uint64_t dn;
+  SHN_DISPATCH(c->k1, l3_allowed_dev(c, &dk, &dw, &dn));
+  if (dn && keys_dev)
+    CUDA_CHECK(cudaMemcpyAsync(keys_dev, dk, dn * key_bytes(c->k1), cudaMemcpyDeviceToDevice, c->stream));
+  if (dn && weights_dev) CUDA_CHECK(cudaMemcpyAsync(weights_dev, dw, dn * 4, cudaMemcpyDeviceToDevice, c->stream));
+  SHN_API_END(c)
+}
+int shn_l3_set_allowed_weights(shn_ctx* c, const uint32_t* weights_dev) {
+  SHN_API_BEGIN
+  bind(c);
+  SHN_DISPATCH(c->k1, l3_set_allowed_weights(c, weights_dev));
+  SHN_API_END(c)
+}
+
+// ---- sharded tables --------------------------------------------------------------------
+int shn_route_lines(shn_ctx* c, const uint64_t* keys_dev, const uint32_t* counts_dev, uint64_t n,
+                    uint64_t first_line, int double_stranded, int k1, uint32_t nranks, uint64_t* counts_host,
+                    void* send_dev) {
+  SHN_API_BEGIN
+  bind(c);
+  SHN_CHECK(k1 >= 1 && k1 <= 33, "k1 must be in 1..33");
+  SHN_DISPATCH(k1, route_lines(c, keys_dev, counts_dev, n, first_line, double_stranded, k1, nranks, counts_host,
+                               send_dev));
+  SHN_API_END(c)
+}
+int shn_table_build_records(shn_ctx* c, const void* recs_dev, uint64_t n, int k1, uint64_t* gline_sorted_dev) {
+  SHN_API_BEGIN
+  bind(c);
+  shn_l3_free(c);
+  SHN_CHECK(k1 >= 1 && k1 <= 33, "k1 must be in 1..33");
+  SHN_DISPATCH(k1, table_build_records(c, recs_dev, n, k1, gline_sorted_dev));
+  SHN_API_END(c)
+}
+int shn_cc_local(shn_ctx* c, uint64_t* n_local) {
+  SHN_API_BEGIN
+  bind(c);
+  SHN_DISPATCH(c->k1, cc_local(c, n_local));
+  SHN_API_END(c)
+}
+int shn_cc_cross(shn_ctx* c, uint32_t nranks, uint32_t rank, uint64_t gid_base, uint64_t* counts_host,
+                 void* send_dev) {
+  SHN_API_BEGIN
+  bind(c);
+  SHN_DISPATCH(c->k1, cc_cross(c, nranks, rank, gid_base, counts_host, send_dev));
+  SHN_API_END(c)
+}
+int shn_cc_resolve(shn_ctx* c, const void* recs_dev, uint64_t n, uint64_t gid_base, uint64_t* edges_dev,
+                   uint64_t* n_edges) {
+  SHN_API_BEGIN
+  bind(c);
+  SHN_DISPATCH(c->k1, cc_resolve(c, recs_dev, n, gid_base, edges_dev, n_edges));
+  SHN_API_END(c)
+}
+int shn_cc_merge(shn_ctx* c, const uint64_t* edges_dev, uint64_t n_edges, uint64_t n_super, uint64_t* n_final) {
+  SHN_API_BEGIN
+  bind(c);
+  SHN_DISPATCH(c->k1, cc_merge(c, edges_dev, n_edges, n_super, n_final));
+  SHN_API_END(c)
+}
+int shn_cc_sizes(shn_ctx* c, uint64_t gid_base, uint64_t* sizes_dev) {
+  SHN_API_BEGIN
+  bind(c);
+  SHN_DISPATCH(c->k1, cc_sizes(c, gid_base, sizes_dev));
+  SHN_API_END(c)
+}
+int shn_cc_route(shn_ctx* c, const uint32_t* owner_of_final_dev, uint64_t gid_base, const uint64_t* gline_dev,
+                 uint32_t nranks, uint64_t* counts_host, void* send_dev) {
+  SHN_API_BEGIN
+  bind(c);
+  SHN_DISPATCH(c->k1, cc_route(c, owner_of_final_dev, gid_base, gline_dev, nranks, counts_host, send_dev));
+  SHN_API_END(c)
+}
+int shn_cc_free(shn_ctx* c) {
+  SHN_API_BEGIN
+  bind(c);
+  shn_shard_free(c);
   SHN_API_END(c)
 }
 

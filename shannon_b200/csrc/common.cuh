@@ -396,6 +396,9 @@ struct shn_ctx {
   void (*count_free)(shn_ctx*) = nullptr;
   void* reads = nullptr;  // packed reads (reads.cu), independent of the key width
   void (*reads_free)(shn_ctx*) = nullptr;
+  void* shard = nullptr;  // cross-rank component labelling (shard.cu)
+  void (*shard_free)(shn_ctx*) = nullptr;
+  cudaStream_t own_stream = nullptr;  // the stream shn_create made (stream may point elsewhere: shn_use_stream)
 
   void* tmp(uint64_t bytes) {
     cub_tmp.reserve(bytes);
@@ -459,6 +462,10 @@ static inline void shn_l4_free(shn_ctx* c) {
 static inline void shn_reads_free(shn_ctx* c) {
   if (c->reads && c->reads_free) c->reads_free(c);
   c->reads = nullptr;
+}
+static inline void shn_shard_free(shn_ctx* c) {
+  if (c->shard && c->shard_free) c->shard_free(c);
+  c->shard = nullptr;
 }
 static inline void shn_count_free(shn_ctx* c) {
   if (c->count_state && c->count_free) c->count_free(c);

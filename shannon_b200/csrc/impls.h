@@ -18,6 +18,29 @@
                     uint8_t* d_found);                                                               \
   void table_dump(shn_ctx* c, uint64_t* h_keys, uint32_t* h_weights, uint32_t* h_idx);               \
   void l3_run(shn_ctx* c, uint32_t min_weight, uint32_t min_length);                                 \
+  void l3_walks(shn_ctx* c, uint32_t min_weight, uint32_t min_length);                               \
+  void l3_filter(shn_ctx* c, const uint8_t* ext_codes, const uint64_t* ext_offs, uint64_t ext_n,     \
+                 int ext, int allow_missing);                                                        \
+  void l3_cand_sizes(shn_ctx* c, uint64_t* n_cand, uint64_t* n_bases);                               \
+  void l3_cand_export(shn_ctx* c, uint32_t* d_weight, uint32_t* d_first_idx, uint64_t* d_offs,       \
+                      uint8_t* d_codes);                                                             \
+  void l3_set_allowed_weights(shn_ctx* c, const uint32_t* d_w);                                      \
+  void route_lines(shn_ctx* c, const uint64_t* d_keys, const uint32_t* d_counts, uint64_t n,         \
+                   uint64_t first_line, int ds, int k1, uint32_t nranks, uint64_t* h_counts,         \
+                   void* send);                                                                      \
+  void table_build_records(shn_ctx* c, const void* d_recs, uint64_t n, int k1,                       \
+                           uint64_t* d_gline_sorted);                                                \
+  void cc_local(shn_ctx* c, uint64_t* n_local);                                                      \
+  void cc_cross(shn_ctx* c, uint32_t nranks, uint32_t rank, uint64_t gid_base, uint64_t* h_counts,   \
+                void* send);                                                                         \
+  void cc_resolve(shn_ctx* c, const void* d_recs, uint64_t n, uint64_t gid_base, uint64_t* d_edges,  \
+                  uint64_t* n_edges);                                                                \
+  void cc_merge(shn_ctx* c, const uint64_t* d_edges, uint64_t n_edges, uint64_t n_super,             \
+                uint64_t* n_final);                                                                  \
+  void cc_sizes(shn_ctx* c, uint64_t gid_base, uint64_t* d_sizes);                                   \
+  void cc_route(shn_ctx* c, const uint32_t* d_owner_of_final, uint64_t gid_base,                     \
+                const uint64_t* d_gline, uint32_t nranks, uint64_t* h_counts, void* send);           \
+  void cc_free(shn_ctx* c);                                                                          \
   void l3_get_sizes(shn_ctx* c, shn_l3_sizes* out);                                                  \
   void l3_get_walks(shn_ctx* c, uint64_t* seed_keys, uint32_t* n_left, uint32_t* n_right,            \
                     uint64_t* tot_wt, uint8_t* flags);                                               \

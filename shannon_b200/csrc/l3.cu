@@ -19,6 +19,7 @@
 #include "impls.h"
 #include "selfjoin.cuh"
 #include "table_dev.cuh"
+#include "uf_dev.cuh"
 
 namespace SHN_NS {
 
@@ -31,6 +32,13 @@ struct L3State {
   DevBuf w_totwt;       // uint64
   DevBuf w_logstart;    // uint64
   DevBuf walk_log;      // uint8 base codes, one per traversed K1-mer (seed entries unused)
+  // candidates (walks passing length + hyperbola, pop order): left by l3_walks for l3_filter / export
+  uint64_t n_cand = 0;
+  DevBuf cand_walk;      // uint32 walk index per candidate
+  DevBuf cand_off;       // uint64 [n_cand+1] offsets into cand_codes
+  DevBuf cand_codes;     // uint8 base codes of the candidate contigs
+  std::vector<uint64_t> h_cand_off;
+  bool foreign = false;  // l3_filter ran on candidates supplied by the caller (sharded path)
   std::vector<uint32_t> h_cand_walk;  // walk index of every candidate (passes length+hyperbola)
   std::vector<uint8_t> h_cand_dup;    // duplicate_check() result per candidate
   std::vector<uint8_t> h_cand_acc;    // accepted per candidate
@@ -126,55 +134,6 @@ __global__ void __launch_bounds__(kBlock) uf_init_kernel(uint32_t* parent, uint6
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (; i < n; i += stride) parent[i] = (uint32_t)i;
-}
-
-__device__ __forceinline__ uint32_t uf_find(uint32_t* parent, uint32_t x) {
-  uint32_t p = __ldcg(&parent[x]);
-  while (p != x) {
-    uint32_t gp = __ldcg(&parent[p]);
-    if (gp != p) parent[x] = gp;  // path halving; x is not a root, so this never races a link
-    x = p;
-    p = gp;
-  }
-  return x;
-}
-
-// read-only variant (no path compression): safe while other threads overwrite parent[i] <- root
-__device__ __forceinline__ uint32_t uf_find_ro(const uint32_t* parent, uint32_t x) {
-  uint32_t p = __ldcg(&parent[x]);
-  while (p != x) {
-    x = p;
-    p = __ldcg(&parent[x]);
-  }
-  return x;
-}
-
-// Rem's algorithm with splicing, lock-free (CAS): the two find paths are climbed together, always
-// on the side whose parent has the larger index, and every node passed is re-pointed at the other
-// side's (smaller) parent; the climb stops as soon as the paths meet instead of walking both to
-// their roots.  Parents always have smaller indices than their children, so the forest stays
-// acyclic under any interleaving, and the root of a finished set is its minimum slot index.
-__device__ __forceinline__ void uf_union(uint32_t* parent, uint32_t a, uint32_t b) {
-  uint32_t pa = __ldcg(&parent[a]), pb = __ldcg(&parent[b]);
-  while (pa != pb) {
-    if (pa < pb) {  // climb on the side with the larger parent
-      uint32_t t = a;
-      a = b;
-      b = t;
-      t = pa;
-      pa = pb;
-      pb = t;
-    }
-    if (a == pa) {  // a is a root: link it under the other side
-      const uint32_t old = atomicCAS(&parent[a], a, pb);
-      if (old == a) return;
-      pa = old;  // somebody linked it first
-      continue;
-    }
-    atomicCAS(&parent[a], pa, pb);  // splice (harmless if it fails: the entry only ever decreases)
-    a = pa;
-    pa = __ldcg(&parent[a]);
-  }
 }
 
 // One thread per K1-mer: probe the four successors, link the ones that exist (1.2 on average).
@@ -1270,7 +1229,9 @@ struct HostTrace {  // SHN_HOST_TRACE=1: wall-clock marks of l3_run's host side 
   }
 };
 
-void l3_run(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
+// a3-a5: seeds, raw components, greedy walks, shape filter, candidate contigs (the part of the
+// seed loop that only needs the K1-mer table; every K1-mer graph component is self-contained)
+void l3_walks(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
   HostTrace ht;
   SHN_CHECK(c->n_buckets > 0, "no K1-mer table built (call shn_table_build first)");
   shn_l3_free(c);
@@ -1639,8 +1600,11 @@ void l3_run(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
   uint64_t n_walks = 0, n_cand = 0;
   std::vector<uint32_t>& cand_walk = s->h_cand_walk;
   cand_walk.clear();
-  std::vector<uint64_t> cand_off(1, 0);
-  DevBuf d_cand_walk, d_cand_off, cand_codes;
+  std::vector<uint64_t>& cand_off = s->h_cand_off;
+  cand_off.assign(1, 0);
+  DevBuf& d_cand_walk = s->cand_walk;
+  DevBuf& d_cand_off = s->cand_off;
+  DevBuf& cand_codes = s->cand_codes;
   if (n_seeds) {
     DevBuf sel, nsel;
     sel.reserve(n_seeds * 4);
@@ -1758,7 +1722,55 @@ void l3_run(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
     KERNEL_CHECK();
   }
 
+  s->n_cand = n_cand;
+  CUDA_CHECK(cudaStreamSynchronize(st));
   ht.mark("assembled candidates");
+}
+
+namespace {
+L3State* need_l3(shn_ctx* c) {
+  SHN_CHECK(c->l3 != nullptr, "shn_l3_run has not been called on this context");
+  return static_cast<L3State*>(c->l3);
+}
+}  // namespace
+
+// a6-a9: duplicate filter, allowed set, contig C-mer graph, contig components -- on the candidates
+// l3_walks left behind (ext == 0), or on a candidate list supplied by the caller (ext != 0: the
+// sharded path merges the candidates of all ranks in global pop order; d_codes / d_offs are device
+// pointers).  allow_missing: allowed K1-mers that are not in THIS context's table get weight 0
+// instead of an error (their owner rank knows the weight).
+void l3_filter(shn_ctx* c, const uint8_t* ext_codes, const uint64_t* ext_offs, uint64_t ext_n, int ext,
+               int allow_missing) {
+  HostTrace ht;
+  L3State* s = need_l3(c);
+  const int k1 = c->k1;
+  ShnTableView tv = table_view(c);
+  cudaStream_t st = c->stream;
+  unsigned long long h[8];
+  unsigned long long* ctr = nullptr;
+  const uint32_t min_weight = s->min_weight;
+  (void)min_weight;
+  if (ext) {
+    s->foreign = true;
+    s->n_cand = ext_n;
+    s->cand_off.reserve((ext_n + 1) * 8);
+    if (ext_n) {
+      CUDA_CHECK(cudaMemcpyAsync(s->cand_off.p, ext_offs, (ext_n + 1) * 8, cudaMemcpyDeviceToDevice, st));
+      d2h(c, s->h_cand_off, s->cand_off.p, ext_n + 1);
+    } else {
+      CUDA_CHECK(cudaMemsetAsync(s->cand_off.p, 0, 8, st));
+      s->h_cand_off.assign(1, 0);
+    }
+    const uint64_t nb = s->h_cand_off.back();
+    s->cand_codes.reserve(std::max<uint64_t>(nb, 1));
+    if (nb) CUDA_CHECK(cudaMemcpyAsync(s->cand_codes.p, ext_codes, nb, cudaMemcpyDeviceToDevice, st));
+  }
+  const uint64_t n_cand = s->n_cand;
+  std::vector<uint64_t>& cand_off = s->h_cand_off;
+  const uint64_t cand_bases = cand_off.back();
+  DevBuf& d_cand_off = s->cand_off;
+  DevBuf& cand_codes = s->cand_codes;
+  s->sz.n_candidates = n_cand;
   // ---- a6: duplicate filter ------------------------------------------------------------------
   std::vector<uint8_t> h_status(n_cand, 1);
   std::vector<uint8_t> h_dup(n_cand, 0);
@@ -1906,7 +1918,7 @@ void l3_run(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
           tv, s->allowed_keys.as<uint64_t>(), n_allowed, s->allowed_w.as<uint32_t>(), ctr);
       KERNEL_CHECK();
       read_counters(c, h, 1);
-      SHN_CHECK(h[0] == 0, "internal error: a contig K1-mer is missing from the table");
+      SHN_CHECK(h[0] == 0 || allow_missing, "internal error: a contig K1-mer is missing from the table");
     }
   }
   s->sz.n_allowed = n_allowed;
@@ -1969,13 +1981,13 @@ void l3_run(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
   ht.mark("contig components (end)");
 }
 
-// ---- getters -----------------------------------------------------------------------------------
-namespace {
-L3State* need_l3(shn_ctx* c) {
-  SHN_CHECK(c->l3 != nullptr, "shn_l3_run has not been called on this context");
-  return static_cast<L3State*>(c->l3);
+void l3_run(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
+  l3_walks(c, min_weight, min_length);
+  l3_filter(c, nullptr, nullptr, 0, 0, 0);
 }
 
+// ---- getters -----------------------------------------------------------------------------------
+namespace {
 __global__ void __launch_bounds__(kBlock)
     seed_keys_kernel(const ShnSlot* __restrict__ slots, const uint32_t* __restrict__ w_slot, uint64_t n,
                      uint64_t* __restrict__ keys) {
@@ -1991,6 +2003,52 @@ __global__ void __launch_bounds__(kBlock)
 }  // namespace
 
 void l3_get_sizes(shn_ctx* c, shn_l3_sizes* out) { *out = need_l3(c)->sz; }
+
+// ---- candidates of this context's walks, for the merge across ranks (device pointers) -----------
+namespace {
+__global__ void __launch_bounds__(kBlock)
+    cand_seed_kernel(const ShnSlot* __restrict__ slots, const uint32_t* __restrict__ cand_walk,
+                     const uint32_t* __restrict__ w_slot, uint64_t n, uint32_t* __restrict__ weight,
+                     uint32_t* __restrict__ first_idx) {
+  uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  shn_key_t key;
+  uint32_t wz, wi;
+  table_load_slot(slots, w_slot[cand_walk[j]], &key, &wz, &wi);
+  weight[j] = wz & SHN_WEIGHT_MASK;
+  first_idx[j] = wi;
+}
+}  // namespace
+
+void l3_cand_sizes(shn_ctx* c, uint64_t* n_cand, uint64_t* n_bases) {
+  L3State* s = need_l3(c);
+  SHN_CHECK(!s->foreign, "the candidates of this context were replaced by shn_l3_filter");
+  *n_cand = s->n_cand;
+  *n_bases = s->h_cand_off.back();
+}
+
+// pop-order key of every candidate = (seed weight desc, seed first-occurrence index desc)
+void l3_cand_export(shn_ctx* c, uint32_t* d_weight, uint32_t* d_first_idx, uint64_t* d_offs,
+                    uint8_t* d_codes) {
+  L3State* s = need_l3(c);
+  SHN_CHECK(!s->foreign, "the candidates of this context were replaced by shn_l3_filter");
+  const uint64_t n = s->n_cand, nb = s->h_cand_off.back();
+  cudaStream_t st = c->stream;
+  if (n) {
+    cand_seed_kernel<<<shn_grid(n, kBlock), kBlock, 0, st>>>(table_view(c).slots, s->cand_walk.as<uint32_t>(),
+                                                            s->w_seed_slot.as<uint32_t>(), n, d_weight,
+                                                            d_first_idx);
+    KERNEL_CHECK();
+  }
+  CUDA_CHECK(cudaMemcpyAsync(d_offs, s->cand_off.p, (n + 1) * 8, cudaMemcpyDeviceToDevice, st));
+  if (nb) CUDA_CHECK(cudaMemcpyAsync(d_codes, s->cand_codes.p, nb, cudaMemcpyDeviceToDevice, st));
+}
+
+void l3_set_allowed_weights(shn_ctx* c, const uint32_t* d_w) {
+  L3State* s = need_l3(c);
+  if (s->sz.n_allowed)
+    CUDA_CHECK(cudaMemcpyAsync(s->allowed_w.p, d_w, s->sz.n_allowed * 4, cudaMemcpyDeviceToDevice, c->stream));
+}
 
 // device-resident accepted contigs (2-bit codes, offsets) for the L4 map
 void l3_contigs_dev(shn_ctx* c, const uint8_t** codes, const uint64_t** offs, uint64_t* n,
@@ -2032,9 +2090,9 @@ void l3_get_walks(shn_ctx* c, uint64_t* seed_keys, uint32_t* n_left, uint32_t* n
   if (flags) {
     memset(flags, 0, n);
     for (size_t j = 0; j < s->h_cand_walk.size(); ++j) {
-      uint8_t f = 1;
-      if (s->h_cand_dup[j]) f |= 2;
-      if (s->h_cand_acc[j]) f |= 4;
+      uint8_t f = 1;   // bits 1-2 describe this context's own candidates only
+      if (!s->foreign && s->h_cand_dup[j]) f |= 2;
+      if (!s->foreign && s->h_cand_acc[j]) f |= 4;
       flags[s->h_cand_walk[j]] = f;
     }
   }

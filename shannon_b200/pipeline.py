@@ -183,6 +183,20 @@ def correct(ctx, keys, counts, k1, double_stranded, min_weight, min_length, on_d
     tm["l3_run"] = time.perf_counter() - t0
     if after_l3_run is not None:
         after_l3_run()           # e.g. queue the read packing: it runs under the host-side ordering
+    return collect_correction(ctx, k1, cor.n_loaded, tm, fetch_allowed, cor)
+
+
+def collect_correction(ctx, k1, n_loaded, timings=None, fetch_allowed=True, cor=None):
+    """The contig-level results of the L3 stage this context holds (after shn_l3_run, or after the
+    sharded path's shn_l3_filter), ordered like the reference's dicts: contigs, allowed set, contig
+    adjacency in insertion order, DFS components (extension_correction.py:403-450)."""
+    import time
+    tm = timings if timings is not None else {}
+    if cor is None:
+        cor = Correction()
+        cor.k1 = k1
+        cor.n_loaded = n_loaded
+        cor.sizes = ctx.l3_sizes()
     t0 = time.perf_counter()
     n_contigs = cor.sizes["n_contigs"]
     bases, offs = ctx.l3_contigs()
@@ -273,19 +287,11 @@ def partition_reads(ctx, mates, paired, k1, n_comps, staged=False, loaded=False,
                                                   "valid_records": n_valid}
 
 
-def frontend_in_memory(ctx, keys, counts, k1, mates, paired, min_weight=3, min_length=75,
-                       partition_size=500, on_device=False, n_kmers=None):
-    """Whole hot path without files: what shannon.py:459+467 compute, for bench.py.  Oversized
-    components (more than partition_size contigs) are split into contiguous blocks, the rule of
-    the gpmetis stand-in.  The returned record_idx is a view of a page-locked buffer that the
-    next call re-uses: copy it to keep it."""
-    import time
-    tm = {}
-    loaded = []   # set once the read packing has been queued (under the host-side ordering)
-    cor = correct(ctx, keys, counts, k1, False, min_weight, min_length, on_device, n_kmers, tm,
-                  fetch_allowed=False, after_table_build=lambda: upload_reads_early(ctx, mates),
-                  after_l3_run=lambda: loaded.append(load_reads(ctx, mates, staged=True)))
-    t0 = time.perf_counter()
+def component_ids(cor, partition_size):
+    """Partition id of every accepted contig for the in-memory pipelines (index 0 unused;
+    0xFFFFFFFF = single-contig component, not partitioned): the parts of every oversized component
+    (contiguous blocks of its DFS order, the rule of the gpmetis stand-in), then the
+    remaining_contigs groups in file order.  Returns (comp_of_contig, n_comps, packing)."""
     pk = pack_components(cor, partition_size)
     n_contigs = cor.sizes["n_contigs"]
     comp_of_contig = np.full(n_contigs + 1, 0xFFFFFFFF, dtype=np.uint32)   # singles stay NONE
@@ -300,6 +306,23 @@ def frontend_in_memory(ctx, keys, counts, k1, mates, paired, min_weight=3, min_l
             continue
         comp_of_contig[group] = n_comps
         n_comps += 1
+    return comp_of_contig, n_comps, pk
+
+
+def frontend_in_memory(ctx, keys, counts, k1, mates, paired, min_weight=3, min_length=75,
+                       partition_size=500, on_device=False, n_kmers=None):
+    """Whole hot path without files: what shannon.py:459+467 compute, for bench.py.  Oversized
+    components (more than partition_size contigs) are split into contiguous blocks, the rule of
+    the gpmetis stand-in.  The returned record_idx is a view of a page-locked buffer that the
+    next call re-uses: copy it to keep it."""
+    import time
+    tm = {}
+    loaded = []   # set once the read packing has been queued (under the host-side ordering)
+    cor = correct(ctx, keys, counts, k1, False, min_weight, min_length, on_device, n_kmers, tm,
+                  fetch_allowed=False, after_table_build=lambda: upload_reads_early(ctx, mates),
+                  after_l3_run=lambda: loaded.append(load_reads(ctx, mates, staged=True)))
+    t0 = time.perf_counter()
+    comp_of_contig, n_comps, pk = component_ids(cor, partition_size)
     tm["pack_host"] = time.perf_counter() - t0
     t0 = time.perf_counter()
     # the accepted contigs and the allowed set are still on the device: no round trip

@@ -263,3 +263,18 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] == 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     assert line["e2e"]["value"] == line["value"] and "workload" in line["config"]
+
+
+def test_assign_components_balances_and_is_deterministic():
+    """owner rank of every K1-mer graph component in the sharded path (shannon_b200/sharded.py)"""
+    import numpy as np
+    from shannon_b200 import sharded
+    sizes = np.array([100, 90, 10, 10, 10, 5, 5, 1, 1, 1])
+    own = sharded.assign_components(sizes, 3)
+    load = np.bincount(own, weights=sizes, minlength=3)
+    assert load.max() <= 100 and (own == sharded.assign_components(sizes, 3)).all()
+    assert (sharded.assign_components(sizes, 1) == 0).all()
+    big = np.concatenate([np.full(5, 1000), np.ones(40000, dtype=np.int64)])
+    own = sharded.assign_components(big, 4, exact_top=8)
+    load = np.bincount(own, weights=big, minlength=4)
+    assert load.max() - load.min() <= 2048
