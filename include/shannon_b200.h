@@ -90,6 +90,11 @@ int shn_write_fasta_subset(shn_ctx* ctx, const char* path, int append, const cha
                            const uint64_t* offsets, const uint32_t* read_idx, uint64_t m,
                            uint64_t first_index, const char* suffix);
 
+/* Writes `KMER<TAB>count` lines (the k1mer.dict_org format of `jellyfish dump -c -t`,
+ * shannon.py:441) for n packed keys (host arrays), formatted by all host threads. */
+int shn_write_kmer_file(shn_ctx* ctx, const char* path, const uint64_t* keys, const uint32_t* counts,
+                        uint64_t n, int k1);
+
 /* component{comp}k1mers_allowed.dict (kmers_for_component.py:457-476): for each listed contig (index
  * into bases/offsets), for each K1-mer window, `K1MER\tweight\n`; the weights of contig c start
  * at weights[win_off[c]]. */
@@ -291,6 +296,9 @@ int shn_revcomp_reads(shn_ctx* ctx, const char* in_dev, char* out_dev, uint64_t 
 int shn_count_k1mers(shn_ctx* ctx, const char* const* read_arrays_dev, const uint64_t* n_reads,
                      int n_arrays, int read_len, int k1, uint64_t expected_distinct,
                      uint64_t** keys_dev, uint32_t** counts_dev, uint64_t* n_distinct);
+
+/* frees the device arrays the last shn_count_k1mers returned */
+int shn_count_release(shn_ctx* ctx);
 
 #ifdef __cplusplus
 }

@@ -73,6 +73,8 @@ SIGNATURES = {
     "shn_load_fasta": (C.c_int, [vp, C.c_char_p, C.c_int64, C.POINTER(vp), C.POINTER(vp), u64p]),
     "shn_write_fasta_subset": (C.c_int, [vp, C.c_char_p, C.c_int, vp, vp, vp, C.c_uint64,
                                          C.c_uint64, C.c_char_p]),
+    "shn_write_kmer_file": (C.c_int, [vp, C.c_char_p, vp, vp, C.c_uint64, C.c_int]),
+    "shn_count_release": (C.c_int, [vp]),
     "shn_write_k1mer_windows": (C.c_int, [vp, C.c_char_p, vp, vp, vp, C.c_uint64, C.c_int, vp, vp]),
     "shn_pack_kmers": (C.c_int, [vp, vp, C.c_uint64, C.c_int, vp, C.c_int]),
     "shn_table_build": (C.c_int, [vp, vp, vp, C.c_uint64, C.c_int, C.c_int, C.c_int]),
@@ -201,6 +203,13 @@ class HostIO(object):
         self.call("shn_write_fasta_subset", os.fsencode(path), int(bool(append)), ptr(bases),
                   ptr(offsets), ptr(read_idx), C.c_uint64(len(read_idx)), C.c_uint64(first_index),
                   suffix.encode())
+
+    def write_kmer_file(self, path, keys, counts, k1):
+        """k1mer.dict_org (`KMER\\tcount` lines) from packed keys."""
+        keys = np.ascontiguousarray(keys, dtype=np.uint64)
+        counts = np.ascontiguousarray(counts, dtype=np.uint32)
+        self.call("shn_write_kmer_file", os.fsencode(path), ptr(keys), ptr(counts),
+                  C.c_uint64(len(counts)), int(k1))
 
     def write_k1mer_windows(self, path, bases, offsets, contig_ids, k1, weights, win_off):
         contig_ids = np.ascontiguousarray(contig_ids, dtype=np.uint32)
@@ -575,6 +584,9 @@ class Context(HostIO):
 
     def revcomp_reads(self, d_in, d_out, n_reads, read_len):
         self.call("shn_revcomp_reads", vp(d_in), vp(d_out), C.c_uint64(n_reads), int(read_len))
+
+    def count_release(self):
+        self.call("shn_count_release")
 
     def count_k1mers(self, d_arrays, n_reads, read_len, k1, expected_distinct):
         na = len(d_arrays)

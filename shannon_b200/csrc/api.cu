@@ -15,6 +15,8 @@ void shn_write_fasta_subset_impl(const char* path, int append, const char* bases
 void shn_write_k1mer_windows_impl(const char* path, const char* bases, const uint64_t* offsets,
                                   const uint32_t* contig_ids, uint64_t m, int k1,
                                   const uint32_t* weights, const uint64_t* win_off);
+void shn_write_kmer_file_impl(const char* path, const uint64_t* keys, const uint32_t* counts, uint64_t n,
+                              int k1);
 void shn_synth_pairs_impl(shn_ctx* c, const uint8_t* tx, const uint64_t* tx_offs, const uint64_t* thr,
                           uint64_t n_tx, uint64_t n_pairs, uint64_t first_pair, uint64_t seed,
                           int read_len, int frag_len, uint32_t err_thr, char* m1, char* m2);
@@ -289,6 +291,13 @@ int shn_write_k1mer_windows(shn_ctx* c, const char* path, const char* bases, con
                             const uint64_t* win_off) {
   SHN_API_BEGIN
   shn_write_k1mer_windows_impl(path, bases, offsets, contig_ids, m, k1, weights, win_off);
+  SHN_API_END(c)
+}
+
+int shn_write_kmer_file(shn_ctx* c, const char* path, const uint64_t* keys, const uint32_t* counts,
+                        uint64_t n, int k1) {
+  SHN_API_BEGIN
+  shn_write_kmer_file_impl(path, keys, counts, n, k1);
   SHN_API_END(c)
 }
 
@@ -679,6 +688,13 @@ int shn_revcomp_reads(shn_ctx* c, const char* in_dev, char* out_dev, uint64_t n_
   bind(c);
   shn_revcomp_reads_impl(c, in_dev, out_dev, n_reads, read_len);
   CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  SHN_API_END(c)
+}
+int shn_count_release(shn_ctx* c) {
+  SHN_API_BEGIN
+  bind(c);
+  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  shn_count_free(c);
   SHN_API_END(c)
 }
 int shn_count_k1mers(shn_ctx* c, const char* const* read_arrays_dev, const uint64_t* n_reads,

@@ -313,3 +313,48 @@ void shn_write_k1mer_windows_impl(const char* path, const char* bases, const uin
   }
   out.write(buf);
 }
+
+// k1mer.dict_org writer (`jellyfish dump -c -t` format, shannon.py:441): `KMER\tcount\n` per entry,
+// formatted by all host threads in batches.  keys: 1 or 2 words per key (low word first).
+void shn_write_kmer_file_impl(const char* path, const uint64_t* keys, const uint32_t* counts, uint64_t n,
+                              int k1) {
+  if (k1 < 1 || k1 > 33) SHN_FAIL("k1 must be in 1..33");
+  OutFile out(path, 0);
+  const uint64_t kw = k1 > 32 ? 2 : 1;
+  unsigned nt = std::thread::hardware_concurrency();
+  nt = std::max(1u, std::min(nt, 32u));
+  const uint64_t batch = 1ull << 22;  // lines per thread and round
+  std::vector<std::string> bufs(nt);
+  for (uint64_t lo = 0; lo < n; lo += batch * nt) {
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; ++t)
+      th.emplace_back([&, t] {
+        std::string& b = bufs[t];
+        b.clear();
+        const uint64_t a = std::min(n, lo + batch * t), e = std::min(n, a + batch);
+        b.reserve((e - a) * (k1 + 8));
+        char line[64];
+        for (uint64_t i = a; i < e; ++i) {
+          u128 x = kw == 2 ? (((u128)keys[2 * i + 1] << 64) | keys[2 * i]) : (u128)keys[i];
+          for (int j = k1 - 1; j >= 0; --j) {
+            line[j] = shn_base_of((uint32_t)x & 3u);
+            x >>= 2;
+          }
+          int m = k1;
+          line[m++] = '\t';
+          char num[12];
+          int d = 0;
+          uint32_t v = counts[i];
+          do {
+            num[d++] = (char)('0' + v % 10);
+            v /= 10;
+          } while (v);
+          while (d) line[m++] = num[--d];
+          line[m++] = '\n';
+          b.append(line, m);
+        }
+      });
+    for (auto& x : th) x.join();
+    for (unsigned t = 0; t < nt; ++t) out.write(bufs[t]);
+  }
+}

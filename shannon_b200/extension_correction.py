@@ -15,6 +15,7 @@ from .pipeline import (contig_adjacency, correct, decode_kmers, dfs_components, 
                        encode_kmer, keys_array, keys_as_ints, pack_components)
 
 _default_ctx = None
+LAST_TIMINGS = {}     # wall-clock seconds of the sections of the last run_correction call
 
 
 def get_context(device=None):
@@ -78,8 +79,14 @@ def run_correction(infile, outfile, min_weight, min_length, double_stranded,
     print("{:s}: Starting Kmer error correction..".format(time.asctime()))
     f_log.write("{:s}: Starting..".format(time.asctime()) + "\n")
 
+    LAST_TIMINGS.clear()
+    t0 = time.perf_counter()
     keys, counts, k1 = ctx.parse_kmer_file(infile)
+    LAST_TIMINGS["ec_parse_k1mer_file"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
     cor = correct(ctx, keys, counts, k1, double_stranded, min_weight, min_length)
+    LAST_TIMINGS["ec_gpu_and_ordering"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
     del keys, counts
     print("{:s}: {:d} K-mers loaded.".format(time.asctime(), cor.n_loaded))
     f_log.write("{:s}: {:d} K-mers loaded.".format(time.asctime(), cor.n_loaded) + "\n")
@@ -127,6 +134,7 @@ def run_correction(infile, outfile, min_weight, min_length, double_stranded,
     for m, group in enumerate(pk.remaining):
         with open(d + "/remaining_contigs" + str(m + 1) + ".txt", 'w') as f:
             f.write("".join(contigs[c] + "\n" for c in group))
+    LAST_TIMINGS["ec_write_files"] = time.perf_counter() - t0
     f_log.write(str(time.asctime()) + ": " + "Metis Input File Created " + "\n")
     f_log.write("{:s}: Read-loader in background process joinig back.".format(time.asctime()) + "\n")
     reads = []

@@ -14,6 +14,9 @@ from .pipeline import build_component_map, contig_arrays, partition_reads
 from .weight_updated_graph import weight_updated_graph
 
 
+LAST_TIMINGS = {}     # wall-clock seconds of the sections of the last kmers_for_component call
+
+
 def run_cmd(s1):
     print(s1)
     os.system(s1)
@@ -59,6 +62,14 @@ def kmers_for_component(k1mer_dictionary, kmer_directory, reads, reads_files, di
         return None
     ctx = ctx or get_context()
     k1 = K + 1
+    LAST_TIMINGS.clear()
+    t_sec = time.perf_counter()
+
+    def section(name):
+        nonlocal t_sec
+        now = time.perf_counter()
+        LAST_TIMINGS[name] = LAST_TIMINGS.get(name, 0.0) + now - t_sec
+        t_sec = now
     log_path = directory_name + "/before_sp_log.txt"
     f_log = open(log_path, 'a' if os.path.exists(log_path) else 'w')
 
@@ -95,6 +106,7 @@ def kmers_for_component(k1mer_dictionary, kmer_directory, reads, reads_files, di
                 run_cmd(gpmetis_path + " -ufactor=" + str(ufactor) + " " + base + "r2.txt " + str(partitions))
     write_log(str(time.asctime()) + ": " + "gpmetis for partitioning is complete \n " + temp_string)
 
+    section("kfc_gpmetis")
     # ---- component membership of every contig (:244-305), host side: contig-level text -------
     new_components = {}          # name -> [contig strings], insertion ordered
     comp_index = {}              # name -> dense id
@@ -132,6 +144,7 @@ def kmers_for_component(k1mer_dictionary, kmer_directory, reads, reads_files, di
     d_keys, d_w = _dict_arrays(ctx, k1mer_dictionary, k1)
     build_component_map(ctx, ctg_bases, ctg_offs, ctg_comp, k1, d_keys, d_w)
     write_log(str(time.asctime()) + ": " + "k1mers2component dictionary created ")
+    section("kfc_component_map")
 
     # ---- read partition (a11) ---------------------------------------------------------------
     n_files = 2 if paired_end else 1
@@ -143,10 +156,12 @@ def kmers_for_component(k1mer_dictionary, kmer_directory, reads, reads_files, di
         rb1, ro1 = ctx.load_fasta(reads_files[1], n_records)
         read_bases.append(rb1)
         read_offs.append(ro1)
+    section("kfc_read_fasta")
     n_comps = len(new_components)
     comp_offs, rec_idx, _ = partition_reads(
         ctx, [(b, o, None, False) for b, o in zip(read_bases, read_offs)], paired_end, k1, n_comps)
 
+    section("kfc_partition_gpu")
     part = [dict() for _ in range(n_files)]
     read_text = [b.tobytes().decode() for b in read_bases] if inMem else None
     read_offs_l = [o.tolist() for o in read_offs] if inMem else None
@@ -160,6 +175,7 @@ def kmers_for_component(k1mer_dictionary, kmer_directory, reads, reads_files, di
                 ctx.write_fasta_subset(directory_name + "/reads" + str(comp) + suffix[m] + ".fasta",
                                        True, read_bases[m], read_offs[m], sel, 0, suffix[m])
     write_log(str(time.asctime()) + ": " + "reads partititoned ")
+    section("kfc_write_reads")
 
     # ---- per-component K1-mer files (a12) -----------------------------------------------------
     contig_weights = {}
@@ -178,6 +194,7 @@ def kmers_for_component(k1mer_dictionary, kmer_directory, reads, reads_files, di
             else:
                 ctx.write_k1mer_windows(path, ctg_bases, ctg_offs, ids, k1, win_w, win_off)
         write_log(str(time.asctime()) + ": " + "k1mers written to file ")
+    section("kfc_write_k1mers")
     write_log(str(time.asctime()) + ": " + "kmers written to file " + "\n")
     f_log.close()
 
