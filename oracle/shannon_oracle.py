@@ -157,27 +157,11 @@ def duplicate_check(contig, rmer_to_contig, r=R_MER):
     return 2 * sum(covered) > n
 
 
-class CorrectionResult(object):
-    """Everything run_correction computes, kept for parity checks."""
-    pass
-
-
-def run_correction(infile, outfile, min_weight, min_length, double_stranded,
-                   comp_directory_name, comp_size_threshold, polyA_del=True, inMem=False,
-                   write_files=True):
-    """extension_correction.py:309-524.  Writes the same files and returns a
-    CorrectionResult (``.allowed_kmer_dict`` and ``.reads`` are the reference's return)."""
-    res = CorrectionResult()
-    log = []
-    log.append("{:s}: Starting..".format(time.asctime()))
-    kmers, k1 = load_kmers(infile, double_stranded, polyA_del)
-    res.kmers, res.k1 = kmers, k1
-    log.append("{:s}: {:d} K-mers loaded.".format(time.asctime(), len(kmers)))
-    log.append("{:s}: Reads loading in background process.".format(time.asctime()))
-
-    walks, traversed = greedy_walks(kmers, min_weight)
-    res.walks, res.traversed = walks, traversed
-
+def accept_walks(walks, k1, min_weight, min_length):
+    """The accept / index half of the seed loop (extension_correction.py:356-397) for walks given
+    in pop order: duplicate_check against the accepted contigs so far, the length + hyperbola terms,
+    allowed K1-mers, contig C-mer graph, r-mer index.  Returns (contigs 1-based, connections,
+    allowed as an ordered dict)."""
     rmer_to_contig = {}
     cmer_to_contig = {}
     connections = {}            # contig index -> {neighbour: weight}, insertion ordered
@@ -214,6 +198,31 @@ def run_correction(infile, outfile, min_weight, min_length, double_stranded,
             lst.append(idx)
         for i in range(len(contig) - R_MER + 1):                         # :393-397
             rmer_to_contig.setdefault(contig[i:i + R_MER], []).append(idx)
+    return contigs, connections, allowed
+
+
+class CorrectionResult(object):
+    """Everything run_correction computes, kept for parity checks."""
+    pass
+
+
+def run_correction(infile, outfile, min_weight, min_length, double_stranded,
+                   comp_directory_name, comp_size_threshold, polyA_del=True, inMem=False,
+                   write_files=True):
+    """extension_correction.py:309-524.  Writes the same files and returns a
+    CorrectionResult (``.allowed_kmer_dict`` and ``.reads`` are the reference's return)."""
+    res = CorrectionResult()
+    log = []
+    log.append("{:s}: Starting..".format(time.asctime()))
+    kmers, k1 = load_kmers(infile, double_stranded, polyA_del)
+    res.kmers, res.k1 = kmers, k1
+    log.append("{:s}: {:d} K-mers loaded.".format(time.asctime(), len(kmers)))
+    log.append("{:s}: Reads loading in background process.".format(time.asctime()))
+
+    walks, traversed = greedy_walks(kmers, min_weight)
+    res.walks, res.traversed = walks, traversed
+
+    contigs, connections, allowed = accept_walks(walks, k1, min_weight, min_length)
     res.contigs = contigs
     res.connections = connections
     log.append("{:s}: {:d} K-mers remaining after error correction. ".format(

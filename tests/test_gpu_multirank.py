@@ -123,3 +123,58 @@ def test_sharded_read_partition_two_gpus(tmp_path):
     world = 2
     mp.spawn(_partition_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     assert sorted(os.listdir(tmp_path)) == ["pok0", "pok1"]
+
+
+def _sharded_worker(rank, world, port, out_dir, case_dir):
+    """The whole front end over NCCL (sharded.TorchComm) against the single-GPU path."""
+    from shannon_b200 import _lib, sharded
+    from shannon_b200 import dist as sdist
+    import test_gpu_sharded as tgs
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        s1, s2 = helpers.synthetic_seqs(40, 20000, 71)
+        case = helpers.make_case(os.path.join(case_dir, "r%d" % rank), 24, s1, s2, fast_count=True)
+        ctx = _lib.Context(rank)
+        keys, counts, k1, mates = tgs.load_case_arrays(ctx, case)
+        ref = None
+        if rank == 0:
+            cor, offs, idx, stats = __import__("shannon_b200.pipeline", fromlist=["x"]).frontend_in_memory(
+                ctx, keys, counts, k1, [(b, o, None, False) for b, o in mates], True, 3, 75, 4)
+            ref = tgs.snapshot(ctx, cor, offs, idx.copy(), stats)
+        ops = sharded.GpuOps(ctx, dev)
+        comm = sharded.TorchComm(device=dev)
+        lo, hi = sdist.shard_range(len(counts), rank, world)
+        d_keys = ctx.to_device(np.ascontiguousarray(keys[lo:hi]))
+        d_counts = ctx.to_device(np.ascontiguousarray(counts[lo:hi]))
+        n_rec = len(mates[0][1]) - 1
+        rlo, rhi = sdist.shard_range(n_rec, rank, world)
+        mine = []
+        for b, o in mates:
+            o = np.asarray(o, dtype=np.uint64)
+            mine.append((np.ascontiguousarray(b[int(o[rlo]):int(o[rhi])]),
+                         np.ascontiguousarray(o[rlo:rhi + 1] - o[rlo]), None, False))
+        for _ in range(2):     # twice: the path is re-runnable on the same contexts
+            cor, offs, idx, stats = sharded.frontend_sharded(comm, ops, ctx, d_keys, d_counts, hi - lo, lo, k1,
+                                                             mine, rlo, True, 3, 75, 4)
+        got = tgs.snapshot(ctx, cor, offs, idx, stats)
+        if rank == 0:
+            tgs.assert_same_result(ref, got, "NCCL world %d" % world)
+            assert stats["cross_edges"] > 0 and len(ref["idx"]) > 5000 and comm.bytes_sent > 0
+        ops.close()
+        ctx.close()
+        open(os.path.join(out_dir, "shok%d" % rank), "w").close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_frontend_two_gpus(tmp_path):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    world = min(torch.cuda.device_count(), 4)
+    case_dir = str(tmp_path / "cases")
+    mp.spawn(_sharded_worker, args=(world, _free_port(), str(tmp_path), case_dir), nprocs=world, join=True)
+    assert sorted(f for f in os.listdir(tmp_path) if f.startswith("shok")) == ["shok%d" % r for r in range(world)]

@@ -191,3 +191,21 @@ def test_sharded_small_k_and_empty_ranks(workdir):
     ref = single_gpu(keys, counts, k1, mates, False, 500, min_weight=2, min_length=20)
     res = run_sharded(4, keys, counts, k1, mates, False, 500, min_weight=2, min_length=20)
     assert_same_result(ref, res[0], "k1=9, world 4")
+
+
+def test_minimizer_owner_matches_numpy_twin():
+    """the CPU stand-in of the gloo protocol tests routes like the kernel (csrc/shard.cu owner_of)"""
+    import dist_testlib
+    rng = np.random.default_rng(17)
+    for k1, world in ((25, 8), (15, 3), (32, 5)):
+        n = 50000
+        hi = (1 << (2 * k1)) - 1
+        keys = rng.integers(0, hi, size=n, dtype=np.uint64, endpoint=True)
+        counts = np.ones(n, dtype=np.uint32)
+        ctx = _lib.Context(0)
+        d_keys, d_counts = ctx.to_device(keys), ctx.to_device(counts)
+        got = ctx.route_lines(d_keys, d_counts, n, 0, False, k1, world)
+        exp = np.bincount(dist_testlib.minimizer_owner(keys, k1, world), minlength=world).tolist()
+        assert got == exp
+        assert min(got) > 0.7 * n / world            # minimizer owners are balanced
+        ctx.close()

@@ -142,3 +142,68 @@ def test_merge_partitions_orders_by_rank_inside_components():
     assert offs.tolist() == [0, 3, 5, 8] and idx.tolist() == [1, 3, 10, 11, 12, 0, 2, 4]
     offs, idx = sdist.merge_partitions([(np.zeros(4, np.int64), np.zeros(0, np.uint32))] * 2, 3)
     assert offs.tolist() == [0, 0, 0, 0] and len(idx) == 0
+
+
+# ---- the whole L3 stage on sharded tables (shannon_b200/sharded.py) under gloo ----------------------
+def _sharded_worker(rank, world, port, out_dir, ds):
+    import dist_testlib
+    import helpers
+    from oracle import shannon_oracle as so
+    from shannon_b200 import sharded
+    from shannon_b200.pipeline import encode_kmer
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        work = os.path.join(out_dir, "case%d" % rank)
+        s1, s2 = helpers.synthetic_seqs(6, 500, 77)
+        case = helpers.make_case(work, 14, s1, s2, double_stranded=not ds)     # same files on every rank
+        lines = [l.split() for l in open(case.k1mer_org)]
+        keys = np.array([encode_kmer(k) for k, _ in lines], dtype=np.uint64)
+        counts = np.array([int(c) for _, c in lines], dtype=np.int64)
+        lo, hi = sdist.shard_range(len(keys), rank, world)
+        ops = dist_testlib.OracleShardOps()
+        comm = sharded.TorchComm()
+        st = {}
+        n_loaded = sharded.correct_sharded(comm, ops, keys[lo:hi], counts[lo:hi], hi - lo, lo, 15, ds, 3, 40,
+                                           stats=st)
+        # the reference's whole seed loop on the un-sharded input
+        res = so.run_correction(case.k1mer_org, os.path.join(work, "k1mer.dict"), 3, 40, ds, work, 500,
+                                write_files=False)
+        assert n_loaded == len(res.kmers)
+        assert ops.contigs[1:] == res.contigs[1:], "contigs differ from the sequential loop"
+        assert len(res.contigs) > 4
+        assert dict(zip(ops.allowed, ops.allowed_w)) == res.allowed_kmer_dict
+        assert list(ops.allowed) == list(res.allowed_kmer_dict)
+        assert dict((a, dict(b)) for a, b in ops.connections.items()) == \
+            dict((a, dict(b)) for a, b in res.connections.items())
+        assert st["cross_edges"] > 0 and st["n_super"] > st["n_raw_comps_global"]
+        open(os.path.join(out_dir, "sok%d" % rank), "w").close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,ds", [(2, False), (3, False), (2, True)])
+def test_sharded_correction_equals_sequential_loop(tmp_path, world, ds):
+    """Routing by minimizer owner, cross-rank components, component re-sharding, per-rank walks,
+    merged candidates and the replicated accept loop reproduce the reference's sequential seed
+    loop (oracle) on every rank -- protocol test with CPU stand-ins for the kernels."""
+    mp.spawn(_sharded_worker, args=(world, _free_port(), str(tmp_path), ds), nprocs=world, join=True)
+    assert sorted(f for f in os.listdir(tmp_path) if f.startswith("sok")) == ["sok%d" % r for r in range(world)]
+
+
+def test_merge_partitions_device_matches_host_merge():
+    from shannon_b200 import sharded
+    rng = np.random.default_rng(3)
+    n_comps, world = 5, 3
+    parts = []
+    for r in range(world):
+        sizes = rng.integers(0, 6, size=n_comps)
+        offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+        idx = np.sort(rng.integers(0, 100, size=int(offs[-1]))).astype(np.uint32) + 1000 * r
+        parts.append((offs, idx))
+    eo, ei = sdist.merge_partitions(parts, n_comps)
+    go, gi = sharded.merge_partitions_device([torch.from_numpy(o) for o, _ in parts],
+                                             [torch.from_numpy(i.astype(np.int64)) for _, i in parts],
+                                             n_comps, torch.device("cpu"))
+    assert go.tolist() == eo.tolist() and gi.tolist() == ei.tolist()
