@@ -693,7 +693,12 @@ def main_sharded(args, rank, world, local_rank):
             "setup_seconds": setup_s, "kmer_count_seconds": wl.count_s,
             "n_kmers_total": wl.n_kmers_total,
         }
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
+    try:
+        ops.close()
+    except Exception:
+        pass
+    ctx.close()
     dist.destroy_process_group()
 
 
@@ -848,8 +853,10 @@ def main():
         "stage_wall_ms": stats_i.get("host_timings_ms"),
         "setup_seconds": setup_s, "kmer_count_seconds": wl.count_s,
     }
-    print(json.dumps(out))
+    print(json.dumps(out), flush=True)
 
 
 if __name__ == "__main__":
+    import faulthandler
+    faulthandler.enable()
     main()

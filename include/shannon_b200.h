@@ -67,6 +67,9 @@ int shn_prof_enable(shn_ctx* ctx, int enable);
 int shn_prof_get(shn_ctx* ctx, const char* name, double* total_ms, uint64_t* launches);
 int shn_prof_dump(shn_ctx* ctx, char* buf, uint64_t buf_bytes);
 uint64_t shn_launch_count(shn_ctx* ctx); /* kernels launched by this ctx so far */
+/* Return the cached blocks of the context's device allocator to the driver (the library keeps
+ * freed blocks for re-use; a second allocator in the process, e.g. torch's, cannot see them). */
+int shn_trim(shn_ctx* ctx);
 /* Write `bytes` of scratch larger than L2 to evict cached lines between timed iterations. */
 int shn_flush_l2(shn_ctx* ctx);
 
@@ -173,9 +176,9 @@ int shn_l3_get_sizes(shn_ctx* ctx, shn_l3_sizes* out);
  * shn_l3_run == shn_l3_walks + shn_l3_filter(NULL, NULL, 0, 0, 0). */
 int shn_l3_walks(shn_ctx* ctx, uint32_t min_weight, uint32_t min_length);
 int shn_l3_cand_sizes(shn_ctx* ctx, uint64_t* n_candidates, uint64_t* n_bases);
-/* candidates of shn_l3_walks in pop order: weight and first-occurrence index of the seed (the pop
- * order key: weight descending, index descending), offsets, base codes.  Device pointers. */
-int shn_l3_cand_export(shn_ctx* ctx, uint32_t* seed_weight_dev, uint32_t* seed_first_idx_dev,
+/* candidates of shn_l3_walks in pop order: weight and (global) input line of the seed (the pop
+ * order key: weight descending, line descending), offsets, base codes.  Device pointers. */
+int shn_l3_cand_export(shn_ctx* ctx, uint32_t* seed_weight_dev, uint64_t* seed_line_dev,
                        uint64_t* offsets_dev, uint8_t* codes_dev);
 int shn_l3_filter(shn_ctx* ctx, const uint8_t* codes_dev, const uint64_t* offsets_dev, uint64_t n_cand,
                   int external, int allow_missing);
@@ -241,6 +244,11 @@ int shn_l4_assign(shn_ctx* ctx, int paired, int k1, uint64_t* n_assignments, uin
 int shn_l4_get_assignments(shn_ctx* ctx, uint32_t n_comps, uint64_t* comp_offsets,
                            uint32_t* record_idx);
 
+/* the same into device buffers (n_comps+1 offsets, n_assignments indices), record indices shifted
+ * by first_record: the lists of the ranks of the sharded path are merged on the device. */
+int shn_l4_assignments_dev(shn_ctx* ctx, uint32_t n_comps, uint64_t first_record,
+                           uint64_t* comp_offsets_dev, uint32_t* record_idx_dev);
+
 /* ---- e: the path on hash-sharded tables, one shard per rank (shannon_b200/dist.py drives the
  * exchanges with torch.distributed all_to_all_single on the same stream) -------------------------
  * Records on the wire have the size of a table slot (16 bytes for k1 <= 32, 32 bytes for k1 = 33):
@@ -256,10 +264,10 @@ int shn_l4_get_assignments(shn_ctx* ctx, uint32_t n_comps, uint64_t* comp_offset
 int shn_route_lines(shn_ctx* ctx, const uint64_t* keys_dev, const uint32_t* counts_dev, uint64_t n,
                     uint64_t first_line, int double_stranded, int k1, uint32_t nranks,
                     uint64_t* counts_host, void* send_dev);
-/* shn_table_build from received records: first-occurrence index = rank of the record's global line
- * among the received ones (order-preserving); gline_sorted_dev[i] = global line of local index i. */
-int shn_table_build_records(shn_ctx* ctx, const void* recs_dev, uint64_t n, int k1,
-                            uint64_t* gline_sorted_dev);
+/* shn_table_build from received records.  The context remembers the global input line of every
+ * record: the seed order of shn_l3_walks (weight descending, LATER global line first) and
+ * shn_cc_route read it; a key received on several lines keeps the smallest one. */
+int shn_table_build_records(shn_ctx* ctx, const void* recs_dev, uint64_t n, int k1);
 /* connected components of the successor graph restricted to this shard (lock-free union-find). */
 int shn_cc_local(shn_ctx* ctx, uint64_t* n_local_components);
 /* successor candidates owned by other ranks: {successor key, gid_base + my local component}. */
@@ -275,8 +283,8 @@ int shn_cc_merge(shn_ctx* ctx, const uint64_t* edges_dev, uint64_t n_edges, uint
 /* sizes_dev[f] = K1-mers of this shard in final component f (n_final entries, zeroed here). */
 int shn_cc_sizes(shn_ctx* ctx, uint64_t gid_base, uint64_t* sizes_dev);
 /* every table entry {key, global line << 30 | weight} to owner_of_final[its component]. */
-int shn_cc_route(shn_ctx* ctx, const uint32_t* owner_of_final_dev, uint64_t gid_base,
-                 const uint64_t* gline_dev, uint32_t nranks, uint64_t* counts_host, void* send_dev);
+int shn_cc_route(shn_ctx* ctx, const uint32_t* owner_of_final_dev, uint64_t gid_base, uint32_t nranks,
+                 uint64_t* counts_host, void* send_dev);
 int shn_cc_free(shn_ctx* ctx);
 
 /* ---- f1/f2 (inputs of the path): RC doubling, K1-mer counting, synthetic reads ---------- */

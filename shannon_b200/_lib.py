@@ -52,13 +52,14 @@ SIGNATURES = {
     "shn_l3_set_allowed_weights": (C.c_int, [vp, vp]),
     "shn_route_lines": (C.c_int, [vp, vp, vp, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_uint32,
                                   u64p, vp]),
-    "shn_table_build_records": (C.c_int, [vp, vp, C.c_uint64, C.c_int, vp]),
+    "shn_table_build_records": (C.c_int, [vp, vp, C.c_uint64, C.c_int]),
+    "shn_trim": (C.c_int, [vp]),
     "shn_cc_local": (C.c_int, [vp, u64p]),
     "shn_cc_cross": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_uint64, u64p, vp]),
     "shn_cc_resolve": (C.c_int, [vp, vp, C.c_uint64, C.c_uint64, vp, u64p]),
     "shn_cc_merge": (C.c_int, [vp, vp, C.c_uint64, C.c_uint64, u64p]),
     "shn_cc_sizes": (C.c_int, [vp, C.c_uint64, vp]),
-    "shn_cc_route": (C.c_int, [vp, vp, C.c_uint64, vp, C.c_uint32, u64p, vp]),
+    "shn_cc_route": (C.c_int, [vp, vp, C.c_uint64, C.c_uint32, u64p, vp]),
     "shn_cc_free": (C.c_int, [vp]),
     "shn_timer_start": (C.c_int, [vp]),
     "shn_timer_stop": (C.c_int, [vp, C.POINTER(C.c_float)]),
@@ -100,6 +101,7 @@ SIGNATURES = {
     "shn_l4_load_reads_staged": (C.c_int, [vp, C.c_int]),
     "shn_l4_assign": (C.c_int, [vp, C.c_int, C.c_int, u64p, u64p, u64p]),
     "shn_l4_get_assignments": (C.c_int, [vp, C.c_uint32, vp, vp]),
+    "shn_l4_assignments_dev": (C.c_int, [vp, C.c_uint32, C.c_uint64, vp, vp]),
     "shn_synth_pairs": (C.c_int, [vp, vp, vp, vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64,
                                   C.c_int, C.c_int, C.c_uint32, vp, vp]),
     "shn_revcomp_reads": (C.c_int, [vp, vp, vp, C.c_uint64, C.c_int]),
@@ -405,8 +407,8 @@ class Context(HostIO):
         self.call("shn_l3_cand_sizes", C.byref(n), C.byref(nb))
         return n.value, nb.value
 
-    def l3_cand_export(self, d_weight, d_first_idx, d_offs, d_codes):
-        self.call("shn_l3_cand_export", vp(d_weight), vp(d_first_idx), vp(d_offs), vp(d_codes))
+    def l3_cand_export(self, d_weight, d_line, d_offs, d_codes):
+        self.call("shn_l3_cand_export", vp(d_weight), vp(d_line), vp(d_offs), vp(d_codes))
 
     def l3_filter_phase(self, d_codes=None, d_offs=None, n_cand=0, external=False, allow_missing=False):
         self.call("shn_l3_filter", vp(d_codes or None), vp(d_offs or None), C.c_uint64(int(n_cand)),
@@ -431,9 +433,11 @@ class Context(HostIO):
                            vp(d_counts or None), C.c_uint64(int(n)), C.c_uint64(int(first_line)),
                            int(bool(double_stranded)), int(k1), C.c_uint32(nranks))
 
-    def table_build_records(self, d_recs, n, k1, d_gline_sorted):
-        self.call("shn_table_build_records", vp(d_recs or None), C.c_uint64(int(n)), int(k1),
-                  vp(d_gline_sorted or None))
+    def table_build_records(self, d_recs, n, k1):
+        self.call("shn_table_build_records", vp(d_recs or None), C.c_uint64(int(n)), int(k1))
+
+    def trim(self):
+        self.call("shn_trim")
 
     def cc_local(self):
         n = C.c_uint64()
@@ -459,9 +463,9 @@ class Context(HostIO):
     def cc_sizes(self, gid_base, d_sizes):
         self.call("shn_cc_sizes", C.c_uint64(int(gid_base)), vp(d_sizes))
 
-    def cc_route(self, d_owner_of_final, gid_base, d_gline, nranks, counts=None, d_send=None):
+    def cc_route(self, d_owner_of_final, gid_base, nranks, counts=None, d_send=None):
         return self._route("shn_cc_route", nranks, counts, d_send, vp(d_owner_of_final),
-                           C.c_uint64(int(gid_base)), vp(d_gline or None), C.c_uint32(nranks))
+                           C.c_uint64(int(gid_base)), C.c_uint32(nranks))
 
     def cc_free(self):
         self.call("shn_cc_free")
@@ -574,6 +578,10 @@ class Context(HostIO):
             idx = np.empty(max(n_assign, 1), dtype=np.uint32)
         self.call("shn_l4_get_assignments", C.c_uint32(n_comps), ptr(offs), ptr(idx))
         return offs, idx[:n_assign]
+
+    def l4_assignments_dev(self, n_comps, first_record, d_offs, d_idx):
+        self.call("shn_l4_assignments_dev", C.c_uint32(n_comps), C.c_uint64(int(first_record)),
+                  vp(d_offs), vp(d_idx or None))
 
     # ---- inputs of the path -----------------------------------------------------------------
     def synth_pairs(self, d_tx, d_tx_offs, d_thr, n_tx, n_pairs, first_pair, seed, read_len,

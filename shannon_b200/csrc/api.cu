@@ -113,6 +113,7 @@ void shn_destroy(shn_ctx* c) {
   shn_count_free(c);
   shn_reads_free(c);
   shn_shard_free(c);
+  c->gline_buf.release();
   c->table.release();
   c->cub_tmp.release();
   c->flush_buf.release();
@@ -256,6 +257,12 @@ int shn_prof_dump(shn_ctx* c, char* buf, uint64_t buf_bytes) {
 }
 uint64_t shn_launch_count(shn_ctx* c) { return c ? c->launches : 0; }
 
+int shn_trim(shn_ctx* c) {
+  SHN_API_BEGIN
+  bind(c);
+  c->pool.trim();
+  SHN_API_END(c)
+}
 int shn_flush_l2(shn_ctx* c) {
   SHN_API_BEGIN
   bind(c);
@@ -489,11 +496,11 @@ int shn_l3_cand_sizes(shn_ctx* c, uint64_t* n_cand, uint64_t* n_bases) {
   SHN_DISPATCH(c->k1, l3_cand_sizes(c, n_cand, n_bases));
   SHN_API_END(c)
 }
-int shn_l3_cand_export(shn_ctx* c, uint32_t* weight_dev, uint32_t* first_idx_dev, uint64_t* offs_dev,
+int shn_l3_cand_export(shn_ctx* c, uint32_t* weight_dev, uint64_t* line_dev, uint64_t* offs_dev,
                        uint8_t* codes_dev) {
   SHN_API_BEGIN
   bind(c);
-  SHN_DISPATCH(c->k1, l3_cand_export(c, weight_dev, first_idx_dev, offs_dev, codes_dev));
+  SHN_DISPATCH(c->k1, l3_cand_export(c, weight_dev, line_dev, offs_dev, codes_dev));
   SHN_API_END(c)
 }
 int shn_l3_filter(shn_ctx* c, const uint8_t* codes_dev, const uint64_t* offs_dev, uint64_t n_cand,
@@ -533,12 +540,13 @@ int shn_route_lines(shn_ctx* c, const uint64_t* keys_dev, const uint32_t* counts
                                send_dev));
   SHN_API_END(c)
 }
-int shn_table_build_records(shn_ctx* c, const void* recs_dev, uint64_t n, int k1, uint64_t* gline_sorted_dev) {
+int shn_table_build_records(shn_ctx* c, const void* recs_dev, uint64_t n, int k1) {
   SHN_API_BEGIN
   bind(c);
   shn_l3_free(c);
+  shn_shard_free(c);
   SHN_CHECK(k1 >= 1 && k1 <= 33, "k1 must be in 1..33");
-  SHN_DISPATCH(k1, table_build_records(c, recs_dev, n, k1, gline_sorted_dev));
+  SHN_DISPATCH(k1, table_build_records(c, recs_dev, n, k1));
   SHN_API_END(c)
 }
 int shn_cc_local(shn_ctx* c, uint64_t* n_local) {
@@ -573,11 +581,11 @@ int shn_cc_sizes(shn_ctx* c, uint64_t gid_base, uint64_t* sizes_dev) {
   SHN_DISPATCH(c->k1, cc_sizes(c, gid_base, sizes_dev));
   SHN_API_END(c)
 }
-int shn_cc_route(shn_ctx* c, const uint32_t* owner_of_final_dev, uint64_t gid_base, const uint64_t* gline_dev,
-                 uint32_t nranks, uint64_t* counts_host, void* send_dev) {
+int shn_cc_route(shn_ctx* c, const uint32_t* owner_of_final_dev, uint64_t gid_base, uint32_t nranks,
+                 uint64_t* counts_host, void* send_dev) {
   SHN_API_BEGIN
   bind(c);
-  SHN_DISPATCH(c->k1, cc_route(c, owner_of_final_dev, gid_base, gline_dev, nranks, counts_host, send_dev));
+  SHN_DISPATCH(c->k1, cc_route(c, owner_of_final_dev, gid_base, nranks, counts_host, send_dev));
   SHN_API_END(c)
 }
 int shn_cc_free(shn_ctx* c) {
@@ -668,6 +676,14 @@ int shn_l4_get_assignments(shn_ctx* c, uint32_t n_comps, uint64_t* comp_offsets,
   SHN_API_BEGIN
   bind(c);
   SHN_DISPATCH(c->l4_k1, l4_get_assignments(c, n_comps, comp_offsets, record_idx));
+  SHN_API_END(c)
+}
+
+int shn_l4_assignments_dev(shn_ctx* c, uint32_t n_comps, uint64_t first_record, uint64_t* comp_offsets_dev,
+                           uint32_t* record_idx_dev) {
+  SHN_API_BEGIN
+  bind(c);
+  SHN_DISPATCH(c->l4_k1, l4_assignments_dev(c, n_comps, first_record, comp_offsets_dev, record_idx_dev));
   SHN_API_END(c)
 }
 

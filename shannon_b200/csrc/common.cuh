@@ -387,6 +387,10 @@ struct shn_ctx {
   int k1 = 0;
   int l4_k1 = 0;  // k1 of the component map (may differ from the table's in a fresh process)
   uint64_t n_distinct = 0, n_lowcomplexity = 0, n_items = 0;
+  // sharded path: the idx word of a slot is the position of its record in the receive buffer and
+  // gline_dev[position] the global input line (nullptr: idx IS the line)
+  DevBuf gline_buf;
+  const uint64_t* gline_dev = nullptr;
   // stage states, owned by the key-width specific code that created them
   void* l3 = nullptr;
   void (*l3_free)(shn_ctx*) = nullptr;

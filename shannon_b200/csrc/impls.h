@@ -22,14 +22,13 @@
   void l3_filter(shn_ctx* c, const uint8_t* ext_codes, const uint64_t* ext_offs, uint64_t ext_n,     \
                  int ext, int allow_missing);                                                        \
   void l3_cand_sizes(shn_ctx* c, uint64_t* n_cand, uint64_t* n_bases);                               \
-  void l3_cand_export(shn_ctx* c, uint32_t* d_weight, uint32_t* d_first_idx, uint64_t* d_offs,       \
+  void l3_cand_export(shn_ctx* c, uint32_t* d_weight, uint64_t* d_line, uint64_t* d_offs,            \
                       uint8_t* d_codes);                                                             \
   void l3_set_allowed_weights(shn_ctx* c, const uint32_t* d_w);                                      \
   void route_lines(shn_ctx* c, const uint64_t* d_keys, const uint32_t* d_counts, uint64_t n,         \
                    uint64_t first_line, int ds, int k1, uint32_t nranks, uint64_t* h_counts,         \
                    void* send);                                                                      \
-  void table_build_records(shn_ctx* c, const void* d_recs, uint64_t n, int k1,                       \
-                           uint64_t* d_gline_sorted);                                                \
+  void table_build_records(shn_ctx* c, const void* d_recs, uint64_t n, int k1);                      \
   void cc_local(shn_ctx* c, uint64_t* n_local);                                                      \
   void cc_cross(shn_ctx* c, uint32_t nranks, uint32_t rank, uint64_t gid_base, uint64_t* h_counts,   \
                 void* send);                                                                         \
@@ -38,8 +37,8 @@
   void cc_merge(shn_ctx* c, const uint64_t* d_edges, uint64_t n_edges, uint64_t n_super,             \
                 uint64_t* n_final);                                                                  \
   void cc_sizes(shn_ctx* c, uint64_t gid_base, uint64_t* d_sizes);                                   \
-  void cc_route(shn_ctx* c, const uint32_t* d_owner_of_final, uint64_t gid_base,                     \
-                const uint64_t* d_gline, uint32_t nranks, uint64_t* h_counts, void* send);           \
+  void cc_route(shn_ctx* c, const uint32_t* d_owner_of_final, uint64_t gid_base, uint32_t nranks,    \
+                uint64_t* h_counts, void* send);                                                     \
   void cc_free(shn_ctx* c);                                                                          \
   void l3_get_sizes(shn_ctx* c, shn_l3_sizes* out);                                                  \
   void l3_get_walks(shn_ctx* c, uint64_t* seed_keys, uint32_t* n_left, uint32_t* n_right,            \
@@ -61,6 +60,8 @@
   void l4_assign(shn_ctx* c, int paired, int k1, uint64_t* n_assign, uint64_t* n_lookups,            \
                  uint64_t* n_valid);                                                                 \
   void l4_get_assignments(shn_ctx* c, uint32_t n_comps, uint64_t* h_offs, uint32_t* h_idx);          \
+  void l4_assignments_dev(shn_ctx* c, uint32_t n_comps, uint64_t first_record, uint64_t* d_offs,     \
+                          uint32_t* d_idx);                                                          \
   void count_k1mers(shn_ctx* c, const char* const* arrays, const uint64_t* n_reads, int n_arrays,    \
                     int read_len, int k1, uint64_t expected_distinct, uint64_t** keys_dev,           \
                     uint32_t** counts_dev, uint64_t* n_distinct);                                    \

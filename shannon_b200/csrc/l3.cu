@@ -79,8 +79,8 @@ __global__ void __launch_bounds__(kBlock)
 // weight descending, then first-occurrence index descending (stable ascending sort + pop()).
 __global__ void __launch_bounds__(kBlock)
     seed_emit_kernel(const ShnSlot* __restrict__ slots, uint64_t n_slots, uint32_t min_weight,
-                     uint64_t* __restrict__ sortkey, uint32_t* __restrict__ sslot,
-                     unsigned long long* cursor) {
+                     const uint64_t* __restrict__ gline, uint64_t* __restrict__ sortkey,
+                     uint32_t* __restrict__ sslot, unsigned long long* cursor) {
   __shared__ unsigned long long block_base;
   __shared__ int warp_off[kBlock / 32];
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -105,7 +105,10 @@ __global__ void __launch_bounds__(kBlock)
   __syncthreads();
   if (is_seed) {
     uint64_t o = block_base + warp_off[warp] + __popc(b & ((1u << lane) - 1u));
-    sortkey[o] = ((uint64_t)(~wt) << 32) | (uint64_t)(~first_idx);
+    // sharded tables: first_idx is a receive-buffer position, the global input line (34 bits) is
+    // behind gline[]; weights have 30 bits
+    sortkey[o] = gline ? (((uint64_t)(~wt & SHN_WEIGHT_MASK) << 34) | (~gline[first_idx] & 0x3FFFFFFFFull))
+                       : (((uint64_t)(~wt) << 32) | (uint64_t)(~first_idx));
     sslot[o] = (uint32_t)i;
   }
 }
@@ -1270,7 +1273,7 @@ void l3_walks(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
     {
       ProfScope ps(c, "seed_emit");
       seed_emit_kernel<<<shn_grid(n_slots, kBlock), kBlock, 0, st>>>(
-          tv.slots, n_slots, min_weight, skey.as<uint64_t>(), sslot.as<uint32_t>(), ctr);
+          tv.slots, n_slots, min_weight, c->gline_dev, skey.as<uint64_t>(), sslot.as<uint32_t>(), ctr);
       KERNEL_CHECK();
     }
     ProfScope ps(c, "seed_sort");
@@ -2008,15 +2011,15 @@ void l3_get_sizes(shn_ctx* c, shn_l3_sizes* out) { *out = need_l3(c)->sz; }
 namespace {
 __global__ void __launch_bounds__(kBlock)
     cand_seed_kernel(const ShnSlot* __restrict__ slots, const uint32_t* __restrict__ cand_walk,
-                     const uint32_t* __restrict__ w_slot, uint64_t n, uint32_t* __restrict__ weight,
-                     uint32_t* __restrict__ first_idx) {
+                     const uint32_t* __restrict__ w_slot, uint64_t n, const uint64_t* __restrict__ gline,
+                     uint32_t* __restrict__ weight, uint64_t* __restrict__ line) {
   uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
   shn_key_t key;
   uint32_t wz, wi;
   table_load_slot(slots, w_slot[cand_walk[j]], &key, &wz, &wi);
   weight[j] = wz & SHN_WEIGHT_MASK;
-  first_idx[j] = wi;
+  line[j] = gline ? gline[wi] : (uint64_t)wi;
 }
 }  // namespace
 
@@ -2027,8 +2030,8 @@ void l3_cand_sizes(shn_ctx* c, uint64_t* n_cand, uint64_t* n_bases) {
   *n_bases = s->h_cand_off.back();
 }
 
-// pop-order key of every candidate = (seed weight desc, seed first-occurrence index desc)
-void l3_cand_export(shn_ctx* c, uint32_t* d_weight, uint32_t* d_first_idx, uint64_t* d_offs,
+// pop-order key of every candidate = (seed weight desc, input line of the seed desc)
+void l3_cand_export(shn_ctx* c, uint32_t* d_weight, uint64_t* d_line, uint64_t* d_offs,
                     uint8_t* d_codes) {
   L3State* s = need_l3(c);
   SHN_CHECK(!s->foreign, "the candidates of this context were replaced by shn_l3_filter");
@@ -2036,8 +2039,8 @@ void l3_cand_export(shn_ctx* c, uint32_t* d_weight, uint32_t* d_first_idx, uint6
   cudaStream_t st = c->stream;
   if (n) {
     cand_seed_kernel<<<shn_grid(n, kBlock), kBlock, 0, st>>>(table_view(c).slots, s->cand_walk.as<uint32_t>(),
-                                                            s->w_seed_slot.as<uint32_t>(), n, d_weight,
-                                                            d_first_idx);
+                                                            s->w_seed_slot.as<uint32_t>(), n, c->gline_dev,
+                                                            d_weight, d_line);
     KERNEL_CHECK();
   }
   CUDA_CHECK(cudaMemcpyAsync(d_offs, s->cand_off.p, (n + 1) * 8, cudaMemcpyDeviceToDevice, st));

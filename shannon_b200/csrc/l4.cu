@@ -381,6 +381,13 @@ __global__ void __launch_bounds__(kBlock)
   if (i < n) out[i] = (uint32_t)entries[i];
 }
 
+__global__ void __launch_bounds__(kBlock)
+    entries_low32_add_kernel(const uint64_t* __restrict__ entries, uint64_t n, uint32_t add,
+                             uint32_t* __restrict__ out) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (uint32_t)entries[i] + add;
+}
+
 void l4_state_free(shn_ctx* c) {
   delete static_cast<L4State*>(c->l4);
   c->l4 = nullptr;
@@ -596,6 +603,22 @@ void l4_get_assignments(shn_ctx* c, uint32_t n_comps, uint64_t* h_offs, uint32_t
   CUDA_CHECK(cudaMemcpyAsync(h_offs, offs.p, (uint64_t)(n_comps + 1) * 8, cudaMemcpyDeviceToHost,
                              c->stream));
   CUDA_CHECK(cudaStreamSynchronize(c->stream));
+}
+
+// the same into caller-owned DEVICE buffers (sharded path: the lists of the ranks are merged on
+// the device); record indices are shifted by `first_record` (this rank's first global record)
+void l4_assignments_dev(shn_ctx* c, uint32_t n_comps, uint64_t first_record, uint64_t* d_offs,
+                        uint32_t* d_idx) {
+  L4State* s = l4_of(c);
+  uint64_t m = s->n_assign;
+  comp_offsets_kernel<<<shn_grid(m + 1, kBlock), kBlock, 0, c->stream>>>(s->assign.as<uint64_t>(), m,
+                                                                         n_comps, d_offs);
+  KERNEL_CHECK();
+  if (m) {
+    entries_low32_add_kernel<<<shn_grid(m, kBlock), kBlock, 0, c->stream>>>(s->assign.as<uint64_t>(), m,
+                                                                            (uint32_t)first_record, d_idx);
+    KERNEL_CHECK();
+  }
 }
 
 }  // namespace SHN_NS

@@ -274,33 +274,32 @@ void route(shn_ctx* c, const char* name, const Src& src, uint64_t n_items, uint3
 }
 
 // ---- table shard from routed records ------------------------------------------------------------
+// The first-occurrence word of a slot holds the POSITION of the record in the receive buffer;
+// gline[position] is its global input line, and the seed order of the walks reads the line through
+// that table (l3.cu seed_emit_kernel), so nothing has to be sorted here.  A key that arrives on
+// several lines (repeated lines, palindromes under -d) keeps the record with the smallest global
+// line: the later arrivals are listed and resolved by dup_resolve_kernel.
+// counters as table_insert_kernel: [0]=new keys [1]=low-complexity [2]=later arrivals [3]=bad
 __global__ void __launch_bounds__(kBlock)
-    rec_gline_kernel(const ShnRec* __restrict__ recs, uint64_t n, uint64_t* __restrict__ gl,
-                     uint32_t* __restrict__ iota) {
-  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  gl[i] = recs[i].payload >> kGlineShift;
-  iota[i] = (uint32_t)i;
-}
-
-// record perm[i] is the i-th in global line order: its local first-occurrence index is i
-// counters as table_insert_kernel: [0]=new keys [1]=low-complexity [3]=bad
-__global__ void __launch_bounds__(kBlock)
-    insert_records_kernel(ShnTableView t, const ShnRec* __restrict__ recs, const uint32_t* __restrict__ perm,
-                          uint64_t n, int k1, unsigned long long* counters) {
+    insert_records_kernel(ShnTableView t, const ShnRec* __restrict__ recs, uint64_t n, int k1,
+                          uint64_t* __restrict__ gline, uint32_t* __restrict__ dups,
+                          unsigned long long* counters) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int n_new = 0, n_low = 0, n_bad = 0;
   if (i < n) {
-    const ShnRec r = recs[perm[i]];
+    const ShnRec r = recs[i];
     const uint32_t w = (uint32_t)(r.payload & SHN_WEIGHT_MASK);
+    gline[i] = r.payload >> kGlineShift;
     if (r.key & ~shn_key_mask(k1)) {
       n_bad = 1;
     } else if (shn_low_complexity(r.key, k1)) {
       n_low = 1;
     } else {
       uint32_t old = 0;
-      const uint64_t slot = table_insert_add(t, r.key, w, (uint32_t)i, &n_new, &old);
+      const int before = n_new;
+      const uint64_t slot = table_insert_add(t, r.key, w, (uint32_t)i, &n_new, &old, false);
       if (slot == ~0ull || (uint64_t)old + w >= (uint64_t)SHN_WEIGHT_MASK) n_bad = 1;
+      else if (n_new == before) dups[atomicAdd(&counters[2], 1ull)] = (uint32_t)i;
     }
   }
   int tot_new = __syncthreads_count(n_new), tot_low = __syncthreads_count(n_low),
@@ -309,6 +308,25 @@ __global__ void __launch_bounds__(kBlock)
     if (tot_new) atomicAdd(&counters[0], (unsigned long long)tot_new);
     if (tot_low) atomicAdd(&counters[1], (unsigned long long)tot_low);
     if (tot_bad) atomicAdd(&counters[3], (unsigned long long)tot_bad);
+  }
+}
+
+// runs after insert_records_kernel has finished: every slot's idx word is initialised
+__global__ void __launch_bounds__(kBlock)
+    dup_resolve_kernel(ShnTableView t, const ShnRec* __restrict__ recs, const uint32_t* __restrict__ dups,
+                       uint64_t n_dups, const uint64_t* __restrict__ gline) {
+  uint64_t d = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= n_dups) return;
+  const uint32_t i = dups[d];
+  uint32_t w;
+  const uint64_t slot = table_find(t, recs[i].key, &w);
+  if (slot == ~0ull) return;
+  uint32_t* p = &t.slots[slot].idx;
+  uint32_t cur = *reinterpret_cast<volatile uint32_t*>(p);
+  while (gline[i] < gline[cur]) {
+    const uint32_t old = atomicCAS(p, cur, i);
+    if (old == cur) break;
+    cur = old;
   }
 }
 
@@ -454,33 +472,35 @@ void route_lines(shn_ctx* c, const uint64_t* d_keys, const uint32_t* d_counts, u
   route(c, send ? "route_lines_fill" : "route_lines_count", src, n, nranks, h_counts, send);
 }
 
-void table_build_records(shn_ctx* c, const void* d_recs, uint64_t n, int k1, uint64_t* d_gline_sorted) {
+void table_build_records(shn_ctx* c, const void* d_recs, uint64_t n, int k1) {
   const ShnRec* recs = static_cast<const ShnRec*>(d_recs);
   table_begin(c, n, k1, 0);
+  c->gline_buf.reserve(std::max<uint64_t>(n, 1) * 8);
+  uint64_t* d_gline = c->gline_buf.as<uint64_t>();
   cudaStream_t st = c->stream;
   if (n) {
-    DevBuf gl, iota, perm;
-    gl.reserve(n * 8);
-    iota.reserve(n * 4);
-    perm.reserve(n * 4);
+    DevBuf dups;
+    dups.reserve(n * 4);
+    unsigned long long* ctr = c->counters.as<unsigned long long>();
     {
-      ProfScope ps(c, "records_sort", 3);
-      rec_gline_kernel<<<shn_grid(n, kBlock), kBlock, 0, st>>>(recs, n, gl.as<uint64_t>(), iota.as<uint32_t>());
+      ProfScope ps(c, "table_insert");
+      insert_records_kernel<<<shn_grid(n, kBlock), kBlock, 0, st>>>(table_view(c), recs, n, k1, d_gline,
+                                                                   dups.as<uint32_t>(), ctr);
       KERNEL_CHECK();
-      size_t tb = 0;
-      CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, tb, gl.as<uint64_t>(), d_gline_sorted, iota.as<uint32_t>(),
-                                                 perm.as<uint32_t>(), (int64_t)n, 0, 64 - kGlineShift, st));
-      CUDA_CHECK(cub::DeviceRadixSort::SortPairs(c->tmp(tb), tb, gl.as<uint64_t>(), d_gline_sorted,
-                                                 iota.as<uint32_t>(), perm.as<uint32_t>(), (int64_t)n, 0,
-                                                 64 - kGlineShift, st));
     }
-    ProfScope ps(c, "table_insert");
-    insert_records_kernel<<<shn_grid(n, kBlock), kBlock, 0, st>>>(table_view(c), recs, perm.as<uint32_t>(), n, k1,
-                                                                 c->counters.as<unsigned long long>());
-    KERNEL_CHECK();
-    CUDA_CHECK(cudaStreamSynchronize(st));  // gl / iota / perm go back to the pool only after their last use
+    unsigned long long n_dups = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&n_dups, ctr + 2, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    if (n_dups) {
+      ProfScope ps(c, "table_dup_lines");
+      dup_resolve_kernel<<<shn_grid(n_dups, kBlock), kBlock, 0, st>>>(table_view(c), recs, dups.as<uint32_t>(),
+                                                                     n_dups, d_gline);
+      KERNEL_CHECK();
+      CUDA_CHECK(cudaStreamSynchronize(st));  // dups returns to the pool
+    }
   }
   table_finish(c);
+  c->gline_dev = d_gline;  // the seed order of shn_l3_walks reads global lines through it
 }
 
 void cc_local(shn_ctx* c, uint64_t* n_local) {
@@ -615,10 +635,11 @@ void cc_sizes(shn_ctx* c, uint64_t gid_base, uint64_t* d_sizes) {
   CUDA_CHECK(cudaStreamSynchronize(st));  // `local` returns to the pool
 }
 
-void cc_route(shn_ctx* c, const uint32_t* d_owner_of_final, uint64_t gid_base, const uint64_t* d_gline,
-              uint32_t nranks, uint64_t* h_counts, void* send) {
+void cc_route(shn_ctx* c, const uint32_t* d_owner_of_final, uint64_t gid_base, uint32_t nranks,
+              uint64_t* h_counts, void* send) {
   ShardState* s = shard_of(c);
-  ByCompSrc src{cc_view(c, s, gid_base), s->final_of_super.as<uint32_t>(), d_owner_of_final, d_gline};
+  SHN_CHECK(c->gline_dev != nullptr, "the table was not built with shn_table_build_records");
+  ByCompSrc src{cc_view(c, s, gid_base), s->final_of_super.as<uint32_t>(), d_owner_of_final, c->gline_dev};
   route(c, send ? "cc_route_fill" : "cc_route_count", src, s->n_slots, nranks, h_counts, send);
 }
 

@@ -158,6 +158,7 @@ void table_begin(shn_ctx* c, uint64_t n, int k1, int double_stranded) {
   c->n_buckets = n_buckets;
   c->k1 = k1;
   c->n_items = items;
+  c->gline_dev = nullptr;  // set again by table_build_records
   c->counters.reserve(64 * sizeof(unsigned long long));
   unsigned long long* ctr = c->counters.as<unsigned long long>();
   CUDA_CHECK(cudaMemsetAsync(ctr, 0, 8 * sizeof(unsigned long long), c->stream));

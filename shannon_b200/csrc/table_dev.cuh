@@ -162,8 +162,10 @@ __device__ __forceinline__ uint64_t table_upsert_slot(const ShnTableView& t, shn
 // 128-bit CAS of the whole slot {key, w, idx} against the pristine pattern {EMPTY, 0, 0xFFFFFFFF}
 // (one atomic round trip instead of CAS + add + min); only a key that is already present takes
 // the add/min path.  Returns the slot (~0: table full); *old_w = weight before this insert.
+// min_idx == false: an already present key keeps its idx word (the caller resolves first occurrences).
 __device__ __forceinline__ uint64_t table_insert_add(const ShnTableView& t, shn_key_t key, uint32_t w,
-                                                     uint32_t idx, int* is_new, uint32_t* old_w) {
+                                                     uint32_t idx, int* is_new, uint32_t* old_w,
+                                                     bool min_idx = true) {
 #ifdef SHN_WIDE
   // 128-bit keys: the key is claimed with a 128-bit CAS; a freshly claimed slot then gets its
   // {weight, idx} pair with ONE 64-bit CAS against the pristine {0, 0xFFFFFFFF} (it fails only if a
@@ -179,7 +181,7 @@ __device__ __forceinline__ uint64_t table_insert_add(const ShnTableView& t, shn_
     }
   }
   *old_w = atomicAdd(&t.slots[slot].weight, w) & SHN_WEIGHT_MASK;
-  atomicMin(&t.slots[slot].idx, idx);
+  if (min_idx) atomicMin(&t.slots[slot].idx, idx);
   return slot;
 #else
   const u128 pristine = ((u128)0xFFFFFFFF00000000ull << 64) | (u128)SHN_EMPTY_KEY;
@@ -207,7 +209,7 @@ __device__ __forceinline__ uint64_t table_insert_add(const ShnTableView& t, shn_
     }
     if (hit != ~0ull) {
       *old_w = atomicAdd(&t.slots[hit].weight, w) & SHN_WEIGHT_MASK;
-      atomicMin(&t.slots[hit].idx, idx);
+      if (min_idx) atomicMin(&t.slots[hit].idx, idx);
       return hit;
     }
     // every slot holds another key: leave the trail marker for lookups, then move on

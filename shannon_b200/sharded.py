@@ -198,9 +198,7 @@ class GpuOps(object):
         return send, counts
 
     def build_from_records(self, recs, k1):
-        gl = self._empty(recs.shape[0], torch.int64)
-        self.ctx.table_build_records(recs.data_ptr(), recs.shape[0], k1, gl.data_ptr())
-        return gl
+        self.ctx.table_build_records(recs.data_ptr(), recs.shape[0], k1)
 
     def n_distinct(self):
         return self.ctx.table_stats()["n_distinct"]
@@ -227,11 +225,11 @@ class GpuOps(object):
         self.ctx.cc_sizes(gid_base, sizes.data_ptr())
         return sizes[:n_final]
 
-    def cc_route(self, owner_of_final, gid_base, gline, world, k1):
+    def cc_route(self, owner_of_final, gid_base, world, k1):
         own = owner_of_final.to(device=self.device, dtype=torch.int32).contiguous()
-        counts = self.ctx.cc_route(own.data_ptr(), gid_base, gline.data_ptr(), world)
+        counts = self.ctx.cc_route(own.data_ptr(), gid_base, world)
         send = self._empty((sum(counts), self.rec_words(k1)), torch.int64)
-        self.ctx.cc_route(own.data_ptr(), gid_base, gline.data_ptr(), world, counts, send.data_ptr())
+        self.ctx.cc_route(own.data_ptr(), gid_base, world, counts, send.data_ptr())
         return send, counts
 
     def cc_free(self):
@@ -243,11 +241,11 @@ class GpuOps(object):
     def cand_export(self):
         n, nb = self.ctx.l3_cand_sizes()
         w = self._empty(n, torch.int32)
-        idx = self._empty(n, torch.int32)
+        line = self._empty(n, torch.int64)
         offs = torch.empty(n + 1, dtype=torch.int64, device=self.device)
         codes = self._empty(nb, torch.uint8)
-        self.ctx.l3_cand_export(w.data_ptr(), idx.data_ptr(), offs.data_ptr(), codes.data_ptr())
-        return w, idx.to(torch.int64) & 0xFFFFFFFF, offs, codes
+        self.ctx.l3_cand_export(w.data_ptr(), line.data_ptr(), offs.data_ptr(), codes.data_ptr())
+        return w, line, offs, codes
 
     def l3_filter(self, codes, offs, n_cand):
         return self.ctx.l3_filter_phase(codes.data_ptr() if codes.numel() else None, offs.data_ptr(),
@@ -260,6 +258,24 @@ class GpuOps(object):
 
     def set_allowed_weights(self, w):
         self.ctx.l3_set_allowed_weights(w.data_ptr() if w.numel() else None)
+
+    def assignments(self, n_comps, n_assign, first_record):
+        """(comp_offsets int64 [n_comps+1], global record indices int32 [n_assign]) on the device"""
+        offs = torch.empty(n_comps + 1, dtype=torch.int64, device=self.device)
+        idx = self._empty(n_assign, torch.int32)
+        self.ctx.l4_assignments_dev(n_comps, first_record, offs.data_ptr(), idx.data_ptr())
+        return offs, idx
+
+    def to_host(self, t):
+        """device tensor -> numpy through a cached page-locked buffer (valid until the next call)"""
+        nbytes = t.numel() * t.element_size()
+        buf = getattr(self, "_pinned", None)
+        if buf is None or buf.numel() < nbytes:
+            buf = self._pinned = torch.empty(max(nbytes + nbytes // 2, 1), dtype=torch.uint8, pin_memory=True)
+        view = buf[:nbytes].view(t.dtype)
+        view.copy_(t.reshape(-1), non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return view.numpy()
 
 
 # ---- host-side decisions ---------------------------------------------------------------------------
@@ -331,7 +347,7 @@ def correct_sharded(comm, ops, d_keys, d_counts, n_lines, first_line, k1, double
     send, counts = ops.route_lines(d_keys, d_counts, n_lines, first_line, double_stranded, k1, world)
     recs, _ = comm.all_to_all_rows(send, counts)
     del send
-    gline = ops.build_from_records(recs, k1)
+    ops.build_from_records(recs, k1)
     del recs
     n_shard = ops.n_distinct()
     tm["shard_build"] = time.perf_counter() - t0
@@ -357,11 +373,11 @@ def correct_sharded(comm, ops, d_keys, d_counts, n_lines, first_line, k1, double
     tm["components"] = time.perf_counter() - t0
     t0 = time.perf_counter()
     # 3. whole components to their ranks
-    send, counts = ops.cc_route(torch.from_numpy(owner), gid_base, gline, world, k1)
+    send, counts = ops.cc_route(torch.from_numpy(owner), gid_base, world, k1)
     ops.cc_free()
     recs, _ = comm.all_to_all_rows(send, counts)
-    del send, gline
-    gline2 = ops.build_from_records(recs, k1)
+    del send
+    ops.build_from_records(recs, k1)
     del recs
     tm["reshard"] = time.perf_counter() - t0
     t0 = time.perf_counter()
@@ -372,10 +388,9 @@ def correct_sharded(comm, ops, d_keys, d_counts, n_lines, first_line, k1, double
     tm["walks"] = time.perf_counter() - t0
     t0 = time.perf_counter()
     # 5. merge candidates, replicated filter stage
-    w, idx, offs, codes = ops.cand_export()
-    cg = gline2[idx] if idx.numel() else idx
+    w, line, offs, codes = ops.cand_export()
     st["n_local_candidates"] = int(w.shape[0])
-    mcodes, moffs, n_cand = merge_candidates(comm, w, cg, offs, codes)
+    mcodes, moffs, n_cand = merge_candidates(comm, w, line, offs, codes)
     sz = ops.l3_filter(mcodes, moffs, n_cand)
     aw = ops.allowed_weights(sz["n_allowed"])
     comm.all_reduce_sum(aw)
@@ -394,7 +409,7 @@ def merge_partitions_device(offs_list, idx_list, n_comps, device):
     goff = torch.zeros(n_comps + 1, dtype=torch.int64, device=device)
     goff[1:] = torch.cumsum(total, 0)
     before = torch.cumsum(sizes, 0) - sizes
-    out = torch.empty(int(goff[-1].item()), dtype=torch.int64, device=device)
+    out = torch.empty(int(goff[-1].item()), dtype=idx_list[0].dtype, device=device)
     comp_ids = torch.arange(n_comps, dtype=torch.int64, device=device)
     for r, (offs, idx) in enumerate(zip(offs_list, idx_list)):
         n = idx.shape[0]
@@ -422,10 +437,8 @@ def frontend_sharded(comm, ops, ctx, d_keys, d_counts, n_lines, first_line, k1, 
     ctx.l4_map_add_l3_contigs(comp_of_contig[1:], True)
     ctx.l4_map_set_weights(None, None)
     n_assign, n_lookups, n_valid = ctx.l4_assign(paired, k1)
-    offs, idx = ctx.l4_assignments(n_comps, n_assign, pinned=True)
     dev = ops.device
-    t_offs = torch.from_numpy(offs.astype(np.int64)).to(dev)
-    t_idx = torch.from_numpy(idx.astype(np.int64)).to(dev) + int(rec_lo)
+    t_offs, t_idx = ops.assignments(n_comps, n_assign, rec_lo)
     all_offs, _ = comm.all_gather_rows(t_offs.view(1, -1))
     all_idx, icounts = comm.all_gather_rows(t_idx)
     tot = comm.exchange_ints([n_assign, n_lookups, n_valid])
@@ -436,7 +449,7 @@ def frontend_sharded(comm, ops, ctx, d_keys, d_counts, n_lines, first_line, k1, 
             [all_offs[r] for r in range(comm.world)],
             [all_idx[int(bounds[r]):int(bounds[r + 1])] for r in range(comm.world)], n_comps, dev)
         comp_offs = goff.cpu().numpy()
-        rec_idx = merged.to(torch.int32).cpu().numpy().view(np.uint32)
+        rec_idx = ops.to_host(merged).view(np.uint32)
     tm["partition_reads"] = time.perf_counter() - t0
     stats = {"assignments": sum(v[0] for v in tot), "lookups": sum(v[1] for v in tot),
              "valid_records": sum(v[2] for v in tot)}

@@ -210,7 +210,7 @@ class OracleShardOps(object):
                 continue
             e = self.table.setdefault(key, [0, i])
             e[0] += w
-        return torch.from_numpy(gl[order].astype(np.int64))
+        self.gline = gl[order]
 
     def n_distinct(self):
         return len(self.table)
@@ -281,9 +281,9 @@ class OracleShardOps(object):
             sizes[self.final_of_super[gid_base + lc]] += 1
         return torch.from_numpy(sizes)
 
-    def cc_route(self, owner_of_final, gid_base, gline, world, k1):
+    def cc_route(self, owner_of_final, gid_base, world, k1):
         own = owner_of_final.numpy()
-        gl = gline.numpy().astype(np.uint64)
+        gl = self.gline
         rows, dest = [], []
         for k, (w, idx) in self.table.items():
             rows.append((k, (int(gl[idx]) << 30) | w))
@@ -306,7 +306,7 @@ class OracleShardOps(object):
 
     def cand_export(self):
         w = [self.kmers[c.seed] for c in self.cands]
-        idx = [self.table[self._kint(c.seed)][1] for c in self.cands]
+        idx = [int(self.gline[self.table[self._kint(c.seed)][1]]) for c in self.cands]
         lens = [len(c.contig) for c in self.cands]
         offs = np.zeros(len(lens) + 1, dtype=np.int64)
         offs[1:] = np.cumsum(lens)
