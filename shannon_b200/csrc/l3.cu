@@ -358,6 +358,7 @@ struct WalkArgs {
   uint64_t* totwt;
   uint64_t* logstart;
   unsigned long long* counters;  // [0]=traversed [1]=max rounds of a warp [2]=log overflow [3]=windows
+                                 // [4]=speculative path buffer overflow
   unsigned long long* trace;     // optional: per warp {end time ns, rounds, cycles} (SHN_WALK_TRACE)
 };
 
@@ -647,7 +648,7 @@ __global__ void __launch_bounds__(kSpecWarps * 32, kSpecCtasPerSM * 16 / kSpecWa
     sh_lp = a.log_off[comp];
   }
   unsigned long long rounds = 0, traversed = 0, windows = 0, n_commit = 0, n_retry = 0;
-  bool overflow = false;
+  bool overflow = false, path_overflow = false;
   __syncthreads();
 
   for (;;) {
@@ -778,7 +779,7 @@ __global__ void __launch_bounds__(kSpecWarps * 32, kSpecCtasPerSM * 16 / kSpecWa
               my_path_slot[len] = c1slot;
               my_path_base[len] = (uint8_t)w1;
             }
-            overflow |= len >= path_cap;
+            path_overflow |= len >= path_cap;
             ++len;
             tot += bw1;
             ++n_dir[dir];
@@ -810,7 +811,7 @@ __global__ void __launch_bounds__(kSpecWarps * 32, kSpecCtasPerSM * 16 / kSpecWa
               my_path_slot[len] = c2slot;
               my_path_base[len] = (uint8_t)w2;
             }
-            overflow |= len >= path_cap;
+            path_overflow |= len >= path_cap;
             ++len;
             tot += bw2;
             ++n_dir[dir];
@@ -838,7 +839,8 @@ __global__ void __launch_bounds__(kSpecWarps * 32, kSpecCtasPerSM * 16 / kSpecWa
 
     // ---- 3. which paths are intact, and who holds the seeds? -----------------------------------
     for (uint32_t ws = warp; ws < win_n; ws += kSpecWarps) {
-      const uint32_t len = sh_len[ws], stamp = (uint32_t)kSpecWindow - ws;
+      // (a walk longer than its buffer is only stamped/cleared up to the buffer: the stage is rerun)
+      const uint32_t len = (uint32_t)min((uint64_t)sh_len[ws], path_cap), stamp = (uint32_t)kSpecWindow - ws;
       const uint32_t* ps = cta_path_slot + (uint64_t)ws * path_cap;
       bool mine = true;
       for (uint32_t e = lane; e < len; e += 32)
@@ -883,7 +885,7 @@ __global__ void __launch_bounds__(kSpecWarps * 32, kSpecCtasPerSM * 16 / kSpecWa
 
     // ---- 4. commit the intact prefix in order, roll the rest back ---------------------------
     for (uint32_t ws = warp; ws < win_n; ws += kSpecWarps) {
-      const uint32_t len = sh_len[ws], stamp = (uint32_t)kSpecWindow - ws;
+      const uint32_t len = (uint32_t)min((uint64_t)sh_len[ws], path_cap), stamp = (uint32_t)kSpecWindow - ws;
       const uint32_t* ps = cta_path_slot + (uint64_t)ws * path_cap;
       const uint8_t* pb = cta_path_base + (uint64_t)ws * path_cap;
       if (ws < P && sh_status[ws] == 1) {
@@ -916,6 +918,7 @@ __global__ void __launch_bounds__(kSpecWarps * 32, kSpecCtasPerSM * 16 / kSpecWa
     atomicAdd(&a.counters[0], traversed);
     atomicMax(&a.counters[1], rounds);
     if (overflow) atomicAdd(&a.counters[2], 1ull);
+    if (path_overflow) atomicAdd(&a.counters[4], 1ull);  // a walk longer than its path buffer: the host reruns serially
     if (warp == 0) atomicAdd(&a.counters[3], windows);
     if (warp == 0 && a.trace) {
       unsigned long long tns;
@@ -1234,7 +1237,15 @@ struct HostTrace {  // SHN_HOST_TRACE=1: wall-clock marks of l3_run's host side 
 
 // a3-a5: seeds, raw components, greedy walks, shape filter, candidate contigs (the part of the
 // seed loop that only needs the K1-mer table; every K1-mer graph component is self-contained)
+static bool l3_walks_impl(shn_ctx* c, uint32_t min_weight, uint32_t min_length, bool no_spec);
 void l3_walks(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
+  // second attempt without the speculative tiers if a walk outgrew its (capped) path buffer
+  if (!l3_walks_impl(c, min_weight, min_length, false)) {
+    const bool ok = l3_walks_impl(c, min_weight, min_length, true);
+    SHN_CHECK(ok, "internal error: path overflow without speculative walks");
+  }
+}
+static bool l3_walks_impl(shn_ctx* c, uint32_t min_weight, uint32_t min_length, bool no_spec) {
   HostTrace ht;
   SHN_CHECK(c->n_buckets > 0, "no K1-mer table built (call shn_table_build first)");
   shn_l3_free(c);
@@ -1480,9 +1491,15 @@ void l3_walks(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
       const uint64_t budget = (envb ? strtoull(envb, nullptr, 10) : 32ull) << 30;  // scratch for the paths
       const char* envc = getenv("SHN_SPEC_MAX_COMPS");
       const uint32_t max_spec = envc ? (uint32_t)strtoul(envc, nullptr, 10) : 4u * (uint32_t)c->sm_count;
-      while (n_spec < peek && n_spec < max_spec && top[n_spec] >= min_nodes &&
-             (h_path_off.back() + (uint64_t)kSpecWindow * top[n_spec]) * 5 <= budget) {
-        h_path_off.push_back(h_path_off.back() + (uint64_t)kSpecWindow * top[n_spec]);
+      // path buffers: one per window position, as long as the longest walk can be.  A walk can in
+      // principle visit its whole component; buffers are capped (SHN_SPEC_PATH_CAP entries) and the
+      // rare walk that does not fit makes the whole stage fall back to the serial kernel (below).
+      const char* envp = getenv("SHN_SPEC_PATH_CAP");
+      const uint64_t path_cap = no_spec ? 0 : (envp ? strtoull(envp, nullptr, 10) : (4ull << 20));
+      while (path_cap && n_spec < peek && n_spec < max_spec && top[n_spec] >= min_nodes) {
+        const uint64_t cap = std::min<uint64_t>(top[n_spec], path_cap);
+        if ((h_path_off.back() + (uint64_t)kSpecWindow * cap) * 5 > budget) break;
+        h_path_off.push_back(h_path_off.back() + (uint64_t)kSpecWindow * cap);
         ++n_spec;
       }
     }
@@ -1591,7 +1608,8 @@ void l3_walks(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
     parking.unpark();
     CUDA_CHECK(cudaGetLastError());
   }
-  read_counters(c, h, 4);
+  read_counters(c, h, 5);
+  if (h[4] != 0) return false;  // the idx words are restored (unpark above); nothing else was changed
   SHN_CHECK(h[2] == 0, "internal error: walk log overflow (component node count mismatch)");
   s->sz.n_traversed = h[0];
   s->sz.walk_rounds = h[1];
@@ -1728,6 +1746,7 @@ void l3_walks(shn_ctx* c, uint32_t min_weight, uint32_t min_length) {
   s->n_cand = n_cand;
   CUDA_CHECK(cudaStreamSynchronize(st));
   ht.mark("assembled candidates");
+  return true;
 }
 
 namespace {

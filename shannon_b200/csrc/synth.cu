@@ -263,11 +263,9 @@ void count_k1mers(shn_ctx* c, const char* const* arrays, const uint64_t* n_reads
   if (n) {
     DevBuf ord_lo, ord_hi, cnt, iota, lo_s, perm;
     ord_lo.reserve(n1 * 8);
-    ord_hi.reserve(n1 * 8);
+    ord_hi.reserve(SHN_KEY_WORDS == 2 ? n1 * 8 : 8);
     cnt.reserve(n1 * 4);
     iota.reserve(n1 * 4);
-    lo_s.reserve(n1 * 8);
-    perm.reserve(n1 * 4);
     CUDA_CHECK(cudaMemsetAsync(ctr, 0, 8, c->stream));
     {
       ProfScope ps(c, "count_compact");
@@ -276,6 +274,10 @@ void count_k1mers(shn_ctx* c, const char* const* arrays, const uint64_t* n_reads
           iota.as<uint32_t>(), ctr);
       KERNEL_CHECK();
     }
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    table.release();  // the counting table is the largest buffer: free it before the sort buffers
+    lo_s.reserve(n1 * 8);
+    perm.reserve(n1 * 4);
     ProfScope ps(c, "count_sort", 4);
     // LSD radix over the ASCII-order key: low word first, then (stable) the high word
     size_t tb = 0;

@@ -259,6 +259,15 @@ class GpuOps(object):
     def set_allowed_weights(self, w):
         self.ctx.l3_set_allowed_weights(w.data_ptr() if w.numel() else None)
 
+    def relieve(self, min_free=0.35):
+        """Two caching allocators share the device (torch's and the library's): when less than
+        `min_free` of the memory is free, both hand their cached blocks back to the driver."""
+        _, free, total = self.ctx.device_info()
+        if free < min_free * total:
+            torch.cuda.current_stream(self.device).synchronize()
+            torch.cuda.empty_cache()
+            self.ctx.trim()
+
     def assignments(self, n_comps, n_assign, first_record):
         """(comp_offsets int64 [n_comps+1], global record indices int32 [n_assign]) on the device"""
         offs = torch.empty(n_comps + 1, dtype=torch.int64, device=self.device)
@@ -347,6 +356,7 @@ def correct_sharded(comm, ops, d_keys, d_counts, n_lines, first_line, k1, double
     send, counts = ops.route_lines(d_keys, d_counts, n_lines, first_line, double_stranded, k1, world)
     recs, _ = comm.all_to_all_rows(send, counts)
     del send
+    ops.relieve()
     ops.build_from_records(recs, k1)
     del recs
     n_shard = ops.n_distinct()
@@ -368,6 +378,7 @@ def correct_sharded(comm, ops, d_keys, d_counts, n_lines, first_line, k1, double
     del edges
     n_final = ops.cc_merge(all_edges, n_super)
     del all_edges
+    ops.relieve()
     sizes = comm.all_reduce_sum(ops.cc_sizes(gid_base, n_final))
     owner = assign_components(sizes.cpu().numpy(), world)
     tm["components"] = time.perf_counter() - t0
@@ -377,8 +388,10 @@ def correct_sharded(comm, ops, d_keys, d_counts, n_lines, first_line, k1, double
     ops.cc_free()
     recs, _ = comm.all_to_all_rows(send, counts)
     del send
+    ops.relieve()
     ops.build_from_records(recs, k1)
     del recs
+    ops.relieve()
     tm["reshard"] = time.perf_counter() - t0
     t0 = time.perf_counter()
     st.update(n_shard_keys=int(n_shard), n_local_comps=int(n_local), n_super=int(n_super),

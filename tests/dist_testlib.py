@@ -291,6 +291,9 @@ class OracleShardOps(object):
         rows = np.array(rows, dtype=np.uint64).reshape(-1, 2)
         return self._group(np.array(dest, dtype=np.int64), rows, world)
 
+    def relieve(self, min_free=0.35):
+        pass
+
     def cc_free(self):
         self.local_comp = self.final_of_super = None
 
