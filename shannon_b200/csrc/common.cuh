@@ -184,11 +184,35 @@ SHN_HD shn_key_t shn_key_mask(int k) { return shn_kmer_mask(k); }
 #endif
 #define SHN_EMPTY ((shn_key_t)~(shn_key_t)0)
 
+// Minimizer-clustered placement: the table is cut into regions of 2^kRegionShift buckets (256 KB)
+// and a K1-mer goes to region hash(its minimizer), bucket hash(key) inside the region.  Consecutive
+// K1-mers of a chain (x and x[1:].b) share their minimizer -- the 12-mer with the smallest hash --
+// about 7 times out of 8, so successor / predecessor probes mostly stay inside the 256 KB the
+// kernel is streaming through (L2 hits instead of one DRAM burst each: uf_edges), and so do the
+// parent words of the union-find.  Overflow still probes linearly over buckets, across regions.
+// Tables smaller than one region, and k1 < 12, use the plain hash.
+constexpr int kRegionShift = 12;
+constexpr int kRegionM = 12;
+SHN_HD uint32_t shn_minimizer_hash(shn_key_t key, int k1) {
+  const uint32_t mmask = (1u << (2 * kRegionM)) - 1u;
+  uint32_t best = 0xFFFFFFFFu;
+  for (int p = 0; p <= k1 - kRegionM; ++p) {
+    const uint32_t h = ((uint32_t)(key >> (2 * p)) & mmask) * 0x9E3779B1u;  // odd multiplier: a bijection
+    best = h < best ? h : best;
+  }
+  return best;
+}
+
 struct ShnTableView {
   ShnSlot* slots;      // SHN_BSLOTS * n_buckets
   uint64_t n_buckets;
+  uint32_t n_regions = 0;  // 0: plain hashing
+  int k1 = 0;
   __device__ __forceinline__ uint64_t bucket_of(shn_key_t key) const {
-    return __umul64hi(shn_key_hash(key), n_buckets);
+    const uint64_t h = shn_key_hash(key);
+    if (n_regions == 0) return __umul64hi(h, n_buckets);
+    const uint64_t hm = shn_mix64((uint64_t)shn_minimizer_hash(key, k1) + 0x9E3779B97F4A7C15ull);
+    return (__umul64hi(hm, (uint64_t)n_regions) << kRegionShift) | (h >> (64 - kRegionShift));
   }
 };
 
@@ -384,6 +408,7 @@ struct shn_ctx {
   // K1-mer weight table
   DevBuf table;
   uint64_t n_buckets = 0;
+  uint32_t n_regions = 0;  // minimizer-clustered placement (ShnTableView); 0 = plain hashing
   int k1 = 0;
   int l4_k1 = 0;  // k1 of the component map (may differ from the table's in a fresh process)
   uint64_t n_distinct = 0, n_lowcomplexity = 0, n_items = 0;
@@ -478,6 +503,6 @@ static inline void shn_count_free(shn_ctx* c) {
 
 namespace SHN_NS {
 static inline ShnTableView table_view(const shn_ctx* c) {
-  return ShnTableView{c->table.as<ShnSlot>(), c->n_buckets};
+  return ShnTableView{c->table.as<ShnSlot>(), c->n_buckets, c->n_regions, c->k1};
 }
 }  // namespace SHN_NS

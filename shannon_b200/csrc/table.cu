@@ -154,6 +154,15 @@ void table_begin(shn_ctx* c, uint64_t n, int k1, int double_stranded) {
   SHN_CHECK(items < 0xFFFFFFFEull, "more than 2^32-2 input K1-mers per table");
   // slots >= 2 * items  (load factor <= 0.5)
   uint64_t n_buckets = items < 1024 ? 1024 / SHN_BSLOTS : (2 * items + SHN_BSLOTS - 1) / SHN_BSLOTS;
+  // minimizer-clustered regions (common.cuh) once the table spans at least a few of them
+  const uint64_t region = 1ull << kRegionShift;
+  const char* envr = getenv("SHN_TABLE_REGIONS");  // 0 = plain hashing (A/B measurements, tests)
+  const bool regions = (!envr || atoi(envr) != 0) && k1 >= kRegionM && n_buckets >= 4 * region;
+  c->n_regions = 0;
+  if (regions) {
+    n_buckets = (n_buckets + region - 1) / region * region;
+    c->n_regions = (uint32_t)(n_buckets >> kRegionShift);
+  }
   c->table.reserve(n_buckets * SHN_BSLOTS * sizeof(ShnSlot));
   c->n_buckets = n_buckets;
   c->k1 = k1;

@@ -181,7 +181,9 @@ __device__ __forceinline__ uint64_t table_insert_add(const ShnTableView& t, shn_
     }
   }
   *old_w = atomicAdd(&t.slots[slot].weight, w) & SHN_WEIGHT_MASK;
-  if (min_idx) atomicMin(&t.slots[slot].idx, idx);
+  // (the thread that claimed the key always records its index, even when a concurrent duplicate
+  // beat its {weight, idx} CAS)
+  if (min_idx || *is_new != before) atomicMin(&t.slots[slot].idx, idx);
   return slot;
 #else
   const u128 pristine = ((u128)0xFFFFFFFF00000000ull << 64) | (u128)SHN_EMPTY_KEY;

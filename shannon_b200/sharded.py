@@ -340,6 +340,27 @@ def merge_candidates(comm, w, gline, offs, codes):
     return merged, moffs, n
 
 
+class _Trace(object):
+    """SHN_SHARD_TRACE=1: wall-clock time of every sub-step (with a device synchronisation in front
+    of each mark, so the times are attributable) on stderr."""
+
+    def __init__(self, ops, rank):
+        import os
+        self.on = bool(os.environ.get("SHN_SHARD_TRACE"))
+        self.ops, self.rank = ops, rank
+        self.t = time.perf_counter()
+
+    def __call__(self, what):
+        if not self.on:
+            return
+        import sys
+        if getattr(self.ops, "device", None) is not None and self.ops.device.type == "cuda":
+            torch.cuda.synchronize(self.ops.device)
+        now = time.perf_counter()
+        sys.stderr.write("[shard %d] %-28s %8.2f ms\n" % (self.rank, what, 1000.0 * (now - self.t)))
+        self.t = now
+
+
 # ---- the sharded L3 stage ----------------------------------------------------------------------------
 def correct_sharded(comm, ops, d_keys, d_counts, n_lines, first_line, k1, double_stranded, min_weight,
                     min_length, timings=None, stats=None):
@@ -351,60 +372,79 @@ def correct_sharded(comm, ops, d_keys, d_counts, n_lines, first_line, k1, double
     tm = timings if timings is not None else {}
     st = stats if stats is not None else {}
     world, rank = comm.world, comm.rank
+    trace = _Trace(ops, rank)
     t0 = time.perf_counter()
     # 1. lines -> minimizer owners
     send, counts = ops.route_lines(d_keys, d_counts, n_lines, first_line, double_stranded, k1, world)
+    trace("route_lines")
     recs, _ = comm.all_to_all_rows(send, counts)
     del send
+    trace("all_to_all lines")
     ops.relieve()
     ops.build_from_records(recs, k1)
     del recs
     n_shard = ops.n_distinct()
+    trace("shard table build")
     tm["shard_build"] = time.perf_counter() - t0
     t0 = time.perf_counter()
     # 2. global components of the successor graph
     n_local = ops.cc_local()
+    trace("cc_local")
     locs = [v[0] for v in comm.exchange_ints([n_local])]
     gid_base = sum(locs[:rank])
     n_super = sum(locs)
+    trace("exchange n_local")
     q, qcounts = ops.cc_cross(world, rank, gid_base, k1)
+    trace("cc_cross")
     rq, _ = comm.all_to_all_rows(q, qcounts)
     st["cross_queries"] = int(q.shape[0])
     del q
+    trace("all_to_all queries")
     edges = ops.cc_resolve(rq, gid_base)
     del rq
+    trace("cc_resolve")
     all_edges, ecounts = comm.all_gather_rows(edges)
     st["cross_edges"] = int(sum(ecounts))
     del edges
+    trace("all_gather edges")
     n_final = ops.cc_merge(all_edges, n_super)
     del all_edges
+    trace("cc_merge")
     ops.relieve()
     sizes = comm.all_reduce_sum(ops.cc_sizes(gid_base, n_final))
+    trace("cc_sizes + all_reduce")
     owner = assign_components(sizes.cpu().numpy(), world)
+    trace("assign_components")
     tm["components"] = time.perf_counter() - t0
     t0 = time.perf_counter()
     # 3. whole components to their ranks
     send, counts = ops.cc_route(torch.from_numpy(owner), gid_base, world, k1)
     ops.cc_free()
+    trace("cc_route")
     recs, _ = comm.all_to_all_rows(send, counts)
     del send
+    trace("all_to_all components")
     ops.relieve()
     ops.build_from_records(recs, k1)
     del recs
     ops.relieve()
+    trace("component table build")
     tm["reshard"] = time.perf_counter() - t0
     t0 = time.perf_counter()
     st.update(n_shard_keys=int(n_shard), n_local_comps=int(n_local), n_super=int(n_super),
               n_raw_comps_global=int(n_final), n_owned_keys=int(ops.n_distinct()))
     # 4. per-rank walks
     ops.l3_walks(min_weight, min_length)
+    trace("l3_walks")
     tm["walks"] = time.perf_counter() - t0
     t0 = time.perf_counter()
     # 5. merge candidates, replicated filter stage
     w, line, offs, codes = ops.cand_export()
     st["n_local_candidates"] = int(w.shape[0])
     mcodes, moffs, n_cand = merge_candidates(comm, w, line, offs, codes)
+    trace("merge candidates")
     sz = ops.l3_filter(mcodes, moffs, n_cand)
+    trace("l3_filter")
     aw = ops.allowed_weights(sz["n_allowed"])
     comm.all_reduce_sum(aw)
     ops.set_allowed_weights(aw)
