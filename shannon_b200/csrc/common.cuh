@@ -184,14 +184,13 @@ SHN_HD shn_key_t shn_key_mask(int k) { return shn_kmer_mask(k); }
 #endif
 #define SHN_EMPTY ((shn_key_t)~(shn_key_t)0)
 
-// Minimizer-clustered placement: the table is cut into regions of 2^kRegionShift buckets (256 KB)
+// Minimizer-clustered placement: the table is cut into regions of 2^region_shift buckets (8 MB)
 // and a K1-mer goes to region hash(its minimizer), bucket hash(key) inside the region.  Consecutive
 // K1-mers of a chain (x and x[1:].b) share their minimizer -- the 12-mer with the smallest hash --
-// about 7 times out of 8, so successor / predecessor probes mostly stay inside the 256 KB the
+// about 7 times out of 8, so successor / predecessor probes mostly stay inside the 8 MB the
 // kernel is streaming through (L2 hits instead of one DRAM burst each: uf_edges), and so do the
 // parent words of the union-find.  Overflow still probes linearly over buckets, across regions.
 // Tables smaller than one region, and k1 < 12, use the plain hash.
-constexpr int kRegionShift = 12;
 constexpr int kRegionM = 12;
 SHN_HD uint32_t shn_minimizer_hash(shn_key_t key, int k1) {
   const uint32_t mmask = (1u << (2 * kRegionM)) - 1u;
@@ -208,11 +207,12 @@ struct ShnTableView {
   uint64_t n_buckets;
   uint32_t n_regions = 0;  // 0: plain hashing
   int k1 = 0;
+  int region_shift = 17;   // log2(buckets per region): 2^17 x 64 B = 8 MB
   __device__ __forceinline__ uint64_t bucket_of(shn_key_t key) const {
     const uint64_t h = shn_key_hash(key);
     if (n_regions == 0) return __umul64hi(h, n_buckets);
     const uint64_t hm = shn_mix64((uint64_t)shn_minimizer_hash(key, k1) + 0x9E3779B97F4A7C15ull);
-    return (__umul64hi(hm, (uint64_t)n_regions) << kRegionShift) | (h >> (64 - kRegionShift));
+    return (__umul64hi(hm, (uint64_t)n_regions) << region_shift) | (h >> (64 - region_shift));
   }
 };
 
@@ -409,6 +409,7 @@ struct shn_ctx {
   DevBuf table;
   uint64_t n_buckets = 0;
   uint32_t n_regions = 0;  // minimizer-clustered placement (ShnTableView); 0 = plain hashing
+  int region_shift = 17;
   int k1 = 0;
   int l4_k1 = 0;  // k1 of the component map (may differ from the table's in a fresh process)
   uint64_t n_distinct = 0, n_lowcomplexity = 0, n_items = 0;
@@ -503,6 +504,6 @@ static inline void shn_count_free(shn_ctx* c) {
 
 namespace SHN_NS {
 static inline ShnTableView table_view(const shn_ctx* c) {
-  return ShnTableView{c->table.as<ShnSlot>(), c->n_buckets, c->n_regions, c->k1};
+  return ShnTableView{c->table.as<ShnSlot>(), c->n_buckets, c->n_regions, c->k1, c->region_shift};
 }
 }  // namespace SHN_NS

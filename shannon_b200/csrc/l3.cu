@@ -374,9 +374,21 @@ __device__ __forceinline__ int walk_resolve(const ShnTableView& tv, const ShnBuc
   return state;
 }
 // the rare continuation of a probe sequence (the key was displaced from its home bucket)
+#ifdef SHN_WALK_STATS
+#define SHN_CHASE_COUNT(n) (n)
+__device__ unsigned long long g_chase_iters = 0, g_chase_calls = 0;
+#else
+#define SHN_CHASE_COUNT(n) 0
+#endif
 __device__ __forceinline__ int walk_chase(const ShnTableView& tv, shn_key_t cand, uint64_t* cslot,
                                           uint32_t* wraw, uint32_t* caux, uint64_t* nextb) {
+#ifdef SHN_WALK_STATS
+  atomicAdd(&g_chase_calls, 1ull);
+#endif
   for (;;) {
+#ifdef SHN_WALK_STATS
+    atomicAdd(&g_chase_iters, 1ull);
+#endif
     ShnBucket bk;
     table_load_bucket(tv, *nextb, &bk);
     const uint64_t hb = *nextb;
@@ -1609,6 +1621,15 @@ static bool l3_walks_impl(shn_ctx* c, uint32_t min_weight, uint32_t min_length, 
     CUDA_CHECK(cudaGetLastError());
   }
   read_counters(c, h, 5);
+#ifdef SHN_WALK_STATS
+  {
+    unsigned long long it = 0, ca = 0;
+    cudaMemcpyFromSymbol(&it, g_chase_iters, 8);
+    cudaMemcpyFromSymbol(&ca, g_chase_calls, 8);
+    fprintf(stderr, "[walk stats] chase calls=%llu iterations=%llu (cumulative) rounds(max warp)=%llu traversed=%llu\n",
+            ca, it, h[1], h[0]);
+  }
+#endif
   if (h[4] != 0) return false;  // the idx words are restored (unpark above); nothing else was changed
   SHN_CHECK(h[2] == 0, "internal error: walk log overflow (component node count mismatch)");
   s->sz.n_traversed = h[0];

@@ -155,13 +155,17 @@ void table_begin(shn_ctx* c, uint64_t n, int k1, int double_stranded) {
   // slots >= 2 * items  (load factor <= 0.5)
   uint64_t n_buckets = items < 1024 ? 1024 / SHN_BSLOTS : (2 * items + SHN_BSLOTS - 1) / SHN_BSLOTS;
   // minimizer-clustered regions (common.cuh) once the table spans at least a few of them
-  const uint64_t region = 1ull << kRegionShift;
+  const char* envs = getenv("SHN_REGION_SHIFT");
+  // 2^17 buckets = 8 MB per region: measured at 10 M pairs (uf_edges 94 -> 57 ms); 256 KB regions
+  // have a load spread of +-30 % and triple the length of the walks' probe sequences
+  c->region_shift = envs ? std::max(4, std::min(24, atoi(envs))) : 17;
+  const uint64_t region = 1ull << c->region_shift;
   const char* envr = getenv("SHN_TABLE_REGIONS");  // 0 = plain hashing (A/B measurements, tests)
   const bool regions = (!envr || atoi(envr) != 0) && k1 >= kRegionM && n_buckets >= 4 * region;
   c->n_regions = 0;
   if (regions) {
     n_buckets = (n_buckets + region - 1) / region * region;
-    c->n_regions = (uint32_t)(n_buckets >> kRegionShift);
+    c->n_regions = (uint32_t)(n_buckets >> c->region_shift);
   }
   c->table.reserve(n_buckets * SHN_BSLOTS * sizeof(ShnSlot));
   c->n_buckets = n_buckets;
