@@ -305,6 +305,29 @@ int shn_count_k1mers(shn_ctx* ctx, const char* const* read_arrays_dev, const uin
                      int n_arrays, int read_len, int k1, uint64_t expected_distinct,
                      uint64_t** keys_dev, uint32_t** counts_dev, uint64_t* n_distinct);
 
+/* Variable-length twins for real read files (rows f1/f2 of SURVEY 8f):
+ * shn_revcomp_var: out = reverse complement of every read (rc_s.py: A<->T, C<->G, N stays; any other
+ * character is an error, as in rc_s.py); same offsets for input and output.
+ * shn_count_begin / shn_count_add_reads / shn_count_finish: `jellyfish count -m k1` + `dump -c -t -L
+ * min_count` (shannon.py:439-441) over reads added in chunks (only one chunk has to be resident);
+ * windows with a character outside ACGT are skipped; result in ascending ASCII order of the k-mer,
+ * device arrays owned by the context -- feed them to shn_table_build(on_device = 1) or to
+ * shn_write_kmer_file after a copy to the host. */
+int shn_revcomp_var(shn_ctx* ctx, const char* bases, const uint64_t* offsets, uint64_t n_reads, char* out,
+                    int on_device);
+int shn_count_begin(shn_ctx* ctx, int k1, uint64_t expected_distinct);
+int shn_count_add_reads(shn_ctx* ctx, const char* bases, const uint64_t* offsets, uint64_t n_reads,
+                        int on_device);
+int shn_count_finish(shn_ctx* ctx, uint32_t min_count, uint64_t** keys_dev, uint32_t** counts_dev,
+                     uint64_t* n_distinct);
+/* FASTA with names, as rc_s.py reads it (blank lines dropped, header = stripped line starting with
+ * '>', sequence = first field of the next line); malloc'ed arrays (shn_host_free), names without '>'. */
+int shn_load_fasta_named(shn_ctx* ctx, const char* path, char** names, uint64_t** name_offsets,
+                         char** bases, uint64_t** offsets, uint64_t* n);
+/* `>name\nSEQ\n` records (the format rc_s.py writes). */
+int shn_write_fasta_named(shn_ctx* ctx, const char* path, int append, const char* names,
+                          const uint64_t* name_offsets, const char* bases, const uint64_t* offsets,
+                          uint64_t n);
 /* frees the device arrays the last shn_count_k1mers returned */
 int shn_count_release(shn_ctx* ctx);
 

@@ -76,6 +76,13 @@ SIGNATURES = {
                                          C.c_uint64, C.c_char_p]),
     "shn_write_kmer_file": (C.c_int, [vp, C.c_char_p, vp, vp, C.c_uint64, C.c_int]),
     "shn_count_release": (C.c_int, [vp]),
+    "shn_revcomp_var": (C.c_int, [vp, vp, vp, C.c_uint64, vp, C.c_int]),
+    "shn_count_begin": (C.c_int, [vp, C.c_int, C.c_uint64]),
+    "shn_count_add_reads": (C.c_int, [vp, vp, vp, C.c_uint64, C.c_int]),
+    "shn_count_finish": (C.c_int, [vp, C.c_uint32, C.POINTER(vp), C.POINTER(vp), u64p]),
+    "shn_load_fasta_named": (C.c_int, [vp, C.c_char_p, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp),
+                                       C.POINTER(vp), u64p]),
+    "shn_write_fasta_named": (C.c_int, [vp, C.c_char_p, C.c_int, vp, vp, vp, vp, C.c_uint64]),
     "shn_write_k1mer_windows": (C.c_int, [vp, C.c_char_p, vp, vp, vp, C.c_uint64, C.c_int, vp, vp]),
     "shn_pack_kmers": (C.c_int, [vp, vp, C.c_uint64, C.c_int, vp, C.c_int]),
     "shn_table_build": (C.c_int, [vp, vp, vp, C.c_uint64, C.c_int, C.c_int, C.c_int]),
@@ -199,6 +206,27 @@ class HostIO(object):
             self.lib.shn_host_free(bases)
             self.lib.shn_host_free(offs)
         return b, o
+
+    def load_fasta_named(self, path):
+        """(names uint8, name_offsets, bases uint8, offsets) of a FASTA file read like rc_s.py does."""
+        names, noffs, bases, offs = vp(), vp(), vp(), vp()
+        n = C.c_uint64()
+        self.call("shn_load_fasta_named", os.fsencode(path), C.byref(names), C.byref(noffs),
+                  C.byref(bases), C.byref(offs), C.byref(n))
+        try:
+            no = np.ctypeslib.as_array(C.cast(noffs, u64p), shape=(n.value + 1,)).copy()
+            o = np.ctypeslib.as_array(C.cast(offs, u64p), shape=(n.value + 1,)).copy()
+            nn, nb = int(no[-1]), int(o[-1])
+            nm = np.ctypeslib.as_array(C.cast(names, u8p), shape=(max(nn, 1),))[:nn].copy()
+            b = np.ctypeslib.as_array(C.cast(bases, u8p), shape=(max(nb, 1),))[:nb].copy()
+        finally:
+            for x in (names, noffs, bases, offs):
+                self.lib.shn_host_free(x)
+        return nm, no, b, o
+
+    def write_fasta_named(self, path, append, names, name_offsets, bases, offsets):
+        self.call("shn_write_fasta_named", os.fsencode(path), int(bool(append)), ptr(names),
+                  ptr(name_offsets), ptr(bases), ptr(offsets), C.c_uint64(len(offsets) - 1))
 
     def write_fasta_subset(self, path, append, bases, offsets, read_idx, first_index, suffix):
         read_idx = np.ascontiguousarray(read_idx, dtype=np.uint32)
@@ -595,6 +623,33 @@ class Context(HostIO):
 
     def count_release(self):
         self.call("shn_count_release")
+
+    def revcomp_var(self, bases, offsets):
+        """reverse complement of every read of (bases uint8, offsets uint64), host arrays"""
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        out = np.empty(max(len(bases), 1), dtype=np.uint8)
+        self.call("shn_revcomp_var", ptr(bases), ptr(offsets), C.c_uint64(len(offsets) - 1), ptr(out), 0)
+        return out[:len(bases)]
+
+    def revcomp_var_dev(self, d_bases, d_offsets, n_reads, d_out):
+        self.call("shn_revcomp_var", vp(d_bases), vp(d_offsets), C.c_uint64(n_reads), vp(d_out), 1)
+
+    def count_begin(self, k1, expected_distinct):
+        self.call("shn_count_begin", int(k1), C.c_uint64(int(expected_distinct)))
+
+    def count_add_reads(self, bases, offsets, n=None, on_device=False):
+        if not on_device:
+            bases = np.ascontiguousarray(bases, dtype=np.uint8)
+            offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+            n = len(offsets) - 1
+        self.call("shn_count_add_reads", ptr(bases), ptr(offsets), C.c_uint64(n), int(bool(on_device)))
+
+    def count_finish(self, min_count=1):
+        keys, counts = vp(), vp()
+        n = C.c_uint64()
+        self.call("shn_count_finish", C.c_uint32(min_count), C.byref(keys), C.byref(counts), C.byref(n))
+        return keys.value or 0, counts.value or 0, n.value
 
     def count_k1mers(self, d_arrays, n_reads, read_len, k1, expected_distinct):
         na = len(d_arrays)

@@ -21,6 +21,12 @@ void shn_synth_pairs_impl(shn_ctx* c, const uint8_t* tx, const uint64_t* tx_offs
                           uint64_t n_tx, uint64_t n_pairs, uint64_t first_pair, uint64_t seed,
                           int read_len, int frag_len, uint32_t err_thr, char* m1, char* m2);
 void shn_revcomp_reads_impl(shn_ctx* c, const char* in, char* out, uint64_t n_reads, int read_len);
+void shn_revcomp_var_impl(shn_ctx* c, const char* in, const uint64_t* offs, uint64_t n_reads, uint64_t total,
+                          char* out);
+void shn_load_fasta_named_impl(const char* path, char** names_out, uint64_t** name_offs_out, char** bases_out,
+                               uint64_t** offs_out, uint64_t* n_out);
+void shn_write_fasta_named_impl(const char* path, int append, const char* names, const uint64_t* name_offs,
+                                const char* bases, const uint64_t* offs, uint64_t n);
 void shn_route_plan_impl(shn_ctx* c, const uint64_t* d_keys, uint64_t n, uint32_t nranks,
                          uint32_t* d_perm, uint64_t* h_counts);
 void shn_permute_impl(shn_ctx* c, const void* src, const uint32_t* d_perm, uint64_t n, int elem_bytes,
@@ -704,6 +710,83 @@ int shn_revcomp_reads(shn_ctx* c, const char* in_dev, char* out_dev, uint64_t n_
   bind(c);
   shn_revcomp_reads_impl(c, in_dev, out_dev, n_reads, read_len);
   CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  SHN_API_END(c)
+}
+int shn_revcomp_var(shn_ctx* c, const char* bases, const uint64_t* offsets, uint64_t n_reads, char* out,
+                    int on_device) {
+  SHN_API_BEGIN
+  bind(c);
+  if (n_reads) {
+    uint64_t total = 0;
+    DevBuf sb, so, sout;
+    const uint64_t* d_offs = offsets;
+    if (on_device) {
+      CUDA_CHECK(cudaMemcpyAsync(&total, offsets + n_reads, 8, cudaMemcpyDeviceToHost, c->stream));
+      CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    } else {
+      total = offsets[n_reads];
+      d_offs = (const uint64_t*)InputView::get(c, offsets, (n_reads + 1) * 8, 0, so);
+    }
+    const char* d_in = (const char*)InputView::get(c, bases, total, on_device, sb);
+    char* d_out = out;
+    if (!on_device) {
+      sout.reserve(std::max<uint64_t>(total, 1));
+      d_out = sout.as<char>();
+    }
+    shn_revcomp_var_impl(c, d_in, d_offs, n_reads, total, d_out);
+    if (!on_device && total) {
+      CUDA_CHECK(cudaMemcpyAsync(out, d_out, total, cudaMemcpyDeviceToHost, c->stream));
+      CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    }
+  }
+  SHN_API_END(c)
+}
+int shn_count_begin(shn_ctx* c, int k1, uint64_t expected_distinct) {
+  SHN_API_BEGIN
+  bind(c);
+  SHN_CHECK(k1 >= 1 && k1 <= 33, "k1 must be in 1..33");
+  SHN_DISPATCH(k1, count_begin(c, k1, expected_distinct));
+  c->count_k1 = k1;
+  SHN_API_END(c)
+}
+int shn_count_add_reads(shn_ctx* c, const char* bases, const uint64_t* offsets, uint64_t n_reads, int on_device) {
+  SHN_API_BEGIN
+  bind(c);
+  SHN_CHECK(c->count_k1 > 0, "shn_count_begin has not been called");
+  if (n_reads) {
+    uint64_t total = 0;
+    DevBuf sb, so;
+    const uint64_t* d_offs = offsets;
+    if (on_device) {
+      CUDA_CHECK(cudaMemcpyAsync(&total, offsets + n_reads, 8, cudaMemcpyDeviceToHost, c->stream));
+      CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    } else {
+      total = offsets[n_reads];
+      d_offs = (const uint64_t*)InputView::get(c, offsets, (n_reads + 1) * 8, 0, so);
+    }
+    const char* d_in = (const char*)InputView::get(c, bases, total, on_device, sb);
+    SHN_DISPATCH(c->count_k1, count_add_var(c, d_in, d_offs, n_reads, total));
+  }
+  SHN_API_END(c)
+}
+int shn_count_finish(shn_ctx* c, uint32_t min_count, uint64_t** keys_dev, uint32_t** counts_dev,
+                     uint64_t* n_distinct) {
+  SHN_API_BEGIN
+  bind(c);
+  SHN_CHECK(c->count_k1 > 0, "shn_count_begin has not been called");
+  SHN_DISPATCH(c->count_k1, count_finish(c, min_count, keys_dev, counts_dev, n_distinct));
+  SHN_API_END(c)
+}
+int shn_load_fasta_named(shn_ctx* c, const char* path, char** names, uint64_t** name_offsets, char** bases,
+                         uint64_t** offsets, uint64_t* n) {
+  SHN_API_BEGIN
+  shn_load_fasta_named_impl(path, names, name_offsets, bases, offsets, n);
+  SHN_API_END(c)
+}
+int shn_write_fasta_named(shn_ctx* c, const char* path, int append, const char* names,
+                          const uint64_t* name_offsets, const char* bases, const uint64_t* offsets, uint64_t n) {
+  SHN_API_BEGIN
+  shn_write_fasta_named_impl(path, append, names, name_offsets, bases, offsets, n);
   SHN_API_END(c)
 }
 int shn_count_release(shn_ctx* c) {

@@ -422,6 +422,7 @@ struct shn_ctx {
   void (*l3_free)(shn_ctx*) = nullptr;
   void* l4 = nullptr;
   void (*l4_free)(shn_ctx*) = nullptr;
+  int count_k1 = 0;  // k1 of the counting table between shn_count_begin and shn_count_finish
   void* count_state = nullptr;
   void (*count_free)(shn_ctx*) = nullptr;
   void* reads = nullptr;  // packed reads (reads.cu), independent of the key width

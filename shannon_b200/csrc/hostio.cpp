@@ -358,3 +358,80 @@ void shn_write_kmer_file_impl(const char* path, const uint64_t* keys, const uint
     for (unsigned t = 0; t < nt; ++t) out.write(bufs[t]);
   }
 }
+
+// FASTA as rc_s.py reads it (rc_s.py:7-19): blank lines are dropped, a line whose first field starts
+// with '>' is a header (kept stripped), any other line is one sequence = its first whitespace-
+// delimited field.  The driver's files have one sequence line per header; a header without a
+// sequence line or a sequence line without a header is refused (rc_s.py would still copy it, but
+// nothing downstream reads such files).  Returns names (without '>') and sequences, concatenated.
+void shn_load_fasta_named_impl(const char* path, char** names_out, uint64_t** name_offs_out, char** bases_out,
+                               uint64_t** offs_out, uint64_t* n_out) {
+  MappedFile f(path);
+  std::string names, bases;
+  std::vector<uint64_t> noffs(1, 0), offs(1, 0);
+  bases.reserve(f.n / 2 + 16);
+  const char* p = f.p;
+  const char* e = f.p + f.n;
+  bool have_header = false;
+  while (p < e) {
+    const char* nl = (const char*)memchr(p, '\n', e - p);
+    const char* le = nl ? nl : e;
+    const char* b = p;
+    p = nl ? nl + 1 : e;
+    while (b < le && (is_ws(*b) || *b == '\n')) ++b;
+    while (le > b && (is_ws(le[-1]) || le[-1] == '\n')) --le;
+    if (b == le) continue;  // blank line
+    if (*b == '>') {
+      if (have_header) SHN_FAIL(std::string(path) + ": header line without a sequence line");
+      names.append(b + 1, le - b - 1);
+      noffs.push_back(names.size());
+      have_header = true;
+    } else {
+      if (!have_header) SHN_FAIL(std::string(path) + ": sequence line without a header (multi-line FASTA records are not supported)");
+      const char* t = b;
+      while (t < le && !is_ws(*t)) ++t;  // fields[0]
+      bases.append(b, t - b);
+      offs.push_back(bases.size());
+      have_header = false;
+    }
+  }
+  if (have_header) SHN_FAIL(std::string(path) + ": header line without a sequence line");
+  const uint64_t n = offs.size() - 1;
+  char* no = (char*)malloc(std::max<size_t>(names.size(), 1));
+  char* bo = (char*)malloc(std::max<size_t>(bases.size(), 1));
+  uint64_t* nf = (uint64_t*)malloc(noffs.size() * 8);
+  uint64_t* of = (uint64_t*)malloc(offs.size() * 8);
+  if (!no || !bo || !nf || !of) {
+    free(no); free(bo); free(nf); free(of);
+    SHN_FAIL("out of host memory loading reads");
+  }
+  memcpy(no, names.data(), names.size());
+  memcpy(bo, bases.data(), bases.size());
+  memcpy(nf, noffs.data(), noffs.size() * 8);
+  memcpy(of, offs.data(), offs.size() * 8);
+  *names_out = no;
+  *name_offs_out = nf;
+  *bases_out = bo;
+  *offs_out = of;
+  *n_out = n;
+}
+
+// `>name\nSEQ\n` per record (what rc_s.py writes: '\n'.join(lines) + '\n')
+void shn_write_fasta_named_impl(const char* path, int append, const char* names, const uint64_t* name_offs,
+                                const char* bases, const uint64_t* offs, uint64_t n) {
+  OutFile out(path, append);
+  std::string buf;
+  buf.reserve(1 << 22);
+  for (uint64_t i = 0; i < n; ++i) {
+    buf.push_back('>');
+    buf.append(names + name_offs[i], name_offs[i + 1] - name_offs[i]);
+    buf.push_back('\n');
+    buf.append(bases + offs[i], offs[i + 1] - offs[i]);
+    buf.push_back('\n');
+    if (buf.size() > (1u << 22) - 65536) {
+      out.write(buf);
+      buf.clear();
+    }
+  }
+  out.write(buf);
+}

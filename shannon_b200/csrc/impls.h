@@ -62,6 +62,11 @@
   void l4_get_assignments(shn_ctx* c, uint32_t n_comps, uint64_t* h_offs, uint32_t* h_idx);          \
   void l4_assignments_dev(shn_ctx* c, uint32_t n_comps, uint64_t first_record, uint64_t* d_offs,     \
                           uint32_t* d_idx);                                                          \
+  void count_begin(shn_ctx* c, int k1, uint64_t expected_distinct);                                  \
+  void count_add_var(shn_ctx* c, const char* d_bases, const uint64_t* d_offs, uint64_t n_reads,      \
+                     uint64_t total_bases);                                                          \
+  void count_finish(shn_ctx* c, uint32_t min_count, uint64_t** keys_dev, uint32_t** counts_dev,      \
+                    uint64_t* n_distinct);                                                           \
   void count_k1mers(shn_ctx* c, const char* const* arrays, const uint64_t* n_reads, int n_arrays,    \
                     int read_len, int k1, uint64_t expected_distinct, uint64_t** keys_dev,           \
                     uint32_t** counts_dev, uint64_t* n_distinct);                                    \

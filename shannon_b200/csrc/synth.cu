@@ -74,7 +74,52 @@ __global__ void __launch_bounds__(kBlock)
   out[g] = o;
 }
 
+// variable-length reads (rc_s.py: D = {A:T, C:G, G:C, T:A, N:N}; anything else is a KeyError there)
+__global__ void __launch_bounds__(kBlock)
+    revcomp_var_kernel(const char* __restrict__ in, const uint64_t* __restrict__ offs, uint64_t n_reads,
+                       uint64_t total, char* __restrict__ out, unsigned long long* bad) {
+  uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= total) return;
+  uint64_t lo = 0, hi = n_reads;  // last read r with offs[r] <= g
+  while (hi - lo > 1) {
+    const uint64_t mid = (lo + hi) >> 1;
+    if (__ldg(&offs[mid]) <= g)
+      lo = mid;
+    else
+      hi = mid;
+  }
+  const uint64_t b = __ldg(&offs[lo]), e = __ldg(&offs[lo + 1]);
+  const char ch = in[g];
+  char o;
+  switch (ch) {
+    case 'A': o = 'T'; break;
+    case 'C': o = 'G'; break;
+    case 'G': o = 'C'; break;
+    case 'T': o = 'A'; break;
+    case 'N': o = 'N'; break;
+    default: o = ch; atomicAdd(bad, 1ull); break;
+  }
+  out[b + (e - 1 - g)] = o;
+}
+
 }  // namespace
+
+void shn_revcomp_var_impl(shn_ctx* c, const char* in, const uint64_t* offs, uint64_t n_reads, uint64_t total,
+                          char* out) {
+  if (n_reads == 0 || total == 0) return;
+  c->counters.reserve(64 * sizeof(unsigned long long));
+  unsigned long long* ctr = c->counters.as<unsigned long long>();
+  CUDA_CHECK(cudaMemsetAsync(ctr, 0, 8, c->stream));
+  {
+    ProfScope ps(c, "revcomp_reads");
+    revcomp_var_kernel<<<shn_grid(total, kBlock), kBlock, 0, c->stream>>>(in, offs, n_reads, total, out, ctr);
+    KERNEL_CHECK();
+  }
+  unsigned long long h = 0;
+  CUDA_CHECK(cudaMemcpyAsync(&h, ctr, 8, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  SHN_CHECK(h == 0, "read contains a character outside ACGTN (rc_s.py raises KeyError on it)");
+}
 
 void shn_synth_pairs_impl(shn_ctx* c, const uint8_t* tx, const uint64_t* tx_offs, const uint64_t* thr,
                           uint64_t n_tx, uint64_t n_pairs, uint64_t first_pair, uint64_t seed,
@@ -144,7 +189,7 @@ __global__ void __launch_bounds__(kCBlock) count_clear_kernel(ShnSlot* slots, ui
 
 // compaction of occupied slots: ASCII-order sort words of the key, count, running index
 __global__ void __launch_bounds__(kCBlock)
-    count_compact_kernel(const ShnSlot* __restrict__ slots, uint64_t n_slots,
+    count_compact_kernel(const ShnSlot* __restrict__ slots, uint64_t n_slots, uint32_t min_count,
                          uint64_t* __restrict__ ord_lo, uint64_t* __restrict__ ord_hi,
                          uint32_t* __restrict__ counts, uint32_t* __restrict__ iota,
                          unsigned long long* cursor) {
@@ -154,7 +199,7 @@ __global__ void __launch_bounds__(kCBlock)
   shn_key_t key = SHN_EMPTY;
   uint32_t wz = 0, wi = 0;
   if (i < n_slots) table_load_slot(slots, i, &key, &wz, &wi);
-  bool occ = key != SHN_EMPTY;
+  bool occ = key != SHN_EMPTY && (wz & SHN_WEIGHT_MASK) >= min_count;   // jellyfish dump -L min_count
   unsigned b = __ballot_sync(0xFFFFFFFFu, occ);
   int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (lane == 0) warp_off[warp] = __popc(b);
@@ -206,7 +251,10 @@ __global__ void __launch_bounds__(kCBlock)
 }
 
 struct CountState {
-  DevBuf keys, counts;
+  DevBuf table;              // counting table (weight word = count), alive between begin and finish
+  uint64_t nb = 0;
+  int k1 = 0;
+  DevBuf keys, counts;       // result of the last finish
 };
 
 void count_state_free(shn_ctx* c) {
@@ -214,54 +262,142 @@ void count_state_free(shn_ctx* c) {
   c->count_state = nullptr;
 }
 
-}  // namespace
-
-void count_k1mers(shn_ctx* c, const char* const* arrays, const uint64_t* n_reads, int n_arrays,
-                  int read_len, int k1, uint64_t expected_distinct, uint64_t** keys_dev,
-                  uint32_t** counts_dev, uint64_t* n_distinct) {
-  SHN_CHECK(k1 >= 1 && k1 <= SHN_MAX_K1 && read_len >= k1, "bad k1 / read length");
-  uint64_t total_windows = 0;
-  for (int a = 0; a < n_arrays; ++a) total_windows += n_reads[a] * (uint64_t)(read_len - k1 + 1);
-  uint64_t nb = std::max<uint64_t>(256, (2 * std::min(expected_distinct, total_windows) + SHN_BSLOTS - 1) /
-                                            SHN_BSLOTS);
-  DevBuf table;
-  table.reserve(nb * SHN_BSLOTS * sizeof(ShnSlot));
-  ShnTableView view{table.as<ShnSlot>(), nb};
-  c->counters.reserve(64 * sizeof(unsigned long long));
-  unsigned long long* ctr = c->counters.as<unsigned long long>();
-  CUDA_CHECK(cudaMemsetAsync(ctr, 0, 8 * sizeof(unsigned long long), c->stream));
-  {
-    ProfScope ps(c, "count_clear");
-    unsigned grid =
-        (unsigned)std::min<uint64_t>((nb * SHN_BSLOTS + kCBlock - 1) / kCBlock, (uint64_t)c->sm_count * 32);
-    count_clear_kernel<<<grid, kCBlock, 0, c->stream>>>(view.slots, nb * SHN_BSLOTS);
-    KERNEL_CHECK();
-  }
-  for (int a = 0; a < n_arrays; ++a) {
-    uint64_t nw = n_reads[a] * (uint64_t)(read_len - k1 + 1);
-    if (nw == 0) continue;
-    ProfScope ps(c, "count_windows");
-    count_windows_kernel<<<shn_grid(nw, kCBlock), kCBlock, 0, c->stream>>>(view, arrays[a], n_reads[a],
-                                                                           read_len, k1, ctr);
-    KERNEL_CHECK();
-  }
-  unsigned long long h[2];
-  CUDA_CHECK(cudaMemcpyAsync(h, ctr, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
-  CUDA_CHECK(cudaStreamSynchronize(c->stream));
-  SHN_CHECK(h[1] == 0, "k-mer counting table full: raise expected_distinct");
-  uint64_t n = h[0];
-  SHN_CHECK(n < 0xFFFFFFFFull, "more than 2^32-1 distinct K1-mers");
+CountState* count_state_of(shn_ctx* c) {
   if (c->count_state && c->count_free != &count_state_free) shn_count_free(c);
   if (!c->count_state) {
     c->count_state = new CountState();
     c->count_free = &count_state_free;
   }
-  CountState* st = static_cast<CountState*>(c->count_state);
-  const uint64_t n1 = std::max<uint64_t>(n, 1);
-  st->keys.reserve(n1 * 8 * SHN_KEY_WORDS);
-  st->counts.reserve(n1 * 4);
-  if (n) {
-    DevBuf ord_lo, ord_hi, cnt, iota, lo_s, perm;
+  return static_cast<CountState*>(c->count_state);
+}
+
+// last segment index s with offs[s] <= g
+__device__ __forceinline__ uint64_t segment_of(const uint64_t* __restrict__ offs, uint64_t n, uint64_t g) {
+  uint64_t lo = 0, hi = n;
+  while (hi - lo > 1) {
+    const uint64_t mid = (lo + hi) >> 1;
+    if (__ldg(&offs[mid]) <= g)
+      lo = mid;
+    else
+      hi = mid;
+  }
+  return lo;
+}
+
+// variable-length reads: one thread per base position = window start
+__global__ void __launch_bounds__(kCBlock)
+    count_windows_var_kernel(ShnTableView t, const char* __restrict__ bases, const uint64_t* __restrict__ offs,
+                             uint64_t n_reads, uint64_t total, int k1, unsigned long long* counters) {
+  uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int n_new = 0, full = 0;
+  if (g < total) {
+    const uint64_t r = segment_of(offs, n_reads, g);
+    if (g + k1 <= __ldg(&offs[r + 1])) {
+      shn_key_t key = 0;
+      bool ok = true;
+      for (int j = 0; j < k1; ++j) {
+        uint32_t code = shn_code_of_strict((uint8_t)__ldg(&bases[g + j]));
+        ok &= code < 4;
+        key = (key << 2) | (shn_key_t)(code & 3u);
+      }
+      if (ok && key != SHN_EMPTY) {
+        uint64_t slot = table_upsert_slot(t, key, &n_new);
+        if (slot == ~0ull)
+          full = 1;
+        else
+          atomicAdd(&t.slots[slot].weight, 1u);
+      }
+    }
+  }
+  int t_new = __syncthreads_count(n_new), t_full = __syncthreads_count(full);
+  if (threadIdx.x == 0) {
+    if (t_new) atomicAdd(&counters[0], (unsigned long long)t_new);
+    if (t_full) atomicAdd(&counters[1], (unsigned long long)t_full);
+  }
+}
+
+void count_check_full(shn_ctx* c, unsigned long long* h) {
+  CUDA_CHECK(cudaMemcpyAsync(h, c->counters.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  SHN_CHECK(h[1] == 0, "k-mer counting table full: raise expected_distinct");
+}
+
+}  // namespace
+
+// jellyfish count (shannon.py:439): the counting table lives in the context from count_begin to
+// count_finish, so reads can be added in chunks (only one chunk of ASCII has to be resident)
+void count_begin(shn_ctx* c, int k1, uint64_t expected_distinct) {
+  SHN_CHECK(k1 >= 1 && k1 <= SHN_MAX_K1 && (SHN_KEY_WORDS == 1 || k1 > 32), "k1 out of range for this key width");
+  CountState* st = count_state_of(c);
+  st->keys.release();
+  st->counts.release();
+  const uint64_t nb = std::max<uint64_t>(256, (2 * expected_distinct + SHN_BSLOTS - 1) / SHN_BSLOTS);
+  const uint64_t bytes = nb * SHN_BSLOTS * sizeof(ShnSlot);
+  size_t fr = 0, tot = 0;
+  CUDA_CHECK(cudaMemGetInfo(&fr, &tot));
+  SHN_CHECK(bytes <= st->table.bytes + fr + c->pool.cached_bytes,
+            "k-mer counting table of " + std::to_string(bytes >> 20) +
+                " MB does not fit the free device memory: lower expected_distinct or count in more shards");
+  st->table.reserve(bytes);
+  st->nb = nb;
+  st->k1 = k1;
+  c->counters.reserve(64 * sizeof(unsigned long long));
+  CUDA_CHECK(cudaMemsetAsync(c->counters.p, 0, 8 * sizeof(unsigned long long), c->stream));
+  ProfScope ps(c, "count_clear");
+  unsigned grid =
+      (unsigned)std::min<uint64_t>((nb * SHN_BSLOTS + kCBlock - 1) / kCBlock, (uint64_t)c->sm_count * 32);
+  count_clear_kernel<<<grid, kCBlock, 0, c->stream>>>(st->table.as<ShnSlot>(), nb * SHN_BSLOTS);
+  KERNEL_CHECK();
+}
+
+// fixed-length reads (the synthetic generators): n_reads x read_len bytes
+void count_add_fixed(shn_ctx* c, const char* d_reads, uint64_t n_reads, int read_len) {
+  CountState* st = count_state_of(c);
+  SHN_CHECK(st->nb > 0, "shn_count_begin has not been called");
+  if (read_len < st->k1 || n_reads == 0) return;
+  const uint64_t nw = n_reads * (uint64_t)(read_len - st->k1 + 1);
+  ProfScope ps(c, "count_windows");
+  count_windows_kernel<<<shn_grid(nw, kCBlock), kCBlock, 0, c->stream>>>(
+      ShnTableView{st->table.as<ShnSlot>(), st->nb}, d_reads, n_reads, read_len, st->k1,
+      c->counters.as<unsigned long long>());
+  KERNEL_CHECK();
+}
+
+// variable-length reads: concatenated bases + n_reads+1 offsets (device pointers).  Returns after
+// the chunk has been counted: the caller may re-use its buffers.
+void count_add_var(shn_ctx* c, const char* d_bases, const uint64_t* d_offs, uint64_t n_reads,
+                   uint64_t total_bases) {
+  CountState* st = count_state_of(c);
+  SHN_CHECK(st->nb > 0, "shn_count_begin has not been called");
+  if (n_reads == 0 || total_bases == 0) return;
+  {
+    ProfScope ps(c, "count_windows");
+    count_windows_var_kernel<<<shn_grid(total_bases, kCBlock), kCBlock, 0, c->stream>>>(
+        ShnTableView{st->table.as<ShnSlot>(), st->nb}, d_bases, d_offs, n_reads, total_bases, st->k1,
+        c->counters.as<unsigned long long>());
+    KERNEL_CHECK();
+  }
+  unsigned long long h[2];
+  count_check_full(c, h);
+}
+
+// jellyfish dump -c -t -L min_count (shannon.py:441): (k-mer, count) in ascending ASCII order of the
+// k-mer, the documented order of oracle/kmer_count.py; device arrays owned by the context
+void count_finish(shn_ctx* c, uint32_t min_count, uint64_t** keys_dev, uint32_t** counts_dev,
+                  uint64_t* n_distinct) {
+  CountState* st = count_state_of(c);
+  SHN_CHECK(st->nb > 0, "shn_count_begin has not been called");
+  const int k1 = st->k1;
+  const uint64_t nb = st->nb;
+  unsigned long long* ctr = c->counters.as<unsigned long long>();
+  unsigned long long h[2];
+  count_check_full(c, h);
+  const uint64_t n_all = h[0];
+  SHN_CHECK(n_all < 0xFFFFFFFFull, "more than 2^32-1 distinct K1-mers");
+  const uint64_t n1 = std::max<uint64_t>(n_all, 1);
+  DevBuf ord_lo, ord_hi, cnt, iota, lo_s, perm;
+  uint64_t n = 0;
+  if (n_all) {
     ord_lo.reserve(n1 * 8);
     ord_hi.reserve(SHN_KEY_WORDS == 2 ? n1 * 8 : 8);
     cnt.reserve(n1 * 4);
@@ -270,14 +406,22 @@ void count_k1mers(shn_ctx* c, const char* const* arrays, const uint64_t* n_reads
     {
       ProfScope ps(c, "count_compact");
       count_compact_kernel<<<shn_grid(nb * SHN_BSLOTS, kCBlock), kCBlock, 0, c->stream>>>(
-          view.slots, nb * SHN_BSLOTS, ord_lo.as<uint64_t>(), ord_hi.as<uint64_t>(), cnt.as<uint32_t>(),
-          iota.as<uint32_t>(), ctr);
+          st->table.as<ShnSlot>(), nb * SHN_BSLOTS, min_count, ord_lo.as<uint64_t>(), ord_hi.as<uint64_t>(),
+          cnt.as<uint32_t>(), iota.as<uint32_t>(), ctr);
       KERNEL_CHECK();
     }
+    unsigned long long kept = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&kept, ctr, 8, cudaMemcpyDeviceToHost, c->stream));
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
-    table.release();  // the counting table is the largest buffer: free it before the sort buffers
-    lo_s.reserve(n1 * 8);
-    perm.reserve(n1 * 4);
+    n = kept;
+  }
+  st->table.release();  // the counting table is the largest buffer: free it before the sort buffers
+  st->nb = 0;
+  st->keys.reserve(std::max<uint64_t>(n, 1) * 8 * SHN_KEY_WORDS);
+  st->counts.reserve(std::max<uint64_t>(n, 1) * 4);
+  if (n) {
+    lo_s.reserve(n * 8);
+    perm.reserve(n * 4);
     ProfScope ps(c, "count_sort", 4);
     // LSD radix over the ASCII-order key: low word first, then (stable) the high word
     size_t tb = 0;
@@ -291,9 +435,9 @@ void count_k1mers(shn_ctx* c, const char* const* arrays, const uint64_t* n_reads
     uint32_t* final_perm = perm.as<uint32_t>();
 #ifdef SHN_WIDE
     DevBuf hi_g, hi_s, perm2;
-    hi_g.reserve(n1 * 8);
-    hi_s.reserve(n1 * 8);
-    perm2.reserve(n1 * 4);
+    hi_g.reserve(n * 8);
+    hi_s.reserve(n * 8);
+    perm2.reserve(n * 4);
     gather_u64_kernel<<<shn_grid(n, kCBlock), kCBlock, 0, c->stream>>>(ord_hi.as<uint64_t>(),
                                                                      perm.as<uint32_t>(), n,
                                                                      hi_g.as<uint64_t>());
@@ -316,6 +460,18 @@ void count_k1mers(shn_ctx* c, const char* const* arrays, const uint64_t* n_reads
   *keys_dev = st->keys.as<uint64_t>();
   *counts_dev = st->counts.as<uint32_t>();
   *n_distinct = n;
+}
+
+// the three steps in one call for fixed-length read arrays (bench / test inputs)
+void count_k1mers(shn_ctx* c, const char* const* arrays, const uint64_t* n_reads, int n_arrays,
+                  int read_len, int k1, uint64_t expected_distinct, uint64_t** keys_dev,
+                  uint32_t** counts_dev, uint64_t* n_distinct) {
+  SHN_CHECK(k1 >= 1 && k1 <= SHN_MAX_K1 && read_len >= k1, "bad k1 / read length");
+  uint64_t total_windows = 0;
+  for (int a = 0; a < n_arrays; ++a) total_windows += n_reads[a] * (uint64_t)(read_len - k1 + 1);
+  count_begin(c, k1, std::min(expected_distinct, total_windows));
+  for (int a = 0; a < n_arrays; ++a) count_add_fixed(c, arrays[a], n_reads[a], read_len);
+  count_finish(c, 1, keys_dev, counts_dev, n_distinct);
 }
 
 }  // namespace SHN_NS

@@ -93,3 +93,20 @@ def test_repeat_rich_small_k(workdir, seed):
     case = helpers.make_case(workdir, K, reads)
     both(case, min_weight=2, min_length=20 + seed, partition_size=1 + seed % 3,
          inMem=bool(seed & 1))
+
+
+def test_rc_file_oracle_equals_rc_s(workdir):
+    """oracle/preprocess_oracle.py against the real rc_s.py (row f2: RC doubling)."""
+    from oracle import preprocess_oracle as po
+    src = os.path.join(workdir, "in.fasta")
+    with open(src, "w") as f:
+        f.write(">r0 some description\nACGTNNACGT\n\n>r1\nTTTTGCA  \n  >r2\t\nGATTACA trailing\n>r3\nN\n")
+    rc_s = ref_loader.load("rc_s")
+    rc_s.reverse_complement_serial(src, os.path.join(workdir, "ref.fasta"))
+    po.reverse_complement_file(src, os.path.join(workdir, "ora.fasta"))
+    assert open(os.path.join(workdir, "ref.fasta")).read() == open(os.path.join(workdir, "ora.fasta")).read()
+    for name in ("SE_read", "PE_read_1"):
+        p = os.path.join(SAMPLES, name + ".fasta")
+        rc_s.reverse_complement_serial(p, os.path.join(workdir, "ref2.fasta"))
+        po.reverse_complement_file(p, os.path.join(workdir, "ora2.fasta"))
+        assert open(os.path.join(workdir, "ref2.fasta")).read() == open(os.path.join(workdir, "ora2.fasta")).read()
