@@ -328,6 +328,13 @@ int shn_load_fasta_named(shn_ctx* ctx, const char* path, char** names, uint64_t*
 int shn_write_fasta_named(shn_ctx* ctx, const char* path, int append, const char* names,
                           const uint64_t* name_offsets, const char* bases, const uint64_t* offsets,
                           uint64_t n);
+/* ---- f4: faster_reps.py:60-131 (representative selection among the final transcripts) ----------
+ * duplicate_out[c] = 1 iff find_reps would drop transcript c: its first and last 24-mer (of the
+ * transcript, or of its reverse complement when double_stranded) both occur in one other transcript
+ * at a distance within 2 of its own length, and that transcript is longer, or equally long with a
+ * smaller name (name_rank[c] = rank of the name in string order).  Host pointers; ACGT only. */
+int shn_find_reps(shn_ctx* ctx, const char* bases, const uint64_t* offsets, const uint32_t* name_rank,
+                  uint64_t n, int double_stranded, uint8_t* duplicate_out);
 /* frees the device arrays the last shn_count_k1mers returned */
 int shn_count_release(shn_ctx* ctx);
 

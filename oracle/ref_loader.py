@@ -22,6 +22,7 @@ import types
 REFERENCE_DIR = os.environ.get("SHANNON_REFERENCE_DIR", "/root/reference")
 
 _PRINT_STMT = re.compile(r'^(\s*)print (".*)$', re.M)
+_PRINT_STMT2 = re.compile(r"^(\s*)print ('.*)$", re.M)       # mbgraph.py:149
 
 
 def available():
@@ -31,8 +32,11 @@ def available():
 def _patched_source(name):
     with open(os.path.join(REFERENCE_DIR, name + ".py")) as f:
         src = f.read()
+    src = src.expandtabs(8)      # Python 2 reads a tab as "to the next multiple of 8" (faster_reps.py, mbgraph.py)
     src = _PRINT_STMT.sub(lambda m: "%sprint(%s)" % (m.group(1), m.group(2)), src)
+    src = _PRINT_STMT2.sub(lambda m: "%sprint(%s)" % (m.group(1), m.group(2)), src)
     src = src.replace("len(kmers.keys()[0])", "len(next(iter(kmers)))")
+    src = src.replace("from sets import Set\n", "")          # faster_reps.py:6 (unused there)
     return src
 
 
@@ -44,6 +48,9 @@ def load(name):
         raise RuntimeError("reference tree not present at %s" % REFERENCE_DIR)
     mod = types.ModuleType("_shannon_ref_" + name)
     mod.__file__ = os.path.join(REFERENCE_DIR, name + ".py")
+    if name == "multibridging":
+        # it does `from mbgraph import *`
+        sys.modules["mbgraph"] = load("mbgraph")
     if name == "kmers_for_component":
         # it does `from weight_updated_graph import weight_updated_graph`
         wug = load("weight_updated_graph")

@@ -76,6 +76,7 @@ SIGNATURES = {
                                          C.c_uint64, C.c_char_p]),
     "shn_write_kmer_file": (C.c_int, [vp, C.c_char_p, vp, vp, C.c_uint64, C.c_int]),
     "shn_count_release": (C.c_int, [vp]),
+    "shn_find_reps": (C.c_int, [vp, vp, vp, vp, C.c_uint64, C.c_int, vp]),
     "shn_revcomp_var": (C.c_int, [vp, vp, vp, C.c_uint64, vp, C.c_int]),
     "shn_count_begin": (C.c_int, [vp, C.c_int, C.c_uint64]),
     "shn_count_add_reads": (C.c_int, [vp, vp, vp, C.c_uint64, C.c_int]),
@@ -623,6 +624,15 @@ class Context(HostIO):
 
     def count_release(self):
         self.call("shn_count_release")
+
+    def find_reps(self, bases, offsets, name_rank, double_stranded):
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        name_rank = np.ascontiguousarray(name_rank, dtype=np.uint32)
+        dup = np.zeros(max(len(name_rank), 1), dtype=np.uint8)
+        self.call("shn_find_reps", ptr(bases), ptr(offsets), ptr(name_rank), C.c_uint64(len(name_rank)),
+                  int(bool(double_stranded)), ptr(dup))
+        return dup[:len(name_rank)]
 
     def revcomp_var(self, bases, offsets):
         """reverse complement of every read of (bases uint8, offsets uint64), host arrays"""

@@ -17,6 +17,8 @@ void shn_write_k1mer_windows_impl(const char* path, const char* bases, const uin
                                   const uint32_t* weights, const uint64_t* win_off);
 void shn_write_kmer_file_impl(const char* path, const uint64_t* keys, const uint32_t* counts, uint64_t n,
                               int k1);
+void shn_find_reps_impl(shn_ctx* c, const char* bases, const uint64_t* offsets, const uint32_t* name_rank,
+                        uint64_t n, int ds, uint8_t* dup_out);
 void shn_synth_pairs_impl(shn_ctx* c, const uint8_t* tx, const uint64_t* tx_offs, const uint64_t* thr,
                           uint64_t n_tx, uint64_t n_pairs, uint64_t first_pair, uint64_t seed,
                           int read_len, int frag_len, uint32_t err_thr, char* m1, char* m2);
@@ -787,6 +789,13 @@ int shn_write_fasta_named(shn_ctx* c, const char* path, int append, const char* 
                           const uint64_t* name_offsets, const char* bases, const uint64_t* offsets, uint64_t n) {
   SHN_API_BEGIN
   shn_write_fasta_named_impl(path, append, names, name_offsets, bases, offsets, n);
+  SHN_API_END(c)
+}
+int shn_find_reps(shn_ctx* c, const char* bases, const uint64_t* offsets, const uint32_t* name_rank,
+                  uint64_t n, int double_stranded, uint8_t* duplicate_out) {
+  SHN_API_BEGIN
+  bind(c);
+  shn_find_reps_impl(c, bases, offsets, name_rank, n, double_stranded, duplicate_out);
   SHN_API_END(c)
 }
 int shn_count_release(shn_ctx* c) {

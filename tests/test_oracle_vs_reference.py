@@ -110,3 +110,16 @@ def test_rc_file_oracle_equals_rc_s(workdir):
         rc_s.reverse_complement_serial(p, os.path.join(workdir, "ref2.fasta"))
         po.reverse_complement_file(p, os.path.join(workdir, "ora2.fasta"))
         assert open(os.path.join(workdir, "ref2.fasta")).read() == open(os.path.join(workdir, "ora2.fasta")).read()
+
+
+@pytest.mark.parametrize("seed,ds", [(1, False), (2, True), (3, True), (4, False)])
+def test_reps_oracle_equals_faster_reps(workdir, seed, ds):
+    """oracle/reps_oracle.py against the real faster_reps.py (row f4)."""
+    from oracle import reps_oracle
+    src = helpers.transcripts_file(os.path.join(workdir, "t.fasta"), seed)
+    ref = ref_loader.load("faster_reps")
+    ref.find_reps(src, os.path.join(workdir, "ref.fasta"), ds)
+    reps_oracle.find_reps(src, os.path.join(workdir, "ora.fasta"), ds)
+    a, b = open(os.path.join(workdir, "ref.fasta")).read(), open(os.path.join(workdir, "ora.fasta")).read()
+    assert a == b
+    assert 0 < a.count(">") < open(src).read().count(">")
