@@ -203,3 +203,34 @@ def check_against_golden(ec_fn, kfc_fn, name, workdir, label):
                                  "new_comps": new_comps, "contig_weights": cw, "rps": rps}))
     assert got == gold["ret"], label + ": return value differs from golden"
     return case, out
+
+
+def transcripts_file(path, seed, n=60):
+    """Transcript-like FASTA with the cases faster_reps.py is about: exact sub-sequences, equal
+    copies (name order decides), reverse-complement copies, near misses (length off by >= 3)."""
+    import random
+    rnd = random.Random(seed)
+    rand = lambda k: "".join(rnd.choice("ACGT") for _ in range(k))  # noqa: E731
+    base = [rand(rnd.randrange(60, 400)) for _ in range(n // 3)]
+    seqs = list(base)
+    for s in base:
+        a = rnd.randrange(0, len(s) // 3)
+        b = rnd.randrange(2 * len(s) // 3, len(s))
+        kind = rnd.randrange(6)
+        if kind == 0:
+            seqs.append(s[a:b])                                   # contained
+        elif kind == 1:
+            seqs.append(s)                                        # identical copy
+        elif kind == 2:
+            seqs.append(rc_str(s[a:b]))                           # contained on the other strand
+        elif kind == 3:
+            seqs.append(s[a:a + 30] + rand(5) + s[a + 30:b])      # ends match, length off by 5
+        elif kind == 4:
+            seqs.append(s[a:a + 40] + s[a + 42:b])                # ends match, length off by 2
+        else:
+            seqs.append(s[:20])                                   # shorter than r
+    rnd.shuffle(seqs)
+    with open(path, "w") as f:
+        for i, s in enumerate(seqs):
+            f.write(">T%d_%d len=%d\n%s\n" % (rnd.randrange(1000), i, len(s), s))
+    return path
