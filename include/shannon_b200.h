@@ -328,6 +328,22 @@ int shn_load_fasta_named(shn_ctx* ctx, const char* path, char** names, uint64_t*
 int shn_write_fasta_named(shn_ctx* ctx, const char* path, int append, const char* names,
                           const uint64_t* name_offsets, const char* bases, const uint64_t* offsets,
                           uint64_t n);
+/* ---- f3: multibridging.load_single_jellyfish + Node.condense_all (multibridging.py:145-172,
+ * mbgraph.py:479-507,184-258), the first step of the consumer of the per-component k1mer.dict ------
+ * Line i of the file is the edge prefix_kmers[i] -> suffix_kmers[i] (the K-mer prefix / suffix of the
+ * K1-mer, packed like keys, K <= 32) with prevalence[i].  Nodes are numbered in first-appearance
+ * order; every unambiguous edge is condensed, so the result is the unitig graph: per unitig its
+ * bases, count (= norm, the number of K-mers) and prevalence (sum over its K-mers of (K-1) x
+ * out-degree); per remaining edge (source unitig, destination unitig, copy count), weight K-1; the
+ * copy count of an edge touching a condensed node is 0, as in the reference.  Pure cycles of
+ * unambiguous edges (order dependent in the reference) are left uncondensed and counted.
+ * Host pointers; two-phase: run, then get with buffers of the returned sizes. */
+int shn_condense_run(shn_ctx* ctx, const uint64_t* prefix_kmers, const uint64_t* suffix_kmers,
+                     const uint32_t* prevalence, uint64_t n, int K, uint64_t* n_unitigs, uint64_t* n_bases,
+                     uint64_t* n_edges, uint64_t* n_cycle_nodes);
+int shn_condense_get(shn_ctx* ctx, char* bases, uint64_t* offsets, uint32_t* count, uint64_t* prevalence,
+                     uint32_t* edge_src, uint32_t* edge_dst, uint32_t* edge_copy_count);
+
 /* ---- f4: faster_reps.py:60-131 (representative selection among the final transcripts) ----------
  * duplicate_out[c] = 1 iff find_reps would drop transcript c: its first and last 24-mer (of the
  * transcript, or of its reverse complement when double_stranded) both occur in one other transcript

@@ -76,6 +76,8 @@ SIGNATURES = {
                                          C.c_uint64, C.c_char_p]),
     "shn_write_kmer_file": (C.c_int, [vp, C.c_char_p, vp, vp, C.c_uint64, C.c_int]),
     "shn_count_release": (C.c_int, [vp]),
+    "shn_condense_run": (C.c_int, [vp, vp, vp, vp, C.c_uint64, C.c_int, u64p, u64p, u64p, u64p]),
+    "shn_condense_get": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp]),
     "shn_find_reps": (C.c_int, [vp, vp, vp, vp, C.c_uint64, C.c_int, vp]),
     "shn_revcomp_var": (C.c_int, [vp, vp, vp, C.c_uint64, vp, C.c_int]),
     "shn_count_begin": (C.c_int, [vp, C.c_int, C.c_uint64]),
@@ -624,6 +626,29 @@ class Context(HostIO):
 
     def count_release(self):
         self.call("shn_count_release")
+
+    def condense(self, prefix_kmers, suffix_kmers, prevalence, K):
+        """unitig graph of the de Bruijn graph whose edges are the given K1-mer lines; returns a dict
+        of numpy arrays (bases, offsets, count, prevalence, edge_src, edge_dst, edge_copy_count)."""
+        pre = np.ascontiguousarray(prefix_kmers, dtype=np.uint64)
+        suf = np.ascontiguousarray(suffix_kmers, dtype=np.uint64)
+        prev = np.ascontiguousarray(prevalence, dtype=np.uint32)
+        nu, nb, ne, ncyc = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self.call("shn_condense_run", ptr(pre), ptr(suf), ptr(prev), C.c_uint64(len(prev)), int(K),
+                  C.byref(nu), C.byref(nb), C.byref(ne), C.byref(ncyc))
+        out = {"bases": np.empty(max(nb.value, 1), np.uint8), "offsets": np.zeros(nu.value + 1, np.uint64),
+               "count": np.empty(max(nu.value, 1), np.uint32), "prevalence": np.empty(max(nu.value, 1), np.uint64),
+               "edge_src": np.empty(max(ne.value, 1), np.uint32), "edge_dst": np.empty(max(ne.value, 1), np.uint32),
+               "edge_copy_count": np.empty(max(ne.value, 1), np.uint32)}
+        self.call("shn_condense_get", ptr(out["bases"]), ptr(out["offsets"]), ptr(out["count"]),
+                  ptr(out["prevalence"]), ptr(out["edge_src"]), ptr(out["edge_dst"]), ptr(out["edge_copy_count"]))
+        out["bases"] = out["bases"][:nb.value]
+        for k in ("count", "prevalence"):
+            out[k] = out[k][:nu.value]
+        for k in ("edge_src", "edge_dst", "edge_copy_count"):
+            out[k] = out[k][:ne.value]
+        out["n_cycle_nodes"] = ncyc.value
+        return out
 
     def find_reps(self, bases, offsets, name_rank, double_stranded):
         bases = np.ascontiguousarray(bases, dtype=np.uint8)

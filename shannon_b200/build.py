@@ -9,7 +9,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "libshannon_b200.so")
 SOURCES = ["api.cu", "table.cu", "l3.cu", "l4.cu", "selfjoin.cu", "synth.cu", "reads.cu", "route.cu",
-           "shard.cu", "reps.cu", "hostio.cpp"]
+           "shard.cu", "reps.cu", "condense.cu", "hostio.cpp"]
 # translation units that depend on the K1-mer key width: built a second time with -DSHN_WIDE
 # (128-bit keys, K1 = 33) into namespace `wide`; api.cu dispatches on k1
 WIDE_SOURCES = ["table.cu", "l3.cu", "l4.cu", "synth.cu", "shard.cu"]

@@ -17,6 +17,11 @@ void shn_write_k1mer_windows_impl(const char* path, const char* bases, const uin
                                   const uint32_t* weights, const uint64_t* win_off);
 void shn_write_kmer_file_impl(const char* path, const uint64_t* keys, const uint32_t* counts, uint64_t n,
                               int k1);
+void shn_condense_run_impl(shn_ctx* c, const uint64_t* h_pre, const uint64_t* h_suf, const uint32_t* h_prev,
+                           uint64_t n, int K, uint64_t* n_unitigs, uint64_t* n_bases, uint64_t* n_edges,
+                           uint64_t* n_cycle_nodes);
+void shn_condense_get_impl(shn_ctx* c, char* bases, uint64_t* offsets, uint32_t* count, uint64_t* prevalence,
+                           uint32_t* e_src, uint32_t* e_dst, uint32_t* e_cc);
 void shn_find_reps_impl(shn_ctx* c, const char* bases, const uint64_t* offsets, const uint32_t* name_rank,
                         uint64_t n, int ds, uint8_t* dup_out);
 void shn_synth_pairs_impl(shn_ctx* c, const uint8_t* tx, const uint64_t* tx_offs, const uint64_t* thr,
@@ -121,6 +126,7 @@ void shn_destroy(shn_ctx* c) {
   shn_count_free(c);
   shn_reads_free(c);
   shn_shard_free(c);
+  if (c->condense && c->condense_free) c->condense_free(c);
   c->gline_buf.release();
   c->table.release();
   c->cub_tmp.release();
@@ -789,6 +795,21 @@ int shn_write_fasta_named(shn_ctx* c, const char* path, int append, const char* 
                           const uint64_t* name_offsets, const char* bases, const uint64_t* offsets, uint64_t n) {
   SHN_API_BEGIN
   shn_write_fasta_named_impl(path, append, names, name_offsets, bases, offsets, n);
+  SHN_API_END(c)
+}
+int shn_condense_run(shn_ctx* c, const uint64_t* prefix_kmers, const uint64_t* suffix_kmers,
+                     const uint32_t* prevalence, uint64_t n, int K, uint64_t* n_unitigs, uint64_t* n_bases,
+                     uint64_t* n_edges, uint64_t* n_cycle_nodes) {
+  SHN_API_BEGIN
+  bind(c);
+  shn_condense_run_impl(c, prefix_kmers, suffix_kmers, prevalence, n, K, n_unitigs, n_bases, n_edges, n_cycle_nodes);
+  SHN_API_END(c)
+}
+int shn_condense_get(shn_ctx* c, char* bases, uint64_t* offsets, uint32_t* count, uint64_t* prevalence,
+                     uint32_t* edge_src, uint32_t* edge_dst, uint32_t* edge_copy_count) {
+  SHN_API_BEGIN
+  bind(c);
+  shn_condense_get_impl(c, bases, offsets, count, prevalence, edge_src, edge_dst, edge_copy_count);
   SHN_API_END(c)
 }
 int shn_find_reps(shn_ctx* c, const char* bases, const uint64_t* offsets, const uint32_t* name_rank,

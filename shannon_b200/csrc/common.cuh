@@ -427,6 +427,8 @@ struct shn_ctx {
   void (*count_free)(shn_ctx*) = nullptr;
   void* reads = nullptr;  // packed reads (reads.cu), independent of the key width
   void (*reads_free)(shn_ctx*) = nullptr;
+  void* condense = nullptr;  // unitig condensation of a component (condense.cu)
+  void (*condense_free)(shn_ctx*) = nullptr;
   void* shard = nullptr;  // cross-rank component labelling (shard.cu)
   void (*shard_free)(shn_ctx*) = nullptr;
   cudaStream_t own_stream = nullptr;  // the stream shn_create made (stream may point elsewhere: shn_use_stream)

@@ -234,3 +234,56 @@ def transcripts_file(path, seed, n=60):
         for i, s in enumerate(seqs):
             f.write(">T%d_%d len=%d\n%s\n" % (rnd.randrange(1000), i, len(s), s))
     return path
+
+
+def debruijn_case(path, seed, K=8, n_seqs=6, length=120, acyclic=True):
+    """A `k1mer.dict`-style file (K1-mer<TAB>prevalence) of a small graph with branches, tips, a
+    repeated line and shared segments; acyclic=True rejects inputs that contain a pure cycle of
+    unambiguous edges (its condensation depends on the visiting order, mbgraph.py:479)."""
+    import random
+    rnd = random.Random(seed)
+    while True:
+        seqs = []
+        for _ in range(n_seqs):
+            s = "".join(rnd.choice("ACGT") for _ in range(length))
+            seqs.append(s)
+            if rnd.random() < 0.7:                       # a variant sharing both ends: a bubble
+                p = rnd.randrange(K + 2, length - K - 2)
+                seqs.append(s[:p] + rnd.choice("ACGT") + s[p + 1:])
+            if rnd.random() < 0.5:                       # a tip
+                p = rnd.randrange(K, length - K)
+                seqs.append(s[p:p + K + 1 + rnd.randrange(1, 6)][:-1] + "".join(rnd.choice("ACGT") for _ in range(4)))
+        counts = {}
+        for s in seqs:
+            for i in range(len(s) - K):
+                km = s[i:i + K + 1]
+                counts[km] = counts.get(km, 0) + rnd.randrange(1, 9)
+        lines = list(counts.items())
+        rnd.shuffle(lines)
+        lines.append(lines[0])                            # a repeated line = a parallel edge
+        if acyclic and _has_unambiguous_cycle(lines, K):
+            continue
+        with open(path, "w") as f:
+            for km, c in lines:
+                f.write("%s\t%d\n" % (km, c))
+        return path
+
+
+def _has_unambiguous_cycle(lines, K):
+    out_deg, in_deg, nxt = {}, {}, {}
+    for km, _ in lines:
+        a, b = km[:-1], km[1:]
+        out_deg[a] = out_deg.get(a, 0) + 1
+        in_deg[b] = in_deg.get(b, 0) + 1
+    for km, _ in lines:
+        a, b = km[:-1], km[1:]
+        if out_deg[a] == 1 and in_deg[b] == 1 and a != b:
+            nxt[a] = b
+    for start in nxt:
+        seen, cur = set(), start
+        while cur in nxt and cur not in seen:
+            seen.add(cur)
+            cur = nxt[cur]
+        if cur in seen:
+            return True
+    return False

@@ -123,3 +123,43 @@ def test_reps_oracle_equals_faster_reps(workdir, seed, ds):
     a, b = open(os.path.join(workdir, "ref.fasta")).read(), open(os.path.join(workdir, "ora.fasta")).read()
     assert a == b
     assert 0 < a.count(">") < open(src).read().count(">")
+
+
+@pytest.mark.parametrize("seed,K", [(1, 8), (2, 8), (3, 12), (4, 24), (5, 31)])
+def test_mbgraph_oracle_equals_reference(workdir, seed, K):
+    """oracle/mbgraph_oracle.py against the real multibridging.load_single_jellyfish +
+    Node.condense_all (row f3)."""
+    from oracle import mbgraph_oracle
+    path = helpers.debruijn_case(os.path.join(workdir, "k1mer.dict"), seed, K=K, acyclic=False)
+    mb = ref_loader.load("multibridging")
+    mb.Read.K = K
+    mb.load_single_jellyfish(path)
+    mb.Node.condense_all()
+    ref_nodes = sorted((n.bases, float(n.count), float(n.prevalence), float(n.norm), float(n.copy_count))
+                       for n in mb.Node.nodes)
+    ref_edges = sorted((n.bases, e.out_node.bases, int(e.weight), float(e.copy_count))
+                       for n in mb.Node.nodes for e in n.out_edges)
+    g = mbgraph_oracle.load_and_condense(path, K)
+    nodes, edges = g.snapshot()
+    assert nodes == ref_nodes and edges == ref_edges
+    assert len(nodes) > 5 and any(c > 1 for _, c, _, _, _ in nodes)
+
+
+def test_mbgraph_oracle_on_pipeline_output(workdir):
+    """the real consumer path: a per-component k1mer.dict written by kmers_for_component"""
+    from oracle import mbgraph_oracle
+    s1, s2 = helpers.synthetic_seqs(10, 1500, 5)
+    case = helpers.make_case(workdir, 24, s1, s2)
+    out, _, _, ret = helpers.run_frontend(shannon_oracle.extension_correction,
+                                          shannon_oracle.kmers_for_component, case, "ora")
+    path = os.path.join(out, "component" + ret[1][0] + "k1mers_allowed.dict")
+    mb = ref_loader.load("multibridging")
+    mb.Read.K = 24
+    mb.load_single_jellyfish(path)
+    mb.Node.condense_all()
+    g = mbgraph_oracle.load_and_condense(path, 24)
+    nodes, edges = g.snapshot()
+    assert nodes == sorted((n.bases, float(n.count), float(n.prevalence), float(n.norm), float(n.copy_count))
+                           for n in mb.Node.nodes)
+    assert edges == sorted((n.bases, e.out_node.bases, int(e.weight), float(e.copy_count))
+                           for n in mb.Node.nodes for e in n.out_edges)
