@@ -314,6 +314,29 @@ def assign_components(sizes, world, exact_top=1 << 14):
     return owner
 
 
+def check_component_fits(ops, sizes, owner, world, k1):
+    """The walks need every K1-mer graph component whole on one rank.  Error K1-mers link unrelated
+    transcripts whenever two of them share a (K1-1)-mer by chance; beyond ~2.5 x 10^9 distinct K1-mers
+    (k1 = 25) those chance links percolate and most of the input becomes ONE component, which no
+    single table can hold.  Refuse loudly instead of running out of memory in the table build."""
+    from . import _lib
+    load = np.bincount(owner, weights=sizes.astype(np.float64), minlength=world)
+    worst = int(load.max())
+    slot_bytes = 16 if k1 <= 32 else 32
+    need = worst * 2 * slot_bytes + worst * 2 * 4 * 4       # table at load 0.5 + four 32-bit arrays per slot
+    limit = None
+    info = getattr(ops, "ctx", None)
+    if info is not None:
+        _, _, total = info.device_info()
+        limit = 0.9 * total
+    if worst * 2 >= 0xFFFFFFFF or (limit is not None and need > limit):
+        raise _lib.ShnError(
+            "sharded front end: rank load of %d K1-mers (largest K1-mer graph component: %d of %d K1-mers, "
+            "%.1f %%) needs a %d GB table shard: the component-sharded walks cannot hold it (chance links "
+            "between error K1-mers have percolated into a giant component)"
+            % (worst, int(sizes.max()), int(sizes.sum()), 100.0 * sizes.max() / max(sizes.sum(), 1), need >> 30))
+
+
 def merge_candidates(comm, w, gline, offs, codes):
     """All ranks' candidates (rank-local pop order) -> the global pop order of the reference's seed
     loop: seed weight descending, then LATER input line first (stable ascending sort by weight
@@ -413,7 +436,12 @@ def correct_sharded(comm, ops, d_keys, d_counts, n_lines, first_line, k1, double
     ops.relieve()
     sizes = comm.all_reduce_sum(ops.cc_sizes(gid_base, n_final))
     trace("cc_sizes + all_reduce")
-    owner = assign_components(sizes.cpu().numpy(), world)
+    h_sizes = sizes.cpu().numpy()
+    owner = assign_components(h_sizes, world)
+    if len(h_sizes):
+        st["largest_component"] = int(h_sizes.max())
+        st["n_keys_global"] = int(h_sizes.sum())
+        check_component_fits(ops, h_sizes, owner, world, k1)
     trace("assign_components")
     tm["components"] = time.perf_counter() - t0
     t0 = time.perf_counter()
