@@ -192,15 +192,20 @@ SHN_HD shn_key_t shn_key_mask(int k) { return shn_kmer_mask(k); }
 // parent words of the union-find.  Overflow still probes linearly over buckets, across regions.
 // Tables smaller than one region, and k1 < 12, use the plain hash.
 constexpr int kRegionM = 12;
-SHN_HD uint32_t shn_minimizer_hash(shn_key_t key, int k1) {
-  const uint32_t mmask = (1u << (2 * kRegionM)) - 1u;
+// hash of the 12-mer at base offset p counted from the END of the K1-mer (bits 2p .. 2p+23)
+SHN_HD uint32_t shn_mmer_hash(shn_key_t key, int p) {
+  return ((uint32_t)(key >> (2 * p)) & ((1u << (2 * kRegionM)) - 1u)) * 0x9E3779B1u;  // odd multiplier: a bijection
+}
+// smallest 12-mer hash over the offsets [p_lo, p_hi]
+SHN_HD uint32_t shn_minimizer_hash_range(shn_key_t key, int p_lo, int p_hi) {
   uint32_t best = 0xFFFFFFFFu;
-  for (int p = 0; p <= k1 - kRegionM; ++p) {
-    const uint32_t h = ((uint32_t)(key >> (2 * p)) & mmask) * 0x9E3779B1u;  // odd multiplier: a bijection
+  for (int p = p_lo; p <= p_hi; ++p) {
+    const uint32_t h = shn_mmer_hash(key, p);
     best = h < best ? h : best;
   }
   return best;
 }
+SHN_HD uint32_t shn_minimizer_hash(shn_key_t key, int k1) { return shn_minimizer_hash_range(key, 0, k1 - kRegionM); }
 
 struct ShnTableView {
   ShnSlot* slots;      // SHN_BSLOTS * n_buckets
@@ -209,9 +214,15 @@ struct ShnTableView {
   int k1 = 0;
   int region_shift = 17;   // log2(buckets per region): 2^17 x 64 B = 8 MB
   __device__ __forceinline__ uint64_t bucket_of(shn_key_t key) const {
+    if (n_regions == 0) return __umul64hi(shn_key_hash(key), n_buckets);
+    return bucket_with_min(key, shn_minimizer_hash(key, k1));
+  }
+  // the same when the caller already knows the K1-mer's minimizer hash (neighbouring K1-mers share
+  // all 12-mers but one or two: uf_edges and the walks compute the shared minimum once)
+  __device__ __forceinline__ uint64_t bucket_with_min(shn_key_t key, uint32_t min_hash) const {
     const uint64_t h = shn_key_hash(key);
     if (n_regions == 0) return __umul64hi(h, n_buckets);
-    const uint64_t hm = shn_mix64((uint64_t)shn_minimizer_hash(key, k1) + 0x9E3779B97F4A7C15ull);
+    const uint64_t hm = shn_mix64((uint64_t)min_hash + 0x9E3779B97F4A7C15ull);
     return (__umul64hi(hm, (uint64_t)n_regions) << region_shift) | (h >> (64 - region_shift));
   }
 };

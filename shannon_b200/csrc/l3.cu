@@ -159,10 +159,13 @@ __global__ void __launch_bounds__(kBlock)
   shn_key_t pre = (key << 2) & mask;
   const uint32_t first = (uint32_t)(key >> (2 * (k1 - 1))) & 3u;
   uint32_t sm = 0;
+  // the four successors share every 12-mer but their last: one minimum for all of them
+  const uint32_t shared = t.n_regions ? shn_minimizer_hash_range(pre, 1, k1 - kRegionM) : 0u;
 #pragma unroll
   for (int b = 0; b < 4; ++b) {
     uint32_t w;
-    uint64_t s = table_find(t, pre | (shn_key_t)b, &w);
+    const shn_key_t cand = pre | (shn_key_t)b;
+    uint64_t s = table_find_from(t, cand, t.bucket_with_min(cand, min(shared, shn_mmer_hash(cand, 0))), &w);
     if (s != ~0ull) {
       sm |= 1u << b;
       atomicOr(&t.slots[s].idx, 1u << (28 + first));  // the bucket of s was just read: an L2 hit
@@ -362,6 +365,34 @@ struct WalkArgs {
   unsigned long long* trace;     // optional: per warp {end time ns, rounds, cycles} (SHN_WALK_TRACE)
 };
 
+// Minimizer hash of the candidates of one round without the 14-step loop per candidate: the
+// candidates are `cur` shifted by one (level 1) or two (level 2) bases, so they share all 12-mers of
+// `cur` but the ones that fell out; lane p hashes the 12-mer of cur at offset p and two warp
+// reductions give the shared minima (cur is warp-uniform, all lanes call this):
+//   right extension: level 1 shares cur's offsets [0, n-1], level 2 [0, n-2]   (n = k1 - 12)
+//   left extension:  level 1 shares cur's offsets [1, n],   level 2 [2, n]
+// walk_cand_min() then adds the one or two new 12-mers of the candidate itself.
+__device__ __forceinline__ uint32_t walk_shared_min(const ShnTableView& tv, shn_key_t cur, int k1, int dir,
+                                                    int lvl, int lane) {
+  if (tv.n_regions == 0) return 0u;
+  const int n = k1 - kRegionM;
+  const uint32_t hp = lane <= n ? shn_mmer_hash(cur, lane) : 0xFFFFFFFFu;
+  const int lo1 = dir == 0 ? 0 : 1, hi1 = dir == 0 ? n - 1 : n;
+  const int lo2 = dir == 0 ? 0 : 2, hi2 = dir == 0 ? n - 2 : n;
+  const uint32_t m1 = __reduce_min_sync(0xFFFFFFFFu, (lane >= lo1 && lane <= hi1) ? hp : 0xFFFFFFFFu);
+  const uint32_t m2 = __reduce_min_sync(0xFFFFFFFFu, (lane >= lo2 && lane <= hi2) ? hp : 0xFFFFFFFFu);
+  return lvl == 2 ? m2 : m1;
+}
+__device__ __forceinline__ uint32_t walk_cand_min(const ShnTableView& tv, shn_key_t cand, int k1, int dir, int lvl,
+                                                  uint32_t shared) {
+  if (tv.n_regions == 0) return 0u;
+  const int n = k1 - kRegionM;
+  // the new 12-mers sit at the end of the candidate (right extension) or at its start (left)
+  uint32_t m = min(shared, shn_mmer_hash(cand, dir == 0 ? 0 : n));
+  if (lvl == 2 && n >= 1) m = min(m, shn_mmer_hash(cand, dir == 0 ? 1 : n - 1));
+  return m;
+}
+
 // One probe of the walks: the candidate's home bucket is already loaded.
 // state: 1 found (slot, raw weight word, aux word), 0 absent, -1 continues in bucket *nextb.
 __device__ __forceinline__ int walk_resolve(const ShnTableView& tv, const ShnBucket& bk, shn_key_t cand,
@@ -481,6 +512,7 @@ __global__ void __launch_bounds__(kWalkBlock, kWalkBlocksPerSM) walk_kernel(Walk
           uint32_t wraw = 0, caux = 0;
           int state = 0;       // 1 found, 0 absent, -1 undecided after the home bucket
           uint64_t nextb = 0;  // where an undecided lane would continue
+          const uint32_t cand_min = walk_shared_min(tv, cur, a.k1, dir, lvl, lane);
           if (act) {
             if (dir == 0) {
               cand = ((cur << 2) & mask) | b1;
@@ -489,7 +521,7 @@ __global__ void __launch_bounds__(kWalkBlock, kWalkBlocksPerSM) walk_kernel(Walk
               cand = (cur >> 2) | (b1 << top);
               if (lvl == 2) cand = (cand >> 2) | (b2 << top);
             }
-            const uint64_t hb = tv.bucket_of(cand);
+            const uint64_t hb = tv.bucket_with_min(cand, walk_cand_min(tv, cand, a.k1, dir, lvl, cand_min));
             ShnBucket bk0;
             long long tm0 = 0;
             if (tracing) tm0 = clock64();
@@ -750,6 +782,7 @@ __global__ void __launch_bounds__(kSpecWarps * 32, kSpecCtasPerSM * 16 / kSpecWa
             int state = 0;
             uint64_t nextb = 0;
             ShnBucket bk0;
+            const uint32_t cand_min = walk_shared_min(tv, cur, a.k1, dir, lvl, lane);
             if (act) {
               if (dir == 0) {
                 cand = ((cur << 2) & mask) | b1;
@@ -758,7 +791,7 @@ __global__ void __launch_bounds__(kSpecWarps * 32, kSpecCtasPerSM * 16 / kSpecWa
                 cand = (cur >> 2) | (b1 << top);
                 if (lvl == 2) cand = (cand >> 2) | (b2 << top);
               }
-              hb = tv.bucket_of(cand);
+              hb = tv.bucket_with_min(cand, walk_cand_min(tv, cand, a.k1, dir, lvl, cand_min));
               table_load_bucket(tv, hb, &bk0);
             }
             {  // the claims of the previous round, by now usually back from L2

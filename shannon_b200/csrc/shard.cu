@@ -347,12 +347,14 @@ __global__ void __launch_bounds__(kBlock)
     return;
   }
   const shn_key_t pre = (key << 2) & shn_key_mask(k1);
-  // all four home buckets in flight before any is looked at
+  // all four home buckets in flight before any is looked at; one shared minimizer minimum
   ShnBucket bk[4];
   uint64_t hb[4];
+  const uint32_t shared = t.n_regions ? shn_minimizer_hash_range(pre, 1, k1 - kRegionM) : 0u;
 #pragma unroll
   for (int b = 0; b < 4; ++b) {
-    hb[b] = t.bucket_of(pre | (shn_key_t)b);
+    const shn_key_t cand = pre | (shn_key_t)b;
+    hb[b] = t.bucket_with_min(cand, min(shared, shn_mmer_hash(cand, 0)));
     table_load_bucket(t, hb[b], &bk[b]);
   }
 #pragma unroll

@@ -114,9 +114,16 @@ __device__ __forceinline__ int table_match_bucket(const ShnBucket& bk, shn_key_t
 
 // Read-only probe: slot index of `key` or ~0; *w_out = raw weight word (flag bits included).
 // The all-ones key (only possible as a query: it is low-complexity and never stored) is absent.
+__device__ __forceinline__ uint64_t table_find_from(const ShnTableView& t, shn_key_t key, uint64_t b,
+                                                    uint32_t* w_out);
 __device__ __forceinline__ uint64_t table_find(const ShnTableView& t, shn_key_t key, uint32_t* w_out) {
   if (key == SHN_EMPTY) return ~0ull;
-  uint64_t b = t.bucket_of(key);
+  return table_find_from(t, key, t.bucket_of(key), w_out);
+}
+// ... starting at a home bucket the caller computed (ShnTableView::bucket_with_min)
+__device__ __forceinline__ uint64_t table_find_from(const ShnTableView& t, shn_key_t key, uint64_t b,
+                                                    uint32_t* w_out) {
+  if (key == SHN_EMPTY) return ~0ull;
   for (;;) {
     ShnBucket bk;
     table_load_bucket(t, b, &bk);
