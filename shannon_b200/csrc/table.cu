@@ -153,7 +153,14 @@ void table_begin(shn_ctx* c, uint64_t n, int k1, int double_stranded) {
   uint64_t items = n * (double_stranded ? 2 : 1);
   SHN_CHECK(items < 0xFFFFFFFEull, "more than 2^32-2 input K1-mers per table");
   // slots >= 2 * items  (load factor <= 0.5)
-  uint64_t n_buckets = items < 1024 ? 1024 / SHN_BSLOTS : (2 * items + SHN_BSLOTS - 1) / SHN_BSLOTS;
+  // slots = items / load factor.  0.5 by default: at 0.4 the walks need fewer probe continuations
+  // (walk stage 110 -> 103 ms at 10 M pairs) but every pass over the slots grows (uf_edges 50 -> 55 ms):
+  // no net gain, measured.  SHN_TABLE_LOAD in 0.1 .. 0.9.
+  const char* envl = getenv("SHN_TABLE_LOAD");
+  double load = envl ? atof(envl) : 0.5;
+  if (!(load >= 0.1 && load <= 0.9)) load = 0.5;
+  uint64_t n_buckets = items < 1024 ? 1024 / SHN_BSLOTS
+                                    : (uint64_t)((double)items / load + SHN_BSLOTS - 1) / SHN_BSLOTS;
   // minimizer-clustered regions (common.cuh) once the table spans at least a few of them
   const char* envs = getenv("SHN_REGION_SHIFT");
   // 2^17 buckets = 8 MB per region: measured at 10 M pairs (uf_edges 94 -> 57 ms); 256 KB regions
