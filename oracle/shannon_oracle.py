@@ -442,10 +442,10 @@ def kmers_for_component(k1mer_dictionary, kmer_directory, reads, reads_files, di
                         K=24, gpmetis_path="gpmetis", penalty=5, only_reads=False, inMem=False,
                         nJobs=1, NR=10000000):
     """kmers_for_component.py:144-558 restated.  ``double_stranded=True`` (in-process RC
-    fan-out, :117-141,341,381) is not restated: shannon.py:427 forces it to False and its
-    result order depends on process scheduling in the reference."""
-    if double_stranded:
-        raise NotImplementedError("double_stranded=True is never used by shannon.py:427,467")
+    fan-out, :36-52,117-141,341,381; never passed by shannon.py:427) is restated for nJobs = 1,
+    where the reference is deterministic: every chunk of valid reads is followed by its reverse
+    complements (SE), resp. the pairs (r1, rc(r2)) by the pairs (r2, rc(r1)) (PE).  With nJobs > 1
+    the reference concatenates the workers' results in queue-arrival order."""
     if not get_partition_k1mers:
         return None  # the reference falls off the end of the function (:207)
     k1 = K + 1
@@ -493,6 +493,12 @@ def kmers_for_component(k1mer_dictionary, kmer_directory, reads, reads_files, di
     suffix = ["_1", "_2"] if paired_end else [""]
     counter = [0]
     for chunk in _read_records(handles, NR, counter):
+        if double_stranded:                                              # :341,381 with nJobs = 1
+            if paired_end:
+                chunk = [(a, reverse_complement(b.strip())) for a, b in chunk] + \
+                        [(b, reverse_complement(a.strip())) for a, b in chunk]
+            else:
+                chunk = list(chunk) + [(reverse_complement(m[0].strip()),) for m in chunk]
         for mates in chunk:
             assigned = set()
             for m in mates:

@@ -46,18 +46,72 @@ def _dict_arrays(ctx, k1mer_dictionary, k1):
     return keys, np.asarray(ws, dtype=np.uint32)
 
 
+NR = 10000000     # reads per chunk of the reference's partition loop (kmers_for_component.py:322)
+
+
+def _gather_reads(bases, offs, idx):
+    """(bases, offsets) of the reads `idx`, concatenated in that order."""
+    offs = np.asarray(offs, dtype=np.int64)
+    idx = np.asarray(idx, dtype=np.int64)
+    lens = offs[idx + 1] - offs[idx]
+    out_offs = np.zeros(len(idx) + 1, dtype=np.uint64)
+    out_offs[1:] = np.cumsum(lens)
+    total = int(out_offs[-1])
+    if total == 0:
+        return np.empty(0, dtype=np.uint8), out_offs
+    start = np.repeat(offs[idx] - out_offs[:-1].astype(np.int64), lens)
+    return bases[start + np.arange(total, dtype=np.int64)], out_offs
+
+
+def _valid_reads(bases, offs):
+    """not read.strip('ACTG') per read (:336,376)"""
+    offs = np.asarray(offs, dtype=np.int64)
+    bad = np.concatenate([[0], np.cumsum(~np.isin(bases, np.frombuffer(b"ACGT", dtype=np.uint8)))])
+    return bad[offs[1:]] == bad[offs[:-1]]
+
+
+def _double_strand(ctx, read_bases, read_offs, paired_end):
+    """The read list the reference's loop sees with double_stranded=True and nJobs = 1: per chunk of
+    NR valid records, SE: the reads then their reverse complements (rc, :36-42); PE: the pairs
+    (r1, rc(r2)) then the pairs (r2, rc(r1)) (rc_mate_ds, :44-52).  Reverse complements on the GPU."""
+    valid = _valid_reads(read_bases[0], read_offs[0])
+    if paired_end:
+        valid &= _valid_reads(read_bases[1], read_offs[1])
+    v = np.nonzero(valid)[0]
+    out_b = [[] for _ in read_bases]
+    out_n = [[] for _ in read_bases]
+    for lo in range(0, max(len(v), 1), NR):
+        sel = v[lo:lo + NR]
+        m = [_gather_reads(read_bases[k], read_offs[k], sel) for k in range(len(read_bases))]
+        rc = [(ctx.revcomp_var(b, o), o) for b, o in m]
+        if paired_end:
+            parts = [[m[0], m[1]], [rc[1], rc[0]]]
+        else:
+            parts = [[m[0], rc[0]]]
+        for k, seq in enumerate(parts):
+            for b, o in seq:
+                out_b[k].append(b)
+                out_n[k].append(np.diff(o.astype(np.int64)))
+    bases, offs = [], []
+    for k in range(len(read_bases)):
+        bases.append(np.concatenate(out_b[k]) if out_b[k] else np.empty(0, np.uint8))
+        lens = np.concatenate(out_n[k]) if out_n[k] else np.empty(0, np.int64)
+        o = np.zeros(len(lens) + 1, dtype=np.uint64)
+        o[1:] = np.cumsum(lens)
+        offs.append(o)
+    return bases, offs
+
+
 def kmers_for_component(k1mer_dictionary, kmer_directory, reads, reads_files, directory_name,
                         contig_file_extension, get_partition_k1mers, double_stranded=True,
                         paired_end=False, repartition=False, partition_size=500, overload=1.5,
                         K=24, gpmetis_path='gpmetis', penalty=5, only_reads=False, inMem=False,
                         nJobs=1, ctx=None):
     """See the reference docstring (kmers_for_component.py:145-155).  ``kmer_directory`` and
-    ``reads`` are unused there as well.  ``double_stranded=True`` (in-process RC fan-out whose
-    output order depends on process scheduling, :117-141) is never passed by shannon.py:427,467
-    and is not provided."""
-    if double_stranded:
-        raise NotImplementedError("double_stranded=True: shannon.py bakes strandedness into the "
-                                  "read files and always passes False (shannon.py:427)")
+    ``reads`` are unused there as well.  ``double_stranded=True`` (never passed by shannon.py:427,467)
+    follows every chunk of NR valid reads by its reverse complements like the reference with
+    nJobs = 1 (:36-52,117-141,341,381); with nJobs > 1 the reference concatenates its workers'
+    results in queue-arrival order, here the result does not depend on nJobs."""
     if not get_partition_k1mers:
         return None
     ctx = ctx or get_context()
@@ -156,6 +210,8 @@ def kmers_for_component(k1mer_dictionary, kmer_directory, reads, reads_files, di
         rb1, ro1 = ctx.load_fasta(reads_files[1], n_records)
         read_bases.append(rb1)
         read_offs.append(ro1)
+    if double_stranded:
+        read_bases, read_offs = _double_strand(ctx, read_bases, read_offs, paired_end)
     section("kfc_read_fasta")
     n_comps = len(new_components)
     comp_offs, rec_idx, _ = partition_reads(

@@ -98,8 +98,9 @@ def run_frontend(ec_fn, kfc_fn, case, outname, min_weight=3, min_length=75, part
              "1"] + case.reads_files
     k1mer_dictionary, reads = ec_fn(args, ec_inMem)
     kw = dict(extra_kfc or {})
+    ds_kfc = kw.pop("double_stranded", False)
     ret = kfc_fn(k1mer_dictionary, os.path.join(out, "algo_input"), reads, case.reads_files, out,
-                 "contigs.txt", True, False, case.paired_end, repartition, partition_size, 2,
+                 "contigs.txt", True, ds_kfc, case.paired_end, repartition, partition_size, 2,
                  case.K, GPMETIS, 5, only_reads, inMem, 1, **kw)
     return out, dict(k1mer_dictionary), reads, ret
 

@@ -163,3 +163,13 @@ def test_mbgraph_oracle_on_pipeline_output(workdir):
                            for n in mb.Node.nodes)
     assert edges == sorted((n.bases, e.out_node.bases, int(e.weight), float(e.copy_count))
                            for n in mb.Node.nodes for e in n.out_edges)
+
+
+@pytest.mark.parametrize("paired,inmem", [(False, False), (True, False), (True, True)])
+def test_kfc_double_stranded_true_nJobs1(workdir, paired, inmem):
+    """kmers_for_component(double_stranded=True) -- never passed by shannon.py:427, deterministic for
+    nJobs = 1: every chunk of reads is followed by its reverse complements (:36-52,117-141,341,381)."""
+    s1, s2 = helpers.synthetic_seqs(12, 1500, 21)
+    s1[4] = s1[4][:50] + "N" + s1[4][51:]
+    case = helpers.make_case(workdir, 24, s1, s2 if paired else None, double_stranded=False)
+    both(case, inMem=inmem, extra_kfc={"double_stranded": True}, min_weight=2, min_length=60)
