@@ -562,9 +562,18 @@ __global__ void __launch_bounds__(kWalkBlock, kWalkBlocksPerSM) walk_kernel(Walk
           }
           // ---- second step from the prefetched level: group 4+4*w1; c1 is traversed by now ---
           const int g2 = 4 + 4 * w1;
+          // c1's own neighbour mask (in the aux word lane w1 just fetched) says which of its four
+          // children exist: a blind probe that is undecided after its home bucket continues only
+          // if its child exists (most undecided probes are absent keys behind a full bucket)
+          const uint32_t c1mask = (__shfl_sync(FULL, caux, w1) >> (kAuxSuccShift + 4 * dir)) & 0xFu;
           if (lane >= g2 && lane < g2 + 4 && state < 0) {
-            state = walk_chase(tv, cand, &cslot, &wraw, &caux, &nextb);
-            ok = state == 1 && !(caux & kAuxTraversed);
+            if ((c1mask >> (lane - g2)) & 1u) {
+              state = walk_chase(tv, cand, &cslot, &wraw, &caux, &nextb);
+              ok = state == 1 && !(caux & kAuxTraversed);
+            } else {
+              state = 0;
+              ok = false;
+            }
           }
           ok = ok && cand != c1;
           score = ok ? ((((wraw & SHN_WEIGHT_MASK) << 2) | (uint32_t)(3 - (lane & 3))) + 1u) : 0u;
@@ -830,9 +839,16 @@ __global__ void __launch_bounds__(kSpecWarps * 32, kSpecCtasPerSM * 16 / kSpecWa
             ++n_dir[dir];
             // ---- second step from the prefetched level ---------------------------------------
             const int g2 = 4 + 4 * w1;
+            // (as in walk_kernel: c1's neighbour mask decides which undecided blind probes go on)
+            const uint32_t c1mask = (__shfl_sync(FULL, caux, w1) >> (kAuxSuccShift + 4 * dir)) & 0xFu;
             if (lane >= g2 && lane < g2 + 4 && state < 0) {
-              state = walk_chase(tv, cand, &cslot, &wraw, &caux, &nextb);
-              ok = state == 1 && !(caux & kAuxTraversed) && (caux & kAuxStampMask) < stamp;
+              if ((c1mask >> (lane - g2)) & 1u) {
+                state = walk_chase(tv, cand, &cslot, &wraw, &caux, &nextb);
+                ok = state == 1 && !(caux & kAuxTraversed) && (caux & kAuxStampMask) < stamp;
+              } else {
+                state = 0;
+                ok = false;
+              }
             }
             ok = ok && cand != c1;
             if (lane >= g2 && lane < g2 + 4 && state == 1 && !(caux & kAuxTraversed) &&

@@ -425,7 +425,12 @@ void l4_map_add_contigs(shn_ctx* c, const char* bases, const uint64_t* offsets,
   SHN_CHECK(k1 >= 1 && k1 <= SHN_MAX_K1, "k1 out of range for this key width");
   L4State* s = l4_of(c);
   if (reset) {
-    uint64_t nb = expected_total < 1024 ? 1024 : expected_total;
+    // two slots per bucket: nb = expected keys -> load 0.5 (SHN_MAP_LOAD in 0.3 .. 0.9 trades probe
+    // length against the footprint of the map in L2)
+    const char* envl = getenv("SHN_MAP_LOAD");
+    double load = envl ? atof(envl) : 0.5;
+    if (!(load >= 0.3 && load <= 0.9)) load = 0.5;
+    uint64_t nb = expected_total < 1024 ? 1024 : (uint64_t)((double)expected_total * 0.5 / load) + 1;
     s->map.reserve(nb * 2 * sizeof(CompSlot));
     s->map_w.reserve(nb * 2 * sizeof(uint32_t));
     s->n_buckets = nb;
