@@ -509,10 +509,11 @@ def frontend_sharded(comm, ops, ctx, d_keys, d_counts, n_lines, first_line, k1, 
     the read files as [(bases, offsets, n, on_device)].  Returns (cor, comp_offsets, record_idx,
     stats); the partition (global record indices, numpy) is returned on rank 0, None elsewhere."""
     tm, st = {}, {}
+    pipeline.upload_reads_early(ctx, mates)      # host-resident reads: the H2D copy overlaps the L3 stage
     n_loaded = correct_sharded(comm, ops, d_keys, d_counts, n_lines, first_line, k1, double_stranded,
                                min_weight, min_length, tm, st)
     t0 = time.perf_counter()
-    pipeline.load_reads(ctx, mates)
+    pipeline.load_reads(ctx, mates, staged=True)
     cor = pipeline.collect_correction(ctx, k1, n_loaded, tm, fetch_allowed=False)
     comp_of_contig, n_comps, pk = pipeline.component_ids(cor, partition_size)
     ctx.l4_map_add_l3_contigs(comp_of_contig[1:], True)
