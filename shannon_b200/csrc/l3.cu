@@ -666,6 +666,7 @@ struct SpecArgs {
   uint32_t* path_slot;       // per component: kSpecWindow buffers of (node count) entries
   uint8_t* path_base;
   const uint64_t* path_off;  // [n_spec + 1] first entry of every component's buffers
+  unsigned long long* phase_ns;  // optional (SHN_WALK_TRACE): per CTA ns in {collect, walk, check, resolve, commit}
 };
 
 template <int kSpecWarps>
@@ -702,6 +703,16 @@ __global__ void __launch_bounds__(kSpecWarps * 32, kSpecCtasPerSM * 16 / kSpecWa
   }
   unsigned long long rounds = 0, traversed = 0, windows = 0, n_commit = 0, n_retry = 0;
   bool overflow = false, path_overflow = false;
+  unsigned long long ph[6] = {0, 0, 0, 0, 0, 0}, t_ph = 0;
+  const bool ph_on = sa.phase_ns != nullptr && threadIdx.x == 0;
+#define SHN_PHASE(k)                                                  \
+  if (ph_on) {                                                        \
+    unsigned long long t_now;                                         \
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_now));         \
+    ph[k] += t_now - t_ph;                                            \
+    t_ph = t_now;                                                     \
+  }
+  if (ph_on) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_ph));
   __syncthreads();
 
   for (;;) {
@@ -738,6 +749,7 @@ __global__ void __launch_bounds__(kSpecWarps * 32, kSpecCtasPerSM * 16 / kSpecWa
       }
     }
     __syncthreads();
+    SHN_PHASE(0)
     const uint32_t win_n = sh_win_n;
     if (win_n == 0) break;
     ++windows;
@@ -897,23 +909,31 @@ __global__ void __launch_bounds__(kSpecWarps * 32, kSpecCtasPerSM * 16 / kSpecWa
       }
     }
     __syncthreads();  // all claims of the window are in L2
+    SHN_PHASE(1)
 
     // ---- 3. which paths are intact, and who holds the seeds? -----------------------------------
-    for (uint32_t ws = warp; ws < win_n; ws += kSpecWarps) {
+    // The whole CTA re-reads every path of the window (a long walk checked by one warp alone took
+    // as long as the walk itself: measured 38 of 90 ms for the largest component).
+    if (threadIdx.x < win_n) {
+      const uint32_t ws = threadIdx.x, stamp = (uint32_t)kSpecWindow - ws;
+      sh_intact[ws] = (sh_len[ws] && !sh_poison[ws]) ? 1u : 0u;
+      const uint32_t sst = __ldcg(&tv.slots[sh_win_slot[ws]].idx) & kAuxStampMask;
+      sh_thief[ws] = (sst > stamp && sst <= (uint32_t)kSpecWindow) ? (uint32_t)kSpecWindow - sst : 0xFFFFFFFFu;
+    }
+    __syncthreads();
+    SHN_PHASE(5)
+    for (uint32_t ws = 0; ws < win_n; ++ws) {
       // (a walk longer than its buffer is only stamped/cleared up to the buffer: the stage is rerun)
       const uint32_t len = (uint32_t)min((uint64_t)sh_len[ws], path_cap), stamp = (uint32_t)kSpecWindow - ws;
       const uint32_t* ps = cta_path_slot + (uint64_t)ws * path_cap;
       bool mine = true;
-      for (uint32_t e = lane; e < len; e += 32)
+#pragma unroll 4
+      for (uint32_t e = threadIdx.x; e < len; e += kSpecWarps * 32)
         mine &= (__ldcg(&tv.slots[ps[e]].idx) & kAuxStampMask) == stamp;
-      mine = __all_sync(FULL, mine);
-      if (lane == 0) {
-        sh_intact[ws] = (mine && len && !sh_poison[ws]) ? 1u : 0u;
-        const uint32_t sst = __ldcg(&tv.slots[sh_win_slot[ws]].idx) & kAuxStampMask;
-        sh_thief[ws] = (sst > stamp && sst <= (uint32_t)kSpecWindow) ? (uint32_t)kSpecWindow - sst : 0xFFFFFFFFu;
-      }
+      if (!mine) sh_intact[ws] = 0u;   // benign race: every writer stores 0
     }
     __syncthreads();
+    SHN_PHASE(2)
     if (threadIdx.x == 0) {
       // in pop order: COMMIT = intact and never blocked by anything but committed walks;
       // SKIP = the seed belongs to a committed earlier walk (the sequential loop finds it traversed);
@@ -938,6 +958,7 @@ __global__ void __launch_bounds__(kSpecWarps * 32, kSpecCtasPerSM * 16 / kSpecWa
       sh_cursor = P < win_n ? s_begin + sh_win_pos[P] : sh_cursor_after;
     }
     __syncthreads();
+    SHN_PHASE(3)
     const uint32_t P = sh_P;
     if (warp == 0) {
       n_commit += P;
@@ -974,7 +995,11 @@ __global__ void __launch_bounds__(kSpecWarps * 32, kSpecCtasPerSM * 16 / kSpecWa
       }
     }
     __syncthreads();
+    SHN_PHASE(4)
   }
+#undef SHN_PHASE
+  if (ph_on)
+    for (int k = 0; k < 6; ++k) sa.phase_ns[6 * (uint64_t)blockIdx.x + k] = ph[k];
   if (lane == 0) {
     atomicAdd(&a.counters[0], traversed);
     atomicMax(&a.counters[1], rounds);
@@ -1564,7 +1589,7 @@ static bool l3_walks_impl(shn_ctx* c, uint32_t min_weight, uint32_t min_length, 
         ++n_spec;
       }
     }
-    DevBuf path_slot, path_base, path_off;
+    DevBuf path_slot, path_base, path_off, phase_ns;
     cudaEvent_t ev_fork = c->prof_event(), ev_join = c->prof_event(), ev_join3 = c->prof_event();
     {
       ProfScope ps(c, "walk", (n_spec ? 2 : 0) + (n_spec < n_active ? 1 : 0));  // upper bound: two tiers
@@ -1596,6 +1621,12 @@ static bool l3_walks_impl(shn_ctx* c, uint32_t min_weight, uint32_t min_length, 
         sa.path_slot = path_slot.as<uint32_t>();
         sa.path_base = path_base.as<uint8_t>();
         sa.path_off = path_off.as<uint64_t>();
+        sa.phase_ns = nullptr;
+        if (want_trace) {
+          phase_ns.reserve((uint64_t)n_spec * 6 * 8);
+          CUDA_CHECK(cudaMemsetAsync(phase_ns.p, 0, (uint64_t)n_spec * 6 * 8, st));
+          sa.phase_ns = phase_ns.as<unsigned long long>();
+        }
         const char* envt = getenv("SHN_SPEC_TIER16");
         const uint32_t n16 =
             std::min<uint32_t>(n_spec, envt ? (uint32_t)strtoul(envt, nullptr, 10) : (uint32_t)c->sm_count / 4u);
@@ -1615,6 +1646,7 @@ static bool l3_walks_impl(shn_ctx* c, uint32_t min_weight, uint32_t min_length, 
           t.w.comp_order = a.comp_order + n16;
           t.w.n_comps = n_spec - n16;
           t.path_off = sa.path_off + n16;
+          if (t.phase_ns) t.phase_ns += 6 * (uint64_t)n16;
           if (t.w.trace) t.w.trace += 3 * (uint64_t)n16;
           walk_spec_kernel<8><<<n_spec - n16, 8 * 32, 0, c->stream4>>>(t);
           KERNEL_CHECK();
@@ -1658,6 +1690,22 @@ static bool l3_walks_impl(shn_ctx* c, uint32_t min_weight, uint32_t min_length, 
                     "retried=%llu end=+%.1f ms\n",
                     w, top[w], tr[3 * w + 1] >> 32, tr[3 * w + 1] & 0xFFFFFFFFull, tr[3 * w + 2] >> 32,
                     tr[3 * w + 2] & 0xFFFFFFFFull, (tr[3 * w] - t_min) / 1e6);
+      }
+      if (n_spec) {
+        std::vector<unsigned long long> phs;
+        d2h(c, phs, phase_ns.p, (uint64_t)n_spec * 6);
+        for (uint32_t w = 0; w < std::min<uint32_t>(n_spec, 4); ++w)
+          fprintf(stderr,
+                  "[walk trace] spec comp #%u phases (ms of thread 0): collect=%.1f walk=%.1f seed-check=%.1f "
+                  "path-check=%.1f resolve=%.1f commit=%.1f\n",
+                  w, phs[6 * w] / 1e6, phs[6 * w + 1] / 1e6, phs[6 * w + 5] / 1e6, phs[6 * w + 2] / 1e6,
+                  phs[6 * w + 3] / 1e6, phs[6 * w + 4] / 1e6);
+        const uint32_t w8 = std::min<uint32_t>(n_spec - 1, (uint32_t)c->sm_count / 4u);
+        fprintf(stderr,
+                "[walk trace] spec comp #%u (first 8-warp CTA) phases: collect=%.1f walk=%.1f seed-check=%.1f "
+                "path-check=%.1f resolve=%.1f commit=%.1f\n",
+                w8, phs[6 * w8] / 1e6, phs[6 * w8 + 1] / 1e6, phs[6 * w8 + 5] / 1e6, phs[6 * w8 + 2] / 1e6,
+                phs[6 * w8 + 3] / 1e6, phs[6 * w8 + 4] / 1e6);
       }
       for (uint32_t w = n_spec; w < std::min<uint32_t>(n_active, n_spec + 6); ++w)
         fprintf(stderr, "[walk trace] largest component #%u: rounds=%llu seeds=%llu end=+%.1f ms\n", w,

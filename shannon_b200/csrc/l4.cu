@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(kBlock)
       } else {
         uint64_t b = m.bucket_of(key);
         CompSlot* slot = nullptr;
-        while (!slot) {
+        for (uint64_t probes = 0; !slot && probes <= m.n_buckets; ++probes) {
           CompSlot* s = m.slots + 2 * b;
           const ulonglong2 s0 = __ldcg(reinterpret_cast<const ulonglong2*>(&s[0]));
           const ulonglong2 s1 = __ldcg(reinterpret_cast<const ulonglong2*>(&s[1]));
@@ -185,10 +185,14 @@ __global__ void __launch_bounds__(kBlock)
           }
           b = (b + 1 == m.n_buckets) ? 0 : b + 1;
         }
-        uint32_t old = atomicCAS(&slot->comp0, SHN_NONE32, comp);
-        if (old != SHN_NONE32 && old != comp) {
-          old = atomicCAS(&slot->comp1, SHN_NONE32, comp);
-          if (old != SHN_NONE32 && old != comp) n_over = 1;
+        if (!slot) {
+          n_bad = 1;  // map full (cannot happen when the capacity check of the host holds)
+        } else {
+          uint32_t old = atomicCAS(&slot->comp0, SHN_NONE32, comp);
+          if (old != SHN_NONE32 && old != comp) {
+            old = atomicCAS(&slot->comp1, SHN_NONE32, comp);
+            if (old != SHN_NONE32 && old != comp) n_over = 1;
+          }
         }
       }
     }
@@ -460,7 +464,17 @@ void l4_map_add_contigs(shn_ctx* c, const char* bases, const uint64_t* offsets,
   // the component ids always come from the host (they are decided by the host-side packing)
   const uint32_t* d_comp =
       (const uint32_t*)InputView::get(c, comp_of_contig, n_contigs * 4, 0, s->stage_c);
-  SHN_CHECK(s->n_keys + total <= s->n_buckets * 2,
+  // K1-mer windows of this batch: exact from host offsets; device-resident contigs come with the
+  // exact count in expected_total (the allowed set of shn_l3_run)
+  uint64_t windows = expected_total;
+  if (!on_device) {
+    windows = 0;
+    for (uint64_t i = 0; i < n_contigs; ++i) {
+      const uint64_t len = offsets[i + 1] - offsets[i];
+      if (len >= (uint64_t)k1) windows += len - k1 + 1;
+    }
+  }
+  SHN_CHECK(s->n_keys + windows <= s->n_buckets * 2,
             "component map too small: expected_total_k1mers was underestimated");
   unsigned long long* ctr = zero_counters(c);
   if (total) {
@@ -471,7 +485,7 @@ void l4_map_add_contigs(shn_ctx* c, const char* bases, const uint64_t* offsets,
   }
   unsigned long long h[4];
   read_counters(c, h, 4);
-  SHN_CHECK(h[1] == 0, "contig contains a character outside ACGT");
+  SHN_CHECK(h[1] == 0, "contig contains a character outside ACGT (or the component map is full)");
   SHN_CHECK(h[2] == 0, "a K1-mer belongs to more than two components (unsupported)");
   SHN_CHECK(h[3] == 0, "a contig holds the poly-T K1-mer of 32 (64) bases, which the component map cannot store "
                        "(low-complexity: never produced by extension_correction)");
