@@ -1402,13 +1402,34 @@ static bool l3_walks_impl(shn_ctx* c, uint32_t min_weight, uint32_t min_length, 
     uint64_t n_slots;
     unsigned grid;
     DevBuf saved;
-    bool parked = false;
-    void unpark() {
+    bool parked = false, pending = false;
+    cudaEvent_t ev_done = nullptr;
+    // The restore pass only writes the idx words, which nothing between the walks and the end of
+    // l3_walks reads: it runs on a side stream under the compaction / assembly of the candidates.
+    void unpark_async() {
       if (!parked) return;
       parked = false;
-      idx_unpark_kernel<<<grid, kBlock, 0, c->stream>>>(slots, n_slots, saved.as<uint32_t>());
-      cudaStreamSynchronize(c->stream);
+      if (!c->stream3) cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking);
+      cudaEvent_t ev_go = c->prof_event();
+      ev_done = c->prof_event();
+      cudaEventRecord(ev_go, c->stream);
+      cudaStreamWaitEvent(c->stream3, ev_go, 0);
+      idx_unpark_kernel<<<grid, kBlock, 0, c->stream3>>>(slots, n_slots, saved.as<uint32_t>());
+      cudaEventRecord(ev_done, c->stream3);
+      c->prof_pool.push_back(ev_go);
+      pending = true;
+    }
+    void finish() {
+      if (!pending) return;
+      pending = false;
+      cudaStreamWaitEvent(c->stream, ev_done, 0);
+      cudaEventSynchronize(ev_done);
+      c->prof_pool.push_back(ev_done);
       saved.release();
+    }
+    void unpark() {
+      unpark_async();
+      finish();
     }
     ~IdxParking() { unpark(); }  // also on the error paths: the table must stay usable
   } parking{c, tv.slots, n_slots, stream_grid};
@@ -1708,13 +1729,18 @@ static bool l3_walks_impl(shn_ctx* c, uint32_t min_weight, uint32_t min_length, 
                 phs[6 * w8 + 3] / 1e6, phs[6 * w8 + 4] / 1e6);
       }
       for (uint32_t w = n_spec; w < std::min<uint32_t>(n_active, n_spec + 6); ++w)
-        fprintf(stderr, "[walk trace] largest component #%u: rounds=%llu seeds=%llu end=+%.1f ms\n", w,
-                tr[3 * w + 1], tr[3 * w + 2], (tr[3 * w] - t_min) / 1e6);
+        fprintf(stderr,
+                "[walk trace] largest one-warp component #%u: rounds=%llu cycles=%llu (%.0f per round) of which "
+                "waiting for the home buckets=%llu (%.0f per round) end=+%.1f ms\n",
+                w, tr[3 * w + 1], tr[3 * w + 2] >> 32, (double)(tr[3 * w + 2] >> 32) / std::max(1ull, tr[3 * w + 1]),
+                (tr[3 * w + 2] & 0xFFFFFFFFull) << 8,
+                (double)((tr[3 * w + 2] & 0xFFFFFFFFull) << 8) / std::max(1ull, tr[3 * w + 1]),
+                (tr[3 * w] - t_min) / 1e6);
     }
   }
   {
-    ProfScope ps(c, "idx_unpark");
-    parking.unpark();
+    c->launches += 1;
+    parking.unpark_async();
     CUDA_CHECK(cudaGetLastError());
   }
   read_counters(c, h, 5);
@@ -1727,7 +1753,10 @@ static bool l3_walks_impl(shn_ctx* c, uint32_t min_weight, uint32_t min_length, 
             ca, it, h[1], h[0]);
   }
 #endif
-  if (h[4] != 0) return false;  // the idx words are restored (unpark above); nothing else was changed
+  if (h[4] != 0) {  // the idx words are restored; nothing else was changed
+    parking.finish();
+    return false;
+  }
   SHN_CHECK(h[2] == 0, "internal error: walk log overflow (component node count mismatch)");
   s->sz.n_traversed = h[0];
   s->sz.walk_rounds = h[1];
@@ -1862,7 +1891,9 @@ static bool l3_walks_impl(shn_ctx* c, uint32_t min_weight, uint32_t min_length, 
   }
 
   s->n_cand = n_cand;
+  parking.finish();
   CUDA_CHECK(cudaStreamSynchronize(st));
+  CUDA_CHECK(cudaGetLastError());
   ht.mark("assembled candidates");
   return true;
 }
@@ -1939,7 +1970,7 @@ void l3_filter(shn_ctx* c, const uint8_t* ext_codes, const uint64_t* ext_offs, u
             cand_bases, R, 0u, keys.as<uint64_t>(), owner.as<uint32_t>(), pos.as<uint32_t>());
         KERNEL_CHECK();
       }
-      sj.prepare(c, "rmer", keys.as<uint64_t>(), owner.as<uint32_t>(), pos.as<uint32_t>(), n_ent, 2 * R, R);
+      sj.prepare(c, "rmer", keys, owner, pos, ent_off.as<uint64_t>(), n_cand, 0u, n_ent, 2 * R, R);
     }
     // Candidates are resolved in blocks of ascending rank: when a block is joined, every earlier
     // candidate is already accepted or rejected, and rejected ones (the bulk: near-duplicates of a
@@ -2094,7 +2125,7 @@ void l3_filter(shn_ctx* c, const uint8_t* ext_codes, const uint64_t* ext_offs, u
         KERNEL_CHECK();
       }
       SelfJoin cj;
-      cj.prepare(c, "cmer", keys.as<uint64_t>(), owner.as<uint32_t>(), pos.as<uint32_t>(), n_ent, 2 * C, 1);
+      cj.prepare(c, "cmer", keys, owner, pos, off.as<uint64_t>(), n_contigs, 1u, n_ent, 2 * C, 1);
       cj.join(0u, 0xFFFFFFFFu, nullptr, &s->edges);
     }
   }

@@ -10,6 +10,7 @@
 // This routine produces exactly that pair table, sorted by (j, d).
 #pragma once
 #include <string>
+#include <vector>
 
 #include "common.cuh"
 
@@ -28,16 +29,23 @@ struct PairTable {
 struct SelfJoin {
   shn_ctx* c = nullptr;
   std::string tag;
-  uint64_t n = 0;
-  uint32_t r = 1;
+  uint64_t n = 0, n_owner = 0;
+  uint32_t r = 1, owner_base = 0;
   int bits_owner = 1, bits_pos = 1;
-  DevBuf owner_s, pos_s, run_start, grp_start;  // entries sorted by (key, owner, pos)
+  std::vector<uint64_t> h_ent_off;  // first entry of every owner (generation order)
+  DevBuf owner_g, pos_g;            // the caller's entries, generation order (owner, pos ascending)
+  DevBuf owner_s;                   // owners in sorted order (key, owner, pos)
+  DevBuf range_g;                   // per entry (uint2): its partners are the sorted positions [x, y)
 
-  // keys: n entries generated in (owner ascending, pos ascending) order; key_bits: significant
-  // bits; r: interval length for `covered`.
-  void prepare(shn_ctx* ctx, const char* tag_, const uint64_t* d_keys, const uint32_t* d_owner,
-               const uint32_t* d_pos, uint64_t n_, int key_bits, uint32_t r_);
+  // n entries generated in (owner ascending, pos ascending) order; owners are owner_base ..
+  // owner_base + n_owner - 1 and d_ent_off[k] (device, n_owner + 1 values) is the first entry of owner
+  // owner_base + k.  key_bits: significant key bits; r: interval length for `covered`.  The three
+  // buffers are consumed (keys freed, owner / pos kept by the join).
+  void prepare(shn_ctx* ctx, const char* tag_, DevBuf& keys, DevBuf& owner, DevBuf& pos,
+               const uint64_t* d_ent_off, uint64_t n_owner_, uint32_t owner_base_, uint64_t n_, int key_bits,
+               uint32_t r_);
   // Pair table of all (j, d) with j in [lo, hi), d < j sharing a key, restricted to partners with
-  // d >= lo or d_status[d] == 1 (d_status == nullptr: no restriction).  Sorted by (j, d).
+  // d >= lo or d_status[d] == 1 (d_status == nullptr: no restriction, lo must be the first owner).
+  // Sorted by (j, d).
   void join(uint32_t lo, uint32_t hi, const uint8_t* d_status, PairTable* out);
 };
