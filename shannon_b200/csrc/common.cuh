@@ -184,13 +184,19 @@ SHN_HD shn_key_t shn_key_mask(int k) { return shn_kmer_mask(k); }
 #endif
 #define SHN_EMPTY ((shn_key_t)~(shn_key_t)0)
 
-// Minimizer-clustered placement: the table is cut into regions of 2^region_shift buckets (8 MB)
-// and a K1-mer goes to region hash(its minimizer), bucket hash(key) inside the region.  Consecutive
-// K1-mers of a chain (x and x[1:].b) share their minimizer -- the 12-mer with the smallest hash --
-// about 7 times out of 8, so successor / predecessor probes mostly stay inside the 8 MB the
+// Placement by the K-base PREFIX of the K1-mer.  The home bucket is a function of key >> 2 alone, so
+// the four successors (x[1:] . b) of a K1-mer x -- which share their first K bases -- share one home
+// bucket and one probe sequence: uf_edges finds all of them with ONE walk over the buckets instead
+// of four, and the four first-level probes of a right extension read the same 64 bytes.  (A bucket
+// then holds whole successor families; at load 0.5 8 % of the buckets overflow against 5 % for
+// independent keys.)
+// Minimizer-clustered regions on top: the table is cut into regions of 2^region_shift buckets
+// (8 MB) and a K1-mer goes to region hash(minimizer of its prefix), bucket hash(prefix) inside the
+// region.  Consecutive K1-mers of a chain share their minimizer -- the 12-mer with the smallest
+// hash -- about 7 times out of 8, so successor / predecessor probes mostly stay inside the 8 MB the
 // kernel is streaming through (L2 hits instead of one DRAM burst each: uf_edges), and so do the
 // parent words of the union-find.  Overflow still probes linearly over buckets, across regions.
-// Tables smaller than one region, and k1 < 12, use the plain hash.
+// Tables smaller than one region, and k1 < 13, use the plain hash of the prefix.
 constexpr int kRegionM = 12;
 // hash of the 12-mer at base offset p counted from the END of the K1-mer (bits 2p .. 2p+23)
 SHN_HD uint32_t shn_mmer_hash(shn_key_t key, int p) {
@@ -205,7 +211,8 @@ SHN_HD uint32_t shn_minimizer_hash_range(shn_key_t key, int p_lo, int p_hi) {
   }
   return best;
 }
-SHN_HD uint32_t shn_minimizer_hash(shn_key_t key, int k1) { return shn_minimizer_hash_range(key, 0, k1 - kRegionM); }
+// minimizer of the K-base prefix: the 12-mers that do not contain the last base (offsets 1 .. k1-12)
+SHN_HD uint32_t shn_minimizer_hash(shn_key_t key, int k1) { return shn_minimizer_hash_range(key, 1, k1 - kRegionM); }
 
 struct ShnTableView {
   ShnSlot* slots;      // SHN_BSLOTS * n_buckets
@@ -214,13 +221,13 @@ struct ShnTableView {
   int k1 = 0;
   int region_shift = 17;   // log2(buckets per region): 2^17 x 64 B = 8 MB
   __device__ __forceinline__ uint64_t bucket_of(shn_key_t key) const {
-    if (n_regions == 0) return __umul64hi(shn_key_hash(key), n_buckets);
+    if (n_regions == 0) return __umul64hi(shn_key_hash(key >> 2), n_buckets);
     return bucket_with_min(key, shn_minimizer_hash(key, k1));
   }
-  // the same when the caller already knows the K1-mer's minimizer hash (neighbouring K1-mers share
-  // all 12-mers but one or two: uf_edges and the walks compute the shared minimum once)
+  // the same when the caller already knows the minimizer hash of the K1-mer's prefix (neighbouring
+  // K1-mers share all 12-mers but one or two: the walks compute the shared minimum once)
   __device__ __forceinline__ uint64_t bucket_with_min(shn_key_t key, uint32_t min_hash) const {
-    const uint64_t h = shn_key_hash(key);
+    const uint64_t h = shn_key_hash(key >> 2);
     if (n_regions == 0) return __umul64hi(h, n_buckets);
     const uint64_t hm = shn_mix64((uint64_t)min_hash + 0x9E3779B97F4A7C15ull);
     return (__umul64hi(hm, (uint64_t)n_regions) << region_shift) | (h >> (64 - region_shift));

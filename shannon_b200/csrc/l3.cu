@@ -78,15 +78,21 @@ __global__ void __launch_bounds__(kBlock)
 // (sort key, slot) for every K1-mer with weight >= min_weight; sort key ascending = pop order:
 // weight descending, then first-occurrence index descending (stable ascending sort + pop()).
 __global__ void __launch_bounds__(kBlock)
-    seed_emit_kernel(const ShnSlot* __restrict__ slots, uint64_t n_slots, uint32_t min_weight,
+    seed_emit_kernel(ShnSlot* slots, uint64_t n_slots, uint32_t min_weight,
                      const uint64_t* __restrict__ gline, uint64_t* __restrict__ sortkey,
-                     uint32_t* __restrict__ sslot, unsigned long long* cursor) {
+                     uint32_t* __restrict__ sslot, unsigned long long* cursor,
+                     uint32_t* __restrict__ saved) {
   __shared__ unsigned long long block_base;
   __shared__ int warp_off[kBlock / 32];
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   shn_key_t skey = SHN_EMPTY;
   uint32_t wz = 0, first_idx = 0;
-  if (i < n_slots) table_load_slot(slots, i, &skey, &wz, &first_idx);
+  if (i < n_slots) {
+    table_load_slot(slots, i, &skey, &wz, &first_idx);
+    // this pass also parks the idx word (see idx_park_kernel): one table read less
+    saved[i] = first_idx;
+    slots[i].idx = 0;
+  }
   const uint32_t wt = wz & SHN_WEIGHT_MASK;
   bool is_seed = skey != SHN_EMPTY && wt >= min_weight;
   unsigned b = __ballot_sync(0xFFFFFFFFu, is_seed);
@@ -139,10 +145,9 @@ __global__ void __launch_bounds__(kBlock) uf_init_kernel(uint32_t* parent, uint6
   for (; i < n; i += stride) parent[i] = (uint32_t)i;
 }
 
-// One thread per K1-mer: probe the four successors, link the ones that exist (1.2 on average).
-// Measured: bound by the random 4-byte accesses of the union-find (two finds + CAS per link), not
-// by the table probes -- issuing the four bucket loads together (more registers, half the
-// occupancy) was 11 % slower.
+// One thread per K1-mer: find its successors and link them (1.2 on average).  The four candidates
+// share one home bucket (placement by the K-base prefix, common.cuh), so this is ONE probe sequence
+// per K1-mer.
 // The probes also yield the neighbour masks the walks prune their probes with (layout of the aux
 // word: see "greedy walks" below): successor bit b of x = (x[1:] . b) exists, OR-ed by x's own
 // thread; predecessor bit f of y = (f . y[:-1]) exists, OR-ed by the thread of that predecessor.
@@ -155,22 +160,16 @@ __global__ void __launch_bounds__(kBlock)
     parent[i] = SHN_NONE32;  // the later passes tell free slots from the parent array alone
     return;
   }
-  const shn_key_t mask = shn_key_mask(k1);
-  shn_key_t pre = (key << 2) & mask;
   const uint32_t first = (uint32_t)(key >> (2 * (k1 - 1))) & 3u;
-  uint32_t sm = 0;
-  // the four successors share every 12-mer but their last: one minimum for all of them
-  const uint32_t shared = t.n_regions ? shn_minimizer_hash_range(pre, 1, k1 - kRegionM) : 0u;
+  uint64_t slot[4];
+  uint32_t w[4];
+  const uint32_t sm = table_find_successors(t, key, k1, slot, w);
 #pragma unroll
   for (int b = 0; b < 4; ++b) {
-    uint32_t w;
-    const shn_key_t cand = pre | (shn_key_t)b;
-    uint64_t s = table_find_from(t, cand, t.bucket_with_min(cand, min(shared, shn_mmer_hash(cand, 0))), &w);
-    if (s != ~0ull) {
-      sm |= 1u << b;
-      atomicOr(&t.slots[s].idx, 1u << (28 + first));  // the bucket of s was just read: an L2 hit
-      if (s != i) uf_union(parent, (uint32_t)i, (uint32_t)s);
-    }
+    if (!((sm >> b) & 1u)) continue;
+    const uint64_t s = slot[b];
+    atomicOr(&t.slots[s].idx, 1u << (28 + first));  // the bucket of s was just read: an L2 hit
+    if (s != i) uf_union(parent, (uint32_t)i, (uint32_t)s);
   }
   if (sm) atomicOr(&t.slots[i].idx, sm << 24);
 }
@@ -365,20 +364,21 @@ struct WalkArgs {
   unsigned long long* trace;     // optional: per warp {end time ns, rounds, cycles} (SHN_WALK_TRACE)
 };
 
-// Minimizer hash of the candidates of one round without the 14-step loop per candidate: the
-// candidates are `cur` shifted by one (level 1) or two (level 2) bases, so they share all 12-mers of
-// `cur` but the ones that fell out; lane p hashes the 12-mer of cur at offset p and two warp
-// reductions give the shared minima (cur is warp-uniform, all lanes call this):
-//   right extension: level 1 shares cur's offsets [0, n-1], level 2 [0, n-2]   (n = k1 - 12)
-//   left extension:  level 1 shares cur's offsets [1, n],   level 2 [2, n]
-// walk_cand_min() then adds the one or two new 12-mers of the candidate itself.
+// Minimizer hash of the candidates' PREFIXES (the 12-mers at offsets 1..n of a candidate, n = k1 - 12;
+// offsets count from the last base) without a loop per candidate: the candidates are `cur` shifted by
+// one (level 1) or two (level 2) bases and share most 12-mers with it.  Lane p hashes the 12-mer of
+// cur at offset p and two warp reductions give the shared minima (cur is warp-uniform, all lanes call
+// this):
+//   right extension: level 1 = cur's offsets [0, n-1] and nothing else, level 2 = [0, n-2] + one new
+//   left extension:  level 1 = cur's offsets [2, n] + one new,          level 2 = [3, n] + two new
+// walk_cand_min() adds the new 12-mers of the candidate itself.
 __device__ __forceinline__ uint32_t walk_shared_min(const ShnTableView& tv, shn_key_t cur, int k1, int dir,
                                                     int lvl, int lane) {
   if (tv.n_regions == 0) return 0u;
   const int n = k1 - kRegionM;
   const uint32_t hp = lane <= n ? shn_mmer_hash(cur, lane) : 0xFFFFFFFFu;
-  const int lo1 = dir == 0 ? 0 : 1, hi1 = dir == 0 ? n - 1 : n;
-  const int lo2 = dir == 0 ? 0 : 2, hi2 = dir == 0 ? n - 2 : n;
+  const int lo1 = dir == 0 ? 0 : 2, hi1 = dir == 0 ? n - 1 : n;
+  const int lo2 = dir == 0 ? 0 : 3, hi2 = dir == 0 ? n - 2 : n;
   const uint32_t m1 = __reduce_min_sync(0xFFFFFFFFu, (lane >= lo1 && lane <= hi1) ? hp : 0xFFFFFFFFu);
   const uint32_t m2 = __reduce_min_sync(0xFFFFFFFFu, (lane >= lo2 && lane <= hi2) ? hp : 0xFFFFFFFFu);
   return lvl == 2 ? m2 : m1;
@@ -386,10 +386,14 @@ __device__ __forceinline__ uint32_t walk_shared_min(const ShnTableView& tv, shn_
 __device__ __forceinline__ uint32_t walk_cand_min(const ShnTableView& tv, shn_key_t cand, int k1, int dir, int lvl,
                                                   uint32_t shared) {
   if (tv.n_regions == 0) return 0u;
-  const int n = k1 - kRegionM;
-  // the new 12-mers sit at the end of the candidate (right extension) or at its start (left)
-  uint32_t m = min(shared, shn_mmer_hash(cand, dir == 0 ? 0 : n));
-  if (lvl == 2 && n >= 1) m = min(m, shn_mmer_hash(cand, dir == 0 ? 1 : n - 1));
+  const int n = k1 - kRegionM;  // >= 1 when the table has regions
+  uint32_t m = shared;
+  if (dir == 0) {  // the appended bases are not part of the prefix of a level-1 candidate
+    if (lvl == 2) m = min(m, shn_mmer_hash(cand, 1));
+  } else {         // the prepended bases sit at the start of the candidate
+    m = min(m, shn_mmer_hash(cand, n));
+    if (lvl == 2 && n >= 2) m = min(m, shn_mmer_hash(cand, n - 1));
+  }
   return m;
 }
 
@@ -1349,52 +1353,6 @@ static bool l3_walks_impl(shn_ctx* c, uint32_t min_weight, uint32_t min_length, 
   const unsigned stream_grid =
       (unsigned)std::min<uint64_t>((n_slots + kBlock - 1) / kBlock, (uint64_t)c->sm_count * 32);
 
-  // ---- a3: seeds in pop order -------------------------------------------------------------
-  unsigned long long* ctr = zero_counters(c);
-  {
-    ProfScope ps(c, "seed_count");
-    seed_count_kernel<<<stream_grid, kBlock, 0, st>>>(tv.slots, n_slots, min_weight, ctr);
-    KERNEL_CHECK();
-  }
-  read_counters(c, h, 1);
-  const uint64_t n_seeds = h[0];
-  s->sz.n_seeds = n_seeds;
-  DevBuf seed_slot;  // by rank
-  seed_slot.reserve(std::max<uint64_t>(n_seeds, 1) * 4);
-  if (n_seeds) {
-    DevBuf skey, sslot, skey2;
-    skey.reserve(n_seeds * 8);
-    skey2.reserve(n_seeds * 8);
-    sslot.reserve(n_seeds * 4);
-    ctr = zero_counters(c);
-    {
-      ProfScope ps(c, "seed_emit");
-      seed_emit_kernel<<<shn_grid(n_slots, kBlock), kBlock, 0, st>>>(
-          tv.slots, n_slots, min_weight, c->gline_dev, skey.as<uint64_t>(), sslot.as<uint32_t>(), ctr);
-      KERNEL_CHECK();
-    }
-    ProfScope ps(c, "seed_sort");
-    size_t tb = 0;
-    CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, tb, skey.as<uint64_t>(), skey2.as<uint64_t>(),
-                                               sslot.as<uint32_t>(), seed_slot.as<uint32_t>(),
-                                               (int64_t)n_seeds, 0, 64, st));
-    CUDA_CHECK(cub::DeviceRadixSort::SortPairs(c->tmp(tb), tb, skey.as<uint64_t>(),
-                                               skey2.as<uint64_t>(), sslot.as<uint32_t>(),
-                                               seed_slot.as<uint32_t>(), (int64_t)n_seeds, 0, 64, st));
-    CUDA_CHECK(cudaStreamSynchronize(st));
-  }
-
-  ht.mark("seeds sorted");
-  // ---- raw components of the successor graph ------------------------------------------------
-  DevBuf parent, root_flag, root_id;
-  parent.reserve(n_slots * 4);
-  root_flag.reserve((n_slots + 1) * 4);
-  root_id.reserve((n_slots + 1) * 4);
-  {
-    ProfScope ps(c, "uf_init");
-    uf_init_kernel<<<stream_grid, kBlock, 0, st>>>(parent.as<uint32_t>(), n_slots);
-    KERNEL_CHECK();
-  }
   // from here until the walks are done the idx words of the table hold the walks' aux words
   struct IdxParking {
     shn_ctx* c;
@@ -1434,11 +1392,60 @@ static bool l3_walks_impl(shn_ctx* c, uint32_t min_weight, uint32_t min_length, 
     ~IdxParking() { unpark(); }  // also on the error paths: the table must stay usable
   } parking{c, tv.slots, n_slots, stream_grid};
   parking.saved.reserve(n_slots * 4);
+
+  // ---- a3: seeds in pop order -------------------------------------------------------------
+  unsigned long long* ctr = zero_counters(c);
   {
+    ProfScope ps(c, "seed_count");
+    seed_count_kernel<<<stream_grid, kBlock, 0, st>>>(tv.slots, n_slots, min_weight, ctr);
+    KERNEL_CHECK();
+  }
+  read_counters(c, h, 1);
+  const uint64_t n_seeds = h[0];
+  s->sz.n_seeds = n_seeds;
+  DevBuf seed_slot;  // by rank
+  seed_slot.reserve(std::max<uint64_t>(n_seeds, 1) * 4);
+  if (n_seeds) {
+    DevBuf skey, sslot, skey2;
+    skey.reserve(n_seeds * 8);
+    skey2.reserve(n_seeds * 8);
+    sslot.reserve(n_seeds * 4);
+    ctr = zero_counters(c);
+    {
+      ProfScope ps(c, "seed_emit");
+      seed_emit_kernel<<<shn_grid(n_slots, kBlock), kBlock, 0, st>>>(
+          tv.slots, n_slots, min_weight, c->gline_dev, skey.as<uint64_t>(), sslot.as<uint32_t>(), ctr,
+          parking.saved.as<uint32_t>());
+      KERNEL_CHECK();
+      parking.parked = true;
+    }
+    ProfScope ps(c, "seed_sort");
+    size_t tb = 0;
+    CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, tb, skey.as<uint64_t>(), skey2.as<uint64_t>(),
+                                               sslot.as<uint32_t>(), seed_slot.as<uint32_t>(),
+                                               (int64_t)n_seeds, 0, 64, st));
+    CUDA_CHECK(cub::DeviceRadixSort::SortPairs(c->tmp(tb), tb, skey.as<uint64_t>(),
+                                               skey2.as<uint64_t>(), sslot.as<uint32_t>(),
+                                               seed_slot.as<uint32_t>(), (int64_t)n_seeds, 0, 64, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+  }
+
+  if (!parking.parked) {
     ProfScope ps(c, "idx_park");
     idx_park_kernel<<<stream_grid, kBlock, 0, st>>>(tv.slots, n_slots, parking.saved.as<uint32_t>());
     KERNEL_CHECK();
     parking.parked = true;
+  }
+  ht.mark("seeds sorted");
+  // ---- raw components of the successor graph ------------------------------------------------
+  DevBuf parent, root_flag, root_id;
+  parent.reserve(n_slots * 4);
+  root_flag.reserve((n_slots + 1) * 4);
+  root_id.reserve((n_slots + 1) * 4);
+  {
+    ProfScope ps(c, "uf_init");
+    uf_init_kernel<<<stream_grid, kBlock, 0, st>>>(parent.as<uint32_t>(), n_slots);
+    KERNEL_CHECK();
   }
   {
     ProfScope ps(c, "uf_edges");

@@ -346,38 +346,13 @@ __global__ void __launch_bounds__(kBlock)
     parent[i] = SHN_NONE32;
     return;
   }
-  const shn_key_t pre = (key << 2) & shn_key_mask(k1);
-  // all four home buckets in flight before any is looked at; one shared minimizer minimum
-  ShnBucket bk[4];
-  uint64_t hb[4];
-  const uint32_t shared = t.n_regions ? shn_minimizer_hash_range(pre, 1, k1 - kRegionM) : 0u;
+  // the four successors share one home bucket and probe sequence (placement by the K-base prefix)
+  uint64_t slot[4];
+  uint32_t w[4];
+  const uint32_t sm = table_find_successors(t, key, k1, slot, w);
 #pragma unroll
-  for (int b = 0; b < 4; ++b) {
-    const shn_key_t cand = pre | (shn_key_t)b;
-    hb[b] = t.bucket_with_min(cand, min(shared, shn_mmer_hash(cand, 0)));
-    table_load_bucket(t, hb[b], &bk[b]);
-  }
-#pragma unroll
-  for (int b = 0; b < 4; ++b) {
-    const shn_key_t cand = pre | (shn_key_t)b;
-    if (cand == SHN_EMPTY) continue;
-    int j = 0;
-    uint32_t w;
-    int r = table_match_bucket(bk[b], cand, &j, &w);
-    uint64_t s = r == 1 ? SHN_BSLOTS * hb[b] + j : ~0ull;
-    if (r < 0) {  // displaced from its home bucket: continue the probe sequence
-      uint64_t nb = hb[b];
-      for (;;) {
-        nb = (nb + 1 == t.n_buckets) ? 0 : nb + 1;
-        ShnBucket bx;
-        table_load_bucket(t, nb, &bx);
-        r = table_match_bucket(bx, cand, &j, &w);
-        if (r == 1) s = SHN_BSLOTS * nb + j;
-        if (r >= 0) break;
-      }
-    }
-    if (s != ~0ull && s != i) uf_union(parent, (uint32_t)i, (uint32_t)s);
-  }
+  for (int b = 0; b < 4; ++b)
+    if (((sm >> b) & 1u) && slot[b] != i) uf_union(parent, (uint32_t)i, (uint32_t)slot[b]);
 }
 
 __global__ void __launch_bounds__(kBlock)

@@ -168,7 +168,7 @@ void table_begin(shn_ctx* c, uint64_t n, int k1, int double_stranded) {
   c->region_shift = envs ? std::max(4, std::min(24, atoi(envs))) : 17;
   const uint64_t region = 1ull << c->region_shift;
   const char* envr = getenv("SHN_TABLE_REGIONS");  // 0 = plain hashing (A/B measurements, tests)
-  const bool regions = (!envr || atoi(envr) != 0) && k1 >= kRegionM && n_buckets >= 4 * region;
+  const bool regions = (!envr || atoi(envr) != 0) && k1 > kRegionM && n_buckets >= 4 * region;
   c->n_regions = 0;
   if (regions) {
     n_buckets = (n_buckets + region - 1) / region * region;

@@ -135,6 +135,38 @@ __device__ __forceinline__ uint64_t table_find_from(const ShnTableView& t, shn_k
   }
 }
 
+// The four successors (x[1:] . b) of the K1-mer x share their first K bases, hence their home bucket
+// and their probe sequence (ShnTableView::bucket_of): one walk over the buckets finds all of them.
+// Returns the mask of the successors that exist; slot[b] / w[b] = slot index / raw weight word.
+__device__ __forceinline__ uint32_t table_find_successors(const ShnTableView& t, shn_key_t x, int k1,
+                                                           uint64_t* slot, uint32_t* w) {
+  const shn_key_t pre = (x << 2) & shn_key_mask(k1);
+  uint64_t b = t.bucket_of(pre);
+  uint32_t found = 0;
+  for (;;) {
+    ShnBucket bk;
+    table_load_bucket(t, b, &bk);
+    bool has_empty = false;
+#pragma unroll
+    for (int j = 0; j < SHN_BSLOTS; ++j) {
+      const shn_key_t k = bk.key(j);
+      has_empty |= k == SHN_EMPTY;
+      if (k != SHN_EMPTY && (k & ~(shn_key_t)3) == pre) {
+        const int c = (int)((uint32_t)k & 3u);
+        found |= 1u << c;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)  // static indices: the arrays stay in registers
+          if (q == c) {
+            slot[q] = SHN_BSLOTS * b + j;
+            w[q] = bk.weight(j);
+          }
+      }
+    }
+    if (has_empty || !(bk.weight(0) & SHN_OVERFLOW)) return found;
+    b = (b + 1 == t.n_buckets) ? 0 : b + 1;
+  }
+}
+
 // Finds or claims the slot of `key`; returns its global slot index (~0 if the table is full);
 // *is_new += 1 if this call claimed a free slot.
 __device__ __forceinline__ uint64_t table_upsert_slot(const ShnTableView& t, shn_key_t key,
