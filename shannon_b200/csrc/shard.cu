@@ -350,9 +350,11 @@ __global__ void __launch_bounds__(kBlock)
   uint64_t slot[4];
   uint32_t w[4];
   const uint32_t sm = table_find_successors(t, key, k1, slot, w);
-#pragma unroll
-  for (int b = 0; b < 4; ++b)
-    if (((sm >> b) & 1u) && slot[b] != i) uf_union(parent, (uint32_t)i, (uint32_t)slot[b]);
+  for (uint32_t m = sm; m; m &= m - 1) {  // k-th existing successor of every lane together (cf. uf_edges_kernel)
+    const int b = __ffs(m) - 1;
+    const uint64_t s = b == 0 ? slot[0] : (b == 1 ? slot[1] : (b == 2 ? slot[2] : slot[3]));
+    if (s != i) uf_union(parent, (uint32_t)i, (uint32_t)s);
+  }
 }
 
 __global__ void __launch_bounds__(kBlock)
