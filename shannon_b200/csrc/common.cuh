@@ -141,6 +141,15 @@ SHN_HD uint64_t shn_key_hash(u128 x) {
   return shn_mix64((uint64_t)x ^ shn_mix64((uint64_t)(x >> 64) + 0x9E3779B97F4A7C15ull));
 }
 
+// Placement hash of the K1-mer table: only the TOP bits are used (bucket inside a region, or
+// umulhi with the bucket count), and the top bits of a product depend on every bit of the operand,
+// so one multiplication by an odd constant is enough (the walks pay for this hash once per probe on
+// their critical path; the two-multiply finalizer cost 17 dependent instructions).
+SHN_HD uint64_t shn_bucket_hash(uint64_t x) { return x * 0x9E3779B97F4A7C15ull; }
+SHN_HD uint64_t shn_bucket_hash(u128 x) {
+  return ((uint64_t)x ^ ((uint64_t)(x >> 64) * 0xC4CEB9FE1A85EC53ull)) * 0x9E3779B97F4A7C15ull;
+}
+
 // ---------------------------------------------------------------------------------------
 // K1-mer table: open addressing, 64-byte buckets (one DRAM burst per probe), linear probing over
 // buckets; see table_dev.cuh.  Every key-dependent translation unit is compiled twice: once with
@@ -221,16 +230,17 @@ struct ShnTableView {
   int k1 = 0;
   int region_shift = 17;   // log2(buckets per region): 2^17 x 64 B = 8 MB
   __device__ __forceinline__ uint64_t bucket_of(shn_key_t key) const {
-    if (n_regions == 0) return __umul64hi(shn_key_hash(key >> 2), n_buckets);
+    if (n_regions == 0) return __umul64hi(shn_bucket_hash(key >> 2), n_buckets);
     return bucket_with_min(key, shn_minimizer_hash(key, k1));
   }
   // the same when the caller already knows the minimizer hash of the K1-mer's prefix (neighbouring
   // K1-mers share all 12-mers but one or two: the walks compute the shared minimum once)
   __device__ __forceinline__ uint64_t bucket_with_min(shn_key_t key, uint32_t min_hash) const {
-    const uint64_t h = shn_key_hash(key >> 2);
+    const uint64_t h = shn_bucket_hash(key >> 2);
     if (n_regions == 0) return __umul64hi(h, n_buckets);
-    const uint64_t hm = shn_mix64((uint64_t)min_hash + 0x9E3779B97F4A7C15ull);
-    return (__umul64hi(hm, (uint64_t)n_regions) << region_shift) | (h >> (64 - region_shift));
+    // the minimum of a dozen 12-mer hashes is a small number: re-spread it before taking top bits
+    const uint32_t region = __umulhi(min_hash * 0x85EBCA6Bu, n_regions);
+    return ((uint64_t)region << region_shift) | (h >> (64 - region_shift));
   }
 };
 
