@@ -442,12 +442,21 @@ __device__ __forceinline__ int walk_chase(const ShnTableView& tv, shn_key_t cand
 // reference's tie order A,G,C,T.  The kernel is bound by the dependent chain of one round
 // (~1 DRAM round trip + ~250 instructions), not by issue slots or bandwidth.
 constexpr int kWalkBlock = 128;
+#ifdef SHN_WIDE
+constexpr int kWalkK1 = 33;  // K = 32: the one width that needs 128-bit keys in practice
+#else
+constexpr int kWalkK1 = 25;  // K = 24, the reference's default (shannon.py): its own kernel instances
+#endif
 #ifndef SHN_WALK_BLOCKS_PER_SM
 #define SHN_WALK_BLOCKS_PER_SM 8
 #endif
 constexpr int kWalkBlocksPerSM = SHN_WALK_BLOCKS_PER_SM;  // 8 -> 64 registers: co-resident with speculative CTAs
 
+// kK1 != 0: K1 known at compile time (constant masks and shifts; the default K = 24 gets its own
+// instance); kTrace: per-round clock reads for SHN_WALK_TRACE.
+template <int kK1, bool kTrace>
 __global__ void __launch_bounds__(kWalkBlock, kWalkBlocksPerSM) walk_kernel(WalkArgs a) {
+  const int k1 = kK1 ? kK1 : a.k1;
   const unsigned FULL = 0xFFFFFFFFu;
   const int lane = threadIdx.x & 31;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -456,12 +465,12 @@ __global__ void __launch_bounds__(kWalkBlock, kWalkBlocksPerSM) walk_kernel(Walk
   const uint64_t s_begin = a.seed_off[comp], s_end = a.seed_off[comp + 1];
   uint64_t lp = a.log_off[comp];
   const uint64_t le = a.log_off[comp + 1];
-  const shn_key_t mask = shn_key_mask(a.k1);
-  const int top = 2 * (a.k1 - 1);
+  const shn_key_t mask = shn_key_mask(k1);
+  const int top = 2 * (k1 - 1);
   const ShnTableView tv = a.tv;
   unsigned long long rounds = 0, traversed = 0;
   long long mem_cycles = 0, t_begin = clock64();
-  const bool tracing = a.trace != nullptr;
+  const bool tracing = kTrace && a.trace != nullptr;
   bool overflow = false;
   const bool look = a.lookahead != 0;
   // role of this lane inside a round: level 1 (lanes 0..3), level 2 (lanes 4..19), idle
@@ -517,7 +526,7 @@ __global__ void __launch_bounds__(kWalkBlock, kWalkBlocksPerSM) walk_kernel(Walk
           uint32_t wraw = 0, caux = 0;
           int state = 0;       // 1 found, 0 absent, -1 undecided after the home bucket
           uint64_t nextb = 0;  // where an undecided lane would continue
-          const uint32_t cand_min = walk_shared_min(tv, cur, a.k1, dir, lvl, lane);
+          const uint32_t cand_min = walk_shared_min(tv, cur, k1, dir, lvl, lane);
           if (act) {
             if (dir == 0) {
               cand = ((cur << 2) & mask) | b1;
@@ -526,7 +535,7 @@ __global__ void __launch_bounds__(kWalkBlock, kWalkBlocksPerSM) walk_kernel(Walk
               cand = (cur >> 2) | (b1 << top);
               if (lvl == 2) cand = (cand >> 2) | (b2 << top);
             }
-            const uint64_t hb = tv.bucket_with_min(cand, walk_cand_min(tv, cand, a.k1, dir, lvl, cand_min));
+            const uint64_t hb = tv.bucket_with_min(cand, walk_cand_min(tv, cand, k1, dir, lvl, cand_min));
             ShnBucket bk0;
             long long tm0 = 0;
             if (tracing) tm0 = clock64();
@@ -665,6 +674,10 @@ constexpr int kSpecWindow = SHN_SPEC_WINDOW;
 #define SHN_SPEC_CTAS_PER_SM 2
 #endif
 constexpr int kSpecCtasPerSM = SHN_SPEC_CTAS_PER_SM;  // x 16 warps: 64 registers per thread
+#ifndef SHN_SPEC16_PER_SM
+#define SHN_SPEC16_PER_SM 2
+#endif
+constexpr int kSpec16PerSM = SHN_SPEC16_PER_SM;  // register budget of the 16-warp tier (1 -> 128 registers)
 
 struct SpecArgs {
   WalkArgs w;
@@ -674,17 +687,19 @@ struct SpecArgs {
   unsigned long long* phase_ns;  // optional (SHN_WALK_TRACE): per CTA ns in {collect, walk, check, resolve, commit}
 };
 
-template <int kSpecWarps>
-__global__ void __launch_bounds__(kSpecWarps * 32, kSpecCtasPerSM * 16 / kSpecWarps) walk_spec_kernel(SpecArgs sa) {
+template <int kSpecWarps, int kK1>
+__global__ void __launch_bounds__(kSpecWarps * 32, kSpecWarps == 16 ? kSpec16PerSM : kSpecCtasPerSM * 16 / kSpecWarps)
+    walk_spec_kernel(SpecArgs sa) {
   const WalkArgs& a = sa.w;
+  const int k1 = kK1 ? kK1 : a.k1;
   const unsigned FULL = 0xFFFFFFFFu;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const uint32_t comp = a.comp_order[blockIdx.x];
   const uint64_t s_begin = a.seed_off[comp], s_end = a.seed_off[comp + 1];
   const uint64_t le = a.log_off[comp + 1];
-  const shn_key_t mask = shn_key_mask(a.k1);
-  const int top = 2 * (a.k1 - 1);
+  const shn_key_t mask = shn_key_mask(k1);
+  const int top = 2 * (k1 - 1);
   const ShnTableView tv = a.tv;
   const uint64_t path_cap = (sa.path_off[blockIdx.x + 1] - sa.path_off[blockIdx.x]) / kSpecWindow;
   uint32_t* const cta_path_slot = sa.path_slot + sa.path_off[blockIdx.x];
@@ -808,7 +823,7 @@ __global__ void __launch_bounds__(kSpecWarps * 32, kSpecCtasPerSM * 16 / kSpecWa
             int state = 0;
             uint64_t nextb = 0;
             ShnBucket bk0;
-            const uint32_t cand_min = walk_shared_min(tv, cur, a.k1, dir, lvl, lane);
+            const uint32_t cand_min = walk_shared_min(tv, cur, k1, dir, lvl, lane);
             if (act) {
               if (dir == 0) {
                 cand = ((cur << 2) & mask) | b1;
@@ -817,7 +832,7 @@ __global__ void __launch_bounds__(kSpecWarps * 32, kSpecCtasPerSM * 16 / kSpecWa
                 cand = (cur >> 2) | (b1 << top);
                 if (lvl == 2) cand = (cand >> 2) | (b2 << top);
               }
-              hb = tv.bucket_with_min(cand, walk_cand_min(tv, cand, a.k1, dir, lvl, cand_min));
+              hb = tv.bucket_with_min(cand, walk_cand_min(tv, cand, k1, dir, lvl, cand_min));
               table_load_bucket(tv, hb, &bk0);
             }
             {  // the claims of the previous round, by now usually back from L2
@@ -1635,7 +1650,13 @@ static bool l3_walks_impl(shn_ctx* c, uint32_t min_weight, uint32_t min_length, 
         b.comp_order = a.comp_order + n_spec;
         b.n_comps = n_active - n_spec;
         if (b.trace) b.trace += 3 * (uint64_t)n_spec;
-        walk_kernel<<<shn_grid((uint64_t)b.n_comps * 32, kWalkBlock), kWalkBlock, 0, c->stream3>>>(b);
+        const unsigned grid = shn_grid((uint64_t)b.n_comps * 32, kWalkBlock);
+        if (b.trace)
+          walk_kernel<0, true><<<grid, kWalkBlock, 0, c->stream3>>>(b);
+        else if (k1 == kWalkK1)
+          walk_kernel<kWalkK1, false><<<grid, kWalkBlock, 0, c->stream3>>>(b);
+        else
+          walk_kernel<0, false><<<grid, kWalkBlock, 0, c->stream3>>>(b);
         KERNEL_CHECK();
         CUDA_CHECK(cudaEventRecord(ev_join, c->stream3));
         CUDA_CHECK(cudaStreamWaitEvent(st, ev_join, 0));
@@ -1662,7 +1683,10 @@ static bool l3_walks_impl(shn_ctx* c, uint32_t min_weight, uint32_t min_length, 
         if (n16) {
           SpecArgs t = sa;
           t.w.n_comps = n16;
-          walk_spec_kernel<16><<<n16, 16 * 32, 0, st>>>(t);
+          if (k1 == kWalkK1)
+            walk_spec_kernel<16, kWalkK1><<<n16, 16 * 32, 0, st>>>(t);
+          else
+            walk_spec_kernel<16, 0><<<n16, 16 * 32, 0, st>>>(t);
           KERNEL_CHECK();
         }
         // Launch order = block scheduling order: the 16-warp CTAs and the one-warp components hold
@@ -1677,7 +1701,10 @@ static bool l3_walks_impl(shn_ctx* c, uint32_t min_weight, uint32_t min_length, 
           t.path_off = sa.path_off + n16;
           if (t.phase_ns) t.phase_ns += 6 * (uint64_t)n16;
           if (t.w.trace) t.w.trace += 3 * (uint64_t)n16;
-          walk_spec_kernel<8><<<n_spec - n16, 8 * 32, 0, c->stream4>>>(t);
+          if (k1 == kWalkK1)
+            walk_spec_kernel<8, kWalkK1><<<n_spec - n16, 8 * 32, 0, c->stream4>>>(t);
+          else
+            walk_spec_kernel<8, 0><<<n_spec - n16, 8 * 32, 0, c->stream4>>>(t);
           KERNEL_CHECK();
           CUDA_CHECK(cudaEventRecord(ev_join3, c->stream4));
           CUDA_CHECK(cudaStreamWaitEvent(st, ev_join3, 0));
