@@ -709,9 +709,10 @@ __global__ void __launch_bounds__(kSpecWarps * 32, kSpecWarps == 16 ? kSpec16Per
   const shn_key_t b2 = (lane - 4) & 3;
 
   __shared__ uint64_t sh_cursor, sh_cursor_after, sh_lp;
-  __shared__ uint32_t sh_win_pos[kSpecWindow], sh_win_slot[kSpecWindow], sh_len[kSpecWindow];
-  __shared__ uint32_t sh_nr[kSpecWindow], sh_nl[kSpecWindow], sh_intact[kSpecWindow], sh_poison[kSpecWindow];
-  __shared__ unsigned long long sh_tot[kSpecWindow];
+  __shared__ uint32_t sh_win_pos[kSpecWindow], sh_win_slot[kSpecWindow];
+  __shared__ uint32_t sh_len_r[kSpecWindow], sh_len_l[kSpecWindow];  // path entries of the two halves (right: + the seed)
+  __shared__ uint32_t sh_intact[kSpecWindow], sh_poison[kSpecWindow];
+  __shared__ unsigned long long sh_tot_r[kSpecWindow], sh_tot_l[kSpecWindow];
   __shared__ unsigned long long sh_block[kSpecWindow];  // window positions whose stamps blocked this walk
   __shared__ uint32_t sh_thief[kSpecWindow];            // position holding this walk's seed (or none)
   __shared__ uint32_t sh_status[kSpecWindow];           // 1 commit, 2 skip
@@ -745,6 +746,12 @@ __global__ void __launch_bounds__(kSpecWarps * 32, kSpecWarps == 16 ? kSpec16Per
       sh_win_n = 0;
       sh_next = 0;
       sh_scan = sh_cursor;
+    }
+    if (threadIdx.x < kSpecWindow) {
+      sh_len_r[threadIdx.x] = sh_len_l[threadIdx.x] = 0u;
+      sh_tot_r[threadIdx.x] = sh_tot_l[threadIdx.x] = 0ull;
+      sh_poison[threadIdx.x] = 0u;
+      sh_block[threadIdx.x] = 0ull;
     }
     __syncthreads();
     for (;;) {
@@ -797,42 +804,58 @@ __global__ void __launch_bounds__(kSpecWarps * 32, kSpecWarps == 16 ? kSpec16Per
     if (win_n == 0) break;
     ++windows;
 
-    // ---- 2. speculative walks: every warp pulls window slots until none is left ----------------
+    // ---- 2. speculative walks: every warp pulls HALF walks until none is left ---------------------
+    // The right and the left extension of a seed run as two units of work (usually on two warps): the
+    // longest walk of a window is its critical path, and its two directions are independent except
+    // that the left extension must treat what the right extension took as traversed.  The right half
+    // carries the stamp 2(W - position), the left half that stamp minus one, so the left half yields
+    // to its own right half like to any earlier seed; if the right half reaches a K1-mer the left half
+    // claimed first (a cycle through the seed), it steals it, the left path is no longer intact and
+    // the walk is retried.  The first seed of a window runs both directions on one warp, one after the
+    // other, exactly like the sequential loop: it is always intact, so every window makes progress.
+    const uint32_t n_units = 2 * win_n - 1;
     for (;;) {
-      uint32_t ws = 0;
-      if (lane == 0) ws = atomicAdd(&sh_next, 1u);
-      ws = __shfl_sync(FULL, ws, 0);
-      if (ws >= win_n) break;
+      uint32_t u = 0;
+      if (lane == 0) u = atomicAdd(&sh_next, 1u);
+      u = __shfl_sync(FULL, u, 0);
+      if (u >= n_units) break;
+      const uint32_t ws = (u + 1) >> 1;
+      const int d_begin = u == 0 ? 0 : (int)((u + 1) & 1u), d_end = u == 0 ? 2 : d_begin + 1;
       uint32_t* my_path_slot = cta_path_slot + (uint64_t)ws * path_cap;
       uint8_t* my_path_base = cta_path_base + (uint64_t)ws * path_cap;
-      uint32_t len = 0, n_dir[2] = {0, 0};
-      uint64_t tot = 0;
       unsigned long long bl = 0;  // per lane: positions of earlier walks whose stamps blocked a candidate
-      const uint32_t stamp = (uint32_t)kSpecWindow - ws;  // earlier seed = larger stamp
+      const uint32_t stamp_r = 2u * ((uint32_t)kSpecWindow - ws);  // earlier seed = larger stamp
       const uint32_t seed_slot = sh_win_slot[ws];
       const uint32_t seed_aux = __ldcg(&tv.slots[seed_slot].idx);
-      // claim the seed; an earlier walk of this window may already hold it
-      uint32_t old = 0;
-      if (lane == 0) old = atomicMax(&tv.slots[seed_slot].idx, (seed_aux & ~kAuxStampMask) | stamp);
-      old = __shfl_sync(FULL, old, 0);
-      if ((old & kAuxStampMask) < stamp) {
+      bool go = true, poisoned = false;
+      if (d_begin == 0) {
+        // the right half claims the seed; an earlier walk of this window may already hold it
+        uint32_t old = 0;
+        if (lane == 0) old = atomicMax(&tv.slots[seed_slot].idx, (seed_aux & ~kAuxStampMask) | stamp_r);
+        old = __shfl_sync(FULL, old, 0);
+        go = (old & kAuxStampMask) < stamp_r;
+        if (lane == 0) sh_len_r[ws] = go ? 1u : 0u;
+      } else {
+        go = (seed_aux & kAuxStampMask) <= stamp_r;  // (a later claim by an earlier seed: the right path fails its check)
+      }
+      if (go) {
         shn_key_t seed_key;
         uint32_t seed_w, seed_i;
         table_load_slot(tv.slots, seed_slot, &seed_key, &seed_w, &seed_i);
-        if (lane == 0) {
+        if (d_begin == 0 && lane == 0) {
           my_path_slot[0] = seed_slot;
           my_path_base[0] = 0xFF;
         }
-        len = 1;
-        tot = seed_w & SHN_WEIGHT_MASK;
         // Claims are OPTIMISTIC: the atomicMax of a step is issued and the walk moves on; its
         // result is looked at one round later, under the latency of the next probes.  A claim
         // that lost against an earlier seed leaves that seed's stamp in the slot, so the walk can
         // never pass the intact check below; it is abandoned as soon as the loss is seen.
         uint32_t pend1 = 0, pend2 = 0;
-        bool poisoned = false;
 #pragma unroll 1
-        for (int dir = 0; dir < 2 && !poisoned; ++dir) {
+        for (int dir = d_begin; dir < d_end && !poisoned; ++dir) {
+          const uint32_t stamp = stamp_r - (uint32_t)dir;
+          uint32_t len = dir == 0 ? 1u : 0u;  // entries of this half's path (the seed opens the right one)
+          uint64_t tot = dir == 0 ? (uint64_t)(seed_w & SHN_WEIGHT_MASK) : 0ull;
           shn_key_t cur = seed_key;
           uint32_t cur_aux = seed_aux;
           for (;;) {
@@ -868,10 +891,11 @@ __global__ void __launch_bounds__(kSpecWarps * 32, kSpecWarps == 16 ? kSpec16Per
             }
             if (act) state = walk_resolve(tv, bk0, cand, hb, &cslot, &wraw, &caux, &nextb);
             if (lvl == 1 && state < 0) state = walk_chase(tv, cand, &cslot, &wraw, &caux, &nextb);
-            // blocked: committed-traversed, or stamped by an earlier seed or by this walk
+            // blocked: committed-traversed, or stamped by an earlier seed, by this half or (left half)
+            // by the right half of the same seed
             bool ok = state == 1 && !(caux & kAuxTraversed) && (caux & kAuxStampMask) < stamp;
-            if (lvl == 1 && state == 1 && !(caux & kAuxTraversed) && (caux & kAuxStampMask) > stamp)
-              bl |= 1ull << ((uint32_t)kSpecWindow - (caux & kAuxStampMask));
+            if (lvl == 1 && state == 1 && !(caux & kAuxTraversed) && (caux & kAuxStampMask) > stamp_r)
+              bl |= 1ull << ((uint32_t)kSpecWindow - (((caux & kAuxStampMask) + 1u) >> 1));
             // ---- first step ------------------------------------------------------------------
             uint32_t score = ok ? ((((wraw & SHN_WEIGHT_MASK) << 2) | (uint32_t)(3 - (lane & 3))) + 1u) : 0u;
             uint32_t m = max(score, __shfl_xor_sync(FULL, score, 1));
@@ -884,14 +908,14 @@ __global__ void __launch_bounds__(kSpecWarps * 32, kSpecWarps == 16 ? kSpec16Per
             const shn_key_t c1 = dir == 0 ? (((cur << 2) & mask) | (shn_key_t)w1)
                                           : ((cur >> 2) | ((shn_key_t)w1 << top));
             const uint32_t c1slot = (uint32_t)__shfl_sync(FULL, (uint32_t)cslot, w1);
-            if (lane == 0 && len < path_cap) {
-              my_path_slot[len] = c1slot;
-              my_path_base[len] = (uint8_t)w1;
+            if (lane == 0 && len < path_cap) {  // right half from the front, left half from the back
+              const uint64_t e = dir == 0 ? (uint64_t)len : path_cap - 1 - len;
+              my_path_slot[e] = c1slot;
+              my_path_base[e] = (uint8_t)w1;
             }
             path_overflow |= len >= path_cap;
             ++len;
             tot += bw1;
-            ++n_dir[dir];
             // ---- second step from the prefetched level ---------------------------------------
             const int g2 = 4 + 4 * w1;
             // (as in walk_kernel: c1's neighbour mask decides which undecided blind probes go on)
@@ -907,8 +931,8 @@ __global__ void __launch_bounds__(kSpecWarps * 32, kSpecWarps == 16 ? kSpec16Per
             }
             ok = ok && cand != c1;
             if (lane >= g2 && lane < g2 + 4 && state == 1 && !(caux & kAuxTraversed) &&
-                (caux & kAuxStampMask) > stamp)
-              bl |= 1ull << ((uint32_t)kSpecWindow - (caux & kAuxStampMask));
+                (caux & kAuxStampMask) > stamp_r)
+              bl |= 1ull << ((uint32_t)kSpecWindow - (((caux & kAuxStampMask) + 1u) >> 1));
             score = ok ? ((((wraw & SHN_WEIGHT_MASK) << 2) | (uint32_t)(3 - (lane & 3))) + 1u) : 0u;
             m = max(score, __shfl_xor_sync(FULL, score, 1));
             m = max(m, __shfl_xor_sync(FULL, m, 2));
@@ -924,31 +948,36 @@ __global__ void __launch_bounds__(kSpecWarps * 32, kSpecWarps == 16 ? kSpec16Per
             cur_aux = __shfl_sync(FULL, caux, g2 + w2);
             const uint32_t c2slot = (uint32_t)__shfl_sync(FULL, (uint32_t)cslot, g2 + w2);
             if (lane == 0 && len < path_cap) {
-              my_path_slot[len] = c2slot;
-              my_path_base[len] = (uint8_t)w2;
+              const uint64_t e = dir == 0 ? (uint64_t)len : path_cap - 1 - len;
+              my_path_slot[e] = c2slot;
+              my_path_base[e] = (uint8_t)w2;
             }
             path_overflow |= len >= path_cap;
             ++len;
             tot += bw2;
-            ++n_dir[dir];
             __syncwarp();
           }
+          // claims still pending when this half ended, and halves abandoned after a lost claim: never
+          // committed from this window, whatever the stamps on the path say
+          poisoned |= __any_sync(FULL, (pend1 & kAuxStampMask) >= stamp || (pend2 & kAuxStampMask) >= stamp) != 0;
+          pend1 = pend2 = 0;
+          if (lane == 0) {
+            if (dir == 0) {
+              sh_len_r[ws] = len;
+              sh_tot_r[ws] = tot;
+            } else {
+              sh_len_l[ws] = len;
+              sh_tot_l[ws] = tot;
+            }
+          }
         }
-        // claims still pending when the walk ended, and walks abandoned after a lost claim: never
-        // committed from this window, whatever the stamps on the path say
-        poisoned |= __any_sync(FULL, (pend1 & kAuxStampMask) >= stamp || (pend2 & kAuxStampMask) >= stamp) != 0;
-        if (lane == 0) sh_poison[ws] = poisoned ? 1u : 0u;
-      } else if (lane == 0) {
-        sh_poison[ws] = 0u;
       }
       const unsigned blo = __reduce_or_sync(FULL, (unsigned)bl);
       const unsigned bhi = __reduce_or_sync(FULL, (unsigned)(bl >> 32));
       if (lane == 0) {
-        sh_len[ws] = len;
-        sh_nr[ws] = n_dir[0];
-        sh_nl[ws] = n_dir[1];
-        sh_tot[ws] = tot;
-        sh_block[ws] = ((unsigned long long)bhi << 32) | blo;
+        if (poisoned) atomicOr(&sh_poison[ws], 1u);
+        const unsigned long long bb = (((unsigned long long)bhi << 32) | blo) & ~(1ull << ws);
+        if (bb) atomicOr(&sh_block[ws], bb);
       }
     }
     __syncthreads();  // all claims of the window are in L2
@@ -958,21 +987,30 @@ __global__ void __launch_bounds__(kSpecWarps * 32, kSpecWarps == 16 ? kSpec16Per
     // The whole CTA re-reads every path of the window (a long walk checked by one warp alone took
     // as long as the walk itself: measured 38 of 90 ms for the largest component).
     if (threadIdx.x < win_n) {
-      const uint32_t ws = threadIdx.x, stamp = (uint32_t)kSpecWindow - ws;
-      sh_intact[ws] = (sh_len[ws] && !sh_poison[ws]) ? 1u : 0u;
+      const uint32_t ws = threadIdx.x, stamp_r = 2u * ((uint32_t)kSpecWindow - ws);
+      // (both halves together longer than the buffer: they may have overwritten each other)
+      if ((uint64_t)sh_len_r[ws] + sh_len_l[ws] > path_cap) atomicAdd(&a.counters[4], 1ull);
+      sh_intact[ws] = (sh_len_r[ws] && !sh_poison[ws]) ? 1u : 0u;
       const uint32_t sst = __ldcg(&tv.slots[sh_win_slot[ws]].idx) & kAuxStampMask;
-      sh_thief[ws] = (sst > stamp && sst <= (uint32_t)kSpecWindow) ? (uint32_t)kSpecWindow - sst : 0xFFFFFFFFu;
+      sh_thief[ws] = (sst > stamp_r && sst <= 2u * (uint32_t)kSpecWindow)
+                         ? (uint32_t)kSpecWindow - ((sst + 1u) >> 1)
+                         : 0xFFFFFFFFu;
     }
     __syncthreads();
     SHN_PHASE(5)
     for (uint32_t ws = 0; ws < win_n; ++ws) {
-      // (a walk longer than its buffer is only stamped/cleared up to the buffer: the stage is rerun)
-      const uint32_t len = (uint32_t)min((uint64_t)sh_len[ws], path_cap), stamp = (uint32_t)kSpecWindow - ws;
+      // (a half longer than the buffer is only stamped/cleared up to the buffer: the stage is rerun)
+      const uint32_t len_r = (uint32_t)min((uint64_t)sh_len_r[ws], path_cap);
+      const uint32_t len_l = (uint32_t)min((uint64_t)sh_len_l[ws], path_cap - len_r);
+      const uint32_t stamp_r = 2u * ((uint32_t)kSpecWindow - ws);
       const uint32_t* ps = cta_path_slot + (uint64_t)ws * path_cap;
       bool mine = true;
 #pragma unroll 4
-      for (uint32_t e = threadIdx.x; e < len; e += kSpecWarps * 32)
-        mine &= (__ldcg(&tv.slots[ps[e]].idx) & kAuxStampMask) == stamp;
+      for (uint32_t e = threadIdx.x; e < len_r + len_l; e += kSpecWarps * 32) {
+        const bool right = e < len_r;
+        const uint64_t at = right ? (uint64_t)e : path_cap - 1 - (e - len_r);
+        mine &= (__ldcg(&tv.slots[ps[at]].idx) & kAuxStampMask) == (right ? stamp_r : stamp_r - 1u);
+      }
       if (!mine) sh_intact[ws] = 0u;   // benign race: every writer stores 0
     }
     __syncthreads();
@@ -993,7 +1031,7 @@ __global__ void __launch_bounds__(kSpecWarps * 32, kSpecWarps == 16 ? kSpec16Per
         if (st == 1) {
           committed |= 1ull << P;
           sh_off[P] = off;
-          off += sh_len[P];
+          off += (uint64_t)sh_len_r[P] + sh_len_l[P];
         }
       }
       sh_P = P;
@@ -1010,28 +1048,35 @@ __global__ void __launch_bounds__(kSpecWarps * 32, kSpecWarps == 16 ? kSpec16Per
 
     // ---- 4. commit the intact prefix in order, roll the rest back ---------------------------
     for (uint32_t ws = warp; ws < win_n; ws += kSpecWarps) {
-      const uint32_t len = (uint32_t)min((uint64_t)sh_len[ws], path_cap), stamp = (uint32_t)kSpecWindow - ws;
+      const uint32_t len_r = (uint32_t)min((uint64_t)sh_len_r[ws], path_cap);
+      const uint32_t len_l = (uint32_t)min((uint64_t)sh_len_l[ws], path_cap - len_r);
+      const uint32_t len = len_r + len_l, stamp_r = 2u * ((uint32_t)kSpecWindow - ws);
       const uint32_t* ps = cta_path_slot + (uint64_t)ws * path_cap;
       const uint8_t* pb = cta_path_base + (uint64_t)ws * path_cap;
       if (ws < P && sh_status[ws] == 1) {
+        // walk log: the seed, the right extension, then the left extension, each in walking order
         const uint64_t off = sh_off[ws];
         for (uint32_t e = lane; e < len; e += 32) {
-          atomicOr(&tv.slots[ps[e]].idx, kAuxTraversed);
-          if (off + e < le) a.walk_log[off + e] = pb[e];
+          const uint64_t at = e < len_r ? (uint64_t)e : path_cap - 1 - (e - len_r);
+          atomicOr(&tv.slots[ps[at]].idx, kAuxTraversed);
+          if (off + e < le) a.walk_log[off + e] = pb[at];
         }
         overflow |= off + len > le;
         if (lane == 0 && len) {
           const uint32_t rank = a.ranks_by_comp[s_begin + sh_win_pos[ws]];
           a.started[rank] = 1;
-          a.nr[rank] = sh_nr[ws];
-          a.nl[rank] = sh_nl[ws];
-          a.totwt[rank] = sh_tot[ws];
+          a.nr[rank] = sh_len_r[ws] - 1u;
+          a.nl[rank] = sh_len_l[ws];
+          a.totwt[rank] = sh_tot_r[ws] + sh_tot_l[ws];
           a.logstart[rank] = off;
         }
         traversed += len;
       } else {
         for (uint32_t e = lane; e < len; e += 32) {
-          uint32_t* p = &tv.slots[ps[e]].idx;
+          const bool right = e < len_r;
+          const uint64_t at = right ? (uint64_t)e : path_cap - 1 - (e - len_r);
+          const uint32_t stamp = right ? stamp_r : stamp_r - 1u;
+          uint32_t* p = &tv.slots[ps[at]].idx;
           const uint32_t v = __ldcg(p);  // only the stamp bits change: the CAS fails iff stolen
           if ((v & kAuxStampMask) == stamp) atomicCAS(p, v, v & ~kAuxStampMask);
         }
