@@ -143,6 +143,7 @@ void shn_destroy(shn_ctx* c) {
   if (c->stream2) cudaStreamDestroy(c->stream2);
   if (c->stream3) cudaStreamDestroy(c->stream3);
   if (c->stream4) cudaStreamDestroy(c->stream4);
+  if (c->stream5) cudaStreamDestroy(c->stream5);
   cudaStreamDestroy(c->own_stream);
   g_shn_pool = nullptr;
   delete c;

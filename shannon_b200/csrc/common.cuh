@@ -386,7 +386,8 @@ struct shn_ctx {
   int sm_count = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;  // asynchronous uploads (created on demand)
-  cudaStream_t stream3 = nullptr, stream4 = nullptr;  // side streams of the walk stage (created on demand)
+  bool explicit_idx = false;  // the table was built with caller-supplied first-occurrence indices (any 32-bit value)
+  cudaStream_t stream3 = nullptr, stream4 = nullptr, stream5 = nullptr;  // side streams of the walk stage (created on demand)
   std::string last_error;
   cudaEvent_t t0 = nullptr, t1 = nullptr;
   // profiling

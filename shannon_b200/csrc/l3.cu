@@ -63,16 +63,22 @@ __global__ void __launch_bounds__(kBlock)
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   unsigned long long mine = 0;
+  uint32_t wmax = 0;
   for (; i < n_slots; i += stride) {
     shn_key_t key;
     uint32_t wz, wi;
     table_load_slot(slots, i, &key, &wz, &wi);
-    mine += (key != SHN_EMPTY && (wz & SHN_WEIGHT_MASK) >= min_weight) ? 1 : 0;
+    const bool seed = key != SHN_EMPTY && (wz & SHN_WEIGHT_MASK) >= min_weight;
+    mine += seed ? 1 : 0;
+    if (seed) wmax = max(wmax, wz & SHN_WEIGHT_MASK);
   }
   typedef cub::BlockReduce<unsigned long long, kBlock> BR;
   __shared__ typename BR::TempStorage tmp;
   unsigned long long tot = BR(tmp).Sum(mine);
   if (threadIdx.x == 0 && tot) atomicAdd(&counters[0], tot);
+  // counters[1] = largest seed weight: the seed sort only looks at the bits that vary
+  wmax = __reduce_max_sync(0xFFFFFFFFu, wmax);
+  if ((threadIdx.x & 31) == 0 && wmax) atomicMax(&counters[1], (unsigned long long)wmax);
 }
 
 // (sort key, slot) for every K1-mer with weight >= min_weight; sort key ascending = pop order:
@@ -81,7 +87,7 @@ __global__ void __launch_bounds__(kBlock)
     seed_emit_kernel(ShnSlot* slots, uint64_t n_slots, uint32_t min_weight,
                      const uint64_t* __restrict__ gline, uint64_t* __restrict__ sortkey,
                      uint32_t* __restrict__ sslot, unsigned long long* cursor,
-                     uint32_t* __restrict__ saved) {
+                     uint32_t* __restrict__ saved, uint32_t wmask, int ibits) {
   __shared__ unsigned long long block_base;
   __shared__ int warp_off[kBlock / 32];
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -113,8 +119,9 @@ __global__ void __launch_bounds__(kBlock)
     uint64_t o = block_base + warp_off[warp] + __popc(b & ((1u << lane) - 1u));
     // sharded tables: first_idx is a receive-buffer position, the global input line (34 bits) is
     // behind gline[]; weights have 30 bits
-    sortkey[o] = gline ? (((uint64_t)(~wt & SHN_WEIGHT_MASK) << 34) | (~gline[first_idx] & 0x3FFFFFFFFull))
-                       : (((uint64_t)(~wt) << 32) | (uint64_t)(~first_idx));
+    // (both fields complemented: ascending key = weight descending, then index descending)
+    const uint64_t imask = (1ull << ibits) - 1ull;
+    sortkey[o] = ((uint64_t)(~wt & wmask) << ibits) | (~(gline ? gline[first_idx] : (uint64_t)first_idx) & imask);
     sslot[o] = (uint32_t)i;
   }
 }
@@ -1484,8 +1491,19 @@ static bool l3_walks_impl(shn_ctx* c, uint32_t min_weight, uint32_t min_length, 
     seed_count_kernel<<<stream_grid, kBlock, 0, st>>>(tv.slots, n_slots, min_weight, ctr);
     KERNEL_CHECK();
   }
-  read_counters(c, h, 1);
+  read_counters(c, h, 2);
   const uint64_t n_seeds = h[0];
+  int wbits = 1;  // bits of the largest seed weight
+  while (wbits < 30 && (h[1] >> wbits)) ++wbits;
+  const uint32_t wmask = (1u << wbits) - 1u;
+  // index field: input lines of this table, or (sharded tables) 34-bit global lines behind gline[]
+  int ibits = 34;
+  if (c->explicit_idx && !c->gline_dev) {
+    ibits = 32;
+  } else if (!c->gline_dev) {
+    ibits = 1;
+    while (ibits < 32 && (c->n_items >> ibits)) ++ibits;
+  }
   s->sz.n_seeds = n_seeds;
   DevBuf seed_slot;  // by rank
   seed_slot.reserve(std::max<uint64_t>(n_seeds, 1) * 4);
@@ -1499,18 +1517,19 @@ static bool l3_walks_impl(shn_ctx* c, uint32_t min_weight, uint32_t min_length, 
       ProfScope ps(c, "seed_emit");
       seed_emit_kernel<<<shn_grid(n_slots, kBlock), kBlock, 0, st>>>(
           tv.slots, n_slots, min_weight, c->gline_dev, skey.as<uint64_t>(), sslot.as<uint32_t>(), ctr,
-          parking.saved.as<uint32_t>());
+          parking.saved.as<uint32_t>(), wmask, ibits);
       KERNEL_CHECK();
       parking.parked = true;
     }
     ProfScope ps(c, "seed_sort");
+    const int key_bits = ibits + wbits;  // only the bits that vary are sorted
     size_t tb = 0;
     CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, tb, skey.as<uint64_t>(), skey2.as<uint64_t>(),
                                                sslot.as<uint32_t>(), seed_slot.as<uint32_t>(),
-                                               (int64_t)n_seeds, 0, 64, st));
+                                               (int64_t)n_seeds, 0, key_bits, st));
     CUDA_CHECK(cub::DeviceRadixSort::SortPairs(c->tmp(tb), tb, skey.as<uint64_t>(),
                                                skey2.as<uint64_t>(), sslot.as<uint32_t>(),
-                                               seed_slot.as<uint32_t>(), (int64_t)n_seeds, 0, 64, st));
+                                               seed_slot.as<uint32_t>(), (int64_t)n_seeds, 0, key_bits, st));
     CUDA_CHECK(cudaStreamSynchronize(st));
   }
 
@@ -1702,7 +1721,8 @@ static bool l3_walks_impl(shn_ctx* c, uint32_t min_weight, uint32_t min_length, 
       }
     }
     DevBuf path_slot, path_base, path_off, phase_ns;
-    cudaEvent_t ev_fork = c->prof_event(), ev_join = c->prof_event(), ev_join3 = c->prof_event();
+    cudaEvent_t ev_fork = c->prof_event(), ev_join = c->prof_event(), ev_join3 = c->prof_event(),
+                ev_join4 = c->prof_event();
     {
       ProfScope ps(c, "walk", (n_spec ? 2 : 0) + (n_spec < n_active ? 1 : 0));  // upper bound: two tiers
       CUDA_CHECK(cudaEventRecord(ev_fork, st));
@@ -1760,22 +1780,38 @@ static bool l3_walks_impl(shn_ctx* c, uint32_t min_weight, uint32_t min_length, 
         // Launch order = block scheduling order: the 16-warp CTAs and the one-warp components hold
         // the long serial chains and must start at once; the short 8-warp CTAs fill what is left.
         if (!getenv("SHN_WALK_SERIAL_LAST")) launch_serial();
-        if (n_spec > n16) {  // second tier on its own stream: all three kernels share the GPU
-          if (!c->stream4) CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream4, cudaStreamNonBlocking));
-          CUDA_CHECK(cudaStreamWaitEvent(c->stream4, ev_fork, 0));
+        // further tiers on their own streams: all kernels share the GPU.  SHN_SPEC_TIER8 = how many
+        // components after the 16-warp tier get 8-warp CTAs (default: all); the rest get 4 warps.
+        const char* envt8 = getenv("SHN_SPEC_TIER8");
+        const uint32_t n8 = std::min<uint32_t>(n_spec - n16, envt8 ? (uint32_t)strtoul(envt8, nullptr, 10) : 0xFFFFFFFFu);
+        const uint32_t n4 = n_spec - n16 - n8;
+        for (int tier = 0; tier < 2; ++tier) {
+          const uint32_t first = tier == 0 ? n16 : n16 + n8, count = tier == 0 ? n8 : n4;
+          if (!count) continue;
+          cudaStream_t& ts = tier == 0 ? c->stream4 : c->stream5;
+          if (!ts) CUDA_CHECK(cudaStreamCreateWithFlags(&ts, cudaStreamNonBlocking));
+          CUDA_CHECK(cudaStreamWaitEvent(ts, ev_fork, 0));
           SpecArgs t = sa;
-          t.w.comp_order = a.comp_order + n16;
-          t.w.n_comps = n_spec - n16;
-          t.path_off = sa.path_off + n16;
-          if (t.phase_ns) t.phase_ns += 6 * (uint64_t)n16;
-          if (t.w.trace) t.w.trace += 3 * (uint64_t)n16;
-          if (k1 == kWalkK1)
-            walk_spec_kernel<8, kWalkK1><<<n_spec - n16, 8 * 32, 0, c->stream4>>>(t);
-          else
-            walk_spec_kernel<8, 0><<<n_spec - n16, 8 * 32, 0, c->stream4>>>(t);
+          t.w.comp_order = a.comp_order + first;
+          t.w.n_comps = count;
+          t.path_off = sa.path_off + first;
+          if (t.phase_ns) t.phase_ns += 6 * (uint64_t)first;
+          if (t.w.trace) t.w.trace += 3 * (uint64_t)first;
+          if (tier == 0) {
+            if (k1 == kWalkK1)
+              walk_spec_kernel<8, kWalkK1><<<count, 8 * 32, 0, ts>>>(t);
+            else
+              walk_spec_kernel<8, 0><<<count, 8 * 32, 0, ts>>>(t);
+          } else {
+            if (k1 == kWalkK1)
+              walk_spec_kernel<4, kWalkK1><<<count, 4 * 32, 0, ts>>>(t);
+            else
+              walk_spec_kernel<4, 0><<<count, 4 * 32, 0, ts>>>(t);
+          }
           KERNEL_CHECK();
-          CUDA_CHECK(cudaEventRecord(ev_join3, c->stream4));
-          CUDA_CHECK(cudaStreamWaitEvent(st, ev_join3, 0));
+          cudaEvent_t ev = tier == 0 ? ev_join3 : ev_join4;
+          CUDA_CHECK(cudaEventRecord(ev, ts));
+          CUDA_CHECK(cudaStreamWaitEvent(st, ev, 0));
         }
       }
       launch_serial();
@@ -1784,6 +1820,7 @@ static bool l3_walks_impl(shn_ctx* c, uint32_t min_weight, uint32_t min_length, 
     c->prof_pool.push_back(ev_fork);
     c->prof_pool.push_back(ev_join);
     c->prof_pool.push_back(ev_join3);
+    c->prof_pool.push_back(ev_join4);
     s->sz.n_spec_comps = n_spec;
     if (want_trace) {  // when does each component's warp finish? (tail = critical path)
       std::vector<unsigned long long> tr;

@@ -179,6 +179,7 @@ void table_begin(shn_ctx* c, uint64_t n, int k1, int double_stranded) {
   c->k1 = k1;
   c->n_items = items;
   c->gline_dev = nullptr;  // set again by table_build_records
+  c->explicit_idx = false;
   c->counters.reserve(64 * sizeof(unsigned long long));
   unsigned long long* ctr = c->counters.as<unsigned long long>();
   CUDA_CHECK(cudaMemsetAsync(ctr, 0, 8 * sizeof(unsigned long long), c->stream));
@@ -194,6 +195,7 @@ void table_insert_chunk(shn_ctx* c, const uint64_t* d_keys, const uint32_t* d_co
                         const uint32_t* d_line_idx, uint64_t n, uint64_t first_line,
                         int double_stranded) {
   if (n == 0) return;
+  if (d_line_idx) c->explicit_idx = true;
   ProfScope ps(c, "table_insert");
   table_insert_kernel<<<shn_grid(n, kBlock), kBlock, 0, c->stream>>>(
       table_view(c), d_keys, d_counts, d_line_idx, n, first_line, c->k1, double_stranded,
