@@ -276,11 +276,11 @@ def algorithmic_bytes(name, s, n_kmers, n_records):
         "table_clear": 16 * n_slots,
         "table_insert": 140 * n_kmers,
         "seed_count": 16 * n_slots,
-        "seed_emit": 16 * n_slots + 12 * s["n_seeds"],
+        "seed_emit": 36 * n_slots + 12 * s["n_seeds"],             # slot read + idx parked (4 B) + slot line written back
         "uf_init": 4 * n_slots,
-        "uf_edges": 16 * n_slots + (4 * 64 + 8) * s["n_loaded"],
+        "uf_edges": 16 * n_slots + (64 + 16) * s["n_loaded"],       # ONE successor probe sequence + parent / aux words
         "uf_flatten": 24 * n_slots,
-        "comp_count": 20 * n_slots + 8 * s["n_loaded"],
+        "comp_count": 4 * n_slots + 4 * s["n_loaded"],
         "walk": (4 * 64 + 64 + 1) * s["n_traversed"],
         "pack_reads": 2 * (READ_LEN + 32 + 20) * n_records,
         "l4_assign": (2 * (32 + 12)) * n_records + 32 * s["lookups"] + 8 * s["assignments"],
@@ -776,9 +776,10 @@ def main():
                     "note": "achieved = SURVEY 8(d) algorithmic bytes per unit x units per step (192 B per "
                             "traversed K1-mer, 76 B per inserted line, 161 B per read record) / CUDA-event "
                             "duration inside the timed region; frac_design = the same with this design's "
-                            "64-byte-bucket byte model (DESIGN.md section 5).  The walk stage is bound by the "
-                            "latency of its longest serial chain (walk_rounds dependent 2-step rounds), not "
-                            "by bandwidth"}
+                            "64-byte-bucket byte model (DESIGN.md section 5; the peak is a COPY bandwidth, so "
+                            "a pure read or pure write stream such as seed_count / table_clear can exceed 1).  "
+                            "The walk stage is bound by instruction issue and the latency of its dependent "
+                            "2-step rounds (walk_rounds on the longest one-warp component), not by bandwidth"}
         if dom["kernel"] == "walk" and stats.get("walk_rounds"):
             roofline["round_time_us"] = 1000.0 * dom["ms_per_step"] / stats["walk_rounds"]
 
