@@ -654,13 +654,16 @@ __global__ void __launch_bounds__(kWalkBlock, kWalkBlocksPerSM) walk_kernel(Walk
 // dependent probe rounds).  Large components are therefore given a CTA of kSpecWarps warps that
 // run the next kSpecWindow untraversed seeds of the pop order CONCURRENTLY and commit them IN ORDER
 // ("deterministic reservations"):
-//   * every walk of a window carries a stamp = kSpecWindow - its position in the window (earlier
-//     seed = larger stamp) and claims a K1-mer with atomicMax on the slot's aux word (stamp in the
-//     low bits; the bits above it are the same for every claimant of an untraversed slot);
-//   * a candidate is blocked for a walk iff it is committed-traversed or stamped by an EARLIER
-//     seed (or by the walk itself); stamps of later seeds are ignored and overwritten (stolen);
-//   * after the window every walk re-reads its path: it is intact iff every slot still carries its
-//     stamp.  The longest prefix of intact walks is exactly what the sequential loop would have
+//   * the right extension of the walk at window position p carries the stamp 2 (kSpecWindow - p),
+//     its left extension that stamp minus one (earlier seed = larger stamps; the two halves are
+//     separate units of work, see phase 2), and both claim a K1-mer with atomicMax on the slot's aux
+//     word (stamp in the low bits; the bits above it are the same for every claimant of an
+//     untraversed slot);
+//   * a candidate is blocked for a half walk iff it is committed-traversed or carries a stamp >= its
+//     own: an EARLIER seed, the half itself, or -- for a left half -- the right half of its own
+//     seed; smaller stamps are ignored and overwritten (stolen);
+//   * after the window every path is re-read: a walk is intact iff every slot of its right path
+//     still carries the right stamp and every slot of its left path the left stamp.  The longest prefix of intact walks is exactly what the sequential loop would have
 //     produced (an intact walk only ever yielded to walks before it, all of which are intact and
 //     final; nothing it examined-and-rejected can matter): those are
 //     committed (traversed bits, log, metas); the others clear their stamps and are retried in
@@ -679,9 +682,10 @@ __global__ void __launch_bounds__(kWalkBlock, kWalkBlocksPerSM) walk_kernel(Walk
 #ifndef SHN_SPEC_WINDOW
 #define SHN_SPEC_WINDOW 32
 #endif
-// Seeds per window.  The warps of the CTA pull the window's seeds from a shared counter, so one long
-// walk occupies one warp while the others work through the many short ones (98 % of the seeds of a
-// large component are found traversed, or are taken by an earlier walk of the same window).
+// Seeds per window (<= 64: window positions are bits of a 64-bit blocker mask).  The warps of the
+// CTA pull the window's half walks from a shared counter, so one long extension occupies one warp
+// while the others work through the many short ones (98 % of the seeds of a large component are
+// found traversed, or are taken by an earlier walk of the same window).
 constexpr int kSpecWindow = SHN_SPEC_WINDOW;
 #ifndef SHN_SPEC_CTAS_PER_SM
 #define SHN_SPEC_CTAS_PER_SM 2
