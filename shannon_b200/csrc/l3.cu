@@ -234,14 +234,37 @@ __global__ void __launch_bounds__(kBlock)
 __global__ void __launch_bounds__(kBlock)
     seed_comp_kernel(const uint32_t* __restrict__ seed_slot, const uint32_t* __restrict__ parent,
                      const uint32_t* __restrict__ root_id, uint64_t n_seeds,
-                     uint32_t* __restrict__ seed_comp, uint32_t* __restrict__ rank,
-                     uint32_t* __restrict__ comp_seeds) {
+                     uint32_t* __restrict__ seed_comp, uint32_t* __restrict__ rank) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_seeds) return;
   uint32_t cid = root_id[parent[seed_slot[i]]];
   seed_comp[i] = cid;
   rank[i] = (uint32_t)i;
-  atomicAdd(&comp_seeds[cid], 1u);
+}
+
+// seeds per component and their offsets from the component-sorted seed list: two binary searches per
+// component instead of one atomic per seed (87 M atomics on a few thousand counters)
+__global__ void __launch_bounds__(kBlock)
+    seed_offsets_kernel(const uint32_t* __restrict__ seed_comp_s, uint64_t n_seeds, uint32_t n_comps,
+                        uint64_t* __restrict__ seed_off, uint32_t* __restrict__ comp_seeds) {
+  uint32_t cid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cid > n_comps) return;
+  uint64_t bound[2];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const uint64_t want = (uint64_t)cid + k;  // first seed whose component is >= want
+    uint64_t lo = 0, up = n_seeds;
+    while (lo < up) {
+      const uint64_t mid = (lo + up) >> 1;
+      if ((uint64_t)seed_comp_s[mid] < want)
+        lo = mid + 1;
+      else
+        up = mid;
+    }
+    bound[k] = lo;
+  }
+  seed_off[cid] = bound[0];
+  comp_seeds[cid] = cid < n_comps ? (uint32_t)(bound[1] - bound[0]) : 0u;
 }
 
 __global__ void __launch_bounds__(kBlock)
@@ -1617,7 +1640,7 @@ static bool l3_walks_impl(shn_ctx* c, uint32_t min_weight, uint32_t min_length, 
     ProfScope ps(c, "seed_group", 3);
     seed_comp_kernel<<<shn_grid(n_seeds, kBlock), kBlock, 0, st>>>(
         seed_slot.as<uint32_t>(), parent.as<uint32_t>(), root_id.as<uint32_t>(), n_seeds,
-        seed_comp.as<uint32_t>(), rank_in.as<uint32_t>(), comp_seeds.as<uint32_t>());
+        seed_comp.as<uint32_t>(), rank_in.as<uint32_t>());
     KERNEL_CHECK();
     int bits = 1;
     while (bits < 32 && (n_comps >> bits)) ++bits;
@@ -1641,7 +1664,13 @@ static bool l3_walks_impl(shn_ctx* c, uint32_t min_weight, uint32_t min_length, 
   parent.release();
   root_id.release();
   exclusive_sum_u32(c, comp_nodes.as<uint32_t>(), log_off.as<uint64_t>(), (uint64_t)n_comps + 1);
-  exclusive_sum_u32(c, comp_seeds.as<uint32_t>(), seed_off.as<uint64_t>(), (uint64_t)n_comps + 1);
+  if (n_seeds) {
+    seed_offsets_kernel<<<shn_grid((uint64_t)n_comps + 1, kBlock), kBlock, 0, st>>>(
+        seed_comp_s.as<uint32_t>(), n_seeds, n_comps, seed_off.as<uint64_t>(), comp_seeds.as<uint32_t>());
+    KERNEL_CHECK();
+  } else {
+    CUDA_CHECK(cudaMemsetAsync(seed_off.p, 0, ((uint64_t)n_comps + 1) * 8, st));
+  }
   // components that own at least one seed, in descending node count: similar-sized components
   // share a warp and the big ones start first
   DevBuf comp_order;
