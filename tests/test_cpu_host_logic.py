@@ -190,6 +190,98 @@ def test_duplicate_closed_form_equals_reference_loop(workdir, seed):
     assert seed < 3 or n_dup > 0
 
 
+def _frontier_resolution(cands, contigs, n_blocks, r):
+    """CPU model of the duplicate filter as the GPU runs it (l3.cu: l3_filter + dup_round_kernel,
+    selfjoin.cu): candidates in rank blocks; a block's pair table holds the partners d < j that are in
+    the block or ACCEPTED in an earlier block; inside a block synchronous frontier rounds resolve every
+    candidate whose `best` can no longer change.  Returns {candidate: 1 accepted / 2 rejected}, rounds."""
+    occ = {}
+
+    def rows_of(j, partners):
+        cj = contigs[j]
+        rows = []
+        for d in partners:
+            if d not in occ:
+                cd = contigs[d]
+                o = occ[d] = {}
+                for p in range(len(cd) - r + 1):
+                    o[cd[p:p + r]] = o.get(cd[p:p + r], 0) + 1
+            o = occ[d]
+            hits = [(i, o[cj[i:i + r]]) for i in range(len(cj) - r + 1) if cj[i:i + r] in o]
+            if hits:
+                cov = set()
+                for i, _ in hits:
+                    cov.update(range(i, i + r))
+                rows.append((d, sum(m for _, m in hits), hits[-1][0], len(cov)))
+        return rows
+
+    status = dict((j, 0) for j in cands)
+    size = max(1, (len(cands) + n_blocks - 1) // n_blocks)
+    total_rounds = 0
+    for b0 in range(0, len(cands), size):
+        block = cands[b0:b0 + size]
+        lo = block[0]
+        table = dict((j, rows_of(j, [d for d in cands if d < j and (d >= lo or status[d] == 1)])) for j in block)
+        for rounds in range(len(block) + 2):
+            new = dict(status)
+            unresolved = 0
+            for j in block:
+                if status[j]:
+                    continue
+                have = have_u = u_after = False
+                best = (0, 0, 0)
+                u = (0, 0)
+                for d, cnt, last, cov in table[j]:          # ascending d, like the pair table
+                    sd = status[d]
+                    if sd == 2:
+                        continue
+                    if sd == 1:
+                        if not have or cnt > best[0] or (cnt == best[0] and last >= best[1]):
+                            have, best, u_after = True, (cnt, last, cov), False
+                    else:
+                        if not have_u or cnt > u[0] or (cnt == u[0] and last >= u[1]):
+                            have_u, u = True, (cnt, last)
+                        if have and cnt == best[0] and last == best[1]:
+                            u_after = True
+                ready = not have_u
+                if have_u and have:
+                    u_wins = u[0] > best[0] or (u[0] == best[0] and u[1] > best[1]) or \
+                        (u[0] == best[0] and u[1] == best[1] and u_after)
+                    ready = not u_wins
+                if not ready:
+                    unresolved += 1
+                    continue
+                new[j] = 2 if (have and 2 * best[2] > len(contigs[j])) else 1
+            status = new
+            total_rounds += 1
+            if unresolved == 0:
+                break
+        else:
+            raise AssertionError("the frontier rounds do not converge")
+    return status, total_rounds
+
+
+@pytest.mark.parametrize("seed", range(6))
+@pytest.mark.parametrize("n_blocks", [1, 4])
+def test_duplicate_frontier_rounds_in_rank_blocks_equal_the_sequential_loop(workdir, seed, n_blocks):
+    """The parallel resolution order of the GPU's duplicate filter (rank blocks, accepted-only
+    partners from earlier blocks, frontier rounds) gives the accept / reject decisions of the
+    reference's sequential loop (extension_correction.py:358-361)."""
+    if seed < 3:
+        res = _oracle_result(workdir, seed, K=10 + seed % 3)
+    else:   # low thresholds: hundreds of error-bubble candidates, nearly all duplicates of a few contigs
+        s1, s2 = helpers.synthetic_seqs(10, 3000 if seed == 5 else 1200, seed)
+        case = helpers.make_case(workdir, 24, s1, s2)
+        out = case.outdir("o")
+        res = so.run_correction(case.k1mer_org, out + "/k", 2, 40, False, out, 500, True, True)
+    contigs = [w.contig for w in res.walks]
+    cands = [j for j, w in enumerate(res.walks) if w.passes_shape]   # the GPU's candidates (a5)
+    status, rounds = _frontier_resolution(cands, contigs, n_blocks, so.R_MER)
+    for j in cands:
+        assert (status[j] == 1) == bool(res.walks[j].accepted), "candidate %d" % j
+    assert rounds >= n_blocks and (seed < 3 or any(v == 2 for v in status.values()))
+
+
 @pytest.mark.parametrize("seed", range(4))
 def test_cmer_closed_form_equals_reference_loop(workdir, seed):
     """w(a,b) = sum over shared C-mers of occ_a * occ_b."""
